@@ -1,0 +1,183 @@
+/*
+ * mcsce_b200 — C ABI of the B200-native MCSCE side-chain growth path.
+ *
+ * The reference (THGLab/MCSCE) has no FFI for this path; its seam is a set of Python
+ * callables.  Each entry point below names the reference code it replaces (paths are
+ * relative to the reference's src/mcsce/).  The Python side of the drop-in
+ * (mcsce_b200/core, mcsce_b200/libs) binds these with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *  - every function returns 0 on success, <0 on error; mcsce_last_error() gives the text;
+ *  - pointers named d_* are device pointers (caller-owned, e.g. torch tensor data_ptr()),
+ *    pointers named h_* are host pointers; the library allocates only inside the handle;
+ *  - all launches go to the cudaStream_t passed as `stream` (void* here, 0 = default);
+ *  - a handle is bound to one device and is not thread-safe (one process per GPU);
+ *  - atoms are in "growth order": input (backbone) atoms in file order, then one side-chain
+ *    block per residue (libs/libstructure.py:498-514).
+ */
+#ifndef MCSCE_B200_H
+#define MCSCE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCSCE_MAX_CLS 64      /* distinct (sigma, epsilon, clash element) atom classes        */
+#define MCSCE_MAX_SP_ENV 16   /* environment atoms per residue scored pair-by-pair            */
+#define MCSCE_MAX_CHI 6       /* chi columns in a trial row (KCX carries 6, 5 are applied)    */
+#define MCSCE_MAX_CHI_ROT 5   /* chi rotations applied (libs/libscbuild.py:103-206)           */
+#define MCSCE_MAX_TMPL 32     /* template atoms (M3L: 31)                                     */
+#define MCSCE_MAX_SC 28       /* side-chain atoms (M3L: 26)                                   */
+
+typedef struct mcsce_handle_s *mcsce_handle;
+
+/* Static tables of one sequence.  Replaces what initialize_func_calc builds
+ * (core/side_chain_builder.py:42-107) and prepare_energy_function captures per residue
+ * (libs/libenergy.py:27-233): per-atom parameters instead of per-pair arrays, plus a short
+ * exact-coefficient list for the pairs within three bonds of each new side chain.          */
+typedef struct {
+    int32_t n_atoms, n_input, n_res, n_cls, n_types, n_sp_total;
+    /* per atom, growth order */
+    const int32_t *slot_of_atom;   /* [n_atoms] position in the class-sorted environment array   */
+    const int32_t *cls_of_atom;    /* [n_atoms]                                                  */
+    const double  *charge;         /* [n_atoms] e; zeros disable Coulomb                         */
+    const int32_t *resnum;         /* [n_atoms] residue number (bonded rules are keyed on it, libenergy.py:262-270) */
+    /* atom classes */
+    const int32_t *cls_start;      /* [n_cls+1] slot offsets                                     */
+    const int32_t *cls_active;     /* [(n_res+1)*n_cls] atoms of each class present when residue i grows */
+    const double  *cls_s2;         /* [n_cls*n_cls] ((sigma_i+sigma_j)*5)^2  A^2  (libenergy.py:478) */
+    const double  *cls_e4;         /* [n_cls*n_cls] 4*sqrt(eps_i*eps_j) kJ/mol (libenergy.py:474-481) */
+    const double  *cls_thr;        /* [n_cls*n_cls] 0.6*(r_i+r_j) A (libenergy.py:151-152); 0 = no clash test */
+    /* residue templates in use */
+    const int32_t *tmpl_n_atoms;   /* [n_types]                                                  */
+    const float   *tmpl_xyz;       /* [n_types*MAX_TMPL*3] float32 template, CA at origin        */
+    const int32_t *tmpl_sc_pos;    /* [n_types*MAX_SC] template position of the k-th side-chain atom */
+    const int32_t *tmpl_n_chi;     /* [n_types] rotations defined                                */
+    const int32_t *tmpl_axis;      /* [n_types*MAX_CHI_ROT*2] axis (from,to); `to` is the pivot  */
+    const uint32_t *tmpl_move;     /* [n_types*MAX_CHI_ROT] bit a set = template atom a moves    */
+    const double  *tmpl_ori;       /* [n_types*MAX_CHI_ROT] template dihedral, rad               */
+    /* per residue */
+    const int32_t *step_kind;      /* [n_res] 0 retained, 1 rigid (GLY/ALA), 2 grown             */
+    const int32_t *step_type;      /* [n_res] template index                                     */
+    const int32_t *step_n_sc;      /* [n_res]                                                    */
+    const int32_t *step_sc_start;  /* [n_res] growth index of the first side-chain atom          */
+    const int32_t *step_n_sp_env;  /* [n_res]                                                    */
+    const int32_t *step_sp_env;    /* [n_res*MAX_SP_ENV] growth indices of the special environment atoms */
+    const int32_t *step_sp_off;    /* [n_res] offset into sp_*                                   */
+    const int32_t *step_n_sp;      /* [n_res]                                                    */
+    const int32_t *sp_k;           /* [n_sp_total] new-atom index within the side chain          */
+    const int32_t *sp_partner;     /* [n_sp_total] >=0: index into the residue's special env list; <0: -(k'+1) */
+    const double  *sp_coef;        /* [n_sp_total*4] A, B, Q, clash distance  (exact per-pair values) */
+    /* input-atom self energy (core/side_chain_builder.py:149): special pairs of the input atoms */
+    int32_t n_bb_pairs;
+    const int32_t *bb_i, *bb_j;    /* [n_bb_pairs] growth indices, i<j                           */
+    const double  *bb_coef;        /* [n_bb_pairs*4]                                             */
+} mcsce_system_desc;
+
+/* Tables that depend on the backbone conformation: trial sets
+ * (core/rotamer_library.py:131-177) and the rigid placement of every residue template
+ * (libs/libcalc.py:449-482; depends on the backbone only).                                  */
+typedef struct {
+    int32_t n_trials_total;
+    const int32_t *step_n_trials;  /* [n_res]                                                    */
+    const int32_t *step_trial_off; /* [n_res]                                                    */
+    const int32_t *step_n_chi_lib; /* [n_res] chi columns in the trial rows                      */
+    const int32_t *step_n_chi;     /* [n_res] rotations applied                                  */
+    const double  *chi_mean;       /* [n_trials_total*MAX_CHI] degrees                           */
+    const double  *chi_sigma;      /* [n_trials_total*MAX_CHI] degrees (PTM extra chis), else 0  */
+    const double  *prob;           /* [n_trials_total] prior weights                             */
+    const double  *place_q1;       /* [n_res*4] quaternion (cos, sin*axis) of the N-CA alignment */
+    const double  *place_q2;       /* [n_res*4] quaternion of the N-CA-C plane alignment         */
+    const float   *place_ca;       /* [n_res*3] backbone CA                                      */
+    const float   *input_xyz;      /* [n_input*3] input atom coordinates (unrounded float32)     */
+} mcsce_backbone_desc;
+
+/* Options of one ensemble growth. */
+typedef struct {
+    int32_t n_conf;                /* conformers grown by this call                              */
+    int64_t conf_id0;              /* global id of the first conformer (RNG stream key; rank offset) */
+    uint64_t seed;
+    double beta;                   /* 1/(kT) mol/kJ (core/side_chain_builder.py:313)             */
+    double noise_deg;              /* chi perturbation sigma, 0.5 in the reference (:173)        */
+    /* optional replay inputs (parity runs); NULL = on-device Philox */
+    const double *d_chis;          /* [n_conf*n_trials_total*MAX_CHI] perturbed chi rows, degrees */
+    const double *d_uniform;       /* [n_conf*n_res] uniforms for the selection                  */
+    /* optional dumps; NULL = not written */
+    double *d_trial_energy;        /* [n_conf*n_trials_total] per-trial energies (inf = clash)   */
+    double *d_chis_out;            /* [n_conf*n_trials_total*MAX_CHI] chi rows actually used     */
+    int32_t *d_selected;           /* [n_conf*n_res] selected trial per residue (-1 = none)      */
+    int32_t env_split;             /* >0 forces the environment split factor; 0 = automatic      */
+} mcsce_grow_opts;
+
+const char *mcsce_last_error(void);
+int mcsce_version(void);
+
+int mcsce_create(mcsce_handle *out, int device);
+int mcsce_destroy(mcsce_handle h);
+
+/* replaces initialize_func_calc (core/side_chain_builder.py:42-107) */
+int mcsce_set_system(mcsce_handle h, const mcsce_system_desc *h_desc);
+/* per-backbone part: rotamer trial sets + template placement (side_chain_builder.py:144-147,171) */
+int mcsce_set_backbone(mcsce_handle h, const mcsce_backbone_desc *h_desc);
+
+/* bytes of caller-provided device workspace mcsce_grow needs for n_conf conformers */
+size_t mcsce_workspace_bytes(mcsce_handle h, int n_conf);
+
+/* Fused growth of n_conf independent conformers: for every residue, place the trial rotamers,
+ * score them against the conformer's environment, pick one by Boltzmann weight, append it.
+ * Replaces create_side_chain_structure (core/side_chain_builder.py:109-205) for a batch.
+ *   d_coords  [n_conf*n_atoms*3] float32, growth order (out)
+ *   d_energy  [n_conf] float64 accumulated energy incl. the input-atom self energy (out)
+ *   d_ok      [n_conf] uint8, 0 = every trial of some residue clashed (out)                  */
+int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *opts, void *d_workspace, size_t workspace_bytes,
+               float *d_coords, double *d_energy, uint8_t *d_ok, void *stream);
+
+/* Same with HOST result buffers: copies results device->host on `stream` and synchronises.
+ * Needs workspace_bytes(n_conf) + n_conf*(n_atoms*12+9) extra bytes of workspace.            */
+int mcsce_grow_host(mcsce_handle h, const mcsce_grow_opts *opts, void *d_workspace, size_t workspace_bytes,
+                    float *h_coords, double *h_energy, uint8_t *h_ok, void *stream);
+
+/* K1 - chi angles -> placed side-chain coordinates.  Replaces rotate_sidechain
+ * (libs/libscbuild.py:56-206) + place_sidechain_template (libs/libcalc.py:419-482) for a batch.
+ *   d_chis  [n_rows*MAX_CHI] degrees;  d_xyz [n_rows*n_sc*4] float32 (x,y,z,0) out            */
+int mcsce_place_trials(mcsce_handle h, int residue, int n_rows, const double *d_chis, float *d_xyz, void *stream);
+
+/* K2 - per-trial energy of residue `residue`'s side chain against an environment.  Replaces the
+ * closure returned by prepare_energy_function (libs/libenergy.py:786-810) incl. the clash filter.
+ *   n_env_sets environments of n_atoms slots each (float4 x,y,z,q; class-sorted slot order),
+ *   trials_per_env trial side chains per environment:
+ *   d_trial [n_env_sets*trials_per_env*n_sc*4] float32;  d_env [n_env_sets*n_atoms*4] float32
+ *   d_energy [n_env_sets*trials_per_env] float64 out, +inf where the clash filter fires       */
+int mcsce_score_trials(mcsce_handle h, int residue, int n_env_sets, int trials_per_env, const float *d_trial,
+                       const float *d_env, double *d_energy, void *d_workspace, size_t workspace_bytes,
+                       int env_split, void *stream);
+
+size_t mcsce_score_workspace_bytes(mcsce_handle h, int n_env_sets, int trials_per_env);
+
+/* growth-order coordinates -> environment arrays for mcsce_score_trials:
+ *   d_old_xyz [n_env_sets*n_old*3] float32 (the first n_old atoms in growth order)
+ *   d_env     [n_env_sets*n_atoms*4] float32 out (slot order, charge in w; other slots parked far away) */
+int mcsce_pack_env(mcsce_handle h, int n_env_sets, int n_old, const float *d_old_xyz, float *d_env, void *stream);
+
+/* K3 - Boltzmann selection.  Replaces side_chain_builder.py:183-193 + choose_random (:33-40).
+ *   d_energy [n_sets*n_trials], d_prob [n_trials], d_uniform [n_sets] ->
+ *   d_selected [n_sets] (-1 if every trial is +inf), d_emin [n_sets]                           */
+int mcsce_select(mcsce_handle h, int n_sets, int n_trials, const double *d_energy, const double *d_prob,
+                 double beta, const double *d_uniform, int32_t *d_selected, double *d_e_selected, void *stream);
+
+/* energy of the input atoms alone (core/side_chain_builder.py:149); uses the set backbone */
+int mcsce_input_energy(mcsce_handle h, double *d_energy, void *stream);
+
+/* scatter input + rigid atoms into environment arrays: d_env [n_env_sets*n_atoms*4] float32 */
+int mcsce_init_env(mcsce_handle h, int n_env_sets, float *d_env, void *stream);
+
+/* counters for the benchmark: kernels launched / algorithmic pair evaluations since the last reset */
+int mcsce_counters(mcsce_handle h, int64_t *launches, int64_t *pairs, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

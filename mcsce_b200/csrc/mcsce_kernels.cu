@@ -1,0 +1,1145 @@
+// mcsce_b200 — hand-written sm_100a kernels + C ABI for the MCSCE side-chain growth path.
+//
+// Kernels (one launch each per grown residue, all conformers at once):
+//   place_trials_kernel   K1  chi angles -> placed trial side chains          (warp = one trial, lane = one template atom)
+//   score_generic_kernel  K2  trial atoms x environment atoms, generic pairs  (thread = R trial atoms, env tiles in smem)
+//   score_special_kernel  K2s pairs within three bonds + intra-side-chain     (warp = one trial, exact float64)
+//   select_kernel         K3  clash mask + Boltzmann selection + append       (block = one conformer)
+// plus init_env / input_energy / gather kernels.  Reference file:line citations are in
+// include/mcsce_b200.h and DESIGN.md.
+//
+// Numerics contract: pair difference and d^2 in float32 with the reference's
+// operation order and no FMA contraction (libcalc.py:64-67,73-76), so clash decisions are bit-exact;
+// generic-pair energies in float32 with float64 accumulation every FLUSH pairs; special pairs and
+// the selection in float64; chi rotations in float64 with float32 rounding where the reference rounds.
+
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/mcsce_b200.h"
+
+#define MAX_CLS MCSCE_MAX_CLS
+#define MAX_SP_ENV MCSCE_MAX_SP_ENV
+#define MAX_CHI MCSCE_MAX_CHI
+#define MAX_ROT MCSCE_MAX_CHI_ROT
+#define MAX_TMPL MCSCE_MAX_TMPL
+#define MAX_SC MCSCE_MAX_SC
+
+static thread_local std::string g_err;
+static int fail(const std::string &m) { g_err = m; return -1; }
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    return fail(std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+// Coulomb prefactor: charges_ij *= 0.25; *= 1389.35  (libenergy.py:521-522)
+#define COULOMB_PREF (0.25 * 1389.35)
+
+// ------------------------------------------------------------------------------------------------
+// device-side tables
+// ------------------------------------------------------------------------------------------------
+struct StepDev {
+    int kind, type, n_sc, sc_start;
+    int n_sp_env, sp_off, n_sp, pad0;
+    int sp_env_slot[MAX_SP_ENV];
+    // backbone-dependent
+    int n_trials, trial_off, n_chi_lib, n_chi;
+    float ca[4];
+    double q1[4], q2[4];
+};
+
+struct TmplDev {
+    int n_atoms, n_chi;
+    float xyz[MAX_TMPL][3];
+    int sc_rank[MAX_TMPL];              // -1 for backbone atoms
+    int axis_from[MAX_ROT], axis_to[MAX_ROT];
+    unsigned move[MAX_ROT];
+    double ori[MAX_ROT];
+};
+
+struct SysDev {
+    int n_atoms, n_input, n_res, n_cls, n_types;
+    const int *slot_of_atom, *cls_of_atom, *cls_start, *cls_active;
+    const double *charge;
+    const float *cls_s2f, *cls_thr2f;
+    const double *cls_e4, *cls_s2d, *cls_thrd;
+    const StepDev *steps;
+    const TmplDev *tmpl;
+    const int *sp_k, *sp_partner;
+    const double *sp_coef;
+    const int *resnum;
+    int n_bb_pairs;
+    const int *bb_i, *bb_j;
+    const double *bb_coef;
+    // backbone
+    const double *chi_mean, *chi_sigma, *prob;
+    const float *input_xyz, *rigid_xyz;
+    int n_trials_total;
+};
+
+// ------------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float dist2_ref(float ax, float ay, float az, float bx, float by, float bz) {
+    // x = b - a ; x*x + y*y + z*z, float32, unfused (libcalc.py:64-67)
+    float x = __fsub_rn(bx, ax), y = __fsub_rn(by, ay), z = __fsub_rn(bz, az);
+    return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+}
+
+__device__ __forceinline__ void quat_rotate(const double b1, const double b2, const double b3, const double b4,
+                                            double x, double y, double z, double &ox, double &oy, double &oz) {
+    // two Hamilton products evaluated term by term, left to right, unfused (libcalc.py:359-366, 404-412)
+    double c1 = __dsub_rn(__dsub_rn(__dsub_rn(__dmul_rn(b1, 0.0), __dmul_rn(b2, x)), __dmul_rn(b3, y)), __dmul_rn(b4, z));
+    double c2 = __dsub_rn(__dadd_rn(__dadd_rn(__dmul_rn(b1, x), __dmul_rn(b2, 0.0)), __dmul_rn(b3, z)), __dmul_rn(b4, y));
+    double c3 = __dadd_rn(__dadd_rn(__dsub_rn(__dmul_rn(b1, y), __dmul_rn(b2, z)), __dmul_rn(b3, 0.0)), __dmul_rn(b4, x));
+    double c4 = __dadd_rn(__dsub_rn(__dadd_rn(__dmul_rn(b1, z), __dmul_rn(b2, y)), __dmul_rn(b3, x)), __dmul_rn(b4, 0.0));
+    double n2 = -b2, n3 = -b3, n4 = -b4;
+    ox = __dsub_rn(__dadd_rn(__dadd_rn(__dmul_rn(c1, n2), __dmul_rn(c2, b1)), __dmul_rn(c3, n4)), __dmul_rn(c4, n3));
+    oy = __dadd_rn(__dadd_rn(__dsub_rn(__dmul_rn(c1, n3), __dmul_rn(c2, n4)), __dmul_rn(c3, b1)), __dmul_rn(c4, n2));
+    oz = __dadd_rn(__dsub_rn(__dadd_rn(__dmul_rn(c1, n4), __dmul_rn(c2, n3)), __dmul_rn(c3, n2)), __dmul_rn(c4, b1));
+}
+
+// Philox4x32-10 (Salmon et al. 2011), counter-based: one call per (conformer, residue, trial, chi)
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+    const unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        unsigned hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        unsigned hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0; key.y += W1;
+    }
+    return ctr;
+}
+__device__ __forceinline__ double u01_open(unsigned a, unsigned b) {   // (0,1]
+    unsigned long long v = ((unsigned long long)a << 21) ^ (unsigned long long)(b >> 11);
+    return ((double)(v & ((1ull << 53) - 1)) + 1.0) * (1.0 / 9007199254740992.0);
+}
+__device__ __forceinline__ double u01_halfopen(unsigned a, unsigned b) {   // [0,1)
+    unsigned long long v = ((unsigned long long)a << 21) ^ (unsigned long long)(b >> 11);
+    return (double)(v & ((1ull << 53) - 1)) * (1.0 / 9007199254740992.0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: chi -> xyz.   grid (ceil(n_trials/4), n_sets), block 128: one warp per trial row
+// ------------------------------------------------------------------------------------------------
+struct PlaceArgs {
+    SysDev s;
+    int step;
+    int n_trials;             // rows per set
+    const double *chis_in;    // explicit rows [set][row_stride] or null
+    long long chis_set_stride;  // doubles between sets in chis_in / chis_out
+    long long chis_row_off;     // offset (in rows) of this residue's first row inside a set
+    double *chis_out;         // optional dump, same layout
+    float4 *trial;            // [set][n_trials*n_sc]
+    long long trial_set_stride;
+    const unsigned char *alive;
+    unsigned long long seed;
+    long long conf_id0;
+    double noise_deg;
+};
+
+__global__ void __launch_bounds__(128) place_trials_kernel(PlaceArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int set = blockIdx.y;
+    if (t >= a.n_trials) return;
+    if (a.alive && !a.alive[set]) return;
+    const StepDev &st = a.s.steps[a.step];
+    const TmplDev &tm = a.s.tmpl[st.type];
+    const bool has = lane < tm.n_atoms;
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (has) { x = tm.xyz[lane][0]; y = tm.xyz[lane][1]; z = tm.xyz[lane][2]; }
+
+    // --- trial chi row (degrees) ---
+    double chi[MAX_ROT];
+    {
+        const long long row = a.chis_row_off + t;
+        if (a.chis_in) {
+#pragma unroll
+            for (int k = 0; k < MAX_ROT; ++k)
+                chi[k] = (k < st.n_chi) ? a.chis_in[(long long)set * a.chis_set_stride + row * MAX_CHI + k] : 0.0;
+            if (a.chis_out && lane < MAX_CHI)
+                a.chis_out[(long long)set * a.chis_set_stride + row * MAX_CHI + lane] =
+                    a.chis_in[(long long)set * a.chis_set_stride + row * MAX_CHI + lane];
+        } else {
+            // wrap(mean + sigma*z1) + noise*z2   (rotamer_library.py:155,165 ; side_chain_builder.py:173)
+            double mine = 0.0;
+            if (lane < st.n_chi_lib) {
+                const long long trow = (long long)st.trial_off + t;
+                uint4 r = philox4x32(make_uint4((unsigned)(a.conf_id0 + set), (unsigned)((a.conf_id0 + set) >> 32),
+                                                (unsigned)a.step, ((unsigned)t << 3) | (unsigned)lane),
+                                     make_uint2((unsigned)a.seed, (unsigned)(a.seed >> 32)));
+                double u1 = u01_open(r.x, r.y), u2 = u01_halfopen(r.z, r.w);
+                double rad = sqrt(-2.0 * log(u1)), sn, cs;
+                sincospi(2.0 * u2, &sn, &cs);
+                double v = a.s.chi_mean[trow * MAX_CHI + lane];
+                double sg = a.s.chi_sigma[trow * MAX_CHI + lane];
+                if (sg != 0.0) {
+                    v = v + sg * (rad * cs);
+                    if (v > 180.0) v -= 360.0;
+                    if (v < -180.0) v += 360.0;
+                }
+                mine = v + a.noise_deg * (rad * sn);
+                if (a.chis_out) a.chis_out[(long long)set * a.chis_set_stride + row * MAX_CHI + lane] = mine;
+            } else if (a.chis_out && lane < MAX_CHI) {
+                a.chis_out[(long long)set * a.chis_set_stride + row * MAX_CHI + lane] = 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < MAX_ROT; ++k) chi[k] = __shfl_sync(0xffffffffu, mine, k);
+        }
+    }
+
+    // --- chi rotations, innermost atoms last; float32 storage after every rotation (libscbuild.py:108) ---
+    const int n_rot = st.n_chi;
+    for (int k = 0; k < n_rot; ++k) {
+        const int af = tm.axis_from[k], at = tm.axis_to[k];
+        const float fx = __shfl_sync(0xffffffffu, x, af), fy = __shfl_sync(0xffffffffu, y, af), fz = __shfl_sync(0xffffffffu, z, af);
+        const float px = __shfl_sync(0xffffffffu, x, at), py = __shfl_sync(0xffffffffu, y, at), pz = __shfl_sync(0xffffffffu, z, at);
+        // unit axis in float32: (to - from)/|to - from|   (libscbuild.py:105,115,169,185,199)
+        const float ux = __fsub_rn(px, fx), uy = __fsub_rn(py, fy), uz = __fsub_rn(pz, fz);
+        const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)), __fmul_rn(uz, uz)));
+        const float ex = __fdiv_rn(ux, nrm), ey = __fdiv_rn(uy, nrm), ez = __fdiv_rn(uz, nrm);
+        double rot = tm.ori[k] - chi[k] * CUDART_PI / 180.0;          // measured - target (libscbuild.py:47)
+        if (rot > CUDART_PI) rot -= 2.0 * CUDART_PI;
+        else if (rot < -CUDART_PI) rot += 2.0 * CUDART_PI;
+        double sn, cs;
+        sincos(rot * 0.5, &sn, &cs);
+        // rotation about MINUS the unit axis (libscbuild.py:52)
+        const double b2 = sn * (double)(-ex), b3 = sn * (double)(-ey), b4 = sn * (double)(-ez);
+        if (has && ((tm.move[k] >> lane) & 1u)) {
+            const float dx = __fsub_rn(x, px), dy = __fsub_rn(y, py), dz = __fsub_rn(z, pz);   // float32 (libscbuild.py:44)
+            double ox, oy, oz;
+            quat_rotate(cs, b2, b3, b4, (double)dx, (double)dy, (double)dz, ox, oy, oz);
+            x = __double2float_rn(__dadd_rn(ox, (double)px));
+            y = __double2float_rn(__dadd_rn(oy, (double)py));
+            z = __double2float_rn(__dadd_rn(oz, (double)pz));
+        }
+    }
+
+    // --- rigid placement: two rotations (first stored to float32) + CA (libcalc.py:465,480-482) ---
+    if (has) {
+        double ox, oy, oz;
+        quat_rotate(st.q1[0], st.q1[1], st.q1[2], st.q1[3], (double)x, (double)y, (double)z, ox, oy, oz);
+        const float rx = __double2float_rn(ox), ry = __double2float_rn(oy), rz = __double2float_rn(oz);
+        quat_rotate(st.q2[0], st.q2[1], st.q2[2], st.q2[3], (double)rx, (double)ry, (double)rz, ox, oy, oz);
+        const int rank = tm.sc_rank[lane];
+        if (rank >= 0) {
+            float4 o;
+            o.x = __double2float_rn(__dadd_rn(ox, (double)st.ca[0]));
+            o.y = __double2float_rn(__dadd_rn(oy, (double)st.ca[1]));
+            o.z = __double2float_rn(__dadd_rn(oz, (double)st.ca[2]));
+            o.w = 0.f;
+            a.trial[(long long)set * a.trial_set_stride + (long long)t * st.n_sc + rank] = o;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: generic pairs.  grid (trial tiles, n_sets, env_split), block SCORE_THREADS.
+// ------------------------------------------------------------------------------------------------
+#define SCORE_THREADS 256
+#define SCORE_R 2                       // trial atoms per thread
+#define TILE_A (SCORE_THREADS * SCORE_R)
+#define TILE_E 1024                     // environment atoms staged per smem tile
+#define FLUSH 32                        // pairs accumulated in float32 before a float64 flush
+
+struct ScoreArgs {
+    SysDev s;
+    int step;
+    int n_trials;                      // per set
+    int trials_per_tile;
+    int n_split;
+    const float4 *env;                 // [set][n_atoms]  slot order
+    const float4 *trial;               // [set][n_trials*n_sc]
+    long long trial_set_stride;
+    double2 *partial;                  // [set][n_trials][n_split] (energy, clash)
+    const unsigned char *alive;
+};
+
+__global__ void __launch_bounds__(SCORE_THREADS) score_generic_kernel(ScoreArgs a) {
+    __shared__ float4 s_env[TILE_E];
+    __shared__ int s_prefix[MAX_CLS + 1];
+    __shared__ int s_sp[MAX_SP_ENV];
+    __shared__ double s_e[TILE_A];
+    __shared__ unsigned char s_clash[TILE_A];
+
+    const int set = blockIdx.y;
+    if (a.alive && !a.alive[set]) return;
+    const int tid = threadIdx.x;
+    const StepDev &st = a.s.steps[a.step];
+    const int n_cls = a.s.n_cls;
+    const int n_sc = st.n_sc;
+
+    if (tid == 0) {
+        int acc = 0;
+        for (int c = 0; c < n_cls; ++c) { s_prefix[c] = acc; acc += a.s.cls_active[a.step * n_cls + c]; }
+        s_prefix[n_cls] = acc;
+    }
+    if (tid < MAX_SP_ENV) s_sp[tid] = (tid < st.n_sp_env) ? st.sp_env_slot[tid] : -1;
+    __syncthreads();
+    const int n_active = s_prefix[n_cls];
+
+    // this block's trial atoms
+    const int t0 = blockIdx.x * a.trials_per_tile;
+    const int nt = min(a.trials_per_tile, a.n_trials - t0);
+    const int n_local = nt * n_sc;
+    const float4 *trial = a.trial + (long long)set * a.trial_set_stride + (long long)t0 * n_sc;
+
+    float xi[SCORE_R], yi[SCORE_R], zi[SCORE_R];
+    int ci[SCORE_R];
+    bool valid[SCORE_R];
+    double e_lj[SCORE_R], e_c[SCORE_R];
+    bool clash[SCORE_R];
+#pragma unroll
+    for (int r = 0; r < SCORE_R; ++r) {
+        const int la = r * SCORE_THREADS + tid;
+        valid[r] = la < n_local;
+        const int la_c = valid[r] ? la : 0;
+        const float4 p = trial[la_c];
+        xi[r] = p.x; yi[r] = p.y; zi[r] = p.z;
+        ci[r] = a.s.cls_of_atom[st.sc_start + (la_c % n_sc)];
+        e_lj[r] = 0.0; e_c[r] = 0.0; clash[r] = false;
+    }
+
+    // environment chunk of this block (active order = class-major prefix order)
+    const int per = (n_active + a.n_split - 1) / a.n_split;
+    const int lo = blockIdx.z * per;
+    const int hi = min(n_active, lo + per);
+    const float4 *env = a.env + (long long)set * a.s.n_atoms;
+
+    for (int tile_lo = lo; tile_lo < hi; tile_lo += TILE_E) {
+        const int tile_n = min(TILE_E, hi - tile_lo);
+        __syncthreads();
+        for (int e = tid; e < tile_n; e += SCORE_THREADS) {
+            const int ae = tile_lo + e;
+            int c_lo = 0, c_hi = n_cls;                     // largest c with prefix[c] <= ae
+            while (c_hi - c_lo > 1) { int m = (c_lo + c_hi) >> 1; if (s_prefix[m] <= ae) c_lo = m; else c_hi = m; }
+            const int slot = a.s.cls_start[c_lo] + (ae - s_prefix[c_lo]);
+            float4 v = env[slot];
+            bool special = false;
+#pragma unroll
+            for (int q = 0; q < MAX_SP_ENV; ++q) special |= (s_sp[q] == slot);
+            if (special) v = make_float4(1.0e15f, 1.0e15f, 1.0e15f, 0.f);   // scored by the special-pair kernel
+            s_env[e] = v;
+        }
+        __syncthreads();
+        // classes intersecting the tile
+        int c = 0;
+        { int c_lo = 0, c_hi = n_cls; while (c_hi - c_lo > 1) { int m = (c_lo + c_hi) >> 1; if (s_prefix[m] <= tile_lo) c_lo = m; else c_hi = m; } c = c_lo; }
+        for (; c < n_cls && s_prefix[c] < tile_lo + tile_n; ++c) {
+            const int j0 = max(s_prefix[c], tile_lo) - tile_lo;
+            const int j1 = min(s_prefix[c + 1], tile_lo + tile_n) - tile_lo;
+            if (j0 >= j1) continue;
+            float s2[SCORE_R], thr2[SCORE_R];
+            double e4[SCORE_R];
+#pragma unroll
+            for (int r = 0; r < SCORE_R; ++r) {
+                s2[r] = __ldg(&a.s.cls_s2f[ci[r] * n_cls + c]);
+                thr2[r] = __ldg(&a.s.cls_thr2f[ci[r] * n_cls + c]);
+                e4[r] = __ldg(&a.s.cls_e4[ci[r] * n_cls + c]);
+            }
+            for (int jb = j0; jb < j1; jb += FLUSH) {
+                const int je = min(jb + FLUSH, j1);
+                float lj[SCORE_R], cq[SCORE_R];
+#pragma unroll
+                for (int r = 0; r < SCORE_R; ++r) { lj[r] = 0.f; cq[r] = 0.f; }
+#pragma unroll 4
+                for (int j = jb; j < je; ++j) {
+                    const float4 ev = s_env[j];
+#pragma unroll
+                    for (int r = 0; r < SCORE_R; ++r) {
+                        const float d2 = dist2_ref(xi[r], yi[r], zi[r], ev.x, ev.y, ev.z);
+                        clash[r] |= (d2 < thr2[r]);
+                        float rinv;
+                        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(d2));
+                        // one Newton step: rinv <- rinv + 0.5*rinv*(1 - d2*rinv^2)
+                        const float h = d2 * rinv;
+                        const float err = fmaf(-h, rinv, 1.0f);
+                        rinv = fmaf(0.5f * rinv, err, rinv);
+                        const float inv2 = rinv * rinv;
+                        const float t = s2[r] * inv2;
+                        const float t3 = t * t * t;
+                        lj[r] = fmaf(t3, t3 - 1.0f, lj[r]);
+                        cq[r] = fmaf(ev.w, rinv, cq[r]);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < SCORE_R; ++r) {
+                    e_lj[r] += e4[r] * (double)lj[r];
+                    e_c[r] += (double)cq[r];
+                }
+            }
+        }
+    }
+
+    // per-atom totals -> per-trial partial sums (fixed order)
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < SCORE_R; ++r) {
+        const int la = r * SCORE_THREADS + tid;
+        if (valid[r]) {
+            const double qi = a.s.charge[st.sc_start + (la % n_sc)];
+            s_e[la] = e_lj[r] + COULOMB_PREF * qi * e_c[r];
+            s_clash[la] = clash[r] ? 1 : 0;
+        }
+    }
+    __syncthreads();
+    if (tid < nt) {
+        double e = 0.0; int cl = 0;
+        for (int k = 0; k < n_sc; ++k) { e += s_e[tid * n_sc + k]; cl |= s_clash[tid * n_sc + k]; }
+        a.partial[((long long)set * a.n_trials + (t0 + tid)) * a.n_split + blockIdx.z] = make_double2(e, cl ? 1.0 : 0.0);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2s: special pairs in float64.  grid (ceil(n_trials/8), n_sets), block 256: one warp per trial
+// ------------------------------------------------------------------------------------------------
+struct SpecialArgs {
+    SysDev s;
+    int step;
+    int n_trials;
+    const float4 *env;
+    const float4 *trial;
+    long long trial_set_stride;
+    double2 *sp_partial;               // [set][n_trials]
+    const unsigned char *alive;
+};
+
+__device__ __forceinline__ double pair_energy_f64(float d2f, double A, double B, double Q, double thr, bool &clash) {
+    // d = sqrt(float64(d2)); clash = d < thr; e = A/d^12 - B/d^6 + Q/d   (libenergy.py:683-688, 720, 798)
+    const double d2 = (double)d2f;
+    const double d = sqrt(d2);
+    clash = d < thr;
+    const double d6 = d2 * d2 * d2;
+    double e = 0.0;
+    if (A != 0.0 || B != 0.0) e = A / (d6 * d6) - B / d6;
+    if (Q != 0.0) e += Q / d;
+    return e;
+}
+
+__global__ void __launch_bounds__(256) score_special_kernel(SpecialArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int set = blockIdx.y;
+    if (t >= a.n_trials) return;
+    if (a.alive && !a.alive[set]) return;
+    const StepDev &st = a.s.steps[a.step];
+    const float4 *trial = a.trial + (long long)set * a.trial_set_stride + (long long)t * st.n_sc;
+    const float4 *env = a.env + (long long)set * a.s.n_atoms;
+    double e = 0.0; bool any = false;
+    for (int p = lane; p < st.n_sp; p += 32) {
+        const int k = a.s.sp_k[st.sp_off + p];
+        const int pa = a.s.sp_partner[st.sp_off + p];
+        const double *cf = a.s.sp_coef + (long long)(st.sp_off + p) * 4;
+        const float4 an = trial[k];
+        const float4 bo = (pa >= 0) ? env[st.sp_env_slot[pa]] : trial[-pa - 1];
+        const float d2 = dist2_ref(an.x, an.y, an.z, bo.x, bo.y, bo.z);
+        bool cl;
+        e += pair_energy_f64(d2, cf[0], cf[1], cf[2], cf[3], cl);
+        any |= cl;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) e += __shfl_xor_sync(0xffffffffu, e, off);
+    any = __any_sync(0xffffffffu, any);
+    if (lane == 0) a.sp_partial[(long long)set * a.n_trials + t] = make_double2(e, any ? 1.0 : 0.0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: clash mask + Boltzmann selection + append.  grid (n_sets), block 128, dyn smem 2*n_trials doubles
+// ------------------------------------------------------------------------------------------------
+struct SelectArgs {
+    SysDev s;
+    int step;
+    int n_trials, n_split;
+    const double2 *partial, *sp_partial;
+    const double *prob;                // [n_trials]
+    double beta;
+    const double *uniform;             // explicit [set*u_stride + step] or null
+    int u_stride;
+    unsigned long long seed;
+    long long conf_id0;
+    float4 *env;
+    const float4 *trial;
+    long long trial_set_stride;
+    unsigned char *alive;
+    double *e_acc;
+    int *selected;                     // optional [set*n_res + step]
+    double *trial_energy;              // optional dump [set*n_trials_total + trial_off + t]
+    unsigned long long *pair_counter;
+    long long pairs_per_set;
+};
+
+__global__ void __launch_bounds__(128) select_kernel(SelectArgs a) {
+    extern __shared__ double s_dyn[];
+    double *s_E = s_dyn, *s_w = s_dyn + a.n_trials;
+    __shared__ double s_red[4];
+    __shared__ int s_sel;
+    const int set = blockIdx.x, tid = threadIdx.x;
+    if (a.alive && !a.alive[set]) {
+        if (a.selected && tid == 0) a.selected[(long long)set * a.s.n_res + a.step] = -1;
+        return;
+    }
+    const StepDev &st = a.s.steps[a.step];
+    double mn = CUDART_INF;
+    for (int t = tid; t < a.n_trials; t += 128) {
+        const double2 sp = a.sp_partial[(long long)set * a.n_trials + t];
+        double e = sp.x; bool cl = sp.y != 0.0;
+        for (int zz = 0; zz < a.n_split; ++zz) {
+            const double2 p = a.partial[((long long)set * a.n_trials + t) * a.n_split + zz];
+            e += p.x; cl |= (p.y != 0.0);
+        }
+        if (cl) e = CUDART_INF;                               // energies[clash] = inf (libenergy.py:801)
+        s_E[t] = e;
+        if (a.trial_energy) a.trial_energy[(long long)set * a.s.n_trials_total + st.trial_off + t] = e;
+        mn = fmin(mn, e);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+    if ((tid & 31) == 0) s_red[tid >> 5] = mn;
+    __syncthreads();
+    mn = fmin(fmin(s_red[0], s_red[1]), fmin(s_red[2], s_red[3]));
+    if (tid == 0 && a.pair_counter) atomicAdd(a.pair_counter, (unsigned long long)a.pairs_per_set);
+    if (isinf(mn) || isnan(mn)) {                             // every trial clashes: growth fails (side_chain_builder.py:187)
+        if (tid == 0) {
+            a.alive[set] = 0;
+            if (a.selected) a.selected[(long long)set * a.s.n_res + a.step] = -1;
+        }
+        return;
+    }
+    for (int t = tid; t < a.n_trials; t += 128)
+        s_w[t] = a.prob[t] * exp(-a.beta * (s_E[t] - mn));    // side_chain_builder.py:191-192
+    __syncthreads();
+    if (tid == 0) {
+        double u;
+        if (a.uniform) u = a.uniform[(long long)set * a.u_stride + a.step];
+        else {
+            uint4 r = philox4x32(make_uint4((unsigned)(a.conf_id0 + set), (unsigned)((a.conf_id0 + set) >> 32),
+                                            (unsigned)a.step, 0xFFFFFFFFu),
+                                 make_uint2((unsigned)a.seed, (unsigned)(a.seed >> 32)));
+            u = u01_halfopen(r.x, r.y);
+        }
+        // sequential float64 running sums, first index whose sum exceeds u*total (side_chain_builder.py:35-40)
+        double total = 0.0;
+        for (int t = 0; t < a.n_trials; ++t) total += s_w[t];
+        const double pointer = u * total;
+        int sel = a.n_trials - 1;
+        double run = 0.0;
+        for (int t = 0; t < a.n_trials; ++t) { run += s_w[t]; if (run > pointer) { sel = t; break; } }
+        s_sel = sel;
+        a.e_acc[set] += (s_E[sel] - mn) + mn;                 // side_chain_builder.py:197
+        if (a.selected) a.selected[(long long)set * a.s.n_res + a.step] = sel;
+    }
+    __syncthreads();
+    const int sel = s_sel;
+    if (tid < st.n_sc) {
+        float4 p = a.trial[(long long)set * a.trial_set_stride + (long long)sel * st.n_sc + tid];
+        const int atom = st.sc_start + tid;
+        p.w = (float)a.s.charge[atom];
+        a.env[(long long)set * a.s.n_atoms + a.s.slot_of_atom[atom]] = p;
+    }
+}
+
+// stand-alone selection on caller-provided energies (C-ABI mcsce_select)
+__global__ void __launch_bounds__(128) select_plain_kernel(int n_trials, const double *energy, const double *prob, double beta,
+                                                           const double *uniform, int *selected, double *e_sel) {
+    extern __shared__ double s_w[];
+    __shared__ double s_red[4];
+    const int set = blockIdx.x, tid = threadIdx.x;
+    const double *E = energy + (long long)set * n_trials;
+    double mn = CUDART_INF;
+    for (int t = tid; t < n_trials; t += 128) mn = fmin(mn, E[t]);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+    if ((tid & 31) == 0) s_red[tid >> 5] = mn;
+    __syncthreads();
+    mn = fmin(fmin(s_red[0], s_red[1]), fmin(s_red[2], s_red[3]));
+    if (isinf(mn) || isnan(mn)) { if (tid == 0) { selected[set] = -1; e_sel[set] = CUDART_INF; } return; }
+    for (int t = tid; t < n_trials; t += 128) s_w[t] = prob[t] * exp(-beta * (E[t] - mn));
+    __syncthreads();
+    if (tid == 0) {
+        double total = 0.0;
+        for (int t = 0; t < n_trials; ++t) total += s_w[t];
+        const double pointer = uniform[set] * total;
+        int sel = n_trials - 1; double run = 0.0;
+        for (int t = 0; t < n_trials; ++t) { run += s_w[t]; if (run > pointer) { sel = t; break; } }
+        selected[set] = sel; e_sel[set] = (E[sel] - mn) + mn;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// environment init, input-atom self energy, result gather
+// ------------------------------------------------------------------------------------------------
+__global__ void init_env_kernel(SysDev s, int n_sets, float4 *env) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)n_sets * s.n_atoms) return;
+    const int atom = (int)(i % s.n_atoms);
+    const int set = (int)(i / s.n_atoms);
+    float4 v = make_float4(1.0e15f, 1.0e15f, 1.0e15f, 0.f);
+    const float q = (float)s.charge[atom];
+    if (atom < s.n_input) v = make_float4(s.input_xyz[atom * 3], s.input_xyz[atom * 3 + 1], s.input_xyz[atom * 3 + 2], q);
+    else {
+        // GLY/ALA side chains are conformer independent: placed once (side_chain_builder.py:164-168)
+        const float rx = s.rigid_xyz[atom * 3];
+        if (!isnan(rx)) v = make_float4(rx, s.rigid_xyz[atom * 3 + 1], s.rigid_xyz[atom * 3 + 2], q);
+    }
+    env[(long long)set * s.n_atoms + s.slot_of_atom[atom]] = v;
+}
+
+__global__ void gather_kernel(SysDev s, int n_sets, const float4 *env, float *coords) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)n_sets * s.n_atoms) return;
+    const int atom = (int)(i % s.n_atoms);
+    const int set = (int)(i / s.n_atoms);
+    const float4 v = env[(long long)set * s.n_atoms + s.slot_of_atom[atom]];
+    coords[i * 3] = v.x; coords[i * 3 + 1] = v.y; coords[i * 3 + 2] = v.z;
+}
+
+// generic input-input pairs, one thread per row i, float64; same/adjacent residue numbers are in bb list
+__global__ void input_energy_rows_kernel(SysDev s, double2 *row_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= s.n_input) return;
+    const float ax = s.input_xyz[i * 3], ay = s.input_xyz[i * 3 + 1], az = s.input_xyz[i * 3 + 2];
+    const int ci = s.cls_of_atom[i], ri = s.resnum[i];
+    const double qi = s.charge[i];
+    double e = 0.0; bool any = false;
+    for (int j = i + 1; j < s.n_input; ++j) {
+        const int dr = s.resnum[j] - ri;
+        if (dr >= -1 && dr <= 1) continue;
+        const int cj = s.cls_of_atom[j];
+        const float d2 = dist2_ref(ax, ay, az, s.input_xyz[j * 3], s.input_xyz[j * 3 + 1], s.input_xyz[j * 3 + 2]);
+        const double s2 = s.cls_s2d[ci * s.n_cls + cj], e4 = s.cls_e4[ci * s.n_cls + cj];
+        const double s6 = s2 * s2 * s2;
+        bool cl;
+        e += pair_energy_f64(d2, e4 * s6 * s6, e4 * s6, COULOMB_PREF * qi * s.charge[j], s.cls_thrd[ci * s.n_cls + cj], cl);
+        any |= cl;
+    }
+    row_out[i] = make_double2(e, any ? 1.0 : 0.0);
+}
+
+__global__ void input_energy_pairs_kernel(SysDev s, double2 *pair_out) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= s.n_bb_pairs) return;
+    const int i = s.bb_i[p], j = s.bb_j[p];
+    const double *cf = s.bb_coef + (long long)p * 4;
+    const float d2 = dist2_ref(s.input_xyz[i * 3], s.input_xyz[i * 3 + 1], s.input_xyz[i * 3 + 2],
+                               s.input_xyz[j * 3], s.input_xyz[j * 3 + 1], s.input_xyz[j * 3 + 2]);
+    bool cl;
+    const double e = pair_energy_f64(d2, cf[0], cf[1], cf[2], cf[3], cl);
+    pair_out[p] = make_double2(e, cl ? 1.0 : 0.0);
+}
+
+__global__ void input_energy_reduce_kernel(int n_rows, const double2 *rows, int n_pairs, const double2 *pairs, double *out) {
+    // single block, fixed-order tree: deterministic
+    __shared__ double s_sum[256];
+    __shared__ int s_cl[256];
+    double e = 0.0; int cl = 0;
+    for (int i = threadIdx.x; i < n_rows; i += 256) { e += rows[i].x; cl |= rows[i].y != 0.0; }
+    for (int i = threadIdx.x; i < n_pairs; i += 256) { e += pairs[i].x; cl |= pairs[i].y != 0.0; }
+    s_sum[threadIdx.x] = e; s_cl[threadIdx.x] = cl;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) { s_sum[threadIdx.x] += s_sum[threadIdx.x + w]; s_cl[threadIdx.x] |= s_cl[threadIdx.x + w]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = s_cl[0] ? CUDART_INF : s_sum[0];
+}
+
+__global__ void init_state_kernel(int n_sets, unsigned char *alive, double *e_acc, const double *e_input) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_sets) { alive[i] = 1; e_acc[i] = e_input[0]; }
+}
+
+__global__ void finish_kernel(int n_sets, const unsigned char *alive, const double *e_acc, double *energy, unsigned char *ok) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_sets) { ok[i] = alive[i]; energy[i] = alive[i] ? e_acc[i] : CUDART_NAN; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: handle, table upload, launch logic
+// ------------------------------------------------------------------------------------------------
+struct mcsce_handle_s {
+    int device = 0;
+    int sm_count = 148;
+    std::vector<void *> sys_allocs, bb_allocs;
+    SysDev d{};
+    bool has_sys = false, has_bb = false;
+    // host mirrors needed for launch geometry
+    std::vector<StepDev> steps;
+    std::vector<int> cls_active;
+    std::vector<int> step_n_sp_env;
+    int max_trials = 0, max_trial_atoms = 0;
+    StepDev *d_steps = nullptr;
+    unsigned long long *d_pairs = nullptr;
+    double *d_input_energy = nullptr;
+    long long launches = 0;
+};
+
+template <typename T>
+static int upload(mcsce_handle h, std::vector<void *> &pool, const T *src, size_t n, const T **dst) {
+    void *p = nullptr;
+    size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    CK(cudaMalloc(&p, bytes));
+    pool.push_back(p);
+    if (n) CK(cudaMemcpy(p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    *dst = (const T *)p;
+    return 0;
+}
+static void free_pool(std::vector<void *> &pool) { for (void *p : pool) cudaFree(p); pool.clear(); }
+
+// float32 t2 such that for every float32 d2: (d2 < t2) <=> (sqrt((double)d2) < thr)
+static float exact_thr2(double thr) {
+    if (!(thr > 0.0)) return 0.0f;
+    auto pred = [&](float x) { return sqrt((double)x) < thr; };
+    float x = (float)(thr * thr);
+    while (pred(x)) x = nextafterf(x, INFINITY);
+    while (x > 0.f && !pred(nextafterf(x, 0.f))) x = nextafterf(x, 0.f);
+    return x;
+}
+
+extern "C" const char *mcsce_last_error(void) { return g_err.c_str(); }
+extern "C" int mcsce_version(void) { return 1; }
+
+extern "C" int mcsce_create(mcsce_handle *out, int device) {
+    if (!out) return fail("null handle pointer");
+    int n = 0;
+    CK(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) return fail("no such CUDA device");
+    CK(cudaSetDevice(device));
+    mcsce_handle h = new mcsce_handle_s();
+    h->device = device;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    h->sm_count = prop.multiProcessorCount;
+    CK(cudaMalloc((void **)&h->d_pairs, sizeof(unsigned long long)));
+    CK(cudaMemset(h->d_pairs, 0, sizeof(unsigned long long)));
+    CK(cudaMalloc((void **)&h->d_input_energy, sizeof(double)));
+    *out = h;
+    return 0;
+}
+
+extern "C" int mcsce_destroy(mcsce_handle h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    free_pool(h->sys_allocs); free_pool(h->bb_allocs);
+    if (h->d_steps) cudaFree(h->d_steps);
+    if (h->d_pairs) cudaFree(h->d_pairs);
+    if (h->d_input_energy) cudaFree(h->d_input_energy);
+    delete h;
+    return 0;
+}
+
+extern "C" int mcsce_set_system(mcsce_handle h, const mcsce_system_desc *s) {
+    if (!h || !s) return fail("null argument");
+    CK(cudaSetDevice(h->device));
+    if (s->n_cls > MAX_CLS) return fail("too many atom classes");
+    free_pool(h->sys_allocs); free_pool(h->bb_allocs);
+    h->has_sys = h->has_bb = false;
+    SysDev &d = h->d;
+    d = SysDev{};
+    d.n_atoms = s->n_atoms; d.n_input = s->n_input; d.n_res = s->n_res; d.n_cls = s->n_cls; d.n_types = s->n_types;
+    auto &P = h->sys_allocs;
+    const size_t nc2 = (size_t)s->n_cls * s->n_cls;
+    if (upload(h, P, s->slot_of_atom, s->n_atoms, &d.slot_of_atom)) return -1;
+    if (upload(h, P, s->cls_of_atom, s->n_atoms, &d.cls_of_atom)) return -1;
+    if (upload(h, P, s->charge, s->n_atoms, &d.charge)) return -1;
+    if (upload(h, P, s->resnum, s->n_atoms, &d.resnum)) return -1;
+    if (upload(h, P, s->cls_start, s->n_cls + 1, &d.cls_start)) return -1;
+    if (upload(h, P, s->cls_active, (size_t)(s->n_res + 1) * s->n_cls, &d.cls_active)) return -1;
+    if (upload(h, P, s->cls_e4, nc2, &d.cls_e4)) return -1;
+    if (upload(h, P, s->cls_s2, nc2, &d.cls_s2d)) return -1;
+    if (upload(h, P, s->cls_thr, nc2, &d.cls_thrd)) return -1;
+    std::vector<float> s2f(nc2), thr2f(nc2);
+    for (size_t i = 0; i < nc2; ++i) { s2f[i] = (float)s->cls_s2[i]; thr2f[i] = exact_thr2(s->cls_thr[i]); }
+    if (upload(h, P, s2f.data(), nc2, &d.cls_s2f)) return -1;
+    if (upload(h, P, thr2f.data(), nc2, &d.cls_thr2f)) return -1;
+    h->cls_active.assign(s->cls_active, s->cls_active + (size_t)(s->n_res + 1) * s->n_cls);
+
+    std::vector<TmplDev> tm(s->n_types);
+    for (int t = 0; t < s->n_types; ++t) {
+        TmplDev &o = tm[t];
+        memset(&o, 0, sizeof(o));
+        o.n_atoms = s->tmpl_n_atoms[t];
+        if (o.n_atoms > MAX_TMPL) return fail("template too large");
+        o.n_chi = s->tmpl_n_chi[t];
+        for (int a = 0; a < MAX_TMPL; ++a) {
+            o.sc_rank[a] = -1;
+            for (int k = 0; k < 3; ++k) o.xyz[a][k] = s->tmpl_xyz[((size_t)t * MAX_TMPL + a) * 3 + k];
+        }
+        for (int k = 0; k < MAX_SC; ++k) {
+            int pos = s->tmpl_sc_pos[(size_t)t * MAX_SC + k];
+            if (pos >= 0) o.sc_rank[pos] = k;
+        }
+        for (int k = 0; k < MAX_ROT; ++k) {
+            o.axis_from[k] = s->tmpl_axis[((size_t)t * MAX_ROT + k) * 2];
+            o.axis_to[k] = s->tmpl_axis[((size_t)t * MAX_ROT + k) * 2 + 1];
+            o.move[k] = s->tmpl_move[(size_t)t * MAX_ROT + k];
+            o.ori[k] = s->tmpl_ori[(size_t)t * MAX_ROT + k];
+        }
+    }
+    if (upload(h, P, tm.data(), tm.size(), &d.tmpl)) return -1;
+
+    h->steps.assign(s->n_res, StepDev{});
+    h->step_n_sp_env.assign(s->n_res, 0);
+    for (int i = 0; i < s->n_res; ++i) {
+        StepDev &o = h->steps[i];
+        memset(&o, 0, sizeof(o));
+        o.kind = s->step_kind[i]; o.type = s->step_type[i]; o.n_sc = s->step_n_sc[i]; o.sc_start = s->step_sc_start[i];
+        o.n_sp_env = s->step_n_sp_env[i]; o.sp_off = s->step_sp_off[i]; o.n_sp = s->step_n_sp[i];
+        if (o.n_sp_env > MAX_SP_ENV) return fail("too many special environment atoms for one residue");
+        if (o.n_sc > MAX_SC) return fail("side chain too large");
+        for (int k = 0; k < MAX_SP_ENV; ++k)
+            o.sp_env_slot[k] = (k < o.n_sp_env) ? s->slot_of_atom[s->step_sp_env[(size_t)i * MAX_SP_ENV + k]] : -1;
+    }
+    if (upload(h, P, s->sp_k, s->n_sp_total, &d.sp_k)) return -1;
+    if (upload(h, P, s->sp_partner, s->n_sp_total, &d.sp_partner)) return -1;
+    if (upload(h, P, s->sp_coef, (size_t)s->n_sp_total * 4, &d.sp_coef)) return -1;
+    d.n_bb_pairs = s->n_bb_pairs;
+    if (upload(h, P, s->bb_i, s->n_bb_pairs, &d.bb_i)) return -1;
+    if (upload(h, P, s->bb_j, s->n_bb_pairs, &d.bb_j)) return -1;
+    if (upload(h, P, s->bb_coef, (size_t)s->n_bb_pairs * 4, &d.bb_coef)) return -1;
+    if (h->d_steps) { cudaFree(h->d_steps); h->d_steps = nullptr; }
+    CK(cudaMalloc((void **)&h->d_steps, sizeof(StepDev) * std::max(1, s->n_res)));
+    d.steps = h->d_steps;
+    h->has_sys = true;
+    return 0;
+}
+
+static int launch_place(mcsce_handle h, int step, int n_sets, int n_rows, const double *chis_in, long long set_stride,
+                        long long row_off, double *chis_out, float4 *trial, long long trial_stride,
+                        const unsigned char *alive, unsigned long long seed, long long conf_id0, double noise,
+                        cudaStream_t st);
+
+__global__ void store_rigid_kernel(const float4 *src, int sc_start, int n_sc, float *rigid) {
+    const int k = threadIdx.x;
+    if (k < n_sc) { rigid[(sc_start + k) * 3] = src[k].x; rigid[(sc_start + k) * 3 + 1] = src[k].y; rigid[(sc_start + k) * 3 + 2] = src[k].z; }
+}
+
+extern "C" int mcsce_set_backbone(mcsce_handle h, const mcsce_backbone_desc *b) {
+    if (!h || !b) return fail("null argument");
+    if (!h->has_sys) return fail("mcsce_set_system must be called first");
+    CK(cudaSetDevice(h->device));
+    free_pool(h->bb_allocs);
+    SysDev &d = h->d;
+    auto &P = h->bb_allocs;
+    d.n_trials_total = b->n_trials_total;
+    if (upload(h, P, b->chi_mean, (size_t)b->n_trials_total * MAX_CHI, &d.chi_mean)) return -1;
+    if (upload(h, P, b->chi_sigma, (size_t)b->n_trials_total * MAX_CHI, &d.chi_sigma)) return -1;
+    if (upload(h, P, b->prob, b->n_trials_total, &d.prob)) return -1;
+    if (upload(h, P, b->input_xyz, (size_t)d.n_input * 3, &d.input_xyz)) return -1;
+    h->max_trials = 0; h->max_trial_atoms = 0;
+    for (int i = 0; i < d.n_res; ++i) {
+        StepDev &o = h->steps[i];
+        o.n_trials = b->step_n_trials[i]; o.trial_off = b->step_trial_off[i];
+        o.n_chi_lib = b->step_n_chi_lib[i]; o.n_chi = b->step_n_chi[i];
+        if (o.n_chi > MAX_ROT || o.n_chi_lib > MAX_CHI) return fail("too many chi angles");
+        for (int k = 0; k < 4; ++k) { o.q1[k] = b->place_q1[(size_t)i * 4 + k]; o.q2[k] = b->place_q2[(size_t)i * 4 + k]; }
+        for (int k = 0; k < 3; ++k) o.ca[k] = b->place_ca[(size_t)i * 3 + k];
+        o.ca[3] = 0.f;
+        if (o.kind == 2) {
+            h->max_trials = std::max(h->max_trials, o.n_trials);
+            h->max_trial_atoms = std::max(h->max_trial_atoms, o.n_trials * o.n_sc);
+        }
+    }
+    CK(cudaMemcpy(h->d_steps, h->steps.data(), sizeof(StepDev) * d.n_res, cudaMemcpyHostToDevice));
+    // GLY/ALA side chains have no chi: placed once per backbone with K1 (zero rotations) and shared
+    // by every conformer (side_chain_builder.py:164-168)
+    {
+        std::vector<float> nanv((size_t)d.n_atoms * 3, NAN);
+        float *rigid = nullptr;
+        if (upload(h, P, nanv.data(), nanv.size(), (const float **)&rigid)) return -1;
+        d.rigid_xyz = rigid;
+        float4 *tmp = nullptr;
+        CK(cudaMalloc((void **)&tmp, sizeof(float4) * MAX_SC));
+        for (int i = 0; i < d.n_res; ++i) {
+            if (h->steps[i].kind != 1) continue;
+            if (launch_place(h, i, 1, 1, nullptr, 0, 0, nullptr, tmp, 0, nullptr, 0, 0, 0.0, 0)) { cudaFree(tmp); return -1; }
+            store_rigid_kernel<<<1, 32>>>(tmp, h->steps[i].sc_start, h->steps[i].n_sc, rigid);
+            h->launches += 1;
+        }
+        CK(cudaDeviceSynchronize());
+        cudaFree(tmp);
+    }
+    h->has_bb = true;
+    return 0;
+}
+
+static inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+static int trials_per_tile_for(int n_sc) { return std::max(1, TILE_A / n_sc); }
+
+static int choose_split(const mcsce_handle h, int step, int n_sets, int n_trials, int forced) {
+    const StepDev &st = h->steps[step];
+    int n_active = 0;
+    for (int c = 0; c < h->d.n_cls; ++c) n_active += h->cls_active[(size_t)step * h->d.n_cls + c];
+    const int tiles = (n_trials + trials_per_tile_for(st.n_sc) - 1) / trials_per_tile_for(st.n_sc);
+    const long long ctas = (long long)tiles * n_sets;
+    int max_split = std::max(1, std::min(32, (n_active + 255) / 256));
+    if (forced > 0) return std::min(forced, max_split);
+    const long long want = 4LL * h->sm_count;
+    int split = (int)std::min<long long>(max_split, std::max<long long>(1, (want + ctas - 1) / ctas));
+    return split;
+}
+static int max_split_for(int n_sets, int sm_count) {
+    // upper bound of choose_split for workspace sizing (tiles >= 1)
+    long long want = 4LL * sm_count;
+    return (int)std::min<long long>(32, std::max<long long>(1, (want + n_sets - 1) / n_sets));
+}
+
+struct Workspace {
+    float4 *env, *trial;
+    double2 *partial, *sp_partial;
+    unsigned char *alive;
+    double *e_acc;
+    double2 *rows, *pairs;
+    size_t total;
+};
+
+static Workspace carve(const mcsce_handle h, int n_conf, int max_trials, int max_trial_atoms, void *base) {
+    Workspace w{};
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return (char *)base + o; };
+    const int ms = max_split_for(n_conf, h->sm_count);
+    w.env = (float4 *)take((size_t)n_conf * h->d.n_atoms * sizeof(float4));
+    w.trial = (float4 *)take((size_t)n_conf * std::max(1, max_trial_atoms) * sizeof(float4));
+    w.partial = (double2 *)take((size_t)n_conf * std::max(1, max_trials) * ms * sizeof(double2));
+    w.sp_partial = (double2 *)take((size_t)n_conf * std::max(1, max_trials) * sizeof(double2));
+    w.alive = (unsigned char *)take((size_t)n_conf);
+    w.e_acc = (double *)take((size_t)n_conf * sizeof(double));
+    w.rows = (double2 *)take((size_t)std::max(1, h->d.n_input) * sizeof(double2));
+    w.pairs = (double2 *)take((size_t)std::max(1, h->d.n_bb_pairs) * sizeof(double2));
+    w.total = off;
+    return w;
+}
+
+extern "C" size_t mcsce_workspace_bytes(mcsce_handle h, int n_conf) {
+    if (!h || !h->has_bb || n_conf <= 0) return 0;
+    return carve(h, n_conf, h->max_trials, h->max_trial_atoms, nullptr).total;
+}
+
+static int launch_input_energy(mcsce_handle h, double2 *rows, double2 *pairs, double *out, cudaStream_t st) {
+    const SysDev &d = h->d;
+    input_energy_rows_kernel<<<(d.n_input + 127) / 128, 128, 0, st>>>(d, rows);
+    if (d.n_bb_pairs) input_energy_pairs_kernel<<<(d.n_bb_pairs + 127) / 128, 128, 0, st>>>(d, pairs);
+    input_energy_reduce_kernel<<<1, 256, 0, st>>>(d.n_input, rows, d.n_bb_pairs, pairs, out);
+    h->launches += 3;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mcsce_input_energy(mcsce_handle h, double *d_energy, void *stream) {
+    if (!h || !h->has_bb) return fail("set_system/set_backbone first");
+    CK(cudaSetDevice(h->device));
+    double2 *rows = nullptr, *pairs = nullptr;
+    CK(cudaMalloc((void **)&rows, sizeof(double2) * std::max(1, h->d.n_input)));
+    CK(cudaMalloc((void **)&pairs, sizeof(double2) * std::max(1, h->d.n_bb_pairs)));
+    int rc = launch_input_energy(h, rows, pairs, d_energy, (cudaStream_t)stream);
+    cudaStreamSynchronize((cudaStream_t)stream);
+    cudaFree(rows); cudaFree(pairs);
+    return rc;
+}
+
+extern "C" int mcsce_init_env(mcsce_handle h, int n_env_sets, float *d_env, void *stream) {
+    if (!h || !h->has_bb) return fail("set_system/set_backbone first");
+    CK(cudaSetDevice(h->device));
+    const long long n = (long long)n_env_sets * h->d.n_atoms;
+    init_env_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->d, n_env_sets, (float4 *)d_env);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int launch_place(mcsce_handle h, int step, int n_sets, int n_rows, const double *chis_in, long long set_stride,
+                        long long row_off, double *chis_out, float4 *trial, long long trial_stride,
+                        const unsigned char *alive, unsigned long long seed, long long conf_id0, double noise,
+                        cudaStream_t st) {
+    PlaceArgs a{};
+    a.s = h->d; a.step = step; a.n_trials = n_rows; a.chis_in = chis_in; a.chis_set_stride = set_stride;
+    a.chis_row_off = row_off; a.chis_out = chis_out; a.trial = trial; a.trial_set_stride = trial_stride;
+    a.alive = alive; a.seed = seed; a.conf_id0 = conf_id0; a.noise_deg = noise;
+    dim3 grid((n_rows + 3) / 4, n_sets);
+    place_trials_kernel<<<grid, 128, 0, st>>>(a);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int launch_score(mcsce_handle h, int step, int n_sets, int n_trials, int n_split, const float4 *env,
+                        const float4 *trial, long long trial_stride, double2 *partial, double2 *sp_partial,
+                        const unsigned char *alive, cudaStream_t st) {
+    const StepDev &sd = h->steps[step];
+    ScoreArgs a{};
+    a.s = h->d; a.step = step; a.n_trials = n_trials; a.trials_per_tile = trials_per_tile_for(sd.n_sc);
+    a.n_split = n_split; a.env = env; a.trial = trial; a.trial_set_stride = trial_stride; a.partial = partial; a.alive = alive;
+    dim3 grid((n_trials + a.trials_per_tile - 1) / a.trials_per_tile, n_sets, n_split);
+    score_generic_kernel<<<grid, SCORE_THREADS, 0, st>>>(a);
+    SpecialArgs b{};
+    b.s = h->d; b.step = step; b.n_trials = n_trials; b.env = env; b.trial = trial; b.trial_set_stride = trial_stride;
+    b.sp_partial = sp_partial; b.alive = alive;
+    dim3 grid2((n_trials + 7) / 8, n_sets);
+    score_special_kernel<<<grid2, 256, 0, st>>>(b);
+    h->launches += 2;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mcsce_place_trials(mcsce_handle h, int residue, int n_rows, const double *d_chis, float *d_xyz, void *stream) {
+    if (!h || !h->has_bb) return fail("set_system/set_backbone first");
+    if (residue < 0 || residue >= h->d.n_res) return fail("residue out of range");
+    if (h->steps[residue].kind == 0) return fail("residue is retained: nothing to place");
+    CK(cudaSetDevice(h->device));
+    return launch_place(h, residue, 1, n_rows, d_chis, 0, 0, nullptr, (float4 *)d_xyz, 0, nullptr, 0, 0, 0.0, (cudaStream_t)stream);
+}
+
+__global__ void combine_kernel(int n, int n_split, const double2 *partial, const double2 *sp_partial, double *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double e = sp_partial[i].x; bool cl = sp_partial[i].y != 0.0;
+    for (int z = 0; z < n_split; ++z) { e += partial[(long long)i * n_split + z].x; cl |= partial[(long long)i * n_split + z].y != 0.0; }
+    out[i] = cl ? CUDART_INF : e;
+}
+
+extern "C" int mcsce_score_trials(mcsce_handle h, int residue, int n_env_sets, int trials_per_env, const float *d_trial,
+                                  const float *d_env, double *d_energy, void *d_workspace, size_t workspace_bytes,
+                                  int env_split, void *stream) {
+    if (!h || !h->has_bb) return fail("set_system/set_backbone first");
+    if (residue < 0 || residue >= h->d.n_res || h->steps[residue].kind != 2) return fail("residue is not a grown residue");
+    CK(cudaSetDevice(h->device));
+    const int split = choose_split(h, residue, n_env_sets, trials_per_env, env_split);
+    const size_t n = (size_t)n_env_sets * trials_per_env;
+    const size_t need = align_up(n * split * sizeof(double2)) + align_up(n * sizeof(double2));
+    if (workspace_bytes < need) return fail("workspace too small for mcsce_score_trials");
+    double2 *partial = (double2 *)d_workspace;
+    double2 *sp = (double2 *)((char *)d_workspace + align_up(n * split * sizeof(double2)));
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long stride = (long long)trials_per_env * h->steps[residue].n_sc;
+    if (launch_score(h, residue, n_env_sets, trials_per_env, split, (const float4 *)d_env, (const float4 *)d_trial, stride,
+                     partial, sp, nullptr, st)) return -1;
+    combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((int)n, split, partial, sp, d_energy);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" size_t mcsce_score_workspace_bytes(mcsce_handle h, int n_env_sets, int trials_per_env) {
+    const size_t n = (size_t)n_env_sets * trials_per_env;
+    return align_up(n * 32 * sizeof(double2)) + align_up(n * sizeof(double2));
+}
+
+__global__ void pack_env_kernel(SysDev s, int n_sets, int n_old, const float *xyz, float4 *env) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)n_sets * s.n_atoms) return;
+    const int atom = (int)(i % s.n_atoms);
+    const int set = (int)(i / s.n_atoms);
+    float4 v = make_float4(1.0e15f, 1.0e15f, 1.0e15f, 0.f);
+    if (atom < n_old) {
+        const float *p = xyz + ((long long)set * n_old + atom) * 3;
+        v = make_float4(p[0], p[1], p[2], (float)s.charge[atom]);
+    }
+    env[(long long)set * s.n_atoms + s.slot_of_atom[atom]] = v;
+}
+
+extern "C" int mcsce_pack_env(mcsce_handle h, int n_env_sets, int n_old, const float *d_old_xyz, float *d_env, void *stream) {
+    if (!h || !h->has_sys) return fail("set_system first");
+    if (n_old < 0 || n_old > h->d.n_atoms) return fail("n_old out of range");
+    CK(cudaSetDevice(h->device));
+    const long long n = (long long)n_env_sets * h->d.n_atoms;
+    pack_env_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->d, n_env_sets, n_old, d_old_xyz, (float4 *)d_env);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mcsce_select(mcsce_handle h, int n_sets, int n_trials, const double *d_energy, const double *d_prob,
+                            double beta, const double *d_uniform, int32_t *d_selected, double *d_e_selected, void *stream) {
+    if (!h) return fail("null handle");
+    CK(cudaSetDevice(h->device));
+    select_plain_kernel<<<n_sets, 128, sizeof(double) * n_trials, (cudaStream_t)stream>>>(n_trials, d_energy, d_prob, beta,
+                                                                                         d_uniform, d_selected, d_e_selected);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *o, void *d_workspace, size_t workspace_bytes,
+                          float *d_coords, double *d_energy, uint8_t *d_ok, void *stream) {
+    if (!h || !o) return fail("null argument");
+    if (!h->has_bb) return fail("set_system/set_backbone first");
+    if (o->n_conf <= 0) return fail("n_conf must be positive");
+    CK(cudaSetDevice(h->device));
+    const SysDev &d = h->d;
+    Workspace w = carve(h, o->n_conf, h->max_trials, h->max_trial_atoms, d_workspace);
+    if (workspace_bytes < w.total) return fail("workspace too small: call mcsce_workspace_bytes");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int C = o->n_conf;
+    const long long trial_stride = std::max(1, h->max_trial_atoms);
+    const long long chi_set_stride = (long long)d.n_trials_total * MAX_CHI;
+
+    if (mcsce_init_env(h, C, (float *)w.env, stream)) return -1;
+    if (launch_input_energy(h, w.rows, w.pairs, h->d_input_energy, st)) return -1;
+    init_state_kernel<<<(C + 255) / 256, 256, 0, st>>>(C, w.alive, w.e_acc, h->d_input_energy);
+    h->launches += 1;
+
+    for (int i = 0; i < d.n_res; ++i) {
+        const StepDev &sd = h->steps[i];
+        if (sd.kind != 2 || sd.n_trials <= 0) continue;
+        const int T = sd.n_trials;
+        if (launch_place(h, i, C, T, o->d_chis, chi_set_stride, sd.trial_off, o->d_chis_out, w.trial, trial_stride,
+                         w.alive, o->seed, o->conf_id0, o->noise_deg, st)) return -1;
+        const int split = choose_split(h, i, C, T, o->env_split);
+        if (launch_score(h, i, C, T, split, w.env, w.trial, trial_stride, w.partial, w.sp_partial, w.alive, st)) return -1;
+        SelectArgs a{};
+        a.s = d; a.step = i; a.n_trials = T; a.n_split = split; a.partial = w.partial; a.sp_partial = w.sp_partial;
+        a.prob = d.prob + sd.trial_off; a.beta = o->beta; a.uniform = o->d_uniform; a.u_stride = d.n_res;
+        a.seed = o->seed; a.conf_id0 = o->conf_id0; a.env = w.env; a.trial = w.trial; a.trial_set_stride = trial_stride;
+        a.alive = w.alive; a.e_acc = w.e_acc; a.selected = o->d_selected; a.trial_energy = o->d_trial_energy;
+        a.pair_counter = h->d_pairs;
+        long long n_active = 0;
+        for (int c = 0; c < d.n_cls; ++c) n_active += h->cls_active[(size_t)i * d.n_cls + c];
+        a.pairs_per_set = (long long)T * ((long long)sd.n_sc * (sd.n_sc - 1) / 2 + (long long)sd.n_sc * n_active);
+        select_kernel<<<C, 128, sizeof(double) * 2 * T, st>>>(a);
+        h->launches += 1;
+    }
+    const long long n = (long long)C * d.n_atoms;
+    gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d, C, w.env, d_coords);
+    finish_kernel<<<(C + 255) / 256, 256, 0, st>>>(C, w.alive, w.e_acc, d_energy, d_ok);
+    h->launches += 2;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mcsce_grow_host(mcsce_handle h, const mcsce_grow_opts *o, void *d_workspace, size_t workspace_bytes,
+                               float *h_coords, double *h_energy, uint8_t *h_ok, void *stream) {
+    if (!h || !o) return fail("null argument");
+    if (!h->has_bb) return fail("set_system/set_backbone first");
+    const size_t base = mcsce_workspace_bytes(h, o->n_conf);
+    const size_t nc = align_up((size_t)o->n_conf * h->d.n_atoms * 3 * sizeof(float));
+    const size_t ne = align_up((size_t)o->n_conf * sizeof(double));
+    const size_t nk = align_up((size_t)o->n_conf);
+    if (workspace_bytes < base + nc + ne + nk) return fail("workspace too small for mcsce_grow_host");
+    char *p = (char *)d_workspace + base;
+    float *dc = (float *)p; double *de = (double *)(p + nc); uint8_t *dk = (uint8_t *)(p + nc + ne);
+    if (mcsce_grow(h, o, d_workspace, base, dc, de, dk, stream)) return -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemcpyAsync(h_coords, dc, (size_t)o->n_conf * h->d.n_atoms * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_energy, de, (size_t)o->n_conf * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_ok, dk, (size_t)o->n_conf, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int mcsce_counters(mcsce_handle h, int64_t *launches, int64_t *pairs, int reset) {
+    if (!h) return fail("null handle");
+    CK(cudaSetDevice(h->device));
+    unsigned long long v = 0;
+    CK(cudaMemcpy(&v, h->d_pairs, sizeof(v), cudaMemcpyDeviceToHost));
+    if (launches) *launches = h->launches;
+    if (pairs) *pairs = (int64_t)v;
+    if (reset) { h->launches = 0; CK(cudaMemset(h->d_pairs, 0, sizeof(v))); }
+    return 0;
+}

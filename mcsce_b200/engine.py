@@ -1,0 +1,304 @@
+"""GrowthEngine: Python host of the CUDA growth path.
+
+Packs a :class:`mcsce_b200.system.GrowthSystem` into the C-ABI descriptors, owns the device
+buffers (torch tensors: device memory and streams only) and calls ``libmcsce_b200.so``.
+No compute happens here and there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from mcsce_b200 import _lib
+from mcsce_b200._lib import (MAX_CHI, MAX_CHI_ROT, MAX_SC, MAX_SP_ENV, MAX_TMPL, BackboneDesc, GrowOpts,
+                             SystemDesc, check, load_library)
+from mcsce_b200.chem.tables import load_tables
+from mcsce_b200.libs.placement import placement_quaternions
+from mcsce_b200.system import placement_backbone
+
+
+def _ptr(a, typ):
+    return a.ctypes.data_as(C.POINTER(typ))
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class GrowthEngine:
+    def __init__(self, device=0):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("mcsce_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.torch = torch
+        self.lib = load_library()
+        self.device_index = int(device)
+        self.device = torch.device("cuda", self.device_index)
+        h = C.c_void_p()
+        check(self.lib.mcsce_create(C.byref(h), self.device_index))
+        self.h = h
+        self.system = None
+        self._keep = []
+        self._workspace = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mcsce_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- tables ---------------------------------------------------------------
+    def set_system(self, sysm, tables=None):
+        t = tables or load_tables()
+        self.system = sysm
+        self.tables = t
+        types = sorted({st.resname for st in sysm.steps if st.kind != "skip"})
+        self.type_index = {r: i for i, r in enumerate(types)}
+        nt = max(1, len(types))
+        tmpl_n = np.zeros(nt, np.int32); tmpl_xyz = np.zeros((nt, MAX_TMPL, 3), np.float32)
+        tmpl_sc = np.full((nt, MAX_SC), -1, np.int32); tmpl_nchi = np.zeros(nt, np.int32)
+        tmpl_axis = np.zeros((nt, MAX_CHI_ROT, 2), np.int32); tmpl_move = np.zeros((nt, MAX_CHI_ROT), np.uint32)
+        tmpl_ori = np.zeros((nt, MAX_CHI_ROT), np.float64)
+        for r, i in self.type_index.items():
+            tm = t.templates[r]
+            assert tm.n_atoms <= MAX_TMPL and tm.n_sc <= MAX_SC, r
+            tmpl_n[i] = tm.n_atoms
+            tmpl_xyz[i, :tm.n_atoms] = tm.coords
+            tmpl_sc[i, :tm.n_sc] = tm.sc_idx
+            prog = tm.chis[:MAX_CHI_ROT]
+            tmpl_nchi[i] = len(prog)
+            for k, chi in enumerate(prog):
+                tmpl_axis[i, k] = chi["axis"]
+                tmpl_move[i, k] = sum(1 << m for m in chi["moving"])
+                tmpl_ori[i, k] = chi["ori"]
+        L = sysm.n_res
+        kind = np.array([{"skip": 0, "rigid": 1, "grow": 2}[st.kind] for st in sysm.steps], np.int32)
+        stype = np.array([self.type_index.get(st.resname, 0) for st in sysm.steps], np.int32)
+        n_sc = np.array([st.n_sc for st in sysm.steps], np.int32)
+        sc_start = np.array([st.sc_start for st in sysm.steps], np.int32)
+        n_sp_env = np.zeros(L, np.int32); sp_env = np.zeros((L, MAX_SP_ENV), np.int32)
+        sp_off = np.zeros(L, np.int32); n_sp = np.zeros(L, np.int32)
+        ks, partners, coefs = [], [], []
+        off = 0
+        for st in sysm.steps:
+            if st.kind != "grow":
+                continue
+            ne = len(st.special_env)
+            if ne > MAX_SP_ENV:
+                raise ValueError("residue %d has %d special environment atoms (max %d)" % (st.resnum, ne, MAX_SP_ENV))
+            n_sp_env[st.index] = ne
+            sp_env[st.index, :ne] = st.special_env
+            sp_off[st.index] = off; n_sp[st.index] = len(st.sp_k)
+            ks.append(st.sp_k); partners.append(st.sp_partner); coefs.append(st.sp_coef)
+            off += len(st.sp_k)
+        cat = lambda xs, dt, shape: (np.concatenate(xs).astype(dt) if xs else np.zeros(shape, dt))  # noqa: E731
+        sp_k = cat(ks, np.int32, (0,)); sp_partner = cat(partners, np.int32, (0,)); sp_coef = cat(coefs, np.float64, (0, 4))
+        charge = sysm.charge if "coulomb" in sysm.terms else np.zeros_like(sysm.charge)
+        bb_i, bb_j, bb_coef = sysm.bb_pairs
+        arrays = dict(
+            slot_of_atom=_i32(sysm.slot_of_atom), cls_of_atom=_i32(sysm.cls_of_atom), charge=_f64(charge),
+            resnum=_i32(sysm.resnums), cls_start=_i32(sysm.cls_start), cls_active=_i32(sysm.cls_active),
+            cls_s2=_f64(sysm.cls_s2), cls_e4=_f64(sysm.cls_e4), cls_thr=_f64(sysm.cls_thr),
+            tmpl_n_atoms=tmpl_n, tmpl_xyz=_f32(tmpl_xyz), tmpl_sc_pos=_i32(tmpl_sc), tmpl_n_chi=tmpl_nchi,
+            tmpl_axis=_i32(tmpl_axis), tmpl_move=np.ascontiguousarray(tmpl_move, np.uint32), tmpl_ori=_f64(tmpl_ori),
+            step_kind=kind, step_type=stype, step_n_sc=n_sc, step_sc_start=sc_start, step_n_sp_env=n_sp_env,
+            step_sp_env=_i32(sp_env), step_sp_off=sp_off, step_n_sp=n_sp, sp_k=sp_k, sp_partner=sp_partner,
+            sp_coef=_f64(sp_coef), bb_i=_i32(bb_i), bb_j=_i32(bb_j), bb_coef=_f64(bb_coef))
+        d = SystemDesc()
+        d.n_atoms, d.n_input, d.n_res, d.n_cls = sysm.n_atoms, sysm.n_input, L, sysm.n_cls
+        d.n_types, d.n_sp_total, d.n_bb_pairs = len(types), len(sp_k), len(bb_i)
+        for name, arr in arrays.items():
+            typ = dict(SystemDesc._fields_)[name]._type_
+            setattr(d, name, _ptr(arr, typ))
+        check(self.lib.mcsce_set_system(self.h, C.byref(d)))
+        self._keep = [arrays, d]
+        self._step_kind = kind
+        self._has_backbone = False
+        return self
+
+    def set_backbone(self, backbone_coords):
+        """Upload the backbone-dependent tables: trial sets, template placement, coordinates."""
+        sysm, t = self.system, self.tables
+        backbone_coords = np.asarray(backbone_coords, dtype=np.float32)
+        assert backbone_coords.shape == (sysm.n_input, 3), "backbone atom count mismatch"
+        L = sysm.n_res
+        bb = placement_backbone(backbone_coords, sysm)
+        q1 = np.zeros((L, 4)); q2 = np.zeros((L, 4)); ca = np.zeros((L, 3), np.float32)
+        q1[:, 0] = q2[:, 0] = 1.0
+        n_tr = np.zeros(L, np.int32); tr_off = np.zeros(L, np.int32)
+        n_lib = np.zeros(L, np.int32); n_chi = np.zeros(L, np.int32)
+        means, sigmas, probs = [], [], []
+        off = 0
+        for st in sysm.steps:
+            if st.kind == "skip":
+                continue
+            tm = t.templates[st.resname]
+            q1[st.index], q2[st.index], ca[st.index] = placement_quaternions(bb[st.index], tm.coords[0], tm.coords[2])
+            if st.kind != "grow":
+                continue
+            if st.chi_mean is None:
+                raise ValueError("system was built without a rotamer library: no trial sets")
+            T = len(st.prob)
+            m = np.zeros((T, MAX_CHI)); s = np.zeros((T, MAX_CHI))
+            m[:, :st.n_chi_lib] = st.chi_mean; s[:, :st.n_chi_lib] = st.chi_sigma
+            means.append(m); sigmas.append(s); probs.append(st.prob)
+            n_tr[st.index], tr_off[st.index], n_lib[st.index], n_chi[st.index] = T, off, st.n_chi_lib, st.n_chi
+            off += T
+        arrays = dict(
+            step_n_trials=n_tr, step_trial_off=tr_off, step_n_chi_lib=n_lib, step_n_chi=n_chi,
+            chi_mean=_f64(np.concatenate(means) if means else np.zeros((0, MAX_CHI))),
+            chi_sigma=_f64(np.concatenate(sigmas) if sigmas else np.zeros((0, MAX_CHI))),
+            prob=_f64(np.concatenate(probs) if probs else np.zeros(0)),
+            place_q1=_f64(q1), place_q2=_f64(q2), place_ca=_f32(ca), input_xyz=_f32(backbone_coords))
+        d = BackboneDesc()
+        d.n_trials_total = off
+        for name, arr in arrays.items():
+            typ = dict(BackboneDesc._fields_)[name]._type_
+            setattr(d, name, _ptr(arr, typ))
+        check(self.lib.mcsce_set_backbone(self.h, C.byref(d)))
+        self.n_trials_total = off
+        self.trial_off = tr_off
+        self.n_trials = n_tr
+        self._has_backbone = True
+        return self
+
+    # -- growth -----------------------------------------------------------------
+    def _ws(self, nbytes):
+        torch = self.torch
+        if self._workspace is None or self._workspace.numel() < nbytes:
+            self._workspace = None
+            self._workspace = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return self._workspace
+
+    def workspace_bytes(self, n_conf):
+        return int(self.lib.mcsce_workspace_bytes(self.h, int(n_conf)))
+
+    def grow(self, n_conf, beta, seed=0, conf_id0=0, noise_deg=0.5, chis=None, uniforms=None, dump=False,
+             env_split=0, host_out=False, stream=None):
+        """Grow ``n_conf`` conformers.  Returns dict(coords (C,N,3) f32 growth order, energy (C,) f64,
+        ok (C,) uint8 [, trial_energy, chis, selected]); torch CUDA tensors, or NumPy arrays (pinned
+        staging inside the C call) with ``host_out``."""
+        torch = self.torch
+        assert self._has_backbone, "set_backbone first"
+        C_ = int(n_conf)
+        N = self.system.n_atoms
+        o = GrowOpts()
+        o.n_conf, o.conf_id0, o.seed, o.beta, o.noise_deg, o.env_split = C_, int(conf_id0), int(seed), float(beta), float(noise_deg), int(env_split)
+        keep = []
+        if chis is not None:
+            ch = torch.as_tensor(np.ascontiguousarray(chis, np.float64), device=self.device)
+            assert ch.numel() == C_ * self.n_trials_total * MAX_CHI, "chis must be (n_conf, n_trials_total, MAX_CHI)"
+            o.d_chis = ch.data_ptr(); keep.append(ch)
+        if uniforms is not None:
+            un = torch.as_tensor(np.ascontiguousarray(uniforms, np.float64), device=self.device)
+            assert un.numel() == C_ * self.system.n_res
+            o.d_uniform = un.data_ptr(); keep.append(un)
+        out = {}
+        if dump:
+            out["trial_energy"] = torch.full((C_, self.n_trials_total), float("nan"), dtype=torch.float64, device=self.device)
+            out["chis"] = torch.zeros((C_, self.n_trials_total, MAX_CHI), dtype=torch.float64, device=self.device)
+            out["selected"] = torch.full((C_, self.system.n_res), -2, dtype=torch.int32, device=self.device)
+            o.d_trial_energy, o.d_chis_out, o.d_selected = (out[k].data_ptr() for k in ("trial_energy", "chis", "selected"))
+        s_ptr = C.c_void_p(stream.cuda_stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream)
+        base = self.workspace_bytes(C_)
+        if host_out:
+            extra = C_ * (N * 12 + 9) + 1024
+            ws = self._ws(base + extra)
+            coords = torch.empty((C_, N, 3), dtype=torch.float32).pin_memory()
+            energy = torch.empty(C_, dtype=torch.float64).pin_memory()
+            ok = torch.empty(C_, dtype=torch.uint8).pin_memory()
+            check(self.lib.mcsce_grow_host(self.h, C.byref(o), C.c_void_p(ws.data_ptr()), ws.numel(),
+                                           C.c_void_p(coords.data_ptr()), C.c_void_p(energy.data_ptr()),
+                                           C.c_void_p(ok.data_ptr()), s_ptr))
+            out.update(coords=coords.numpy(), energy=energy.numpy(), ok=ok.numpy())
+        else:
+            ws = self._ws(base)
+            coords = torch.empty((C_, N, 3), dtype=torch.float32, device=self.device)
+            energy = torch.empty(C_, dtype=torch.float64, device=self.device)
+            ok = torch.empty(C_, dtype=torch.uint8, device=self.device)
+            check(self.lib.mcsce_grow(self.h, C.byref(o), C.c_void_p(ws.data_ptr()), ws.numel(),
+                                      C.c_void_p(coords.data_ptr()), C.c_void_p(energy.data_ptr()),
+                                      C.c_void_p(ok.data_ptr()), s_ptr))
+            out.update(coords=coords, energy=energy, ok=ok)
+        out["_keep"] = keep
+        return out
+
+    # -- single kernels (drop-in entry points and parity tests) -------------------
+    def _stream_ptr(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def place_trials(self, residue, chis):
+        """K1: chis (rows, nchi) degrees -> (rows, n_sc, 3) float32 torch tensor."""
+        torch = self.torch
+        st = self.system.steps[residue]
+        rows = np.zeros((len(chis), MAX_CHI))
+        chis = np.asarray(chis, dtype=np.float64).reshape(len(chis), -1)
+        rows[:, :chis.shape[1]] = chis[:, :MAX_CHI]
+        d_ch = torch.as_tensor(rows, device=self.device)
+        out = torch.empty((len(rows), st.n_sc, 4), dtype=torch.float32, device=self.device)
+        check(self.lib.mcsce_place_trials(self.h, int(residue), len(rows), C.c_void_p(d_ch.data_ptr()),
+                                          C.c_void_p(out.data_ptr()), self._stream_ptr()))
+        return out[:, :, :3]
+
+    def score_trials(self, residue, trial_xyz, old_xyz, env_split=0):
+        """K2: trial_xyz (S, T, n_sc, 3), old_xyz (S, n_old, 3) growth order -> (S, T) float64 energies
+        (+inf = clash).  S environment sets, T trials each."""
+        torch = self.torch
+        st = self.system.steps[residue]
+        trial_xyz = torch.as_tensor(trial_xyz, dtype=torch.float32, device=self.device)
+        old_xyz = torch.as_tensor(old_xyz, dtype=torch.float32, device=self.device).contiguous()
+        S, T = trial_xyz.shape[0], trial_xyz.shape[1]
+        assert trial_xyz.shape[2] == st.n_sc and old_xyz.shape[0] == S
+        n_old = old_xyz.shape[1]
+        assert n_old == st.sc_start, "environment must be the %d atoms that precede this side chain" % st.sc_start
+        t4 = torch.zeros((S, T, st.n_sc, 4), dtype=torch.float32, device=self.device)
+        t4[..., :3] = trial_xyz
+        env = torch.empty((S, self.system.n_atoms, 4), dtype=torch.float32, device=self.device)
+        sp = self._stream_ptr()
+        check(self.lib.mcsce_pack_env(self.h, S, n_old, C.c_void_p(old_xyz.data_ptr()), C.c_void_p(env.data_ptr()), sp))
+        nbytes = int(self.lib.mcsce_score_workspace_bytes(self.h, S, T))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        out = torch.empty((S, T), dtype=torch.float64, device=self.device)
+        check(self.lib.mcsce_score_trials(self.h, int(residue), S, T, C.c_void_p(t4.data_ptr()), C.c_void_p(env.data_ptr()),
+                                          C.c_void_p(out.data_ptr()), C.c_void_p(ws.data_ptr()), nbytes, int(env_split), sp))
+        return out
+
+    def select(self, energies, probs, beta, uniforms):
+        """K3: energies (S, T), probs (T,), uniforms (S,) -> (selected (S,) int32, e_selected (S,) f64)."""
+        torch = self.torch
+        e = torch.as_tensor(energies, dtype=torch.float64, device=self.device).contiguous()
+        p = torch.as_tensor(probs, dtype=torch.float64, device=self.device).contiguous()
+        u = torch.as_tensor(uniforms, dtype=torch.float64, device=self.device).contiguous()
+        S, T = e.shape
+        sel = torch.empty(S, dtype=torch.int32, device=self.device)
+        es = torch.empty(S, dtype=torch.float64, device=self.device)
+        check(self.lib.mcsce_select(self.h, S, T, C.c_void_p(e.data_ptr()), C.c_void_p(p.data_ptr()), float(beta),
+                                    C.c_void_p(u.data_ptr()), C.c_void_p(sel.data_ptr()), C.c_void_p(es.data_ptr()),
+                                    self._stream_ptr()))
+        return sel, es
+
+    def input_energy(self):
+        torch = self.torch
+        out = torch.empty(1, dtype=torch.float64, device=self.device)
+        check(self.lib.mcsce_input_energy(self.h, C.c_void_p(out.data_ptr()), self._stream_ptr()))
+        return float(out.item())
+
+    def counters(self, reset=False):
+        a, b = C.c_int64(), C.c_int64()
+        check(self.lib.mcsce_counters(self.h, C.byref(a), C.byref(b), 1 if reset else 0))
+        return int(a.value), int(b.value)

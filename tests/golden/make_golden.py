@@ -196,9 +196,9 @@ def make_template_fixture(out_dir):
         out[res + "_names"] = np.array(tmpl.data_array[:, 2])
         out[res + "_coords"] = tmpl.coords
         out[res + "_sc_idx"] = np.array(sc_idx)
-        if res in ("ALA", "GLY"):
-            continue
         for n in range(1, 7):
+            if res in ("ALA", "GLY"):
+                break                                        # no chi: rigid placement only
             tors = rng.uniform(-180, 180, size=(3, n))
             try:
                 rot = np.stack([rotate_sidechain(res, t)[0] for t in tors])

@@ -1,0 +1,153 @@
+"""CPU tests of the host tables the CUDA path consumes (mcsce_b200.system): the per-atom classes
+plus the per-residue special-pair lists must reproduce, pair for pair, the coefficient arrays the
+oracle's restatement of prepare_energy_function builds (and those are pinned to the reference by
+tests/test_oracle_golden.py)."""
+import numpy as np
+import pytest
+
+from golden_utils import GoldenCase, library
+from oracle import ref_numpy as O
+
+
+def _system(name):
+    from mcsce_b200.system import build_system
+
+    case = GoldenCase(name)
+    lib, ptm = library()
+    s = case.structure()
+    return case, s, build_system(s, terms=case.terms, rotamer_library=lib, ptm_library=ptm)
+
+
+@pytest.mark.parametrize("name", ["pep12", "ptm14", "twochain", "pep6_ljclash"])
+def test_pair_coefficients_match_oracle(name):
+    from mcsce_b200.chem.tables import load_tables
+
+    case, s, sysm = _system(name)
+    t = load_tables()
+    work = s.copy()
+    for st in sysm.steps:
+        tm = t.templates[st.resname]
+        chain = sysm.chains[st.sc_start]
+        work.append_atoms([tm.names[k] for k in tm.sc_idx], tm.resname, chain, st.resnum, np.zeros((tm.n_sc, 3)))
+        if st.kind != "grow":
+            continue
+        n_all = len(work); n_sc = st.n_sc; n_old = n_all - n_sc
+        assert n_old == st.sc_start
+        n_term, c_term = work.get_terminal_res_atom_arr()
+        ef = O.EnergyFunction(work.atom_labels, work.res_nums, work.res_labels, n_term, c_term,
+                              np.arange(n_old, n_all), np.arange(n_old), terms=case.terms)
+        nn = n_sc * (n_sc - 1) // 2
+        A = np.nan_to_num(ef.acoeff, nan=0.0); B = np.nan_to_num(ef.bcoeff, nan=0.0)
+        Q = np.nan_to_num(ef.charges, nan=0.0); thr = ef.thr
+        if "lj" not in case.terms:
+            A[:] = 0; B[:] = 0
+        if "coulomb" not in case.terms:
+            Q[:] = 0
+        # rebuild the same arrays from classes + special list
+        gA = np.zeros_like(A); gB = np.zeros_like(B); gQ = np.zeros_like(Q); gT = np.zeros_like(thr)
+        q = sysm.charge if "coulomb" in case.terms else np.zeros_like(sysm.charge)
+        for k in range(n_sc):
+            a = st.sc_start + k
+            ca = sysm.cls_of_atom[a]
+            cb = sysm.cls_of_atom[:n_old]
+            s2 = sysm.cls_s2[ca, cb]; e4 = sysm.cls_e4[ca, cb]
+            sl = slice(nn + k * n_old, nn + (k + 1) * n_old)
+            gA[sl] = e4 * s2 ** 6; gB[sl] = e4 * s2 ** 3
+            gQ[sl] = q[a] * q[:n_old] * 0.25 * 1389.35
+            gT[sl] = sysm.cls_thr[ca, cb]
+        iu, ju = np.triu_indices(n_sc, k=1)
+        tri = {(i, j): p for p, (i, j) in enumerate(zip(iu, ju))}
+        seen_env = set()
+        for k, pa, cf in zip(st.sp_k, st.sp_partner, st.sp_coef):
+            if pa < 0:
+                p = tri[(int(k), int(-pa - 1))]
+            else:
+                b = int(st.special_env[pa]); seen_env.add(b)
+                p = nn + int(k) * n_old + b
+            gA[p], gB[p], gQ[p], gT[p] = cf
+        np.testing.assert_allclose(gA, A, rtol=2e-15, atol=0)
+        np.testing.assert_allclose(gB, B, rtol=2e-15, atol=0)
+        np.testing.assert_allclose(gQ, Q, rtol=2e-15, atol=0)
+        np.testing.assert_allclose(gT, thr, rtol=1e-15, atol=0)
+        # every environment atom with a bonded relation to the new side chain is in the special list
+        rel_cols = np.where(np.isnan(ef.acoeff[nn:].reshape(n_sc, n_old)).any(0))[0]
+        assert set(rel_cols) <= seen_env
+        assert len(st.special_env) <= 16
+
+
+def test_slot_layout_prefix_property():
+    case, s, sysm = _system("pep12")
+    n = sysm.n_atoms
+    assert sorted(sysm.slot_of_atom) == list(range(n))
+    for i in range(sysm.n_res + 1):
+        present = set(np.where(sysm.appear < i)[0])
+        got = set()
+        for c in range(sysm.n_cls):
+            lo = sysm.cls_start[c]
+            got |= set(sysm.atom_of_slot[lo:lo + sysm.cls_active[i, c]])
+        assert got == present
+
+
+def test_backbone_pairs_match_oracle():
+    """Input-atom self energy tables: generic classes + special list == oracle level-0 coefficients."""
+    case, s, sysm = _system("twochain")
+    n_term, c_term = s.get_terminal_res_atom_arr()
+    ef = O.EnergyFunction(s.atom_labels, s.res_nums, s.res_labels, n_term, c_term, terms=case.terms)
+    n = sysm.n_input
+    iu, ju = np.triu_indices(n, k=1)
+    ci, cj = sysm.cls_of_atom[iu], sysm.cls_of_atom[ju]
+    gA = sysm.cls_e4[ci, cj] * sysm.cls_s2[ci, cj] ** 6
+    gQ = sysm.charge[iu] * sysm.charge[ju] * 0.25 * 1389.35
+    gT = sysm.cls_thr[ci, cj].copy()
+    idx = {(i, j): p for p, (i, j) in enumerate(zip(iu, ju))}
+    near = np.abs(sysm.resnums[iu] - sysm.resnums[ju]) <= 1
+    bi, bj, coef = sysm.bb_pairs
+    assert near.sum() == len(bi)
+    for i, j, cf in zip(bi, bj, coef):
+        p = idx[(int(i), int(j))]
+        assert near[p]
+        gA[p], gQ[p], gT[p] = cf[0], cf[2], cf[3]
+    np.testing.assert_allclose(gA, np.nan_to_num(ef.acoeff), rtol=2e-15)
+    np.testing.assert_allclose(gQ, np.nan_to_num(ef.charges), rtol=2e-15)
+    np.testing.assert_allclose(gT, ef.thr, rtol=1e-15)
+
+
+def test_placement_quaternions_reproduce_oracle_placement():
+    from mcsce_b200.chem.tables import load_tables
+    from mcsce_b200.libs.placement import _rotate, placement_quaternions
+
+    t = load_tables()
+    z = np.load(__import__("golden_utils").GOLDEN / "templates.npz")
+    for res, tm in t.templates.items():
+        bb = z[res + "_bb"]
+        q1, q2, ca = placement_quaternions(bb, tm.coords[0], tm.coords[2])
+        got = np.array([_rotate(q2, _rotate(q1, p).astype(np.float32)) + ca.astype(np.float64) for p in tm.coords])
+        assert np.abs(got - z[res + "_placed"]).max() < 1e-9, res
+
+
+def test_library_loads_and_exports_every_symbol():
+    """The C-ABI library must exist in-tree and export everything include/mcsce_b200.h declares."""
+    import re
+    from pathlib import Path
+
+    from mcsce_b200 import _lib
+
+    lib = _lib.load_library()
+    header = (Path(__file__).resolve().parents[1] / "include" / "mcsce_b200.h").read_text()
+    declared = set(re.findall(r"\b(mcsce_[a-z_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.mcsce_version() >= 1
+
+
+def test_engine_refuses_to_run_without_cuda():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from mcsce_b200.engine import GrowthEngine
+
+    with pytest.raises(RuntimeError):
+        GrowthEngine(0)
