@@ -177,6 +177,11 @@ int mcsce_init_env(mcsce_handle h, int n_env_sets, float *d_env, void *stream);
 /* counters for the benchmark: kernels launched / algorithmic pair evaluations since the last reset */
 int mcsce_counters(mcsce_handle h, int64_t *launches, int64_t *pairs, int reset);
 
+/* per-kernel-class device timing for the benchmark's roofline: enable=1 starts recording CUDA-event
+ * pairs around every launch (on the launch stream); enable=0 synchronises and returns summed
+ * milliseconds / launch counts for [place, score_generic, score_special, select]. */
+int mcsce_profile(mcsce_handle h, int enable, double *ms_by_class, int64_t *launches_by_class);
+
 #ifdef __cplusplus
 }
 #endif

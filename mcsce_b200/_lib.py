@@ -71,6 +71,7 @@ SYMBOLS = {
                                C.c_void_p, C.c_void_p, C.c_void_p]),
     "mcsce_input_energy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "mcsce_init_env": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "mcsce_profile": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "mcsce_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int]),
 }
 

@@ -678,6 +678,19 @@ struct mcsce_handle_s {
     unsigned long long *d_pairs = nullptr;
     double *d_input_energy = nullptr;
     long long launches = 0;
+    // optional per-kernel-class device timing (CUDA events on the launch stream)
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev[4];     // 0 place, 1 score_generic, 2 score_special, 3 select: begin/end pairs
+};
+
+struct ProfScope {
+    mcsce_handle h; int cls; cudaStream_t st;
+    ProfScope(mcsce_handle h_, int cls_, cudaStream_t st_) : h(h_), cls(cls_), st(st_) {
+        if (h->profiling) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); h->ev[cls].push_back(e); }
+    }
+    ~ProfScope() {
+        if (h->profiling) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); h->ev[cls].push_back(e); }
+    }
 };
 
 template <typename T>
@@ -963,7 +976,7 @@ static int launch_place(mcsce_handle h, int step, int n_sets, int n_rows, const 
     a.chis_row_off = row_off; a.chis_out = chis_out; a.trial = trial; a.trial_set_stride = trial_stride;
     a.alive = alive; a.seed = seed; a.conf_id0 = conf_id0; a.noise_deg = noise;
     dim3 grid((n_rows + 3) / 4, n_sets);
-    place_trials_kernel<<<grid, 128, 0, st>>>(a);
+    { ProfScope ps(h, 0, st); place_trials_kernel<<<grid, 128, 0, st>>>(a); }
     h->launches += 1;
     CK(cudaGetLastError());
     return 0;
@@ -977,12 +990,12 @@ static int launch_score(mcsce_handle h, int step, int n_sets, int n_trials, int 
     a.s = h->d; a.step = step; a.n_trials = n_trials; a.trials_per_tile = trials_per_tile_for(sd.n_sc);
     a.n_split = n_split; a.env = env; a.trial = trial; a.trial_set_stride = trial_stride; a.partial = partial; a.alive = alive;
     dim3 grid((n_trials + a.trials_per_tile - 1) / a.trials_per_tile, n_sets, n_split);
-    score_generic_kernel<<<grid, SCORE_THREADS, 0, st>>>(a);
+    { ProfScope ps(h, 1, st); score_generic_kernel<<<grid, SCORE_THREADS, 0, st>>>(a); }
     SpecialArgs b{};
     b.s = h->d; b.step = step; b.n_trials = n_trials; b.env = env; b.trial = trial; b.trial_set_stride = trial_stride;
     b.sp_partial = sp_partial; b.alive = alive;
     dim3 grid2((n_trials + 7) / 8, n_sets);
-    score_special_kernel<<<grid2, 256, 0, st>>>(b);
+    { ProfScope ps(h, 2, st); score_special_kernel<<<grid2, 256, 0, st>>>(b); }
     h->launches += 2;
     CK(cudaGetLastError());
     return 0;
@@ -1102,7 +1115,7 @@ extern "C" int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *o, void *d_work
         long long n_active = 0;
         for (int c = 0; c < d.n_cls; ++c) n_active += h->cls_active[(size_t)i * d.n_cls + c];
         a.pairs_per_set = (long long)T * ((long long)sd.n_sc * (sd.n_sc - 1) / 2 + (long long)sd.n_sc * n_active);
-        select_kernel<<<C, 128, sizeof(double) * 2 * T, st>>>(a);
+        { ProfScope ps(h, 3, st); select_kernel<<<C, 128, sizeof(double) * 2 * T, st>>>(a); }
         h->launches += 1;
     }
     const long long n = (long long)C * d.n_atoms;
@@ -1130,6 +1143,33 @@ extern "C" int mcsce_grow_host(mcsce_handle h, const mcsce_grow_opts *o, void *d
     CK(cudaMemcpyAsync(h_energy, de, (size_t)o->n_conf * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(h_ok, dk, (size_t)o->n_conf, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int mcsce_profile(mcsce_handle h, int enable, double *ms_by_class, int64_t *launches_by_class) {
+    // enable=1: start recording event pairs around every K1/K2/K2s/K3 launch.
+    // enable=0: synchronise, return summed milliseconds and launch counts per class (4 each), stop.
+    if (!h) return fail("null handle");
+    CK(cudaSetDevice(h->device));
+    if (enable) {
+        for (auto &v : h->ev) { for (auto e : v) cudaEventDestroy(e); v.clear(); }
+        h->profiling = true;
+        return 0;
+    }
+    h->profiling = false;
+    CK(cudaDeviceSynchronize());
+    for (int c = 0; c < 4; ++c) {
+        double ms = 0.0;
+        for (size_t i = 0; i + 1 < h->ev[c].size(); i += 2) {
+            float t = 0.f;
+            CK(cudaEventElapsedTime(&t, h->ev[c][i], h->ev[c][i + 1]));
+            ms += t;
+        }
+        if (ms_by_class) ms_by_class[c] = ms;
+        if (launches_by_class) launches_by_class[c] = (int64_t)(h->ev[c].size() / 2);
+        for (auto e : h->ev[c]) cudaEventDestroy(e);
+        h->ev[c].clear();
+    }
     return 0;
 }
 

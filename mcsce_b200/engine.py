@@ -302,3 +302,13 @@ class GrowthEngine:
         a, b = C.c_int64(), C.c_int64()
         check(self.lib.mcsce_counters(self.h, C.byref(a), C.byref(b), 1 if reset else 0))
         return int(a.value), int(b.value)
+
+    def profile_begin(self):
+        check(self.lib.mcsce_profile(self.h, 1, None, None))
+
+    def profile_end(self):
+        """{kernel class: (milliseconds, launches)} for place / score_generic / score_special / select."""
+        ms = (C.c_double * 4)(); n = (C.c_int64 * 4)()
+        check(self.lib.mcsce_profile(self.h, 0, ms, n))
+        names = ("place_trials", "score_generic", "score_special", "select")
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(names)}

@@ -286,6 +286,29 @@ def choose(weights, u):
     return len(weights) - 1
 
 
+def prepare_energy_functions(structure, retain_idxs=(), terms=("lj", "clash", "coulomb"), tables=None):
+    """{level: EnergyFunction}: level 0 = input atoms alone, level i+1 = residue i's side chain
+    against everything placed before it (initialize_func_calc, side_chain_builder.py:42-107)."""
+    t = tables or load_tables()
+    work = structure.copy()
+    n_term, c_term = work.get_terminal_res_atom_arr()
+    out = {0: EnergyFunction(work.atom_labels, work.res_nums, work.res_labels, n_term, c_term, terms=terms, tables=t)}
+    first = int(work.res_nums[0])
+    for i, (res, chain) in enumerate(zip(work.residue_types, work.residue_chains)):
+        if first + i in retain_idxs:
+            continue
+        tmpl = t.templates[res]
+        work.append_atoms([tmpl.names[k] for k in tmpl.sc_idx], tmpl.resname, chain, first + i,
+                          np.zeros((tmpl.n_sc, 3), dtype=F32))
+        if res in NO_CHI_RESIDUES:
+            continue
+        n_all = len(work)
+        n_term, c_term = work.get_terminal_res_atom_arr()
+        out[i + 1] = EnergyFunction(work.atom_labels, work.res_nums, work.res_labels, n_term, c_term,
+                                    np.arange(n_all - tmpl.n_sc, n_all), np.arange(n_all - tmpl.n_sc), terms=terms, tables=t)
+    return out
+
+
 def grow_conformer(structure, backbone_coords, beta, chi_for_step, uniform_for_step, retain_idxs=(),
                    terms=("lj", "clash", "coulomb"), tables=None, efuncs=None, record=None):
     """One conformer of the growth loop (side_chain_builder.py:109-205).
