@@ -33,13 +33,21 @@ _WELLS = np.array([-65.0, 180.0, 65.0])
 _GRID = np.arange(-180, 181, 10)
 
 
-def write_synthetic_bbdep_library(path, seed=0, concentration=0.3):
+#: prior over the three wells (-65, 180, +65): chi1 avoids g+ (it points back over the residue's own
+#: backbone, as the real bbdep library knows for helical phi/psi), later chis favour trans
+_CHI1_PRIOR = np.array([0.55, 0.37, 0.08])
+_CHIN_PRIOR = np.array([0.28, 0.44, 0.28])
+
+
+def write_synthetic_bbdep_library(path, seed=0, concentration=0.3, well_prior=True):
     """Write a seeded bbdep-format library to ``path``; returns the path.
 
     Rotamers are the 3**nchi combinations of three wells per chi; per
-    (residue, phi, psi) bin the probabilities are Dirichlet(``concentration``)
-    draws (printed with 6 decimals), well centres are jittered by N(0, 4 deg)
-    and sigmas are U(6, 14) deg.  The phi=180 / psi=180 rows repeat the -180
+    (residue, phi, psi) bin the probabilities are Dirichlet draws (printed with
+    6 decimals) whose concentration follows a per-well prior (``well_prior``:
+    chi1 rarely g+, later chis mostly trans; total concentration
+    ``concentration`` * 3**nchi), well centres are jittered by N(0, 4 deg) and
+    sigmas are U(6, 14) deg.  The phi=180 / psi=180 rows repeat the -180
     rows and come after them, as the reference's loader asserts
     (rotamer_library.py:77-80).
     """
@@ -56,7 +64,13 @@ def write_synthetic_bbdep_library(path, seed=0, concentration=0.3):
         rcols = np.zeros((nrot, 4), dtype=int)
         rcols[:, :nchi] = idx + 1
         n_bins = 36 * 36
-        probs = rng.dirichlet(np.full(nrot, concentration), size=n_bins)
+        alpha = np.full(nrot, concentration)
+        if well_prior:
+            w = _CHI1_PRIOR[idx[:, 0]].copy()
+            for k in range(1, nchi):
+                w = w * _CHIN_PRIOR[idx[:, k]]
+            alpha = concentration * nrot * w / w.sum()
+        probs = rng.dirichlet(alpha, size=n_bins)
         centres = np.zeros((n_bins, nrot, 4))
         centres[:, :, :nchi] = _WELLS[idx][None] + rng.normal(0.0, 4.0, size=(n_bins, nrot, nchi))
         centres = (centres + 180.0) % 360.0 - 180.0
@@ -80,13 +94,16 @@ def write_synthetic_bbdep_library(path, seed=0, concentration=0.3):
     return path
 
 
+LIB_VERSION = 2      # bump when the generator changes (cache file name)
+
+
 def synthetic_library_path(seed=0, cache_dir=None):
     """Return the path of the cached synthetic library for ``seed`` (generated on first use)."""
     cache_dir = Path(cache_dir or os.environ.get("MCSCE_B200_CACHE",
                                                  Path(tempfile.gettempdir()) / "mcsce_b200_cache"))
     d = cache_dir / "SimpleOpt1-5"
     d.mkdir(parents=True, exist_ok=True)
-    p = d / ("ALL.bbdep.rotamers.seed%d.lib" % seed)
+    p = d / ("ALL.bbdep.rotamers.v%d.seed%d.lib" % (LIB_VERSION, seed))
     if not p.exists():
         write_synthetic_bbdep_library(p, seed=seed)
     return p
@@ -95,6 +112,9 @@ def synthetic_library_path(seed=0, cache_dir=None):
 # ----------------------------------------------------------------------------
 # synthetic backbones
 # ----------------------------------------------------------------------------
+
+#: axis-to-axis distance of neighbouring helices in the synthetic bundles (Angstrom)
+BUNDLE_SPACING = 16.0
 
 STANDARD_20 = ["ALA", "ARG", "ASN", "ASP", "CYS", "GLN", "GLU", "GLY", "HIP", "ILE",
                "LEU", "LYS", "MET", "PHE", "PRO", "SER", "THR", "TRP", "TYR", "VAL"]
@@ -183,9 +203,16 @@ def format_pdb(records):
     return "".join(out)
 
 
-def random_sequence(n, seed, alphabet=STANDARD_20):
+def random_sequence(n, seed, alphabet=STANDARD_20, chain_starts=(0,)):
+    """Uniform random sequence.  PRO/HYP at a chain's N-terminus is replaced by ALA: the reference
+    cannot parameterise it (it names the N-terminal protons H1/H2, libstructure.py:811-816, while the
+    force field's NPRO residue carries H2/H3 -> KeyError in libparse.py:447)."""
     rng = np.random.default_rng(seed)
-    return [alphabet[k] for k in rng.integers(0, len(alphabet), size=n)]
+    seq = [alphabet[k] for k in rng.integers(0, len(alphabet), size=n)]
+    for p in chain_starts:
+        if seq[p] in ("PRO", "HYP"):
+            seq[p] = "ALA"
+    return seq
 
 
 def helix_bundle_pdb(seqs, spacing=11.0, seed=0, chain_ids=None, one_chain=False,
@@ -246,7 +273,7 @@ def helix_bundle_pdb(seqs, spacing=11.0, seed=0, chain_ids=None, one_chain=False
     return format_pdb(records)
 
 
-def config_backbone(cfg):
+def config_backbone(cfg, spacing=None):
     """PDB text + description for the BASELINE.json configs (1-5) and small test cases.
 
     cfg 1/2: 76 residues, one helix-like chain, seed 1.      cfg 3: 300 residues = 6 x 50
@@ -258,19 +285,21 @@ def config_backbone(cfg):
         return helix_bundle_pdb([seq], seed=1, one_chain=True)
     if cfg in (3, "300"):
         seq = random_sequence(300, 3)
-        return helix_bundle_pdb([seq[i:i + 50] for i in range(0, 300, 50)], seed=3, one_chain=True)
+        return helix_bundle_pdb([seq[i:i + 50] for i in range(0, 300, 50)], seed=3, one_chain=True,
+                                spacing=spacing or BUNDLE_SPACING)
     if cfg in (4, "ptm150"):
         seq = random_sequence(150, 4)
         rng = np.random.default_rng(40)
         pos = rng.permutation(np.arange(2, 148))[: 3 * len(PTM_SET)]
         for k, p in enumerate(pos):
             seq[p] = PTM_SET[k % len(PTM_SET)]
-        return helix_bundle_pdb([seq[i:i + 50] for i in range(0, 150, 50)], seed=4, one_chain=True)
+        return helix_bundle_pdb([seq[i:i + 50] for i in range(0, 150, 50)], seed=4, one_chain=True,
+                                spacing=spacing or BUNDLE_SPACING)
     if cfg in (5, "2000"):
-        seq = random_sequence(2000, 5)
+        seq = random_sequence(2000, 5, chain_starts=range(0, 2000, 250))
         # 8 chains x 250 residues; each chain = 5 helices of 50 (one chain id per 250 residues)
         helices = [seq[i:i + 50] for i in range(0, 2000, 50)]
-        return _multichain_bundle(helices, per_chain=5, seed=5)
+        return _multichain_bundle(helices, per_chain=5, seed=5, spacing=spacing or BUNDLE_SPACING)
     raise ValueError("unknown config %r" % (cfg,))
 
 
