@@ -262,6 +262,92 @@ struct ScoreArgs {
     const unsigned char *alive;
 };
 
+// Inner loop over one class segment [j0,j1) of the staged tile for RR trial atoms of this thread.
+// Per pair (16 issue slots, 13 on the FMA pipe, 1 MUFU):
+//   d2   = fma(dz,dz,fma(dy,dy,dx*dx))           fused: differs from the reference's unfused d2 by <= 4 ulp
+//   dmin = min(dmin, d2)                          clash decision deferred to the end of the segment
+//   y    = rsqrt.approx(d2)                       raw MUFU (<= 2 ulp): good enough for q/d
+//   w    = y*y ; w = w + w*(1 - d2*w)             one Newton step on the reciprocal: 1/d2 to ~1 ulp
+//   i3   = w*w*w ; a6 += i3*i3 ; a3 += i3         sum d^-12 and sum d^-6 (class constants applied at the flush)
+//   cq  += q_j*y
+// The clash test must reproduce  sqrt(float64(d2_ref)) < thr  exactly (d2_ref = the reference's unfused
+// float32 sum, libcalc.py:64-67).  thr2 is the float32 value with  d2_ref < thr2  <=>  that predicate, so
+// the fused minimum decides unless it lands within 1e-6 relative of thr2; then the segment is re-scanned
+// with the reference's operation order (practically never).
+template <int RR>
+__device__ __forceinline__ void score_segment(const float4 *__restrict__ s_env, int j0, int j1,
+                                              const float (&xi)[SCORE_R], const float (&yi)[SCORE_R], const float (&zi)[SCORE_R],
+                                              const float (&thr2)[SCORE_R], double (&E6)[SCORE_R], double (&E3)[SCORE_R],
+                                              double (&EC)[SCORE_R], bool (&clash)[SCORE_R]) {
+    float dmin[RR];
+#pragma unroll
+    for (int r = 0; r < RR; ++r) dmin[r] = CUDART_INF_F;
+    for (int jb = j0; jb < j1; jb += FLUSH) {
+        const int je = min(jb + FLUSH, j1);
+        float a6[RR], a3[RR], cq[RR];
+#pragma unroll
+        for (int r = 0; r < RR; ++r) { a6[r] = 0.f; a3[r] = 0.f; cq[r] = 0.f; }
+#pragma unroll 4
+        for (int j = jb; j < je; ++j) {
+            const float4 ev = s_env[j];
+#pragma unroll
+            for (int r = 0; r < RR; ++r) {
+                const float dx = ev.x - xi[r], dy = ev.y - yi[r], dz = ev.z - zi[r];
+                const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                dmin[r] = fminf(dmin[r], d2);
+                float y;
+                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(d2));
+                float w = y * y;
+                w = fmaf(w, fmaf(-d2, w, 1.0f), w);
+                const float i3 = w * w * w;
+                a6[r] = fmaf(i3, i3, a6[r]);
+                a3[r] += i3;
+                cq[r] = fmaf(ev.w, y, cq[r]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RR; ++r) { E6[r] += (double)a6[r]; E3[r] += (double)a3[r]; EC[r] += (double)cq[r]; }
+    }
+#pragma unroll
+    for (int r = 0; r < RR; ++r) {
+        if (dmin[r] < thr2[r] * (1.0f - 1.0e-6f)) clash[r] = true;
+        else if (dmin[r] < thr2[r] * (1.0f + 1.0e-6f)) {
+            for (int j = j0; j < j1; ++j) {
+                const float4 ev = s_env[j];
+                clash[r] |= dist2_ref(xi[r], yi[r], zi[r], ev.x, ev.y, ev.z) < thr2[r];
+            }
+        }
+    }
+}
+
+template <int RR>
+__device__ __forceinline__ void score_tile(const ScoreArgs &a, const float4 *__restrict__ s_env, const int *s_prefix,
+                                           int tile_lo, int tile_n, const float (&xi)[SCORE_R], const float (&yi)[SCORE_R],
+                                           const float (&zi)[SCORE_R], const int (&ci)[SCORE_R], double (&e_lj)[SCORE_R],
+                                           double (&e_c)[SCORE_R], bool (&clash)[SCORE_R]) {
+    const int n_cls = a.s.n_cls;
+    int c;
+    { int c_lo = 0, c_hi = n_cls; while (c_hi - c_lo > 1) { int m = (c_lo + c_hi) >> 1; if (s_prefix[m] <= tile_lo) c_lo = m; else c_hi = m; } c = c_lo; }
+    for (; c < n_cls && s_prefix[c] < tile_lo + tile_n; ++c) {
+        const int j0 = max(s_prefix[c], tile_lo) - tile_lo;
+        const int j1 = min(s_prefix[c + 1], tile_lo + tile_n) - tile_lo;
+        if (j0 >= j1) continue;
+        float thr2[SCORE_R];
+        double E6[SCORE_R], E3[SCORE_R], EC[SCORE_R];
+#pragma unroll
+        for (int r = 0; r < RR; ++r) { thr2[r] = __ldg(&a.s.cls_thr2f[ci[r] * n_cls + c]); E6[r] = 0.0; E3[r] = 0.0; EC[r] = 0.0; }
+        score_segment<RR>(s_env, j0, j1, xi, yi, zi, thr2, E6, E3, EC, clash);
+#pragma unroll
+        for (int r = 0; r < RR; ++r) {
+            // A/d^12 - B/d^6 with A = e4*s2^6, B = e4*s2^3 (libenergy.py:478-481), class constants in float64
+            const double s2 = __ldg(&a.s.cls_s2d[ci[r] * n_cls + c]), e4 = __ldg(&a.s.cls_e4[ci[r] * n_cls + c]);
+            const double s6 = s2 * s2 * s2;
+            e_lj[r] += e4 * s6 * (s6 * E6[r] - E3[r]);
+            e_c[r] += EC[r];
+        }
+    }
+}
+
 __global__ void __launch_bounds__(SCORE_THREADS) score_generic_kernel(ScoreArgs a) {
     __shared__ float4 s_env[TILE_E];
     __shared__ int s_prefix[MAX_CLS + 1];
@@ -285,7 +371,7 @@ __global__ void __launch_bounds__(SCORE_THREADS) score_generic_kernel(ScoreArgs 
     __syncthreads();
     const int n_active = s_prefix[n_cls];
 
-    // this block's trial atoms
+    // this block's trial atoms: atom la = r*SCORE_THREADS + tid of the tile
     const int t0 = blockIdx.x * a.trials_per_tile;
     const int nt = min(a.trials_per_tile, a.n_trials - t0);
     const int n_local = nt * n_sc;
@@ -293,19 +379,20 @@ __global__ void __launch_bounds__(SCORE_THREADS) score_generic_kernel(ScoreArgs 
 
     float xi[SCORE_R], yi[SCORE_R], zi[SCORE_R];
     int ci[SCORE_R];
-    bool valid[SCORE_R];
     double e_lj[SCORE_R], e_c[SCORE_R];
     bool clash[SCORE_R];
 #pragma unroll
     for (int r = 0; r < SCORE_R; ++r) {
         const int la = r * SCORE_THREADS + tid;
-        valid[r] = la < n_local;
-        const int la_c = valid[r] ? la : 0;
+        const int la_c = la < n_local ? la : 0;
         const float4 p = trial[la_c];
         xi[r] = p.x; yi[r] = p.y; zi[r] = p.z;
         ci[r] = a.s.cls_of_atom[st.sc_start + (la_c % n_sc)];
         e_lj[r] = 0.0; e_c[r] = 0.0; clash[r] = false;
     }
+    // warp-uniform amount of work: rows of the tile this warp has atoms in
+    const int warp_base = tid & ~31;
+    const int rows = (SCORE_R > 1 && SCORE_THREADS + warp_base < n_local) ? 2 : (warp_base < n_local ? 1 : 0);
 
     // environment chunk of this block (active order = class-major prefix order)
     const int per = (n_active + a.n_split - 1) / a.n_split;
@@ -329,53 +416,8 @@ __global__ void __launch_bounds__(SCORE_THREADS) score_generic_kernel(ScoreArgs 
             s_env[e] = v;
         }
         __syncthreads();
-        // classes intersecting the tile
-        int c = 0;
-        { int c_lo = 0, c_hi = n_cls; while (c_hi - c_lo > 1) { int m = (c_lo + c_hi) >> 1; if (s_prefix[m] <= tile_lo) c_lo = m; else c_hi = m; } c = c_lo; }
-        for (; c < n_cls && s_prefix[c] < tile_lo + tile_n; ++c) {
-            const int j0 = max(s_prefix[c], tile_lo) - tile_lo;
-            const int j1 = min(s_prefix[c + 1], tile_lo + tile_n) - tile_lo;
-            if (j0 >= j1) continue;
-            float s2[SCORE_R], thr2[SCORE_R];
-            double e4[SCORE_R];
-#pragma unroll
-            for (int r = 0; r < SCORE_R; ++r) {
-                s2[r] = __ldg(&a.s.cls_s2f[ci[r] * n_cls + c]);
-                thr2[r] = __ldg(&a.s.cls_thr2f[ci[r] * n_cls + c]);
-                e4[r] = __ldg(&a.s.cls_e4[ci[r] * n_cls + c]);
-            }
-            for (int jb = j0; jb < j1; jb += FLUSH) {
-                const int je = min(jb + FLUSH, j1);
-                float lj[SCORE_R], cq[SCORE_R];
-#pragma unroll
-                for (int r = 0; r < SCORE_R; ++r) { lj[r] = 0.f; cq[r] = 0.f; }
-#pragma unroll 4
-                for (int j = jb; j < je; ++j) {
-                    const float4 ev = s_env[j];
-#pragma unroll
-                    for (int r = 0; r < SCORE_R; ++r) {
-                        const float d2 = dist2_ref(xi[r], yi[r], zi[r], ev.x, ev.y, ev.z);
-                        clash[r] |= (d2 < thr2[r]);
-                        float rinv;
-                        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(d2));
-                        // one Newton step: rinv <- rinv + 0.5*rinv*(1 - d2*rinv^2)
-                        const float h = d2 * rinv;
-                        const float err = fmaf(-h, rinv, 1.0f);
-                        rinv = fmaf(0.5f * rinv, err, rinv);
-                        const float inv2 = rinv * rinv;
-                        const float t = s2[r] * inv2;
-                        const float t3 = t * t * t;
-                        lj[r] = fmaf(t3, t3 - 1.0f, lj[r]);
-                        cq[r] = fmaf(ev.w, rinv, cq[r]);
-                    }
-                }
-#pragma unroll
-                for (int r = 0; r < SCORE_R; ++r) {
-                    e_lj[r] += e4[r] * (double)lj[r];
-                    e_c[r] += (double)cq[r];
-                }
-            }
-        }
+        if (rows == 2) score_tile<2>(a, s_env, s_prefix, tile_lo, tile_n, xi, yi, zi, ci, e_lj, e_c, clash);
+        else if (rows == 1) score_tile<1>(a, s_env, s_prefix, tile_lo, tile_n, xi, yi, zi, ci, e_lj, e_c, clash);
     }
 
     // per-atom totals -> per-trial partial sums (fixed order)
@@ -383,7 +425,7 @@ __global__ void __launch_bounds__(SCORE_THREADS) score_generic_kernel(ScoreArgs 
 #pragma unroll
     for (int r = 0; r < SCORE_R; ++r) {
         const int la = r * SCORE_THREADS + tid;
-        if (valid[r]) {
+        if (la < n_local) {
             const double qi = a.s.charge[st.sc_start + (la % n_sc)];
             s_e[la] = e_lj[r] + COULOMB_PREF * qi * e_c[r];
             s_clash[la] = clash[r] ? 1 : 0;
