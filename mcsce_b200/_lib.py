@@ -9,7 +9,9 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "libmcsce_b200.so"
+import os
+
+LIB_PATH = Path(os.environ.get("MCSCE_B200_LIB") or (Path(__file__).resolve().parent / "libmcsce_b200.so"))
 
 MAX_CLS, MAX_SP_ENV, MAX_CHI, MAX_CHI_ROT, MAX_TMPL, MAX_SC = 64, 16, 6, 5, 32, 28
 

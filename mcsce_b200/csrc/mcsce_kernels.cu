@@ -243,11 +243,22 @@ __global__ void __launch_bounds__(128) place_trials_kernel(PlaceArgs a) {
 // ------------------------------------------------------------------------------------------------
 // K2: generic pairs.  grid (trial tiles, n_sets, env_split), block SCORE_THREADS.
 // ------------------------------------------------------------------------------------------------
-#define SCORE_THREADS 256
+#ifndef SCORE_THREADS
+#define SCORE_THREADS 128               // 128 x 2 measured best on B200 (tools/time_variants.py): finer CTA granularity per launch
+#endif
+#ifndef SCORE_R
 #define SCORE_R 2                       // trial atoms per thread
+#endif
+#ifndef SCORE_MINB
+#define SCORE_MINB 1                    // min resident blocks per SM asked of the compiler
+#endif
 #define TILE_A (SCORE_THREADS * SCORE_R)
+#ifndef TILE_E
 #define TILE_E 1024                     // environment atoms staged per smem tile
+#endif
+#ifndef FLUSH
 #define FLUSH 32                        // pairs accumulated in float32 before a float64 flush
+#endif
 
 struct ScoreArgs {
     SysDev s;
@@ -262,81 +273,91 @@ struct ScoreArgs {
     const unsigned char *alive;
 };
 
-// Inner loop over one class segment [j0,j1) of the staged tile for RR trial atoms of this thread.
-// Per pair (16 issue slots, 13 on the FMA pipe, 1 MUFU):
-//   d2   = fma(dz,dz,fma(dy,dy,dx*dx))           fused: differs from the reference's unfused d2 by <= 4 ulp
-//   dmin = min(dmin, d2)                          clash decision deferred to the end of the segment
-//   y    = rsqrt.approx(d2)                       raw MUFU (<= 2 ulp): good enough for q/d
-//   w    = y*y ; w = w + w*(1 - d2*w)             one Newton step on the reciprocal: 1/d2 to ~1 ulp
-//   i3   = w*w*w ; a6 += i3*i3 ; a3 += i3         sum d^-12 and sum d^-6 (class constants applied at the flush)
-//   cq  += q_j*y
+// Inner loop over one class segment of the staged tile for RR trial atoms of this thread, two
+// environment atoms per iteration with Blackwell's packed-pair FP32 instructions (FADD2/FMUL2/FFMA2,
+// PTX add/mul/fma.f32x2, sm_100+): the FMA pipe does the same number of lane-operations but takes half
+// the issue slots, which is what bounds this kernel.  Per environment-atom pair and trial atom:
+//   d   = e - a                                   3 FADD2
+//   d2  = fma(dz,dz,fma(dy,dy,dx*dx))             FMUL2 + 2 FFMA2   (fused: <= 4 ulp from the reference's unfused d2)
+//   dmin= min(dmin, d2.x, d2.y)                   clash decision deferred to the end of the segment
+//   y   = rsqrt.approx(d2)                        2 MUFU (<= 2 ulp): good enough for q/d
+//   w   = y*y ; w = w + w*(1 - d2*w)              FMUL2 + 2 FFMA2: one Newton step on the reciprocal, 1/d2 to ~1 ulp
+//   i3  = w*w*w ; a6 += i3*i3 ; a3 += i3          2 FMUL2 + FFMA2 + FADD2: sum d^-12, sum d^-6 (class constants at the flush)
+//   cq += q*y                                     FFMA2
+// The staged tile is stored pair-interleaved (x0 x1 y0 y1 | z0 z1 q0 q1) and every class segment is padded
+// to an even length with a parked dummy atom, so the loop has no edge handling.
 // The clash test must reproduce  sqrt(float64(d2_ref)) < thr  exactly (d2_ref = the reference's unfused
 // float32 sum, libcalc.py:64-67).  thr2 is the float32 value with  d2_ref < thr2  <=>  that predicate, so
 // the fused minimum decides unless it lands within 1e-6 relative of thr2; then the segment is re-scanned
 // with the reference's operation order (practically never).
 template <int RR>
-__device__ __forceinline__ void score_segment(const float4 *__restrict__ s_env, int j0, int j1,
-                                              const float (&xi)[SCORE_R], const float (&yi)[SCORE_R], const float (&zi)[SCORE_R],
+__device__ __forceinline__ void score_segment(const float4 *__restrict__ s_env, int p0, int p1,
+                                              const float2 (&nx)[SCORE_R], const float2 (&ny)[SCORE_R], const float2 (&nz)[SCORE_R],
                                               const float (&thr2)[SCORE_R], double (&E6)[SCORE_R], double (&E3)[SCORE_R],
                                               double (&EC)[SCORE_R], bool (&clash)[SCORE_R]) {
     float dmin[RR];
 #pragma unroll
     for (int r = 0; r < RR; ++r) dmin[r] = CUDART_INF_F;
-    for (int jb = j0; jb < j1; jb += FLUSH) {
-        const int je = min(jb + FLUSH, j1);
-        float a6[RR], a3[RR], cq[RR];
+    const float2 one2 = make_float2(1.0f, 1.0f);
+    for (int pb = p0; pb < p1; pb += FLUSH / 2) {
+        const int pe = min(pb + FLUSH / 2, p1);
+        float2 a6[RR], a3[RR], cq[RR];
 #pragma unroll
-        for (int r = 0; r < RR; ++r) { a6[r] = 0.f; a3[r] = 0.f; cq[r] = 0.f; }
-#pragma unroll 4
-        for (int j = jb; j < je; ++j) {
-            const float4 ev = s_env[j];
+        for (int r = 0; r < RR; ++r) { a6[r] = make_float2(0.f, 0.f); a3[r] = a6[r]; cq[r] = a6[r]; }
+#pragma unroll 2
+        for (int p = pb; p < pe; ++p) {
+            const float4 exy = s_env[2 * p], ezq = s_env[2 * p + 1];
+            const float2 ex = make_float2(exy.x, exy.y), ey = make_float2(exy.z, exy.w);
+            const float2 ez = make_float2(ezq.x, ezq.y), eq = make_float2(ezq.z, ezq.w);
 #pragma unroll
             for (int r = 0; r < RR; ++r) {
-                const float dx = ev.x - xi[r], dy = ev.y - yi[r], dz = ev.z - zi[r];
-                const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                dmin[r] = fminf(dmin[r], d2);
-                float y;
-                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(d2));
-                float w = y * y;
-                w = fmaf(w, fmaf(-d2, w, 1.0f), w);
-                const float i3 = w * w * w;
-                a6[r] = fmaf(i3, i3, a6[r]);
-                a3[r] += i3;
-                cq[r] = fmaf(ev.w, y, cq[r]);
+                const float2 dx = __fadd2_rn(ex, nx[r]), dy = __fadd2_rn(ey, ny[r]), dz = __fadd2_rn(ez, nz[r]);
+                const float2 d2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+                dmin[r] = fminf(dmin[r], fminf(d2.x, d2.y));
+                float2 y;
+                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y.x) : "f"(d2.x));
+                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y.y) : "f"(d2.y));
+                float2 w = __fmul2_rn(y, y);
+                const float2 nd2 = make_float2(-d2.x, -d2.y);
+                w = __ffma2_rn(w, __ffma2_rn(nd2, w, one2), w);
+                const float2 i3 = __fmul2_rn(__fmul2_rn(w, w), w);
+                a6[r] = __ffma2_rn(i3, i3, a6[r]);
+                a3[r] = __fadd2_rn(a3[r], i3);
+                cq[r] = __ffma2_rn(eq, y, cq[r]);
             }
         }
 #pragma unroll
-        for (int r = 0; r < RR; ++r) { E6[r] += (double)a6[r]; E3[r] += (double)a3[r]; EC[r] += (double)cq[r]; }
+        for (int r = 0; r < RR; ++r) {
+            E6[r] += (double)(a6[r].x + a6[r].y); E3[r] += (double)(a3[r].x + a3[r].y); EC[r] += (double)(cq[r].x + cq[r].y);
+        }
     }
 #pragma unroll
     for (int r = 0; r < RR; ++r) {
         if (dmin[r] < thr2[r] * (1.0f - 1.0e-6f)) clash[r] = true;
         else if (dmin[r] < thr2[r] * (1.0f + 1.0e-6f)) {
-            for (int j = j0; j < j1; ++j) {
-                const float4 ev = s_env[j];
-                clash[r] |= dist2_ref(xi[r], yi[r], zi[r], ev.x, ev.y, ev.z) < thr2[r];
+            for (int p = p0; p < p1; ++p) {
+                const float4 exy = s_env[2 * p], ezq = s_env[2 * p + 1];
+                clash[r] |= dist2_ref(-nx[r].x, -ny[r].x, -nz[r].x, exy.x, exy.z, ezq.x) < thr2[r];
+                clash[r] |= dist2_ref(-nx[r].x, -ny[r].x, -nz[r].x, exy.y, exy.w, ezq.y) < thr2[r];
             }
         }
     }
 }
 
 template <int RR>
-__device__ __forceinline__ void score_tile(const ScoreArgs &a, const float4 *__restrict__ s_env, const int *s_prefix,
-                                           int tile_lo, int tile_n, const float (&xi)[SCORE_R], const float (&yi)[SCORE_R],
-                                           const float (&zi)[SCORE_R], const int (&ci)[SCORE_R], double (&e_lj)[SCORE_R],
+__device__ __forceinline__ void score_tile(const ScoreArgs &a, const float4 *__restrict__ s_env, const int *s_seg, int c_first,
+                                           int c_last, const float2 (&nx)[SCORE_R], const float2 (&ny)[SCORE_R],
+                                           const float2 (&nz)[SCORE_R], const int (&ci)[SCORE_R], double (&e_lj)[SCORE_R],
                                            double (&e_c)[SCORE_R], bool (&clash)[SCORE_R]) {
     const int n_cls = a.s.n_cls;
-    int c;
-    { int c_lo = 0, c_hi = n_cls; while (c_hi - c_lo > 1) { int m = (c_lo + c_hi) >> 1; if (s_prefix[m] <= tile_lo) c_lo = m; else c_hi = m; } c = c_lo; }
-    for (; c < n_cls && s_prefix[c] < tile_lo + tile_n; ++c) {
-        const int j0 = max(s_prefix[c], tile_lo) - tile_lo;
-        const int j1 = min(s_prefix[c + 1], tile_lo + tile_n) - tile_lo;
-        if (j0 >= j1) continue;
+    for (int c = c_first; c <= c_last; ++c) {
+        const int p0 = s_seg[c] >> 1, p1 = s_seg[c + 1] >> 1;          // padded, pair units
+        if (p0 >= p1) continue;
         float thr2[SCORE_R];
         double E6[SCORE_R], E3[SCORE_R], EC[SCORE_R];
 #pragma unroll
         for (int r = 0; r < RR; ++r) { thr2[r] = __ldg(&a.s.cls_thr2f[ci[r] * n_cls + c]); E6[r] = 0.0; E3[r] = 0.0; EC[r] = 0.0; }
-        score_segment<RR>(s_env, j0, j1, xi, yi, zi, thr2, E6, E3, EC, clash);
+        score_segment<RR>(s_env, p0, p1, nx, ny, nz, thr2, E6, E3, EC, clash);
 #pragma unroll
         for (int r = 0; r < RR; ++r) {
             // A/d^12 - B/d^6 with A = e4*s2^6, B = e4*s2^3 (libenergy.py:478-481), class constants in float64
@@ -348,9 +369,12 @@ __device__ __forceinline__ void score_tile(const ScoreArgs &a, const float4 *__r
     }
 }
 
-__global__ void __launch_bounds__(SCORE_THREADS) score_generic_kernel(ScoreArgs a) {
-    __shared__ float4 s_env[TILE_E];
+#define TILE_SLOTS (TILE_E + 2 * MAX_CLS)      // staged atoms + one pad per class, even
+
+__global__ void __launch_bounds__(SCORE_THREADS, SCORE_MINB) score_generic_kernel(ScoreArgs a) {
+    __shared__ float4 s_env[TILE_SLOTS / 2 * 2];     // pair p: [2p] = x0 x1 y0 y1, [2p+1] = z0 z1 q0 q1
     __shared__ int s_prefix[MAX_CLS + 1];
+    __shared__ int s_seg[MAX_CLS + 1];                // padded start of every class segment inside the tile
     __shared__ int s_sp[MAX_SP_ENV];
     __shared__ double s_e[TILE_A];
     __shared__ unsigned char s_clash[TILE_A];
@@ -377,7 +401,7 @@ __global__ void __launch_bounds__(SCORE_THREADS) score_generic_kernel(ScoreArgs 
     const int n_local = nt * n_sc;
     const float4 *trial = a.trial + (long long)set * a.trial_set_stride + (long long)t0 * n_sc;
 
-    float xi[SCORE_R], yi[SCORE_R], zi[SCORE_R];
+    float2 nx[SCORE_R], ny[SCORE_R], nz[SCORE_R];     // minus the trial atom, duplicated into both halves
     int ci[SCORE_R];
     double e_lj[SCORE_R], e_c[SCORE_R];
     bool clash[SCORE_R];
@@ -386,23 +410,43 @@ __global__ void __launch_bounds__(SCORE_THREADS) score_generic_kernel(ScoreArgs 
         const int la = r * SCORE_THREADS + tid;
         const int la_c = la < n_local ? la : 0;
         const float4 p = trial[la_c];
-        xi[r] = p.x; yi[r] = p.y; zi[r] = p.z;
+        nx[r] = make_float2(-p.x, -p.x); ny[r] = make_float2(-p.y, -p.y); nz[r] = make_float2(-p.z, -p.z);
         ci[r] = a.s.cls_of_atom[st.sc_start + (la_c % n_sc)];
         e_lj[r] = 0.0; e_c[r] = 0.0; clash[r] = false;
     }
     // warp-uniform amount of work: rows of the tile this warp has atoms in
     const int warp_base = tid & ~31;
-    const int rows = (SCORE_R > 1 && SCORE_THREADS + warp_base < n_local) ? 2 : (warp_base < n_local ? 1 : 0);
+    int rows = 0;
+#pragma unroll
+    for (int r = 0; r < SCORE_R; ++r) rows += (r * SCORE_THREADS + warp_base < n_local) ? 1 : 0;
 
     // environment chunk of this block (active order = class-major prefix order)
     const int per = (n_active + a.n_split - 1) / a.n_split;
     const int lo = blockIdx.z * per;
     const int hi = min(n_active, lo + per);
     const float4 *env = a.env + (long long)set * a.s.n_atoms;
+    float *s_flat = reinterpret_cast<float *>(s_env);
 
     for (int tile_lo = lo; tile_lo < hi; tile_lo += TILE_E) {
         const int tile_n = min(TILE_E, hi - tile_lo);
         __syncthreads();
+        if (tid == 0) {       // padded (even) segment starts of the classes intersecting the tile
+            int acc = 0;
+            for (int c = 0; c < n_cls; ++c) {
+                s_seg[c] = acc;
+                const int len = max(0, min(s_prefix[c + 1], tile_lo + tile_n) - max(s_prefix[c], tile_lo));
+                acc += (len + 1) & ~1;
+            }
+            s_seg[n_cls] = acc;
+        }
+        __syncthreads();
+        if (tid < n_cls) {    // park a dummy in the pad slot of odd-length segments
+            const int len = max(0, min(s_prefix[tid + 1], tile_lo + tile_n) - max(s_prefix[tid], tile_lo));
+            if (len & 1) {
+                const int P = s_seg[tid] + len, pp = P >> 1, hh = P & 1;
+                s_flat[8 * pp + hh] = 1.0e15f; s_flat[8 * pp + 2 + hh] = 1.0e15f; s_flat[8 * pp + 4 + hh] = 1.0e15f; s_flat[8 * pp + 6 + hh] = 0.f;
+            }
+        }
         for (int e = tid; e < tile_n; e += SCORE_THREADS) {
             const int ae = tile_lo + e;
             int c_lo = 0, c_hi = n_cls;                     // largest c with prefix[c] <= ae
@@ -413,11 +457,17 @@ __global__ void __launch_bounds__(SCORE_THREADS) score_generic_kernel(ScoreArgs 
 #pragma unroll
             for (int q = 0; q < MAX_SP_ENV; ++q) special |= (s_sp[q] == slot);
             if (special) v = make_float4(1.0e15f, 1.0e15f, 1.0e15f, 0.f);   // scored by the special-pair kernel
-            s_env[e] = v;
+            const int P = s_seg[c_lo] + (ae - max(s_prefix[c_lo], tile_lo)), pp = P >> 1, hh = P & 1;
+            s_flat[8 * pp + hh] = v.x; s_flat[8 * pp + 2 + hh] = v.y; s_flat[8 * pp + 4 + hh] = v.z; s_flat[8 * pp + 6 + hh] = v.w;
         }
         __syncthreads();
-        if (rows == 2) score_tile<2>(a, s_env, s_prefix, tile_lo, tile_n, xi, yi, zi, ci, e_lj, e_c, clash);
-        else if (rows == 1) score_tile<1>(a, s_env, s_prefix, tile_lo, tile_n, xi, yi, zi, ci, e_lj, e_c, clash);
+        int c_first, c_last;
+        { int c_lo = 0, c_hi = n_cls; while (c_hi - c_lo > 1) { int m = (c_lo + c_hi) >> 1; if (s_prefix[m] <= tile_lo) c_lo = m; else c_hi = m; } c_first = c_lo; }
+        { int c_lo = 0, c_hi = n_cls; const int last = tile_lo + tile_n - 1;
+          while (c_hi - c_lo > 1) { int m = (c_lo + c_hi) >> 1; if (s_prefix[m] <= last) c_lo = m; else c_hi = m; } c_last = c_lo; }
+        if (rows == SCORE_R) score_tile<SCORE_R>(a, s_env, s_seg, c_first, c_last, nx, ny, nz, ci, e_lj, e_c, clash);
+        else if (SCORE_R > 2 && rows >= 2) score_tile<(SCORE_R > 2 ? SCORE_R - 1 : 1)>(a, s_env, s_seg, c_first, c_last, nx, ny, nz, ci, e_lj, e_c, clash);
+        else if (rows >= 1) score_tile<1>(a, s_env, s_seg, c_first, c_last, nx, ny, nz, ci, e_lj, e_c, clash);
     }
 
     // per-atom totals -> per-trial partial sums (fixed order)
@@ -432,10 +482,10 @@ __global__ void __launch_bounds__(SCORE_THREADS) score_generic_kernel(ScoreArgs 
         }
     }
     __syncthreads();
-    if (tid < nt) {
+    for (int t = tid; t < nt; t += SCORE_THREADS) {
         double e = 0.0; int cl = 0;
-        for (int k = 0; k < n_sc; ++k) { e += s_e[tid * n_sc + k]; cl |= s_clash[tid * n_sc + k]; }
-        a.partial[((long long)set * a.n_trials + (t0 + tid)) * a.n_split + blockIdx.z] = make_double2(e, cl ? 1.0 : 0.0);
+        for (int k = 0; k < n_sc; ++k) { e += s_e[t * n_sc + k]; cl |= s_clash[t * n_sc + k]; }
+        a.partial[((long long)set * a.n_trials + (t0 + t)) * a.n_split + blockIdx.z] = make_double2(e, cl ? 1.0 : 0.0);
     }
 }
 
