@@ -72,6 +72,7 @@ struct SysDev {
     const TmplDev *tmpl;
     const int *sp_k, *sp_partner;
     const double *sp_coef;
+    const float *sp_thr2f;
     const int *resnum;
     int n_bb_pairs;
     const int *bb_i, *bb_j;
@@ -256,6 +257,9 @@ __global__ void __launch_bounds__(128) place_trials_kernel(PlaceArgs a) {
 #ifndef TILE_E
 #define TILE_E 1024                     // environment atoms staged per smem tile
 #endif
+#ifndef RCP_MIX
+#define RCP_MIX 0                       // 1: alternate Newton-corrected y*y with MUFU.RCP for 1/d2
+#endif
 #ifndef FLUSH
 #define FLUSH 32                        // pairs accumulated in float32 before a float64 flush
 #endif
@@ -317,9 +321,18 @@ __device__ __forceinline__ void score_segment(const float4 *__restrict__ s_env, 
                 float2 y;
                 asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y.x) : "f"(d2.x));
                 asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y.y) : "f"(d2.y));
-                float2 w = __fmul2_rn(y, y);
-                const float2 nd2 = make_float2(-d2.x, -d2.y);
-                w = __ffma2_rn(w, __ffma2_rn(nd2, w, one2), w);
+                float2 w;
+#if RCP_MIX
+                if (p & 1) {      // every other pair: 1/d2 straight from the MUFU (<= 1 ulp), balancing the FMA and XU pipes
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(w.x) : "f"(d2.x));
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(w.y) : "f"(d2.y));
+                } else
+#endif
+                {
+                    w = __fmul2_rn(y, y);
+                    const float2 nd2 = make_float2(-d2.x, -d2.y);
+                    w = __ffma2_rn(w, __ffma2_rn(nd2, w, one2), w);
+                }
                 const float2 i3 = __fmul2_rn(__fmul2_rn(w, w), w);
                 a6[r] = __ffma2_rn(i3, i3, a6[r]);
                 a3[r] = __fadd2_rn(a3[r], i3);
@@ -515,6 +528,19 @@ __device__ __forceinline__ double pair_energy_f64(float d2f, double A, double B,
     return e;
 }
 
+// Special-pair energy with no float64 sqrt/div: 1/d from the float32 rsqrt refined by two Newton steps in
+// float64 (relative error ~1e-15), then A/d^12 - B/d^6 + Q/d as products.  The clash decision is the exact
+// float32 comparison d2_ref < thr2f (thr2f precomputed so that it equals sqrt(float64(d2_ref)) < thr).
+__device__ __forceinline__ double pair_energy_fast(float d2f, double A, double B, double Q) {
+    const double d2 = (double)d2f;
+    double y = (double)rsqrtf(d2f);
+    const double h = 0.5 * d2;
+    y = y * (1.5 - h * y * y);
+    y = y * (1.5 - h * y * y);
+    const double w = y * y, w3 = w * w * w;
+    return w3 * (A * w3 - B) + Q * y;
+}
+
 __global__ void __launch_bounds__(256) score_special_kernel(SpecialArgs a) {
     const int lane = threadIdx.x & 31;
     const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -532,9 +558,9 @@ __global__ void __launch_bounds__(256) score_special_kernel(SpecialArgs a) {
         const float4 an = trial[k];
         const float4 bo = (pa >= 0) ? env[st.sp_env_slot[pa]] : trial[-pa - 1];
         const float d2 = dist2_ref(an.x, an.y, an.z, bo.x, bo.y, bo.z);
-        bool cl;
-        e += pair_energy_f64(d2, cf[0], cf[1], cf[2], cf[3], cl);
-        any |= cl;
+        any |= d2 < a.s.sp_thr2f[st.sp_off + p];
+        const double A = cf[0], B = cf[1], Q = cf[2];
+        if (A != 0.0 || B != 0.0 || Q != 0.0) e += pair_energy_fast(d2, A, B, Q);
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) e += __shfl_xor_sync(0xffffffffu, e, off);
@@ -770,6 +796,11 @@ struct mcsce_handle_s {
     unsigned long long *d_pairs = nullptr;
     double *d_input_energy = nullptr;
     long long launches = 0;
+    // second stream + events: placement (K1, FP64 pipe) and the special-pair kernel of a residue run
+    // beside the generic-pair kernel (FP32 pipe) of the same / previous residue
+    cudaStream_t aux = nullptr;
+    std::vector<cudaEvent_t> evP, evQ, evS;
+    cudaEvent_t ev0 = nullptr;
     // optional per-kernel-class device timing (CUDA events on the launch stream)
     bool profiling = false;
     std::vector<cudaEvent_t> ev[4];     // 0 place, 1 score_generic, 2 score_special, 3 select: begin/end pairs
@@ -832,6 +863,11 @@ extern "C" int mcsce_destroy(mcsce_handle h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     free_pool(h->sys_allocs); free_pool(h->bb_allocs);
+    for (auto e : h->evP) cudaEventDestroy(e);
+    for (auto e : h->evQ) cudaEventDestroy(e);
+    for (auto e : h->evS) cudaEventDestroy(e);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->aux) cudaStreamDestroy(h->aux);
     if (h->d_steps) cudaFree(h->d_steps);
     if (h->d_pairs) cudaFree(h->d_pairs);
     if (h->d_input_energy) cudaFree(h->d_input_energy);
@@ -904,6 +940,11 @@ extern "C" int mcsce_set_system(mcsce_handle h, const mcsce_system_desc *s) {
     if (upload(h, P, s->sp_k, s->n_sp_total, &d.sp_k)) return -1;
     if (upload(h, P, s->sp_partner, s->n_sp_total, &d.sp_partner)) return -1;
     if (upload(h, P, s->sp_coef, (size_t)s->n_sp_total * 4, &d.sp_coef)) return -1;
+    {
+        std::vector<float> t2((size_t)s->n_sp_total);
+        for (int i = 0; i < s->n_sp_total; ++i) t2[i] = exact_thr2(s->sp_coef[(size_t)i * 4 + 3]);
+        if (upload(h, P, t2.data(), t2.size(), &d.sp_thr2f)) return -1;
+    }
     d.n_bb_pairs = s->n_bb_pairs;
     if (upload(h, P, s->bb_i, s->n_bb_pairs, &d.bb_i)) return -1;
     if (upload(h, P, s->bb_j, s->n_bb_pairs, &d.bb_j)) return -1;
@@ -997,7 +1038,7 @@ static int max_split_for(int n_sets, int sm_count) {
 }
 
 struct Workspace {
-    float4 *env, *trial;
+    float4 *env, *trial, *trial2;
     double2 *partial, *sp_partial;
     unsigned char *alive;
     double *e_acc;
@@ -1012,6 +1053,7 @@ static Workspace carve(const mcsce_handle h, int n_conf, int max_trials, int max
     const int ms = max_split_for(n_conf, h->sm_count);
     w.env = (float4 *)take((size_t)n_conf * h->d.n_atoms * sizeof(float4));
     w.trial = (float4 *)take((size_t)n_conf * std::max(1, max_trial_atoms) * sizeof(float4));
+    w.trial2 = (float4 *)take((size_t)n_conf * std::max(1, max_trial_atoms) * sizeof(float4));
     w.partial = (double2 *)take((size_t)n_conf * std::max(1, max_trials) * ms * sizeof(double2));
     w.sp_partial = (double2 *)take((size_t)n_conf * std::max(1, max_trials) * sizeof(double2));
     w.alive = (unsigned char *)take((size_t)n_conf);
@@ -1074,23 +1116,37 @@ static int launch_place(mcsce_handle h, int step, int n_sets, int n_rows, const 
     return 0;
 }
 
-static int launch_score(mcsce_handle h, int step, int n_sets, int n_trials, int n_split, const float4 *env,
-                        const float4 *trial, long long trial_stride, double2 *partial, double2 *sp_partial,
-                        const unsigned char *alive, cudaStream_t st) {
+static int launch_generic(mcsce_handle h, int step, int n_sets, int n_trials, int n_split, const float4 *env,
+                          const float4 *trial, long long trial_stride, double2 *partial, const unsigned char *alive,
+                          cudaStream_t st) {
     const StepDev &sd = h->steps[step];
     ScoreArgs a{};
     a.s = h->d; a.step = step; a.n_trials = n_trials; a.trials_per_tile = trials_per_tile_for(sd.n_sc);
     a.n_split = n_split; a.env = env; a.trial = trial; a.trial_set_stride = trial_stride; a.partial = partial; a.alive = alive;
     dim3 grid((n_trials + a.trials_per_tile - 1) / a.trials_per_tile, n_sets, n_split);
     { ProfScope ps(h, 1, st); score_generic_kernel<<<grid, SCORE_THREADS, 0, st>>>(a); }
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int launch_special(mcsce_handle h, int step, int n_sets, int n_trials, const float4 *env, const float4 *trial,
+                          long long trial_stride, double2 *sp_partial, const unsigned char *alive, cudaStream_t st) {
     SpecialArgs b{};
     b.s = h->d; b.step = step; b.n_trials = n_trials; b.env = env; b.trial = trial; b.trial_set_stride = trial_stride;
     b.sp_partial = sp_partial; b.alive = alive;
     dim3 grid2((n_trials + 7) / 8, n_sets);
     { ProfScope ps(h, 2, st); score_special_kernel<<<grid2, 256, 0, st>>>(b); }
-    h->launches += 2;
+    h->launches += 1;
     CK(cudaGetLastError());
     return 0;
+}
+
+static int launch_score(mcsce_handle h, int step, int n_sets, int n_trials, int n_split, const float4 *env,
+                        const float4 *trial, long long trial_stride, double2 *partial, double2 *sp_partial,
+                        const unsigned char *alive, cudaStream_t st) {
+    if (launch_generic(h, step, n_sets, n_trials, n_split, env, trial, trial_stride, partial, alive, st)) return -1;
+    return launch_special(h, step, n_sets, n_trials, env, trial, trial_stride, sp_partial, alive, st);
 }
 
 extern "C" int mcsce_place_trials(mcsce_handle h, int residue, int n_rows, const double *d_chis, float *d_xyz, void *stream) {
@@ -1190,18 +1246,44 @@ extern "C" int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *o, void *d_work
     init_state_kernel<<<(C + 255) / 256, 256, 0, st>>>(C, w.alive, w.e_acc, h->d_input_energy);
     h->launches += 1;
 
+    // Two streams: `st` runs the generic-pair kernel and the selection of every residue in order; `aux` runs the
+    // placement of the next residue (independent of the pending selection) and the special-pair kernel.
+    if (!h->aux) CK(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
+    if (!h->ev0) CK(cudaEventCreateWithFlags(&h->ev0, cudaEventDisableTiming));
+    while ((int)h->evP.size() < d.n_res) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->evP.push_back(e);
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->evQ.push_back(e);
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->evS.push_back(e);
+    }
+    cudaStream_t aux = h->aux;
+    CK(cudaEventRecord(h->ev0, st));
+    CK(cudaStreamWaitEvent(aux, h->ev0, 0));
+    int prev = -1, prev2 = -1, count = 0;
     for (int i = 0; i < d.n_res; ++i) {
         const StepDev &sd = h->steps[i];
         if (sd.kind != 2 || sd.n_trials <= 0) continue;
         const int T = sd.n_trials;
-        if (launch_place(h, i, C, T, o->d_chis, chi_set_stride, sd.trial_off, o->d_chis_out, w.trial, trial_stride,
-                         w.alive, o->seed, o->conf_id0, o->noise_deg, st)) return -1;
+        float4 *trial = (count & 1) ? w.trial2 : w.trial;
+        // aux: K1 into the buffer last read by the residue before the previous one
+        if (prev2 >= 0) CK(cudaStreamWaitEvent(aux, h->evS[prev2], 0));
+        if (launch_place(h, i, C, T, o->d_chis, chi_set_stride, sd.trial_off, o->d_chis_out, trial, trial_stride,
+                         w.alive, o->seed, o->conf_id0, o->noise_deg, aux)) return -1;
+        CK(cudaEventRecord(h->evP[i], aux));
+        // st: generic pairs
+        CK(cudaStreamWaitEvent(st, h->evP[i], 0));
         const int split = choose_split(h, i, C, T, o->env_split);
-        if (launch_score(h, i, C, T, split, w.env, w.trial, trial_stride, w.partial, w.sp_partial, w.alive, st)) return -1;
+        if (launch_generic(h, i, C, T, split, w.env, trial, trial_stride, w.partial, w.alive, st)) return -1;
+        // aux: special pairs (need the environment as updated by the previous selection)
+        if (prev >= 0) CK(cudaStreamWaitEvent(aux, h->evS[prev], 0));
+        if (launch_special(h, i, C, T, w.env, trial, trial_stride, w.sp_partial, w.alive, aux)) return -1;
+        CK(cudaEventRecord(h->evQ[i], aux));
+        // st: selection
+        CK(cudaStreamWaitEvent(st, h->evQ[i], 0));
         SelectArgs a{};
         a.s = d; a.step = i; a.n_trials = T; a.n_split = split; a.partial = w.partial; a.sp_partial = w.sp_partial;
         a.prob = d.prob + sd.trial_off; a.beta = o->beta; a.uniform = o->d_uniform; a.u_stride = d.n_res;
-        a.seed = o->seed; a.conf_id0 = o->conf_id0; a.env = w.env; a.trial = w.trial; a.trial_set_stride = trial_stride;
+        a.seed = o->seed; a.conf_id0 = o->conf_id0; a.env = w.env; a.trial = trial; a.trial_set_stride = trial_stride;
         a.alive = w.alive; a.e_acc = w.e_acc; a.selected = o->d_selected; a.trial_energy = o->d_trial_energy;
         a.pair_counter = h->d_pairs;
         long long n_active = 0;
@@ -1209,6 +1291,8 @@ extern "C" int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *o, void *d_work
         a.pairs_per_set = (long long)T * ((long long)sd.n_sc * (sd.n_sc - 1) / 2 + (long long)sd.n_sc * n_active);
         { ProfScope ps(h, 3, st); select_kernel<<<C, 128, sizeof(double) * 2 * T, st>>>(a); }
         h->launches += 1;
+        CK(cudaEventRecord(h->evS[i], st));
+        prev2 = prev; prev = i; ++count;
     }
     const long long n = (long long)C * d.n_atoms;
     gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d, C, w.env, d_coords);

@@ -219,13 +219,17 @@ class GrowthEngine:
         if host_out:
             extra = C_ * (N * 12 + 9) + 1024
             ws = self._ws(base + extra)
-            coords = torch.empty((C_, N, 3), dtype=torch.float32).pin_memory()
-            energy = torch.empty(C_, dtype=torch.float64).pin_memory()
-            ok = torch.empty(C_, dtype=torch.uint8).pin_memory()
+            key = (C_, N)
+            if getattr(self, "_pinned_key", None) != key:       # pinned staging is reused between calls
+                self._pinned = (torch.empty((C_, N, 3), dtype=torch.float32).pin_memory(),
+                                torch.empty(C_, dtype=torch.float64).pin_memory(),
+                                torch.empty(C_, dtype=torch.uint8).pin_memory())
+                self._pinned_key = key
+            coords, energy, ok = self._pinned
             check(self.lib.mcsce_grow_host(self.h, C.byref(o), C.c_void_p(ws.data_ptr()), ws.numel(),
                                            C.c_void_p(coords.data_ptr()), C.c_void_p(energy.data_ptr()),
                                            C.c_void_p(ok.data_ptr()), s_ptr))
-            out.update(coords=coords.numpy(), energy=energy.numpy(), ok=ok.numpy())
+            out.update(coords=coords.numpy(), energy=energy.numpy(), ok=ok.numpy())   # views of the pinned staging: copy to keep
         else:
             ws = self._ws(base)
             coords = torch.empty((C_, N, 3), dtype=torch.float32, device=self.device)
