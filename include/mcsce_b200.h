@@ -177,6 +177,17 @@ int mcsce_init_env(mcsce_handle h, int n_env_sets, float *d_env, void *stream);
 /* counters for the benchmark: kernels launched / algorithmic pair evaluations since the last reset */
 int mcsce_counters(mcsce_handle h, int64_t *launches, int64_t *pairs, int reset);
 
+/* Stand-alone mirrors of the two per-trial reference functions (HOST buffers; no handle needed):
+ *   rotate_sidechain(res_type, tors)  (libs/libscbuild.py:56-206): template (n_atoms x 3 float32), rotation
+ *   program (axis pairs, moving-atom bit masks, template dihedrals) and n_rows chi rows [n_rows*MAX_CHI] degrees
+ *   -> h_out [n_rows*n_atoms*3] float32, template frame;
+ *   place_sidechain_template(bb, tmpl) (libs/libcalc.py:419-482): the two placement quaternions (host tables,
+ *   mcsce_b200/libs/placement.py) applied to n_atoms float32 points -> float64. */
+int mcsce_rotate_template(int device, int n_atoms, const float *h_tmpl_xyz, int n_rot, const int32_t *h_axis,
+                          const uint32_t *h_move, const double *h_ori, int n_rows, const double *h_chis, float *h_out);
+int mcsce_place_template(int device, int n_atoms, const float *h_xyz, const double *h_q1, const double *h_q2,
+                         const float *h_ca, double *h_out);
+
 /* per-kernel-class device timing for the benchmark's roofline: enable=1 starts recording CUDA-event
  * pairs around every launch (on the launch stream); enable=0 synchronises and returns summed
  * milliseconds / launch counts for [place, score_generic, score_special, select]. */

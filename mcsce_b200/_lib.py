@@ -73,6 +73,8 @@ SYMBOLS = {
                                C.c_void_p, C.c_void_p, C.c_void_p]),
     "mcsce_input_energy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "mcsce_init_env": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "mcsce_rotate_template": (C.c_int, [C.c_int, C.c_int, _f32p, C.c_int, _i32p, _u32p, _f64p, C.c_int, _f64p, _f32p]),
+    "mcsce_place_template": (C.c_int, [C.c_int, C.c_int, _f32p, _f64p, _f64p, _f32p, _f64p]),
     "mcsce_profile": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "mcsce_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int]),
 }

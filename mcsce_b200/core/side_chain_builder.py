@@ -1,0 +1,207 @@
+"""Drop-in for ``mcsce.core.side_chain_builder`` (side_chain_builder.py:42-352): same entry points,
+the growth loop runs on the GPU for all conformers of a call at once.
+
+* ``initialize_func_calc``          builds the O(N) host tables and uploads them (replaces the L+1
+                                    placeholder structures / energy closures, :42-107);
+* ``create_side_chain_structure``   one conformer (:109-205);
+* ``create_side_chain``             best-of-N / first-valid (:207-281);
+* ``create_side_chain_ensemble``    N conformers + ``<n>.pdb`` + ``energies.csv`` (:284-352).
+
+``parallel_worker`` only sized the reference's process pool; it is accepted and ignored (one process
+per GPU here; under ``torchrun`` the conformers of a call are sharded over ranks and the results
+gathered to rank 0 with one collective, see ``mcsce_b200.sharding``).  The reference's in-place drift
+of the cached library rows (quirk Q1, :173) is not reproduced: every conformer perturbs the pristine
+library rows, on the device, with its own Philox stream.
+"""
+from __future__ import annotations
+
+import os
+from functools import partial
+
+import numpy as np
+
+from mcsce_b200 import sharding
+from mcsce_b200.chem.tables import load_tables
+from mcsce_b200.core.rotamer_library import DunbrakRotamerLibrary, ptmRotamerLib
+from mcsce_b200.structure import Structure
+from mcsce_b200.system import build_system
+
+_rotamer_library = None
+_ptm_rotamer_lib = None
+
+# kept for API compatibility: level 0 = the input structure, level i+1 = with residue i's side chain
+sidechain_placeholders = []
+energy_calculators = []
+_state = {}
+
+
+def _libraries():
+    global _rotamer_library, _ptm_rotamer_lib
+    if _rotamer_library is None:
+        _rotamer_library = DunbrakRotamerLibrary()
+        _ptm_rotamer_lib = ptmRotamerLib()
+    return _rotamer_library, _ptm_rotamer_lib
+
+
+class _LazyCalculators:
+    """``energy_calculators[level]`` on demand: the reference prepares every closure up front (63 s at 76
+    residues); the fused growth never needs them, so they are only built when a caller indexes the list."""
+
+    def __init__(self, creator, placeholders, kinds):
+        self.creator, self.placeholders, self.kinds, self.cache = creator, placeholders, kinds, {}
+
+    def __len__(self):
+        return len(self.placeholders)
+
+    def __getitem__(self, level):
+        if level < 0:
+            level += len(self)
+        if level in self.cache:
+            return self.cache[level]
+        if level > 0 and self.kinds[level - 1] != "grow":
+            return None
+        s = self.placeholders[level]
+        n_terms, c_terms = s.get_terminal_res_atom_arr()
+        kw = {}
+        if level > 0:
+            n_sc = len(s) - len(self.placeholders[level - 1])
+            idx = np.arange(len(s))
+            kw["partial_indices"] = [idx[-n_sc:], idx[:-n_sc]]
+        self.cache[level] = self.creator(s.atom_labels, s.res_nums, s.res_labels, n_terms, c_terms, **kw)
+        return self.cache[level]
+
+
+def _terms_of(efunc_creator):
+    kw = getattr(efunc_creator, "keywords", None) or {}
+    terms = kw.get("terms")
+    if terms is None:
+        terms = ["lj", "clash", "coulomb"]
+    return tuple(terms)
+
+
+def initialize_func_calc(efunc_creator, aa_seq=None, structure=None, retain_idxs=[]):
+    """Prepare the growth of one sequence.  ``efunc_creator`` is the reference's
+    ``partial(prepare_energy_function, batch_size=..., forcefield=..., terms=[...])``; only its ``terms``
+    are needed here."""
+    from mcsce_b200.engine import GrowthEngine
+    from mcsce_b200.libs.libenergy import _device
+
+    global sidechain_placeholders, energy_calculators
+    print("Start preparing energy calculators at different sidechain completion levels")
+    if structure is None:
+        from mcsce_b200.structure import AA3TO1
+        structure = Structure(fasta="".join(AA3TO1.get(r, "X") for r in aa_seq)).build()
+    structure = structure.copy()
+    if aa_seq is not None and structure is not None:
+        # the IDPConfGen bridge passes both: the sequence overrides the residue labels (mcsce_sidechain.py:69-70)
+        nums = structure.residues
+        for num, res in zip(nums, aa_seq):
+            structure.cols["resname"][structure.cols["resseq"] == num] = res
+    lib, ptm = _libraries()
+    t = load_tables()
+    terms = _terms_of(efunc_creator)
+    sysm = build_system(structure, retain_idxs=tuple(retain_idxs), terms=terms, rotamer_library=lib, ptm_library=ptm, tables=t)
+    eng = _state.get("engine")
+    if eng is None:
+        eng = GrowthEngine(_device())
+    eng.set_system(sysm, t)
+    # placeholders: atom bookkeeping per completion level (labels only; coordinates are filled at growth)
+    placeholders = [structure.copy()]
+    work = structure.copy()
+    for st in sysm.steps:
+        if st.kind != "skip":
+            tm = t.templates[st.resname]
+            work.append_atoms([tm.names[k] for k in tm.sc_idx], tm.resname, str(sysm.chains[st.sc_start]), st.resnum,
+                              np.zeros((tm.n_sc, 3), np.float32), elements=[tm.elements[k] for k in tm.sc_idx])
+        placeholders.append(work.copy())
+    sidechain_placeholders = placeholders
+    energy_calculators = _LazyCalculators(efunc_creator, placeholders, [st.kind for st in sysm.steps])
+    _state.update(engine=eng, system=sysm, structure=structure, retain=tuple(retain_idxs), backbone=None, seed=_state.get("seed", 0))
+    print("Finished preparing all energy functions. Now start conformer generation")
+
+
+def set_seed(seed):
+    """Seed of the on-device Philox streams (the reference draws from NumPy's / numba's global generators)."""
+    _state["seed"] = int(seed)
+    _state["next_conf"] = 0
+
+
+def _grow(backbone_coords, beta, n_conf):
+    """Grow ``n_conf`` conformers of the prepared sequence on this rank's GPU; returns host arrays."""
+    assert len(sidechain_placeholders) > 0, "Energy functions have not yet initialized!"
+    eng, sysm = _state["engine"], _state["system"]
+    backbone_coords = np.asarray(backbone_coords, dtype=np.float32)
+    assert sysm.n_input == backbone_coords.shape[0], \
+        "Input structures contain extra sidechain atoms or miss sidechain atoms if fix argument is used"
+    key = backbone_coords.tobytes()
+    if _state.get("backbone") != key:
+        eng.set_backbone(backbone_coords)
+        _state["backbone"] = key
+    lo, hi = sharding.my_range(n_conf)
+    first = _state.get("next_conf", 0)
+    _state["next_conf"] = first + n_conf
+    single = sharding.world()[1] == 1
+    if hi > lo:
+        # one rank: results straight into pinned host memory; several ranks: keep them on the device for the gather
+        out = eng.grow(hi - lo, beta, seed=_state.get("seed", 0), conf_id0=first + lo, host_out=single)
+        local = (out["coords"], out["energy"], out["ok"])
+        if single:
+            local = tuple(x.copy() for x in local)
+    else:
+        local = (np.zeros((0, sysm.n_atoms, 3), np.float32), np.zeros(0), np.zeros(0, np.uint8))
+    return sharding.gather_results(*local, n_total=n_conf)
+
+
+def _final_structure(coords_growth_order):
+    s = sidechain_placeholders[-1].copy()
+    s.coords = coords_growth_order          # 3-decimal table, like the reference (libstructure.py:157-160)
+    s.reorder_with_resnum()
+    return s
+
+
+def create_side_chain_structure(inputs):
+    """``[backbone_coords, beta, retain_idxs, save_addr]`` -> ``(Structure | None, ok, energy | None, save_addr | None)``."""
+    backbone_coords, beta, retain_idxs, save_addr = inputs
+    coords, energy, ok = _grow(backbone_coords, beta, 1)
+    if coords is None:                      # non-root rank under torchrun
+        return None, False, None, None
+    if not ok[0]:
+        return None, False, None, None
+    s = _final_structure(coords[0])
+    if save_addr is not None:
+        s.write_PDB(save_addr)
+    return s, True, float(energy[0]), save_addr
+
+
+def create_side_chain(structure, n_trials, temperature, retain_resi=[], parallel_worker=16, return_first_valid=False):
+    """Lowest-energy (or first valid) conformer out of ``n_trials`` grown in one batch."""
+    beta = 1 / (temperature * 0.008314462)
+    coords, energy, ok = _grow(structure.coords, beta, int(n_trials))
+    if coords is None or not ok.any():
+        return None
+    idx = int(np.argmax(ok)) if return_first_valid else int(np.where(ok, energy, np.inf).argmin())
+    return _final_structure(coords[idx])
+
+
+def create_side_chain_ensemble(structure, n_conformations, temperature, save_path, retain_resi=[], parallel_worker=16):
+    """``n_conformations`` conformers; writes ``<save_path>/<n>.pdb`` and ``energies.csv``; returns
+    ``(list[Structure | None], list[bool])``."""
+    beta = 1 / (temperature * 0.008314462)
+    coords, energy, ok = _grow(structure.coords, beta, int(n_conformations))
+    if coords is None:
+        return [], []
+    conformations, success, energies = [], [], {}
+    for n in range(int(n_conformations)):
+        if ok[n]:
+            s = _final_structure(coords[n])
+            addr = save_path + f"/{n}.pdb"
+            s.write_PDB(addr)
+            energies[addr] = float(energy[n])
+            conformations.append(s); success.append(True)
+        else:
+            conformations.append(None); success.append(False)
+    with open(save_path + "/energies.csv", "w") as f:
+        f.write("File name,Energy(kJ/mol)\n")
+        for item in energies:
+            f.write("%s,%f\n" % (item, energies[item]))
+    return conformations, success

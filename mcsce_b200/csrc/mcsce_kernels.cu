@@ -126,6 +126,63 @@ __device__ __forceinline__ double u01_halfopen(unsigned a, unsigned b) {   // [0
     return (double)(v & ((1ull << 53) - 1)) * (1.0 / 9007199254740992.0);
 }
 
+// chi rotations of one trial held one template atom per lane; float32 storage after every rotation
+// (libscbuild.py:108).  Rotation k: angle = wrap(template dihedral - target) about MINUS the unit axis
+// through the pivot atom (libscbuild.py:44-54), applied to the atoms of the moving set.
+__device__ __forceinline__ void apply_chi_rotations(const TmplDev &tm, int n_rot, const double *chi, int lane, bool has,
+                                                    float &x, float &y, float &z) {
+    for (int k = 0; k < n_rot; ++k) {
+        const int af = tm.axis_from[k], at = tm.axis_to[k];
+        const float fx = __shfl_sync(0xffffffffu, x, af), fy = __shfl_sync(0xffffffffu, y, af), fz = __shfl_sync(0xffffffffu, z, af);
+        const float px = __shfl_sync(0xffffffffu, x, at), py = __shfl_sync(0xffffffffu, y, at), pz = __shfl_sync(0xffffffffu, z, at);
+        // unit axis in float32: (to - from)/|to - from|   (libscbuild.py:105,115,169,185,199)
+        const float ux = __fsub_rn(px, fx), uy = __fsub_rn(py, fy), uz = __fsub_rn(pz, fz);
+        const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)), __fmul_rn(uz, uz)));
+        const float ex = __fdiv_rn(ux, nrm), ey = __fdiv_rn(uy, nrm), ez = __fdiv_rn(uz, nrm);
+        double rot = tm.ori[k] - chi[k] * CUDART_PI / 180.0;          // measured - target (libscbuild.py:47)
+        if (rot > CUDART_PI) rot -= 2.0 * CUDART_PI;
+        else if (rot < -CUDART_PI) rot += 2.0 * CUDART_PI;
+        double sn, cs;
+        sincos(rot * 0.5, &sn, &cs);
+        const double b2 = sn * (double)(-ex), b3 = sn * (double)(-ey), b4 = sn * (double)(-ez);
+        if (has && ((tm.move[k] >> lane) & 1u)) {
+            const float dx = __fsub_rn(x, px), dy = __fsub_rn(y, py), dz = __fsub_rn(z, pz);   // float32 (libscbuild.py:44)
+            double ox, oy, oz;
+            quat_rotate(cs, b2, b3, b4, (double)dx, (double)dy, (double)dz, ox, oy, oz);
+            x = __double2float_rn(__dadd_rn(ox, (double)px));
+            y = __double2float_rn(__dadd_rn(oy, (double)py));
+            z = __double2float_rn(__dadd_rn(oz, (double)pz));
+        }
+    }
+}
+
+// stand-alone template rotation (C-ABI mcsce_rotate_template): all template atoms, template frame, no placement
+__global__ void __launch_bounds__(128) rotate_template_kernel(TmplDev tm, int n_rot, int n_rows, const double *chis, float *out) {
+    const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (t >= n_rows) return;
+    const bool has = lane < tm.n_atoms;
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (has) { x = tm.xyz[lane][0]; y = tm.xyz[lane][1]; z = tm.xyz[lane][2]; }
+    double chi[MAX_ROT];
+#pragma unroll
+    for (int k = 0; k < MAX_ROT; ++k) chi[k] = (k < n_rot) ? chis[(long long)t * MAX_CHI + k] : 0.0;
+    apply_chi_rotations(tm, n_rot, chi, lane, has, x, y, z);
+    if (has) { float *o = out + ((long long)t * tm.n_atoms + lane) * 3; o[0] = x; o[1] = y; o[2] = z; }
+}
+
+// stand-alone rigid placement (C-ABI mcsce_place_template): float32 in, float64 out (libcalc.py:465,480-482)
+__global__ void place_template_kernel(int n, const float *xyz, double q10, double q11, double q12, double q13, double q20,
+                                      double q21, double q22, double q23, float cax, float cay, float caz, double *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double ox, oy, oz;
+    quat_rotate(q10, q11, q12, q13, (double)xyz[i * 3], (double)xyz[i * 3 + 1], (double)xyz[i * 3 + 2], ox, oy, oz);
+    const float rx = __double2float_rn(ox), ry = __double2float_rn(oy), rz = __double2float_rn(oz);
+    quat_rotate(q20, q21, q22, q23, (double)rx, (double)ry, (double)rz, ox, oy, oz);
+    out[i * 3] = __dadd_rn(ox, (double)cax); out[i * 3 + 1] = __dadd_rn(oy, (double)cay); out[i * 3 + 2] = __dadd_rn(oz, (double)caz);
+}
+
 // ------------------------------------------------------------------------------------------------
 // K1: chi -> xyz.   grid (ceil(n_trials/4), n_sets), block 128: one warp per trial row
 // ------------------------------------------------------------------------------------------------
@@ -196,32 +253,7 @@ __global__ void __launch_bounds__(128) place_trials_kernel(PlaceArgs a) {
         }
     }
 
-    // --- chi rotations, innermost atoms last; float32 storage after every rotation (libscbuild.py:108) ---
-    const int n_rot = st.n_chi;
-    for (int k = 0; k < n_rot; ++k) {
-        const int af = tm.axis_from[k], at = tm.axis_to[k];
-        const float fx = __shfl_sync(0xffffffffu, x, af), fy = __shfl_sync(0xffffffffu, y, af), fz = __shfl_sync(0xffffffffu, z, af);
-        const float px = __shfl_sync(0xffffffffu, x, at), py = __shfl_sync(0xffffffffu, y, at), pz = __shfl_sync(0xffffffffu, z, at);
-        // unit axis in float32: (to - from)/|to - from|   (libscbuild.py:105,115,169,185,199)
-        const float ux = __fsub_rn(px, fx), uy = __fsub_rn(py, fy), uz = __fsub_rn(pz, fz);
-        const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)), __fmul_rn(uz, uz)));
-        const float ex = __fdiv_rn(ux, nrm), ey = __fdiv_rn(uy, nrm), ez = __fdiv_rn(uz, nrm);
-        double rot = tm.ori[k] - chi[k] * CUDART_PI / 180.0;          // measured - target (libscbuild.py:47)
-        if (rot > CUDART_PI) rot -= 2.0 * CUDART_PI;
-        else if (rot < -CUDART_PI) rot += 2.0 * CUDART_PI;
-        double sn, cs;
-        sincos(rot * 0.5, &sn, &cs);
-        // rotation about MINUS the unit axis (libscbuild.py:52)
-        const double b2 = sn * (double)(-ex), b3 = sn * (double)(-ey), b4 = sn * (double)(-ez);
-        if (has && ((tm.move[k] >> lane) & 1u)) {
-            const float dx = __fsub_rn(x, px), dy = __fsub_rn(y, py), dz = __fsub_rn(z, pz);   // float32 (libscbuild.py:44)
-            double ox, oy, oz;
-            quat_rotate(cs, b2, b3, b4, (double)dx, (double)dy, (double)dz, ox, oy, oz);
-            x = __double2float_rn(__dadd_rn(ox, (double)px));
-            y = __double2float_rn(__dadd_rn(oy, (double)py));
-            z = __double2float_rn(__dadd_rn(oz, (double)pz));
-        }
-    }
+    apply_chi_rotations(tm, st.n_chi, chi, lane, has, x, y, z);
 
     // --- rigid placement: two rotations (first stored to float32) + CA (libcalc.py:465,480-482) ---
     if (has) {
@@ -1319,6 +1351,43 @@ extern "C" int mcsce_grow_host(mcsce_handle h, const mcsce_grow_opts *o, void *d
     CK(cudaMemcpyAsync(h_energy, de, (size_t)o->n_conf * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(h_ok, dk, (size_t)o->n_conf, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int mcsce_rotate_template(int device, int n_atoms, const float *h_tmpl_xyz, int n_rot, const int32_t *h_axis,
+                                     const uint32_t *h_move, const double *h_ori, int n_rows, const double *h_chis, float *h_out) {
+    // replaces rotate_sidechain (libs/libscbuild.py:56-206): host buffers in/out, the rotations run on the device
+    if (n_atoms <= 0 || n_atoms > MAX_TMPL || n_rot < 0 || n_rot > MAX_ROT || n_rows <= 0) return fail("bad template arguments");
+    CK(cudaSetDevice(device));
+    TmplDev tm; memset(&tm, 0, sizeof(tm));
+    tm.n_atoms = n_atoms; tm.n_chi = n_rot;
+    for (int a = 0; a < n_atoms; ++a) for (int k = 0; k < 3; ++k) tm.xyz[a][k] = h_tmpl_xyz[a * 3 + k];
+    for (int k = 0; k < n_rot; ++k) { tm.axis_from[k] = h_axis[2 * k]; tm.axis_to[k] = h_axis[2 * k + 1]; tm.move[k] = h_move[k]; tm.ori[k] = h_ori[k]; }
+    double *d_chis = nullptr; float *d_out = nullptr;
+    CK(cudaMalloc((void **)&d_chis, sizeof(double) * (size_t)n_rows * MAX_CHI));
+    CK(cudaMalloc((void **)&d_out, sizeof(float) * (size_t)n_rows * n_atoms * 3));
+    CK(cudaMemcpy(d_chis, h_chis, sizeof(double) * (size_t)n_rows * MAX_CHI, cudaMemcpyHostToDevice));
+    rotate_template_kernel<<<(n_rows + 3) / 4, 128>>>(tm, n_rot, n_rows, d_chis, d_out);
+    cudaError_t e = cudaMemcpy(h_out, d_out, sizeof(float) * (size_t)n_rows * n_atoms * 3, cudaMemcpyDeviceToHost);
+    cudaFree(d_chis); cudaFree(d_out);
+    if (e != cudaSuccess) return fail(std::string("rotate_template: ") + cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C" int mcsce_place_template(int device, int n_atoms, const float *h_xyz, const double *h_q1, const double *h_q2,
+                                    const float *h_ca, double *h_out) {
+    // replaces the coordinate part of place_sidechain_template (libs/libcalc.py:465-482)
+    if (n_atoms <= 0) return fail("bad template arguments");
+    CK(cudaSetDevice(device));
+    float *d_in = nullptr; double *d_out = nullptr;
+    CK(cudaMalloc((void **)&d_in, sizeof(float) * (size_t)n_atoms * 3));
+    CK(cudaMalloc((void **)&d_out, sizeof(double) * (size_t)n_atoms * 3));
+    CK(cudaMemcpy(d_in, h_xyz, sizeof(float) * (size_t)n_atoms * 3, cudaMemcpyHostToDevice));
+    place_template_kernel<<<(n_atoms + 63) / 64, 64>>>(n_atoms, d_in, h_q1[0], h_q1[1], h_q1[2], h_q1[3], h_q2[0], h_q2[1],
+                                                       h_q2[2], h_q2[3], h_ca[0], h_ca[1], h_ca[2], d_out);
+    cudaError_t e = cudaMemcpy(h_out, d_out, sizeof(double) * (size_t)n_atoms * 3, cudaMemcpyDeviceToHost);
+    cudaFree(d_in); cudaFree(d_out);
+    if (e != cudaSuccess) return fail(std::string("place_template: ") + cudaGetErrorString(e));
     return 0;
 }
 

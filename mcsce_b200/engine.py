@@ -151,8 +151,8 @@ class GrowthEngine:
             q1[st.index], q2[st.index], ca[st.index] = placement_quaternions(bb[st.index], tm.coords[0], tm.coords[2])
             if st.kind != "grow":
                 continue
-            if st.chi_mean is None:
-                raise ValueError("system was built without a rotamer library: no trial sets")
+            if st.chi_mean is None:          # system without trial sets: scoring-only use (energy closures)
+                continue
             T = len(st.prob)
             m = np.zeros((T, MAX_CHI)); s = np.zeros((T, MAX_CHI))
             m[:, :st.n_chi_lib] = st.chi_mean; s[:, :st.n_chi_lib] = st.chi_sigma
@@ -195,6 +195,8 @@ class GrowthEngine:
         staging inside the C call) with ``host_out``."""
         torch = self.torch
         assert self._has_backbone, "set_backbone first"
+        if any(st.kind == "grow" and st.chi_mean is None for st in self.system.steps):
+            raise ValueError("system was built without a rotamer library: no trial sets to grow from")
         C_ = int(n_conf)
         N = self.system.n_atoms
         o = GrowOpts()

@@ -223,20 +223,6 @@ def build_system(structure, retain_idxs=(), terms=("lj", "clash", "coulomb"), ro
         ch_mask = sysm.chains == ch
         sysm.is_nterm |= ch_mask & (sysm.resnums == keys[0])
         sysm.is_cterm |= ch_mask & (sysm.resnums == keys[-1])
-    for a in range(n):
-        q, s, e = tables.atom_params(resnames[a], names[a], sysm.is_nterm[a], sysm.is_cterm[a])
-        sysm.charge[a], sysm.sigma[a], sysm.eps[a] = q, s, e
-        sysm.radius[a] = VDW_RADII[names[a][0]]
-
-    # backbone label per residue number (bonds_intra is looked up with the label of the first
-    # atom of that residue number, libenergy.py:262-267)
-    label_of_num = {}
-    for a in range(n):
-        label_of_num.setdefault(resnums[a], resnames[a])
-    atoms_of_num = {}
-    for a in range(n):
-        atoms_of_num.setdefault(resnums[a], []).append(a)
-
     if rotamer_library is not None:
         for st in steps:
             if st.kind != "grow":
@@ -245,13 +231,71 @@ def build_system(structure, retain_idxs=(), terms=("lj", "clash", "coulomb"), ro
             st.chi_mean, st.chi_sigma, st.prob = np.asarray(mean, float), np.asarray(sig, float), np.asarray(prob, float)
             st.n_chi_lib = st.chi_mean.shape[1]
             st.n_chi = min(st.n_chi_lib, len(tables.templates[st.resname].chis))
+    _finalize(sysm, tables)
+    return sysm
 
-    for st in steps:
-        if st.kind != "grow":
-            continue
-        _build_special_pairs(sysm, st, tables, label_of_num, atoms_of_num)
+
+def _finalize(sysm, tables):
+    """Per-atom parameters, special-pair lists, atom classes and slot layout."""
+    n = sysm.n_atoms
+    names, resnames, resnums = sysm.names, sysm.resnames, sysm.resnums
+    for a in range(n):
+        q, s, e = tables.atom_params(str(resnames[a]), str(names[a]), bool(sysm.is_nterm[a]), bool(sysm.is_cterm[a]))
+        sysm.charge[a], sysm.sigma[a], sysm.eps[a] = q, s, e
+        sysm.radius[a] = VDW_RADII[str(names[a])[0]]
+    # backbone label per residue number (bonds_intra is looked up with the label of the first
+    # atom of that residue number, libenergy.py:262-267)
+    label_of_num, atoms_of_num = {}, {}
+    for a in range(n):
+        label_of_num.setdefault(int(resnums[a]), str(resnames[a]))
+        atoms_of_num.setdefault(int(resnums[a]), []).append(a)
+    for st in sysm.steps:
+        if st.kind == "grow":
+            _build_special_pairs(sysm, st, tables, label_of_num, atoms_of_num)
     _build_classes(sysm)
     _build_backbone_pairs(sysm, tables, label_of_num, atoms_of_num)
+
+
+def build_system_from_labels(atom_labels, res_nums, res_labels, n_term, c_term, partial_indices=None,
+                             terms=("lj", "clash", "coulomb"), tables=None):
+    """GrowthSystem for the argument set of the reference's ``prepare_energy_function``
+    (libenergy.py:27-61): per-atom labels of a partially grown structure and
+    ``partial_indices = [new, old]``.  Supported index patterns are the two the reference's growth
+    driver produces (side_chain_builder.py:81-85, 97-104): ``None`` (every atom scored against every
+    other: the input-atom self energy) and ``[last n atoms of one residue, all atoms before them]``."""
+    tables = tables or load_tables()
+    names = np.array([str(x) for x in atom_labels]); resnames = np.array([str(x) for x in res_labels])
+    resnums = np.array(res_nums, dtype=np.int64)
+    n = len(names)
+    steps = []
+    if partial_indices is None:
+        n_input = n
+        appear = np.full(n, -1, dtype=np.int64)
+    else:
+        new_idx, old_idx = (np.asarray(x, dtype=np.int64) for x in partial_indices)
+        n_new = len(new_idx)
+        if not (np.array_equal(new_idx, np.arange(n - n_new, n)) and np.array_equal(old_idx, np.arange(n - n_new))):
+            raise NotImplementedError("partial_indices must be [last n atoms, all earlier atoms] as built by "
+                                      "initialize_func_calc (side_chain_builder.py:102-103)")
+        num = int(resnums[new_idx[0]])
+        if not (resnums[new_idx] == num).all():
+            raise NotImplementedError("the new atoms must belong to one residue")
+        label = str(resnames[np.where(resnums == num)[0][0]])          # backbone label of that residue
+        tmpl = tables.templates[label]
+        if [tmpl.names[k] for k in tmpl.sc_idx] != list(names[new_idx]):
+            raise ValueError("new atoms are not the %s side chain in template order" % label)
+        n_input = n - n_new
+        appear = np.concatenate([np.full(n_input, -1), np.zeros(n_new)]).astype(np.int64)
+        bb = [int(np.where((resnums[:n_input] == num) & (names[:n_input] == a))[0][0]) if
+              ((resnums[:n_input] == num) & (names[:n_input] == a)).any() else 0 for a in ("N", "CA", "C")]
+        steps.append(GrowthStep(index=0, resnum=num, resname=label, kind="grow", sc_start=n_input, n_sc=n_new,
+                                bb_rows=tuple(bb)))
+    sysm = GrowthSystem(
+        names=names, resnames=resnames, resnums=resnums, chains=np.full(n, "A"), res_index=np.zeros(n, dtype=np.int64),
+        is_nterm=np.asarray(n_term, dtype=bool).copy(), is_cterm=np.asarray(c_term, dtype=bool).copy(),
+        charge=np.zeros(n), sigma=np.zeros(n), eps=np.zeros(n), radius=np.zeros(n),
+        appear=appear, n_input=n_input, steps=steps, terms=tuple(terms))
+    _finalize(sysm, tables)
     return sysm
 
 
