@@ -235,6 +235,22 @@ class ResidueTemplate:
         self.sc_idx = np.array([i for i, n in enumerate(self.names) if n not in BACKBONE_ATOMS], dtype=np.int64)
         self.n_sc = len(self.sc_idx)
         self.chis = self._chi_program()
+        self.n_sound = self._count_sound()
+
+    def _count_sound(self):
+        """Leading rotations whose dihedral is unchanged by every earlier rotation (each of its four atoms
+        either moves with that rotation or sits on its axis).  That holds for every real chi angle and makes
+        the template dihedral a constant; it fails for the position-based "extra" entries the reference
+        would apply if handed more angles than the residue has (e.g. a 4th angle for ASN reaches the
+        backbone H), which no rotamer library row ever does.  The CUDA path applies sound rotations only."""
+        for k, chi in enumerate(self.chis):
+            for prev in self.chis[:k]:
+                fixed_ok = set(prev["axis"])
+                moved = set(prev["moving"])
+                atoms = set(chi["dihedral"])
+                if not (atoms <= (moved | fixed_ok)) and (atoms & moved):
+                    return k
+        return len(self.chis)
 
     def _chi_program(self):
         """List of dicts {dihedral:(a,b,c,d), axis:(from,to), pivot, moving:[positions], ori:float}.

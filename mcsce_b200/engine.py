@@ -80,7 +80,7 @@ class GrowthEngine:
             tmpl_n[i] = tm.n_atoms
             tmpl_xyz[i, :tm.n_atoms] = tm.coords
             tmpl_sc[i, :tm.n_sc] = tm.sc_idx
-            prog = tm.chis[:MAX_CHI_ROT]
+            prog = tm.chis[:min(MAX_CHI_ROT, tm.n_sound)]
             tmpl_nchi[i] = len(prog)
             for k, chi in enumerate(prog):
                 tmpl_axis[i, k] = chi["axis"]
@@ -147,11 +147,11 @@ class GrowthEngine:
         for st in sysm.steps:
             if st.kind == "skip":
                 continue
+            if st.kind == "grow" and st.chi_mean is None:     # no trial sets: scoring-only use (energy closures)
+                continue
             tm = t.templates[st.resname]
             q1[st.index], q2[st.index], ca[st.index] = placement_quaternions(bb[st.index], tm.coords[0], tm.coords[2])
             if st.kind != "grow":
-                continue
-            if st.chi_mean is None:          # system without trial sets: scoring-only use (energy closures)
                 continue
             T = len(st.prob)
             m = np.zeros((T, MAX_CHI)); s = np.zeros((T, MAX_CHI))

@@ -27,7 +27,9 @@ def rotate_sidechain_batch(res_type, tors, device=0):
     tors = np.asarray(tors, dtype=np.float64)
     rows = np.zeros((len(tors), _lib.MAX_CHI))
     rows[:, :min(tors.shape[1], _lib.MAX_CHI)] = tors[:, :_lib.MAX_CHI]
-    n_rot = min(tors.shape[1], len(tm.chis), _lib.MAX_CHI_ROT)
+    # rotations beyond the residue's real chi angles (template positions reused by the reference's generic
+    # rules) are not applied: see ResidueTemplate._count_sound
+    n_rot = min(tors.shape[1], tm.n_sound, _lib.MAX_CHI_ROT)
     axis = np.zeros((_lib.MAX_CHI_ROT, 2), np.int32); move = np.zeros(_lib.MAX_CHI_ROT, np.uint32); ori = np.zeros(_lib.MAX_CHI_ROT)
     for k, chi in enumerate(tm.chis[:n_rot]):
         axis[k] = chi["axis"]; move[k] = sum(1 << m for m in chi["moving"]); ori[k] = chi["ori"]

@@ -230,7 +230,7 @@ def build_system(structure, retain_idxs=(), terms=("lj", "clash", "coulomb"), ro
             mean, sig, prob = rotamer_library.trial_distribution(st.resname, st.phi, st.psi, ptm_library)
             st.chi_mean, st.chi_sigma, st.prob = np.asarray(mean, float), np.asarray(sig, float), np.asarray(prob, float)
             st.n_chi_lib = st.chi_mean.shape[1]
-            st.n_chi = min(st.n_chi_lib, len(tables.templates[st.resname].chis))
+            st.n_chi = min(st.n_chi_lib, tables.templates[st.resname].n_sound)
     _finalize(sysm, tables)
     return sysm
 
