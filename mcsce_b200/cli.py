@@ -104,7 +104,21 @@ def main(input_structure, n_conf, n_worker, output_dir, logfile, mode, fix, batc
 
 
 def maincli():
-    main(**vars(parser.parse_args()))
+    args = vars(parser.parse_args())
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    if ws > 1:                                   # launched with torchrun: one process per GPU
+        import torch
+        import torch.distributed as dist
+
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    try:
+        main(**args)
+    finally:
+        if ws > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
 
 
 if __name__ == "__main__":
