@@ -110,6 +110,8 @@ typedef struct {
     double *d_chis_out;            /* [n_conf*n_trials_total*MAX_CHI] chi rows actually used     */
     int32_t *d_selected;           /* [n_conf*n_res] selected trial per residue (-1 = none)      */
     int32_t env_split;             /* >0 forces the environment split factor; 0 = automatic      */
+    int32_t no_dedup;              /* 1: score the chi-independent side-chain atoms (HA, CB, ...) in every trial like the
+                                      reference does, instead of once per residue (same result, more work) */
 } mcsce_grow_opts;
 
 const char *mcsce_last_error(void);
@@ -174,8 +176,10 @@ int mcsce_input_energy(mcsce_handle h, double *d_energy, void *stream);
 /* scatter input + rigid atoms into environment arrays: d_env [n_env_sets*n_atoms*4] float32 */
 int mcsce_init_env(mcsce_handle h, int n_env_sets, float *d_env, void *stream);
 
-/* counters for the benchmark: kernels launched / algorithmic pair evaluations since the last reset */
-int mcsce_counters(mcsce_handle h, int64_t *launches, int64_t *pairs, int reset);
+/* counters for the benchmark since the last reset: kernels launched, algorithmic pair evaluations (counted as the
+ * reference counts them, libs/libcalc.py:56) and pair evaluations actually executed (fewer: chi-independent atoms
+ * are scored once per residue) */
+int mcsce_counters(mcsce_handle h, int64_t *launches, int64_t *pairs, int64_t *pairs_computed, int reset);
 
 /* Stand-alone mirrors of the two per-trial reference functions (HOST buffers; no handle needed):
  *   rotate_sidechain(res_type, tors)  (libs/libscbuild.py:56-206): template (n_atoms x 3 float32), rotation

@@ -47,7 +47,7 @@ class GrowOpts(C.Structure):
         ("n_conf", C.c_int32), ("conf_id0", C.c_int64), ("seed", C.c_uint64), ("beta", C.c_double),
         ("noise_deg", C.c_double), ("d_chis", C.c_void_p), ("d_uniform", C.c_void_p),
         ("d_trial_energy", C.c_void_p), ("d_chis_out", C.c_void_p), ("d_selected", C.c_void_p),
-        ("env_split", C.c_int32),
+        ("env_split", C.c_int32), ("no_dedup", C.c_int32),
     ]
 
 
@@ -76,7 +76,7 @@ SYMBOLS = {
     "mcsce_rotate_template": (C.c_int, [C.c_int, C.c_int, _f32p, C.c_int, _i32p, _u32p, _f64p, C.c_int, _f64p, _f32p]),
     "mcsce_place_template": (C.c_int, [C.c_int, C.c_int, _f32p, _f64p, _f64p, _f32p, _f64p]),
     "mcsce_profile": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
-    "mcsce_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int]),
+    "mcsce_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int]),
 }
 
 _lib = None

@@ -51,6 +51,11 @@ struct StepDev {
     int n_trials, trial_off, n_chi_lib, n_chi;
     float ca[4];
     double q1[4], q2[4];
+    // side-chain atoms whose coordinates depend on the chi angles (var) and those that do not (fix: never in a
+    // moving set, or the pivot of the first rotation - e.g. HA and CB): the latter are identical in every trial
+    // of a conformer, so the growth scores them once per residue instead of once per trial
+    int n_var, n_fix;
+    unsigned char var_k[MAX_SC], fix_k[MAX_SC];
 };
 
 struct TmplDev {
@@ -305,8 +310,10 @@ struct ScoreArgs {
     const float4 *env;                 // [set][n_atoms]  slot order
     const float4 *trial;               // [set][n_trials*n_sc]
     long long trial_set_stride;
-    double2 *partial;                  // [set][n_trials][n_split] (energy, clash)
+    double2 *partial;                  // [set][n_trials + dedup][n_split] (energy, clash); slot n_trials = chi-independent atoms
     const unsigned char *alive;
+    int dedup;                         // 1: score chi-independent atoms once per residue (trial 0's copy)
+    int fixed_extra_tile;              // 1: they get a tile of their own (the last one); 0: they ride in the last tile
 };
 
 // Inner loop over one class segment of the staged tile for RR trial atoms of this thread, two
@@ -440,23 +447,39 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MINB) score_generic_kerne
     __syncthreads();
     const int n_active = s_prefix[n_cls];
 
-    // this block's trial atoms: atom la = r*SCORE_THREADS + tid of the tile
-    const int t0 = blockIdx.x * a.trials_per_tile;
-    const int nt = min(a.trials_per_tile, a.n_trials - t0);
-    const int n_local = nt * n_sc;
-    const float4 *trial = a.trial + (long long)set * a.trial_set_stride + (long long)t0 * n_sc;
+    // this block's trial atoms: atom la = r*SCORE_THREADS + tid of the tile.  With dedup the tiles hold only the
+    // chi-dependent atoms of whole trials; the chi-independent atoms (trial 0's copy) ride in the free lanes of
+    // the last tile, or in one extra tile when that one is full.
+    const int n_per = a.dedup ? st.n_var : n_sc;                 // atoms per trial in a tile
+    const bool last = blockIdx.x == gridDim.x - 1;
+    const bool extra = a.dedup && a.fixed_extra_tile && last;    // tile of chi-independent atoms only
+    const int t0 = extra ? 0 : blockIdx.x * a.trials_per_tile;
+    const int nt = extra ? 0 : min(a.trials_per_tile, a.n_trials - t0);
+    const int n_varatoms = nt * n_per;
+    const int n_fixatoms = (a.dedup && last) ? st.n_fix : 0;
+    const int n_local = n_varatoms + n_fixatoms;
+    const float4 *trial0 = a.trial + (long long)set * a.trial_set_stride;
+    const float4 *trial = trial0 + (long long)t0 * n_sc;
 
     float2 nx[SCORE_R], ny[SCORE_R], nz[SCORE_R];     // minus the trial atom, duplicated into both halves
-    int ci[SCORE_R];
+    int ci[SCORE_R], katom[SCORE_R];
     double e_lj[SCORE_R], e_c[SCORE_R];
     bool clash[SCORE_R];
 #pragma unroll
     for (int r = 0; r < SCORE_R; ++r) {
         const int la = r * SCORE_THREADS + tid;
-        const int la_c = la < n_local ? la : 0;
-        const float4 p = trial[la_c];
+        int k = 0; float4 p = trial0[0];
+        if (la < n_varatoms) {
+            const int tl = la / n_per, kk = la % n_per;
+            k = a.dedup ? st.var_k[kk] : kk;
+            p = trial[tl * n_sc + k];
+        } else if (la < n_local) {
+            k = st.fix_k[la - n_varatoms];
+            p = trial0[k];
+        }
+        katom[r] = k;
         nx[r] = make_float2(-p.x, -p.x); ny[r] = make_float2(-p.y, -p.y); nz[r] = make_float2(-p.z, -p.z);
-        ci[r] = a.s.cls_of_atom[st.sc_start + (la_c % n_sc)];
+        ci[r] = a.s.cls_of_atom[st.sc_start + k];
         e_lj[r] = 0.0; e_c[r] = 0.0; clash[r] = false;
     }
     // warp-uniform amount of work: rows of the tile this warp has atoms in
@@ -521,16 +544,22 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MINB) score_generic_kerne
     for (int r = 0; r < SCORE_R; ++r) {
         const int la = r * SCORE_THREADS + tid;
         if (la < n_local) {
-            const double qi = a.s.charge[st.sc_start + (la % n_sc)];
+            const double qi = a.s.charge[st.sc_start + katom[r]];
             s_e[la] = e_lj[r] + COULOMB_PREF * qi * e_c[r];
             s_clash[la] = clash[r] ? 1 : 0;
         }
     }
     __syncthreads();
+    const int stride = a.n_trials + (a.dedup ? 1 : 0);
     for (int t = tid; t < nt; t += SCORE_THREADS) {
         double e = 0.0; int cl = 0;
-        for (int k = 0; k < n_sc; ++k) { e += s_e[t * n_sc + k]; cl |= s_clash[t * n_sc + k]; }
-        a.partial[((long long)set * a.n_trials + (t0 + t)) * a.n_split + blockIdx.z] = make_double2(e, cl ? 1.0 : 0.0);
+        for (int k = 0; k < n_per; ++k) { e += s_e[t * n_per + k]; cl |= s_clash[t * n_per + k]; }
+        a.partial[((long long)set * stride + (t0 + t)) * a.n_split + blockIdx.z] = make_double2(e, cl ? 1.0 : 0.0);
+    }
+    if (n_fixatoms > 0 && tid == SCORE_THREADS - 1) {
+        double e = 0.0; int cl = 0;
+        for (int k = 0; k < n_fixatoms; ++k) { e += s_e[n_varatoms + k]; cl |= s_clash[n_varatoms + k]; }
+        a.partial[((long long)set * stride + a.n_trials) * a.n_split + blockIdx.z] = make_double2(e, cl ? 1.0 : 0.0);
     }
 }
 
@@ -608,6 +637,7 @@ struct SelectArgs {
     int step;
     int n_trials, n_split;
     const double2 *partial, *sp_partial;
+    int dedup;
     const double *prob;                // [n_trials]
     double beta;
     const double *uniform;             // explicit [set*u_stride + step] or null
@@ -621,8 +651,8 @@ struct SelectArgs {
     double *e_acc;
     int *selected;                     // optional [set*n_res + step]
     double *trial_energy;              // optional dump [set*n_trials_total + trial_off + t]
-    unsigned long long *pair_counter;
-    long long pairs_per_set;
+    unsigned long long *pair_counter;   // [0] algorithmic pairs (the reference's P), [1] pairs actually evaluated
+    long long pairs_per_set, pairs_computed_per_set;
 };
 
 __global__ void __launch_bounds__(128) select_kernel(SelectArgs a) {
@@ -637,13 +667,21 @@ __global__ void __launch_bounds__(128) select_kernel(SelectArgs a) {
     }
     const StepDev &st = a.s.steps[a.step];
     double mn = CUDART_INF;
+    const int stride = a.n_trials + (a.dedup ? 1 : 0);
+    double e_fix = 0.0; bool cl_fix = false;
+    if (a.dedup)
+        for (int zz = 0; zz < a.n_split; ++zz) {
+            const double2 p = a.partial[((long long)set * stride + a.n_trials) * a.n_split + zz];
+            e_fix += p.x; cl_fix |= (p.y != 0.0);
+        }
     for (int t = tid; t < a.n_trials; t += 128) {
         const double2 sp = a.sp_partial[(long long)set * a.n_trials + t];
-        double e = sp.x; bool cl = sp.y != 0.0;
+        double e = sp.x; bool cl = (sp.y != 0.0) || cl_fix;
         for (int zz = 0; zz < a.n_split; ++zz) {
-            const double2 p = a.partial[((long long)set * a.n_trials + t) * a.n_split + zz];
+            const double2 p = a.partial[((long long)set * stride + t) * a.n_split + zz];
             e += p.x; cl |= (p.y != 0.0);
         }
+        e += e_fix;
         if (cl) e = CUDART_INF;                               // energies[clash] = inf (libenergy.py:801)
         s_E[t] = e;
         if (a.trial_energy) a.trial_energy[(long long)set * a.s.n_trials_total + st.trial_off + t] = e;
@@ -654,7 +692,10 @@ __global__ void __launch_bounds__(128) select_kernel(SelectArgs a) {
     if ((tid & 31) == 0) s_red[tid >> 5] = mn;
     __syncthreads();
     mn = fmin(fmin(s_red[0], s_red[1]), fmin(s_red[2], s_red[3]));
-    if (tid == 0 && a.pair_counter) atomicAdd(a.pair_counter, (unsigned long long)a.pairs_per_set);
+    if (tid == 0 && a.pair_counter) {
+        atomicAdd(a.pair_counter, (unsigned long long)a.pairs_per_set);
+        atomicAdd(a.pair_counter + 1, (unsigned long long)a.pairs_computed_per_set);
+    }
     if (isinf(mn) || isnan(mn)) {                             // every trial clashes: growth fails (side_chain_builder.py:187)
         if (tid == 0) {
             a.alive[set] = 0;
@@ -821,6 +862,7 @@ struct mcsce_handle_s {
     bool has_sys = false, has_bb = false;
     // host mirrors needed for launch geometry
     std::vector<StepDev> steps;
+    std::vector<TmplDev> tmpl_host;
     std::vector<int> cls_active;
     std::vector<int> step_n_sp_env;
     int max_trials = 0, max_trial_atoms = 0;
@@ -884,8 +926,8 @@ extern "C" int mcsce_create(mcsce_handle *out, int device) {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     h->sm_count = prop.multiProcessorCount;
-    CK(cudaMalloc((void **)&h->d_pairs, sizeof(unsigned long long)));
-    CK(cudaMemset(h->d_pairs, 0, sizeof(unsigned long long)));
+    CK(cudaMalloc((void **)&h->d_pairs, 2 * sizeof(unsigned long long)));
+    CK(cudaMemset(h->d_pairs, 0, 2 * sizeof(unsigned long long)));
     CK(cudaMalloc((void **)&h->d_input_energy, sizeof(double)));
     *out = h;
     return 0;
@@ -956,6 +998,7 @@ extern "C" int mcsce_set_system(mcsce_handle h, const mcsce_system_desc *s) {
         }
     }
     if (upload(h, P, tm.data(), tm.size(), &d.tmpl)) return -1;
+    h->tmpl_host = tm;
 
     h->steps.assign(s->n_res, StepDev{});
     h->step_n_sp_env.assign(s->n_res, 0);
@@ -1019,6 +1062,20 @@ extern "C" int mcsce_set_backbone(mcsce_handle h, const mcsce_backbone_desc *b) 
         for (int k = 0; k < 4; ++k) { o.q1[k] = b->place_q1[(size_t)i * 4 + k]; o.q2[k] = b->place_q2[(size_t)i * 4 + k]; }
         for (int k = 0; k < 3; ++k) o.ca[k] = b->place_ca[(size_t)i * 3 + k];
         o.ca[3] = 0.f;
+        o.n_var = 0; o.n_fix = 0;
+        if (o.kind == 2) {
+            const TmplDev &tm = h->tmpl_host[o.type];
+            for (int a = 0; a < tm.n_atoms; ++a) {
+                const int k = tm.sc_rank[a];
+                if (k < 0) continue;
+                bool moves = false;
+                for (int r = 0; r < o.n_chi; ++r) if ((tm.move[r] >> a) & 1u) moves = true;
+                if (o.n_chi > 0 && a == tm.axis_to[0]) moves = false;       // pivot of the first rotation: stays put exactly
+                if (moves) o.var_k[o.n_var++] = (unsigned char)k; else o.fix_k[o.n_fix++] = (unsigned char)k;
+            }
+            // keep the reference's atom order inside each list
+            std::sort(o.var_k, o.var_k + o.n_var); std::sort(o.fix_k, o.fix_k + o.n_fix);
+        }
         if (o.kind == 2) {
             h->max_trials = std::max(h->max_trials, o.n_trials);
             h->max_trial_atoms = std::max(h->max_trial_atoms, o.n_trials * o.n_sc);
@@ -1049,13 +1106,13 @@ extern "C" int mcsce_set_backbone(mcsce_handle h, const mcsce_backbone_desc *b) 
 
 static inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
-static int trials_per_tile_for(int n_sc) { return std::max(1, TILE_A / n_sc); }
+static int trials_per_tile_for(int n_per) { return std::max(1, TILE_A / std::max(1, n_per)); }
 
 static int choose_split(const mcsce_handle h, int step, int n_sets, int n_trials, int forced) {
     const StepDev &st = h->steps[step];
     int n_active = 0;
     for (int c = 0; c < h->d.n_cls; ++c) n_active += h->cls_active[(size_t)step * h->d.n_cls + c];
-    const int tiles = (n_trials + trials_per_tile_for(st.n_sc) - 1) / trials_per_tile_for(st.n_sc);
+    const int tiles = (n_trials + trials_per_tile_for(st.n_sc) - 1) / trials_per_tile_for(st.n_sc);   // (upper bound with dedup)
     const long long ctas = (long long)tiles * n_sets;
     int max_split = std::max(1, std::min(32, (n_active + 255) / 256));
     if (forced > 0) return std::min(forced, max_split);
@@ -1086,7 +1143,7 @@ static Workspace carve(const mcsce_handle h, int n_conf, int max_trials, int max
     w.env = (float4 *)take((size_t)n_conf * h->d.n_atoms * sizeof(float4));
     w.trial = (float4 *)take((size_t)n_conf * std::max(1, max_trial_atoms) * sizeof(float4));
     w.trial2 = (float4 *)take((size_t)n_conf * std::max(1, max_trial_atoms) * sizeof(float4));
-    w.partial = (double2 *)take((size_t)n_conf * std::max(1, max_trials) * ms * sizeof(double2));
+    w.partial = (double2 *)take((size_t)n_conf * (std::max(1, max_trials) + 1) * ms * sizeof(double2));
     w.sp_partial = (double2 *)take((size_t)n_conf * std::max(1, max_trials) * sizeof(double2));
     w.alive = (unsigned char *)take((size_t)n_conf);
     w.e_acc = (double *)take((size_t)n_conf * sizeof(double));
@@ -1150,12 +1207,17 @@ static int launch_place(mcsce_handle h, int step, int n_sets, int n_rows, const 
 
 static int launch_generic(mcsce_handle h, int step, int n_sets, int n_trials, int n_split, const float4 *env,
                           const float4 *trial, long long trial_stride, double2 *partial, const unsigned char *alive,
-                          cudaStream_t st) {
+                          cudaStream_t st, int dedup = 0) {
     const StepDev &sd = h->steps[step];
+    if (dedup && (sd.n_fix <= 0 || sd.n_var <= 0)) dedup = 0;
     ScoreArgs a{};
-    a.s = h->d; a.step = step; a.n_trials = n_trials; a.trials_per_tile = trials_per_tile_for(sd.n_sc);
+    a.s = h->d; a.step = step; a.n_trials = n_trials; a.trials_per_tile = trials_per_tile_for(dedup ? sd.n_var : sd.n_sc);
     a.n_split = n_split; a.env = env; a.trial = trial; a.trial_set_stride = trial_stride; a.partial = partial; a.alive = alive;
-    dim3 grid((n_trials + a.trials_per_tile - 1) / a.trials_per_tile, n_sets, n_split);
+    a.dedup = dedup;
+    const int tiles = (n_trials + a.trials_per_tile - 1) / a.trials_per_tile;
+    const int last_atoms = (n_trials - (tiles - 1) * a.trials_per_tile) * (dedup ? sd.n_var : sd.n_sc);
+    a.fixed_extra_tile = (dedup && last_atoms + sd.n_fix > TILE_A) ? 1 : 0;
+    dim3 grid(tiles + a.fixed_extra_tile, n_sets, n_split);
     { ProfScope ps(h, 1, st); score_generic_kernel<<<grid, SCORE_THREADS, 0, st>>>(a); }
     h->launches += 1;
     CK(cudaGetLastError());
@@ -1305,7 +1367,8 @@ extern "C" int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *o, void *d_work
         // st: generic pairs
         CK(cudaStreamWaitEvent(st, h->evP[i], 0));
         const int split = choose_split(h, i, C, T, o->env_split);
-        if (launch_generic(h, i, C, T, split, w.env, trial, trial_stride, w.partial, w.alive, st)) return -1;
+        const int dedup = (sd.n_fix > 0 && sd.n_var > 0 && !o->no_dedup) ? 1 : 0;
+        if (launch_generic(h, i, C, T, split, w.env, trial, trial_stride, w.partial, w.alive, st, dedup)) return -1;
         // aux: special pairs (need the environment as updated by the previous selection)
         if (prev >= 0) CK(cudaStreamWaitEvent(aux, h->evS[prev], 0));
         if (launch_special(h, i, C, T, w.env, trial, trial_stride, w.sp_partial, w.alive, aux)) return -1;
@@ -1314,6 +1377,7 @@ extern "C" int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *o, void *d_work
         CK(cudaStreamWaitEvent(st, h->evQ[i], 0));
         SelectArgs a{};
         a.s = d; a.step = i; a.n_trials = T; a.n_split = split; a.partial = w.partial; a.sp_partial = w.sp_partial;
+        a.dedup = dedup;
         a.prob = d.prob + sd.trial_off; a.beta = o->beta; a.uniform = o->d_uniform; a.u_stride = d.n_res;
         a.seed = o->seed; a.conf_id0 = o->conf_id0; a.env = w.env; a.trial = trial; a.trial_set_stride = trial_stride;
         a.alive = w.alive; a.e_acc = w.e_acc; a.selected = o->d_selected; a.trial_energy = o->d_trial_energy;
@@ -1321,6 +1385,8 @@ extern "C" int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *o, void *d_work
         long long n_active = 0;
         for (int c = 0; c < d.n_cls; ++c) n_active += h->cls_active[(size_t)i * d.n_cls + c];
         a.pairs_per_set = (long long)T * ((long long)sd.n_sc * (sd.n_sc - 1) / 2 + (long long)sd.n_sc * n_active);
+        a.pairs_computed_per_set = dedup ? ((long long)T * sd.n_var + sd.n_fix) * n_active + (long long)T * sd.n_sp
+                                         : (long long)T * sd.n_sc * n_active + (long long)T * sd.n_sp;
         { ProfScope ps(h, 3, st); select_kernel<<<C, 128, sizeof(double) * 2 * T, st>>>(a); }
         h->launches += 1;
         CK(cudaEventRecord(h->evS[i], st));
@@ -1418,13 +1484,14 @@ extern "C" int mcsce_profile(mcsce_handle h, int enable, double *ms_by_class, in
     return 0;
 }
 
-extern "C" int mcsce_counters(mcsce_handle h, int64_t *launches, int64_t *pairs, int reset) {
+extern "C" int mcsce_counters(mcsce_handle h, int64_t *launches, int64_t *pairs, int64_t *pairs_computed, int reset) {
     if (!h) return fail("null handle");
     CK(cudaSetDevice(h->device));
-    unsigned long long v = 0;
-    CK(cudaMemcpy(&v, h->d_pairs, sizeof(v), cudaMemcpyDeviceToHost));
+    unsigned long long v[2] = {0, 0};
+    CK(cudaMemcpy(v, h->d_pairs, sizeof(v), cudaMemcpyDeviceToHost));
     if (launches) *launches = h->launches;
-    if (pairs) *pairs = (int64_t)v;
+    if (pairs) *pairs = (int64_t)v[0];
+    if (pairs_computed) *pairs_computed = (int64_t)v[1];
     if (reset) { h->launches = 0; CK(cudaMemset(h->d_pairs, 0, sizeof(v))); }
     return 0;
 }

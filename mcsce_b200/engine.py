@@ -189,7 +189,7 @@ class GrowthEngine:
         return int(self.lib.mcsce_workspace_bytes(self.h, int(n_conf)))
 
     def grow(self, n_conf, beta, seed=0, conf_id0=0, noise_deg=0.5, chis=None, uniforms=None, dump=False,
-             env_split=0, host_out=False, stream=None):
+             env_split=0, host_out=False, stream=None, no_dedup=False):
         """Grow ``n_conf`` conformers.  Returns dict(coords (C,N,3) f32 growth order, energy (C,) f64,
         ok (C,) uint8 [, trial_energy, chis, selected]); torch CUDA tensors, or NumPy arrays (pinned
         staging inside the C call) with ``host_out``."""
@@ -201,6 +201,7 @@ class GrowthEngine:
         N = self.system.n_atoms
         o = GrowOpts()
         o.n_conf, o.conf_id0, o.seed, o.beta, o.noise_deg, o.env_split = C_, int(conf_id0), int(seed), float(beta), float(noise_deg), int(env_split)
+        o.no_dedup = 1 if no_dedup else 0
         keep = []
         if chis is not None:
             ch = torch.as_tensor(np.ascontiguousarray(chis, np.float64), device=self.device)
@@ -304,10 +305,11 @@ class GrowthEngine:
         check(self.lib.mcsce_input_energy(self.h, C.c_void_p(out.data_ptr()), self._stream_ptr()))
         return float(out.item())
 
-    def counters(self, reset=False):
-        a, b = C.c_int64(), C.c_int64()
-        check(self.lib.mcsce_counters(self.h, C.byref(a), C.byref(b), 1 if reset else 0))
-        return int(a.value), int(b.value)
+    def counters(self, reset=False, computed=False):
+        """(kernel launches, algorithmic pair evaluations[, pair evaluations executed]) since the last reset."""
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        check(self.lib.mcsce_counters(self.h, C.byref(a), C.byref(b), C.byref(c), 1 if reset else 0))
+        return (int(a.value), int(b.value), int(c.value)) if computed else (int(a.value), int(b.value))
 
     def profile_begin(self):
         check(self.lib.mcsce_profile(self.h, 1, None, None))

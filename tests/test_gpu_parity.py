@@ -301,3 +301,18 @@ def test_sharding_is_invariant():
     assert np.array_equal(a["selected"].cpu().numpy(), sel)
     en = np.concatenate([b0["energy"].cpu().numpy(), b1["energy"].cpu().numpy()])
     assert np.array_equal(a["energy"].cpu().numpy(), en, equal_nan=True)
+
+
+def test_chi_independent_atoms_scored_once_equals_full_scoring():
+    """HA/CB (and every other atom no chi rotation moves) are identical in all trials of a conformer; scoring
+    them once per residue must give what scoring them in every trial gives."""
+    for name in ("pep12", "ptm14", "helix76"):
+        case, s, sysm, eng = engine_for(name)
+        a = eng.grow(5, case.beta, seed=77, dump=True)
+        b = eng.grow(5, case.beta, seed=77, dump=True, no_dedup=True)
+        assert np.array_equal(a["selected"].cpu().numpy(), b["selected"].cpu().numpy())
+        ta, tb = a["trial_energy"].cpu().numpy(), b["trial_energy"].cpu().numpy()
+        assert np.array_equal(np.isinf(ta), np.isinf(tb)) and np.array_equal(np.isnan(ta), np.isnan(tb))
+        fin = np.isfinite(ta)
+        assert np.abs(ta[fin] - tb[fin]).max() <= 1e-9 * max(1.0, np.abs(tb[fin]).max())
+        assert np.allclose(a["energy"].cpu().numpy(), b["energy"].cpu().numpy(), rtol=1e-12, atol=1e-9, equal_nan=True)
