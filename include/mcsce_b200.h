@@ -192,6 +192,15 @@ int mcsce_rotate_template(int device, int n_atoms, const float *h_tmpl_xyz, int 
 int mcsce_place_template(int device, int n_atoms, const float *h_xyz, const double *h_q1, const double *h_q2,
                          const float *h_ca, double *h_out);
 
+/* Batched PDB output (host, multi-threaded): replaces the per-conformer Structure.write_PDB of
+ * create_side_chain_ensemble (core/side_chain_builder.py:200-204, 321-338; libs/libpdb.py:178-195).
+ *   h_coords [n_conf*n_atoms*3] float32 growth order; h_order[i] = growth index of output line i;
+ *   line_template: n_atoms lines of line_len bytes (newline included), coordinate fields blank at
+ *   [coord_off, coord_off+24); writes <dir>/<n>.pdb for every n with h_ok[n] != 0 (h_ok may be NULL). */
+int mcsce_write_pdbs(int n_conf, int n_atoms, const float *h_coords, const uint8_t *h_ok, const int32_t *h_order,
+                     const char *line_template, int line_len, int coord_off, const char *dir, int n_threads,
+                     int32_t *n_written);
+
 /* per-kernel-class device timing for the benchmark's roofline: enable=1 starts recording CUDA-event
  * pairs around every launch (on the launch stream); enable=0 synchronises and returns summed
  * milliseconds / launch counts for [place, score_generic, score_special, select]. */

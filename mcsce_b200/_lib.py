@@ -75,6 +75,8 @@ SYMBOLS = {
     "mcsce_init_env": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "mcsce_rotate_template": (C.c_int, [C.c_int, C.c_int, _f32p, C.c_int, _i32p, _u32p, _f64p, C.c_int, _f64p, _f32p]),
     "mcsce_place_template": (C.c_int, [C.c_int, C.c_int, _f32p, _f64p, _f64p, _f32p, _f64p]),
+    "mcsce_write_pdbs": (C.c_int, [C.c_int, C.c_int, _f32p, C.c_void_p, _i32p, C.c_char_p, C.c_int, C.c_int, C.c_char_p,
+                                   C.c_int, _i32p]),
     "mcsce_profile": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "mcsce_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int]),
 }

@@ -15,11 +15,11 @@ from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
 ROOT = PKG.parent
-CU_SOURCES = [PKG / "csrc" / "mcsce_kernels.cu"]
+CU_SOURCES = [PKG / "csrc" / "mcsce_kernels.cu", PKG / "csrc" / "pdb_writer.cpp"]
 LIB = PKG / "libmcsce_b200.so"
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC"]
+              "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread"]
 
 
 def _stale(target, sources):

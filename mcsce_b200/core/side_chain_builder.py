@@ -116,6 +116,7 @@ def initialize_func_calc(efunc_creator, aa_seq=None, structure=None, retain_idxs
         placeholders.append(work.copy())
     sidechain_placeholders = placeholders
     energy_calculators = _LazyCalculators(efunc_creator, placeholders, [st.kind for st in sysm.steps])
+    _state.pop("final", None)
     _state.update(engine=eng, system=sysm, structure=structure, retain=tuple(retain_idxs), backbone=None, seed=_state.get("seed", 0))
     print("Finished preparing all energy functions. Now start conformer generation")
 
@@ -152,11 +153,43 @@ def _grow(backbone_coords, beta, n_conf):
     return sharding.gather_results(*local, n_total=n_conf)
 
 
+def _final_template():
+    """Finished-structure table in output order (residue-number order, libstructure.py:552-555), the
+    permutation from growth order, and the PDB line template - built once per prepared sequence."""
+    if "final" not in _state:
+        s = sidechain_placeholders[-1].copy()
+        order = np.argsort(s.res_nums, kind="mergesort").astype(np.int32)
+        s.reorder(order)
+        _state["final"] = (s, order, s.pdb_template())
+    return _state["final"]
+
+
 def _final_structure(coords_growth_order):
-    s = sidechain_placeholders[-1].copy()
-    s.coords = coords_growth_order          # 3-decimal table, like the reference (libstructure.py:157-160)
-    s.reorder_with_resnum()
+    from mcsce_b200.structure import _round3_f32
+
+    tmpl, order, _ = _final_template()
+    s = tmpl.copy()
+    s.xyz = _round3_f32(np.asarray(coords_growth_order, dtype=np.float32))[order]   # 3-decimal table (libstructure.py:157-160)
     return s
+
+
+def _write_pdbs(coords, ok, save_path):
+    """All successful conformers of a call to ``<save_path>/<n>.pdb`` through the library's batched writer."""
+    import ctypes as C
+
+    from mcsce_b200 import _lib
+
+    tmpl, order, (text, line_len, off) = _final_template()
+    lib = _lib.load_library()
+    coords = np.ascontiguousarray(coords, dtype=np.float32)
+    okb = np.ascontiguousarray(ok, dtype=np.uint8)
+    n = C.c_int32(0)
+    rc = lib.mcsce_write_pdbs(len(coords), coords.shape[1], coords.ctypes.data_as(C.POINTER(C.c_float)),
+                              okb.ctypes.data_as(C.c_void_p), order.ctypes.data_as(C.POINTER(C.c_int32)), text, line_len, off,
+                              str(save_path).encode(), 0, C.byref(n))
+    if rc != 0:
+        raise OSError("could not write every PDB file under %s" % save_path)
+    return int(n.value)
 
 
 def create_side_chain_structure(inputs):
@@ -190,14 +223,12 @@ def create_side_chain_ensemble(structure, n_conformations, temperature, save_pat
     coords, energy, ok = _grow(structure.coords, beta, int(n_conformations))
     if coords is None:
         return [], []
+    _write_pdbs(coords, ok, save_path)
     conformations, success, energies = [], [], {}
     for n in range(int(n_conformations)):
         if ok[n]:
-            s = _final_structure(coords[n])
-            addr = save_path + f"/{n}.pdb"
-            s.write_PDB(addr)
-            energies[addr] = float(energy[n])
-            conformations.append(s); success.append(True)
+            energies[save_path + f"/{n}.pdb"] = float(energy[n])
+            conformations.append(_final_structure(coords[n])); success.append(True)
         else:
             conformations.append(None); success.append(False)
     with open(save_path + "/energies.csv", "w") as f:

@@ -38,7 +38,10 @@ def _round3_f32(coords):
     """What ``Structure.coords = x`` followed by ``.coords`` yields in the reference:
     round to 3 decimals, store as <=8-char text, read back as float32
     (libstructure.py:149-160)."""
-    return np.round(np.asarray(coords), decimals=3).astype("<U8").astype(np.float32)
+    r = np.round(np.asarray(coords), decimals=3)
+    if r.size and (np.abs(r).max() >= 1000.0 or r.dtype != np.float32):
+        return r.astype("<U8").astype(np.float32)      # the literal route (8-character cells truncate big values)
+    return r.astype(np.float32)                         # same values without the text round trip
 
 
 class Structure:
@@ -301,6 +304,21 @@ class Structure:
                     int(c["resseq"][i]), str(c["icode"][i]), x, y, z, float(c["occ"][i] or 0.0),
                     float(c["temp"][i] or 0.0), str(c["segid"][i]), elem, str(c["model"][i])))
         return lines
+
+    def pdb_template(self):
+        """(template bytes, line length, coordinate offset) for ``mcsce_write_pdbs``: the PDB lines of this
+        table with blank coordinate fields, every line padded to 80 characters + newline."""
+        saved = self.xyz
+        self.xyz = np.zeros_like(saved)
+        try:
+            lines = self.get_PDB()
+        finally:
+            self.xyz = saved
+        out = []
+        for ln in lines:
+            ln = ln.ljust(80)[:80]
+            out.append(ln[:30] + " " * 24 + ln[54:] + "\n")
+        return "".join(out).encode("ascii"), 81, 30
 
     def write_PDB(self, filename):
         lines = self.get_PDB()
