@@ -243,10 +243,15 @@ def run_ours(args, rank, world, local_rank):
     sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
     peak_tflops = sm_count * 128 * 2 * sm_max * 1e6 / 1e12
     achieved = FLOPS_PER_PAIR * prof_pairs / (k2_ms * 1e-3) / 1e12 if k2_ms > 0 else 0.0
+    traffic = None
+    try:          # dram__bytes_read+write of one ncu --set full capture of this kernel (profiles/, per launch of THAT capture)
+        traffic = json.loads((ROOT / "profiles" / "r1_traffic.json").read_text())
+    except Exception:
+        pass
     executed = FLOPS_PER_PAIR * prof_computed / (k2_ms * 1e-3) / 1e12 if k2_ms > 0 else 0.0
     roofline = {
         "bound": "fp32", "kernel": "score_generic_kernel", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
-        "frac": achieved / peak_tflops, "traffic": None,
+        "frac": achieved / peak_tflops, "traffic": traffic,
         "peak_source": "FP32 CUDA-core peak = %d SMs x 128 lanes x 2 x %.0f MHz (sm_max_mhz of MEASURED_PEAKS.json; that file "
                        "holds no FP32 figure)" % (sm_count, sm_max),
         "flops_per_pair": FLOPS_PER_PAIR, "pairs_per_launch_avg": prof_pairs / max(1, k2_n),
