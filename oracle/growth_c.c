@@ -298,6 +298,51 @@ int oracle_grow(const oracle_system *s, int n_conf, double beta, double noise_de
     return 0;
 }
 
+/* Total energy of a finished conformer re-scored level by level (input atoms alone, then every grown side chain
+ * against everything placed before it) and the smallest ratio distance / clash distance over all scored pairs.
+ * Size-independent check for full-size runs: must equal the energy the growth accumulated, and the ratio must
+ * be >= 1 for a conformer reported as grown without clashes. */
+double oracle_rescore(const oracle_system *s, const float *xyz, double *min_clash_ratio) {
+    const int nc = s->n_cls;
+    double *clsA = (double *)malloc(sizeof(double) * nc * nc), *clsB = (double *)malloc(sizeof(double) * nc * nc);
+    for (int i = 0; i < nc * nc; ++i) {
+        const double s6 = s->cls_s2[i] * s->cls_s2[i] * s->cls_s2[i];
+        clsA[i] = s->cls_e4[i] * s6 * s6; clsB[i] = s->cls_e4[i] * s6;
+    }
+    oracle_system tmp = *s;
+    tmp.input_xyz = xyz;
+    double total = oracle_input_energy(&tmp);
+    double ratio = INFINITY;
+    unsigned char *is_special = (unsigned char *)calloc(s->n_atoms, 1);
+    for (int i = 0; i < s->n_res; ++i) {
+        if (s->step_kind[i] != 2) continue;
+        const int n_sc = s->step_n_sc[i], sc0 = s->step_sc_start[i];
+        for (int q = 0; q < s->step_n_sp_env[i]; ++q) is_special[s->step_sp_env[(size_t)i * MAX_SP_ENV + q]] = 1;
+        total += trial_energy(s, i, xyz + (size_t)sc0 * 3, xyz, sc0, is_special, clsA, clsB);
+        for (int k = 0; k < n_sc; ++k) {
+            const int ci = s->cls_of_atom[sc0 + k];
+            for (int j = 0; j < sc0; ++j) {
+                if (is_special[j]) continue;
+                const double thr = s->cls_thr[ci * nc + s->cls_of_atom[j]];
+                if (thr > 0) { const double r = sqrt((double)dist2(xyz + (size_t)(sc0 + k) * 3, xyz + (size_t)j * 3)) / thr; if (r < ratio) ratio = r; }
+            }
+        }
+        for (int p = 0; p < s->step_n_sp[i]; ++p) {
+            const int off = s->step_sp_off[i];
+            const int k = s->sp_k[off + p], pa = s->sp_partner[off + p];
+            const double thr = s->sp_coef[(size_t)(off + p) * 4 + 3];
+            if (thr <= 0) continue;
+            const float *b = pa >= 0 ? xyz + (size_t)s->step_sp_env[(size_t)i * MAX_SP_ENV + pa] * 3 : xyz + (size_t)(sc0 - pa - 1) * 3;
+            const double r = sqrt((double)dist2(xyz + (size_t)(sc0 + k) * 3, b)) / thr;
+            if (r < ratio) ratio = r;
+        }
+        for (int q = 0; q < s->step_n_sp_env[i]; ++q) is_special[s->step_sp_env[(size_t)i * MAX_SP_ENV + q]] = 0;
+    }
+    if (min_clash_ratio) *min_clash_ratio = ratio;
+    free(is_special); free(clsA); free(clsB);
+    return total;
+}
+
 int oracle_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -64,6 +64,8 @@ def load():
     lib.oracle_input_energy.restype = C.c_double
     lib.oracle_input_energy.argtypes = [C.POINTER(_System)]
     lib.oracle_max_threads.restype = C.c_int
+    lib.oracle_rescore.restype = C.c_double
+    lib.oracle_rescore.argtypes = [C.POINTER(_System), C.c_void_p, C.POINTER(C.c_double)]
     return lib
 
 
@@ -142,6 +144,14 @@ class COracle:
 
     def input_energy(self):
         return float(self.lib.oracle_input_energy(C.byref(self.desc)))
+
+    def rescore(self, coords):
+        """(total energy, min distance/clash-distance ratio) of one finished conformer, growth-order (N,3) float32."""
+        xyz = np.ascontiguousarray(coords, np.float32)
+        assert xyz.shape == (self.sysm.n_atoms, 3)
+        r = C.c_double(0.0)
+        e = self.lib.oracle_rescore(C.byref(self.desc), xyz.ctypes.data_as(C.c_void_p), C.byref(r))
+        return float(e), float(r.value)
 
     def grow(self, n_conf, beta, seed=0, noise_deg=0.5, chis=None, uniforms=None, dump=False, n_threads=0):
         N = self.sysm.n_atoms

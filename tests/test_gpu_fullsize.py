@@ -1,0 +1,115 @@
+"""BASELINE.json's full-size configurations on the GPU, checked through size-independent properties:
+the energy the fused growth accumulated equals the C oracle's level-by-level re-scoring of the final
+coordinates, no scored pair of a successful conformer is inside its clash distance, runs are
+deterministic, results do not depend on how conformers are sharded, and a replay of whole conformers
+through the C oracle reproduces every selection."""
+import numpy as np
+import pytest
+
+from golden_utils import library
+
+pytestmark = pytest.mark.gpu
+BETA = 1.0 / (300 * 0.008314462)
+_CACHE = {}
+
+
+def _workload(cfg):
+    if cfg in _CACHE:
+        return _CACHE[cfg]
+    from mcsce_b200 import synth
+    from mcsce_b200.engine import GrowthEngine
+    from mcsce_b200.structure import Structure
+    from mcsce_b200.system import build_system
+    from oracle.growth_c import COracle
+
+    lib, ptm = library()
+    s = Structure(synth.config_backbone(cfg)).build().remove_side_chains([])
+    sysm = build_system(s, rotamer_library=lib, ptm_library=ptm)
+    eng = GrowthEngine(0).set_system(sysm).set_backbone(s.coords)
+    _CACHE[cfg] = (s, sysm, eng, COracle(sysm, s.coords))
+    return _CACHE[cfg]
+
+
+def _check_rescoring(sysm, co, coords, energy, ok, sample, n_grow):
+    checked = 0
+    for c in sample:
+        if not ok[c]:
+            continue
+        e, ratio = co.rescore(coords[c])
+        assert abs(energy[c] - e) <= 4e-4 * n_grow + 2e-5 * abs(e), (c, energy[c], e)
+        assert ratio >= 1.0 - 1e-6, (c, ratio)
+        checked += 1
+    return checked
+
+
+def test_config3_300_residues_2048_conformers():
+    s, sysm, eng, co = _workload(3)
+    n_grow = sum(st.kind == "grow" for st in sysm.steps)
+    a = eng.grow(2048, BETA, seed=42, host_out=True)
+    coords, energy, ok = a["coords"].copy(), a["energy"].copy(), a["ok"].copy()
+    assert ok.mean() > 0.8 and np.isfinite(energy[ok == 1]).all() and np.isnan(energy[ok == 0]).all()
+    assert np.isfinite(coords[ok == 1]).all()
+    # input atoms untouched, every grown conformer different
+    assert np.array_equal(coords[:, :sysm.n_input], np.broadcast_to(s.coords, (2048,) + s.coords.shape))
+    assert len(np.unique(np.round(energy[ok == 1], 6))) > 0.99 * ok.sum()
+    rng = np.random.default_rng(0)
+    assert _check_rescoring(sysm, co, coords, energy, ok, rng.choice(2048, 10, replace=False), n_grow) >= 6
+    # determinism and sharding invariance (conformer streams are keyed by the global id)
+    b = eng.grow(2048, BETA, seed=42, host_out=True)
+    assert np.array_equal(b["energy"], energy, equal_nan=True) and np.array_equal(b["coords"], coords)
+    lo = eng.grow(1024, BETA, seed=42, conf_id0=0, host_out=True)
+    e_lo, c_lo = lo["energy"].copy(), lo["coords"].copy()
+    hi = eng.grow(1024, BETA, seed=42, conf_id0=1024, host_out=True)
+    assert np.array_equal(np.concatenate([e_lo, hi["energy"]]), energy, equal_nan=True)
+    assert np.array_equal(np.concatenate([c_lo, hi["coords"]]), coords)
+    c = eng.grow(64, BETA, seed=43, host_out=True)
+    assert not np.array_equal(c["energy"], energy[:64], equal_nan=True)
+
+
+def test_config3_whole_conformer_replay_through_c_oracle():
+    s, sysm, eng, co = _workload(3)
+    rng = np.random.default_rng(5)
+    n = 6
+    u = rng.random((n, sysm.n_res))
+    out = eng.grow(n, BETA, seed=11, uniforms=u, dump=True)
+    ref = co.grow(n, BETA, chis=out["chis"].cpu().numpy(), uniforms=u, dump=True)
+    sel = out["selected"].cpu().numpy()
+    assert np.array_equal(out["ok"].cpu().numpy(), ref["ok"])
+    grow = [st.index for st in sysm.steps if st.kind == "grow"]
+    n_sel = 0
+    for c in range(n):
+        for i in grow:
+            assert sel[c, i] == ref["selected"][c, i], (c, i, sysm.steps[i].resname)
+            if sel[c, i] < 0:
+                break
+            n_sel += 1
+    assert n_sel > 1000
+    te, tr = out["trial_energy"].cpu().numpy(), ref["trial_energy"]
+    both = ~np.isnan(te) & ~np.isnan(tr)
+    assert np.array_equal(np.isinf(te[both]), np.isinf(tr[both]))
+    fin = both & np.isfinite(tr)
+    bad = np.abs(te[fin] - tr[fin]) > np.maximum(1e-3, 1e-5 * np.abs(tr[fin]))
+    print("cfg3 replay: %d trials, %d selections, %d trials outside tolerance, worst %.2fx" % (
+        fin.sum(), n_sel, bad.sum(), (np.abs(te[fin] - tr[fin]) / np.maximum(1e-3, 1e-5 * np.abs(tr[fin]))).max()))
+    assert bad.mean() < 0.03
+
+
+def test_config5_2000_residues_8_chains():
+    s, sysm, eng, co = _workload(5)
+    assert sysm.n_res == 2000 and len(set(sysm.chains)) == 8
+    n_grow = sum(st.kind == "grow" for st in sysm.steps)
+    a = eng.grow(16, BETA, seed=3, host_out=True)
+    coords, energy, ok = a["coords"].copy(), a["energy"].copy(), a["ok"].copy()
+    assert ok.sum() >= 2
+    assert _check_rescoring(sysm, co, coords, energy, ok, list(np.where(ok)[0][:2]), n_grow) == 2
+    b = eng.grow(16, BETA, seed=3, env_split=7, host_out=True)        # a different environment split: same conformers
+    assert np.array_equal(b["ok"], ok)
+    assert np.allclose(b["energy"], energy, rtol=1e-9, atol=1e-6, equal_nan=True)
+
+
+def test_config2_76_residues_128_conformers():
+    s, sysm, eng, co = _workload(2)
+    n_grow = sum(st.kind == "grow" for st in sysm.steps)
+    a = eng.grow(128, BETA, seed=9, host_out=True)
+    assert a["ok"].mean() > 0.9
+    assert _check_rescoring(sysm, co, a["coords"], a["energy"], a["ok"], range(0, 128, 8), n_grow) >= 12
