@@ -3,7 +3,9 @@
 The reference's only parallelism is a ``multiprocessing.Pool`` over independent conformers
 (``side_chain_builder.py:260-274, 328-347``).  Here a call's conformers ``[0, n)`` are split into
 contiguous ranges, one per rank; RNG streams are keyed by the global conformer id, so the result does
-not depend on the number of ranks.  There is no collective on the growth path; the final coordinates,
+not depend on the number of ranks (bit for bit while every rank holds enough conformers to fill the GPU
+without splitting the environment, about 150 x trial tiles; below that the environment split regroups
+float32 partial sums and conformers agree to rounding).  There is no collective on the growth path; the final coordinates,
 energies and success flags are gathered to rank 0 once (NCCL over NVLink when the ranks hold CUDA
 tensors, gloo for the CPU tests).
 """
