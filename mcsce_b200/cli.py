@@ -10,16 +10,16 @@ from functools import partial
 import numpy as np
 
 parser = argparse.ArgumentParser()
-parser.add_argument("input_structure", help="A single PDB file for the backbone conformation, or a folder in which all PDB files will be processed")
-parser.add_argument("n_conf", type=int, help="Number of side-chain conformations to generate (regardless of whether or not succeeded) for each given input backbone structure")
+parser.add_argument("input_structure", help="backbone PDB file, or a directory whose *.pdb files are all processed")
+parser.add_argument("n_conf", type=int, help="conformers to attempt per input backbone (failed growths count)")
 parser.add_argument("-w", "--n_worker", type=int, default=None, help="Accepted for compatibility (the reference's process-pool size); the GPU path uses one process per GPU")
-parser.add_argument("-o", "--output_dir", default=None, help="The output position of generated PDB files. When not specified, it will be the name of the input file+'_mcsce'")
+parser.add_argument("-o", "--output_dir", default=None, help="where results go; default: <input name>_mcsce next to the working directory")
 parser.add_argument("-s", "--same_structure", action="store_true", default=False, help="All structures in the folder share one amino acid sequence: prepare the tables once")
 parser.add_argument("-b", "--batch_size", default=16, type=int, help="Accepted for compatibility; not used by the GPU path")
 parser.add_argument("-m", "--mode", choices=["ensemble", "simple", "exhaustive"], default="ensemble", help="ensemble: write every conformer; simple: first clash-free conformer; exhaustive: lowest-energy conformer of n_conf")
 parser.add_argument("-f", "--fix", default=None, help="residue ids whose side chains are retained, e.g. 2-5+10-13 (same-structure mode only)")
-parser.add_argument("-l", "--logfile", default="log.csv", help="File name of the log file")
-parser.add_argument("-v", "--verbose", default=False, help="whether to print out warnings")
+parser.add_argument("-l", "--logfile", default="log.csv", help="CSV log: file, number grown, wall time")
+parser.add_argument("-v", "--verbose", default=False, help="print the full missing-atom / HIS renaming warnings")
 parser.add_argument("--seed", type=int, default=0, help="seed of the on-device random streams (extension)")
 
 

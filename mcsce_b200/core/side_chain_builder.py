@@ -173,6 +173,30 @@ def _final_structure(coords_growth_order):
     return s
 
 
+class _Conformations(list):
+    """``list[Structure | None]`` whose Structure objects are assembled when first looked at: building thousands of
+    atom tables in Python would cost more than growing the conformers (the PDB files are already on disk)."""
+
+    def __init__(self, coords, ok):
+        super().__init__([None] * len(ok))
+        self._coords, self._ok, self._done = coords, ok, [False] * len(ok)
+
+    def _fill(self, i):
+        if not self._done[i]:
+            self._done[i] = True
+            if self._ok[i]:
+                super().__setitem__(i, _final_structure(self._coords[i]))
+        return super().__getitem__(i)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self._fill(k) for k in range(*i.indices(len(self)))]
+        return self._fill(i if i >= 0 else i + len(self))
+
+    def __iter__(self):
+        return (self._fill(i) for i in range(len(self)))
+
+
 def _write_pdbs(coords, ok, save_path):
     """All successful conformers of a call to ``<save_path>/<n>.pdb`` through the library's batched writer."""
     import ctypes as C
@@ -224,13 +248,9 @@ def create_side_chain_ensemble(structure, n_conformations, temperature, save_pat
     if coords is None:
         return [], []
     _write_pdbs(coords, ok, save_path)
-    conformations, success, energies = [], [], {}
-    for n in range(int(n_conformations)):
-        if ok[n]:
-            energies[save_path + f"/{n}.pdb"] = float(energy[n])
-            conformations.append(_final_structure(coords[n])); success.append(True)
-        else:
-            conformations.append(None); success.append(False)
+    success = [bool(k) for k in ok]
+    energies = {save_path + f"/{n}.pdb": float(energy[n]) for n in range(int(n_conformations)) if ok[n]}
+    conformations = _Conformations(coords, ok)
     with open(save_path + "/energies.csv", "w") as f:
         f.write("File name,Energy(kJ/mol)\n")
         for item in energies:
