@@ -651,6 +651,7 @@ struct SelectArgs {
     double *e_acc;
     int *selected;                     // optional [set*n_res + step]
     double *trial_energy;              // optional dump [set*n_trials_total + trial_off + t]
+    int *n_dead;                        // conformers that failed so far (read back now and then to re-size the grids)
     unsigned long long *pair_counter;   // [0] algorithmic pairs (the reference's P), [1] pairs actually evaluated
     long long pairs_per_set, pairs_computed_per_set;
 };
@@ -699,6 +700,7 @@ __global__ void __launch_bounds__(128) select_kernel(SelectArgs a) {
     if (isinf(mn) || isnan(mn)) {                             // every trial clashes: growth fails (side_chain_builder.py:187)
         if (tid == 0) {
             a.alive[set] = 0;
+            if (a.n_dead) atomicAdd(a.n_dead, 1);
             if (a.selected) a.selected[(long long)set * a.s.n_res + a.step] = -1;
         }
         return;
@@ -868,6 +870,7 @@ struct mcsce_handle_s {
     int max_trials = 0, max_trial_atoms = 0;
     StepDev *d_steps = nullptr;
     unsigned long long *d_pairs = nullptr;
+    int *d_n_dead = nullptr, *h_n_dead = nullptr;      // device counter + pinned host copy
     double *d_input_energy = nullptr;
     long long launches = 0;
     // second stream + events: placement (K1, FP64 pipe) and the special-pair kernel of a residue run
@@ -929,6 +932,8 @@ extern "C" int mcsce_create(mcsce_handle *out, int device) {
     CK(cudaMalloc((void **)&h->d_pairs, 2 * sizeof(unsigned long long)));
     CK(cudaMemset(h->d_pairs, 0, 2 * sizeof(unsigned long long)));
     CK(cudaMalloc((void **)&h->d_input_energy, sizeof(double)));
+    CK(cudaMalloc((void **)&h->d_n_dead, sizeof(int)));
+    CK(cudaMallocHost((void **)&h->h_n_dead, sizeof(int)));
     *out = h;
     return 0;
 }
@@ -945,6 +950,8 @@ extern "C" int mcsce_destroy(mcsce_handle h) {
     if (h->d_steps) cudaFree(h->d_steps);
     if (h->d_pairs) cudaFree(h->d_pairs);
     if (h->d_input_energy) cudaFree(h->d_input_energy);
+    if (h->d_n_dead) cudaFree(h->d_n_dead);
+    if (h->h_n_dead) cudaFreeHost(h->h_n_dead);
     delete h;
     return 0;
 }
@@ -1121,9 +1128,10 @@ static int choose_split(const mcsce_handle h, int step, int n_sets, int n_trials
     return split;
 }
 static int max_split_for(int n_sets, int sm_count) {
-    // upper bound of choose_split for workspace sizing (tiles >= 1)
+    // split factors the workspace is sized for: 1 when the conformers alone fill the GPU, else the maximum (32),
+    // because the factor is raised while conformers die (see mcsce_grow)
     long long want = 4LL * sm_count;
-    return (int)std::min<long long>(32, std::max<long long>(1, (want + n_sets - 1) / n_sets));
+    return (want + n_sets - 1) / n_sets > 1 ? 32 : 1;
 }
 
 struct Workspace {
@@ -1354,6 +1362,9 @@ extern "C" int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *o, void *d_work
     CK(cudaEventRecord(h->ev0, st));
     CK(cudaStreamWaitEvent(aux, h->ev0, 0));
     int prev = -1, prev2 = -1, count = 0;
+    const int ms_alloc = max_split_for(C, h->sm_count);
+    int n_alive = C;
+    CK(cudaMemsetAsync(h->d_n_dead, 0, sizeof(int), st));
     for (int i = 0; i < d.n_res; ++i) {
         const StepDev &sd = h->steps[i];
         if (sd.kind != 2 || sd.n_trials <= 0) continue;
@@ -1366,7 +1377,14 @@ extern "C" int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *o, void *d_work
         CK(cudaEventRecord(h->evP[i], aux));
         // st: generic pairs
         CK(cudaStreamWaitEvent(st, h->evP[i], 0));
-        const int split = choose_split(h, i, C, T, o->env_split);
+        // few conformers: the environment is split over blockIdx.z to fill the GPU; conformers that died leave empty
+        // CTAs, so the number still alive is read back every 32 residues and the split re-derived from it
+        if (ms_alloc > 1 && o->env_split <= 0 && count > 0 && (count & 31) == 0) {
+            CK(cudaMemcpyAsync(h->h_n_dead, h->d_n_dead, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            n_alive = std::max(1, C - *h->h_n_dead);
+        }
+        const int split = std::min(ms_alloc, choose_split(h, i, n_alive, T, o->env_split));
         const int dedup = (sd.n_fix > 0 && sd.n_var > 0 && !o->no_dedup) ? 1 : 0;
         if (launch_generic(h, i, C, T, split, w.env, trial, trial_stride, w.partial, w.alive, st, dedup)) return -1;
         // aux: special pairs (need the environment as updated by the previous selection)
@@ -1381,7 +1399,7 @@ extern "C" int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *o, void *d_work
         a.prob = d.prob + sd.trial_off; a.beta = o->beta; a.uniform = o->d_uniform; a.u_stride = d.n_res;
         a.seed = o->seed; a.conf_id0 = o->conf_id0; a.env = w.env; a.trial = trial; a.trial_set_stride = trial_stride;
         a.alive = w.alive; a.e_acc = w.e_acc; a.selected = o->d_selected; a.trial_energy = o->d_trial_energy;
-        a.pair_counter = h->d_pairs;
+        a.pair_counter = h->d_pairs; a.n_dead = h->d_n_dead;
         long long n_active = 0;
         for (int c = 0; c < d.n_cls; ++c) n_active += h->cls_active[(size_t)i * d.n_cls + c];
         a.pairs_per_set = (long long)T * ((long long)sd.n_sc * (sd.n_sc - 1) / 2 + (long long)sd.n_sc * n_active);
