@@ -294,6 +294,10 @@ __global__ void __launch_bounds__(128) place_trials_kernel(PlaceArgs a) {
 #ifndef TILE_E
 #define TILE_E 1024                     // environment atoms staged per smem tile
 #endif
+#ifndef PAIR_UNROLL
+#define PAIR_UNROLL 4                   // environment-atom pairs per unrolled iteration of the inner loop
+#endif
+constexpr int kPairUnroll = PAIR_UNROLL;
 #ifndef RCP_MIX
 #define RCP_MIX 0                       // 1: alternate Newton-corrected y*y with MUFU.RCP for 1/d2
 #endif
@@ -347,7 +351,7 @@ __device__ __forceinline__ void score_segment(const float4 *__restrict__ s_env, 
         float2 a6[RR], a3[RR], cq[RR];
 #pragma unroll
         for (int r = 0; r < RR; ++r) { a6[r] = make_float2(0.f, 0.f); a3[r] = a6[r]; cq[r] = a6[r]; }
-#pragma unroll 2
+#pragma unroll kPairUnroll
         for (int p = pb; p < pe; ++p) {
             const float4 exy = s_env[2 * p], ezq = s_env[2 * p + 1];
             const float2 ex = make_float2(exy.x, exy.y), ey = make_float2(exy.z, exy.w);
