@@ -112,6 +112,7 @@ typedef struct {
     int32_t env_split;             /* >0 forces the environment split factor; 0 = automatic      */
     int32_t no_dedup;              /* 1: score the chi-independent side-chain atoms (HA, CB, ...) in every trial like the
                                       reference does, instead of once per residue (same result, more work) */
+    int32_t no_graph;              /* 1: never replay a cached CUDA graph (launch-bound runs do by default) */
 } mcsce_grow_opts;
 
 const char *mcsce_last_error(void);

@@ -88,6 +88,16 @@ struct SysDev {
     int n_trials_total;
 };
 
+// Scalars that change from call to call live in device memory so that a captured CUDA graph of a growth can be
+// replayed with a new seed / conformer offset / temperature without re-capturing.
+struct CallParams {
+    unsigned long long seed;
+    long long conf_id0;
+    double beta, noise_deg;
+};
+
+__global__ void set_call_params_kernel(CallParams *dst, CallParams v) { *dst = v; }
+
 // ------------------------------------------------------------------------------------------------
 // helpers
 // ------------------------------------------------------------------------------------------------
@@ -202,9 +212,7 @@ struct PlaceArgs {
     float4 *trial;            // [set][n_trials*n_sc]
     long long trial_set_stride;
     const unsigned char *alive;
-    unsigned long long seed;
-    long long conf_id0;
-    double noise_deg;
+    const CallParams *cp;     // seed, conformer offset, perturbation sigma (device memory)
 };
 
 __global__ void __launch_bounds__(128) place_trials_kernel(PlaceArgs a) {
@@ -235,9 +243,11 @@ __global__ void __launch_bounds__(128) place_trials_kernel(PlaceArgs a) {
             double mine = 0.0;
             if (lane < st.n_chi_lib) {
                 const long long trow = (long long)st.trial_off + t;
-                uint4 r = philox4x32(make_uint4((unsigned)(a.conf_id0 + set), (unsigned)((a.conf_id0 + set) >> 32),
+                const long long cid = a.cp->conf_id0 + set;
+                const unsigned long long seed = a.cp->seed;
+                uint4 r = philox4x32(make_uint4((unsigned)cid, (unsigned)(cid >> 32),
                                                 (unsigned)a.step, ((unsigned)t << 3) | (unsigned)lane),
-                                     make_uint2((unsigned)a.seed, (unsigned)(a.seed >> 32)));
+                                     make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
                 double u1 = u01_open(r.x, r.y), u2 = u01_halfopen(r.z, r.w);
                 double rad = sqrt(-2.0 * log(u1)), sn, cs;
                 sincospi(2.0 * u2, &sn, &cs);
@@ -248,7 +258,7 @@ __global__ void __launch_bounds__(128) place_trials_kernel(PlaceArgs a) {
                     if (v > 180.0) v -= 360.0;
                     if (v < -180.0) v += 360.0;
                 }
-                mine = v + a.noise_deg * (rad * sn);
+                mine = v + a.cp->noise_deg * (rad * sn);
                 if (a.chis_out) a.chis_out[(long long)set * a.chis_set_stride + row * MAX_CHI + lane] = mine;
             } else if (a.chis_out && lane < MAX_CHI) {
                 a.chis_out[(long long)set * a.chis_set_stride + row * MAX_CHI + lane] = 0.0;
@@ -643,11 +653,9 @@ struct SelectArgs {
     const double2 *partial, *sp_partial;
     int dedup;
     const double *prob;                // [n_trials]
-    double beta;
+    const CallParams *cp;              // beta, seed, conformer offset (device memory)
     const double *uniform;             // explicit [set*u_stride + step] or null
     int u_stride;
-    unsigned long long seed;
-    long long conf_id0;
     float4 *env;
     const float4 *trial;
     long long trial_set_stride;
@@ -710,15 +718,16 @@ __global__ void __launch_bounds__(128) select_kernel(SelectArgs a) {
         return;
     }
     for (int t = tid; t < a.n_trials; t += 128)
-        s_w[t] = a.prob[t] * exp(-a.beta * (s_E[t] - mn));    // side_chain_builder.py:191-192
+        s_w[t] = a.prob[t] * exp(-a.cp->beta * (s_E[t] - mn));    // side_chain_builder.py:191-192
     __syncthreads();
     if (tid == 0) {
         double u;
         if (a.uniform) u = a.uniform[(long long)set * a.u_stride + a.step];
         else {
-            uint4 r = philox4x32(make_uint4((unsigned)(a.conf_id0 + set), (unsigned)((a.conf_id0 + set) >> 32),
-                                            (unsigned)a.step, 0xFFFFFFFFu),
-                                 make_uint2((unsigned)a.seed, (unsigned)(a.seed >> 32)));
+            const long long cid = a.cp->conf_id0 + set;
+            const unsigned long long seed = a.cp->seed;
+            uint4 r = philox4x32(make_uint4((unsigned)cid, (unsigned)(cid >> 32), (unsigned)a.step, 0xFFFFFFFFu),
+                                 make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
             u = u01_halfopen(r.x, r.y);
         }
         // sequential float64 running sums, first index whose sum exceeds u*total (side_chain_builder.py:35-40)
@@ -875,6 +884,13 @@ struct mcsce_handle_s {
     StepDev *d_steps = nullptr;
     unsigned long long *d_pairs = nullptr;
     int *d_n_dead = nullptr, *h_n_dead = nullptr;      // device counter + pinned host copy
+    CallParams *d_call = nullptr;
+    // cached CUDA graph of one growth (small, launch-bound runs)
+    cudaStream_t cap_stream = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    std::vector<long long> graph_key;
+    long long graph_launches = 0;
+    long long table_version = 0;
     double *d_input_energy = nullptr;
     long long launches = 0;
     // second stream + events: placement (K1, FP64 pipe) and the special-pair kernel of a residue run
@@ -937,6 +953,8 @@ extern "C" int mcsce_create(mcsce_handle *out, int device) {
     CK(cudaMemset(h->d_pairs, 0, 2 * sizeof(unsigned long long)));
     CK(cudaMalloc((void **)&h->d_input_energy, sizeof(double)));
     CK(cudaMalloc((void **)&h->d_n_dead, sizeof(int)));
+    CK(cudaMalloc((void **)&h->d_call, sizeof(CallParams)));
+    CK(cudaMemset(h->d_call, 0, sizeof(CallParams)));
     CK(cudaMallocHost((void **)&h->h_n_dead, sizeof(int)));
     *out = h;
     return 0;
@@ -955,6 +973,9 @@ extern "C" int mcsce_destroy(mcsce_handle h) {
     if (h->d_pairs) cudaFree(h->d_pairs);
     if (h->d_input_energy) cudaFree(h->d_input_energy);
     if (h->d_n_dead) cudaFree(h->d_n_dead);
+    if (h->d_call) cudaFree(h->d_call);
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+    if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
     if (h->h_n_dead) cudaFreeHost(h->h_n_dead);
     delete h;
     return 0;
@@ -966,6 +987,7 @@ extern "C" int mcsce_set_system(mcsce_handle h, const mcsce_system_desc *s) {
     if (s->n_cls > MAX_CLS) return fail("too many atom classes");
     free_pool(h->sys_allocs); free_pool(h->bb_allocs);
     h->has_sys = h->has_bb = false;
+    h->table_version++;
     SysDev &d = h->d;
     d = SysDev{};
     d.n_atoms = s->n_atoms; d.n_input = s->n_input; d.n_res = s->n_res; d.n_cls = s->n_cls; d.n_types = s->n_types;
@@ -1044,8 +1066,7 @@ extern "C" int mcsce_set_system(mcsce_handle h, const mcsce_system_desc *s) {
 
 static int launch_place(mcsce_handle h, int step, int n_sets, int n_rows, const double *chis_in, long long set_stride,
                         long long row_off, double *chis_out, float4 *trial, long long trial_stride,
-                        const unsigned char *alive, unsigned long long seed, long long conf_id0, double noise,
-                        cudaStream_t st);
+                        const unsigned char *alive, cudaStream_t st);
 
 __global__ void store_rigid_kernel(const float4 *src, int sc_start, int n_sc, float *rigid) {
     const int k = threadIdx.x;
@@ -1056,7 +1077,9 @@ extern "C" int mcsce_set_backbone(mcsce_handle h, const mcsce_backbone_desc *b) 
     if (!h || !b) return fail("null argument");
     if (!h->has_sys) return fail("mcsce_set_system must be called first");
     CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());          // a growth still in flight reads these tables
     free_pool(h->bb_allocs);
+    h->table_version++;
     SysDev &d = h->d;
     auto &P = h->bb_allocs;
     d.n_trials_total = b->n_trials_total;
@@ -1104,7 +1127,7 @@ extern "C" int mcsce_set_backbone(mcsce_handle h, const mcsce_backbone_desc *b) 
         CK(cudaMalloc((void **)&tmp, sizeof(float4) * MAX_SC));
         for (int i = 0; i < d.n_res; ++i) {
             if (h->steps[i].kind != 1) continue;
-            if (launch_place(h, i, 1, 1, nullptr, 0, 0, nullptr, tmp, 0, nullptr, 0, 0, 0.0, 0)) { cudaFree(tmp); return -1; }
+            if (launch_place(h, i, 1, 1, nullptr, 0, 0, nullptr, tmp, 0, nullptr, 0)) { cudaFree(tmp); return -1; }
             store_rigid_kernel<<<1, 32>>>(tmp, h->steps[i].sc_start, h->steps[i].n_sc, rigid);
             h->launches += 1;
         }
@@ -1204,12 +1227,11 @@ extern "C" int mcsce_init_env(mcsce_handle h, int n_env_sets, float *d_env, void
 
 static int launch_place(mcsce_handle h, int step, int n_sets, int n_rows, const double *chis_in, long long set_stride,
                         long long row_off, double *chis_out, float4 *trial, long long trial_stride,
-                        const unsigned char *alive, unsigned long long seed, long long conf_id0, double noise,
-                        cudaStream_t st) {
+                        const unsigned char *alive, cudaStream_t st) {
     PlaceArgs a{};
     a.s = h->d; a.step = step; a.n_trials = n_rows; a.chis_in = chis_in; a.chis_set_stride = set_stride;
     a.chis_row_off = row_off; a.chis_out = chis_out; a.trial = trial; a.trial_set_stride = trial_stride;
-    a.alive = alive; a.seed = seed; a.conf_id0 = conf_id0; a.noise_deg = noise;
+    a.alive = alive; a.cp = h->d_call;
     dim3 grid((n_rows + 3) / 4, n_sets);
     { ProfScope ps(h, 0, st); place_trials_kernel<<<grid, 128, 0, st>>>(a); }
     h->launches += 1;
@@ -1260,7 +1282,7 @@ extern "C" int mcsce_place_trials(mcsce_handle h, int residue, int n_rows, const
     if (residue < 0 || residue >= h->d.n_res) return fail("residue out of range");
     if (h->steps[residue].kind == 0) return fail("residue is retained: nothing to place");
     CK(cudaSetDevice(h->device));
-    return launch_place(h, residue, 1, n_rows, d_chis, 0, 0, nullptr, (float4 *)d_xyz, 0, nullptr, 0, 0, 0.0, (cudaStream_t)stream);
+    return launch_place(h, residue, 1, n_rows, d_chis, 0, 0, nullptr, (float4 *)d_xyz, 0, nullptr, (cudaStream_t)stream);
 }
 
 __global__ void combine_kernel(int n, int n_split, const double2 *partial, const double2 *sp_partial, double *out) {
@@ -1333,36 +1355,20 @@ extern "C" int mcsce_select(mcsce_handle h, int n_sets, int n_trials, const doub
     return 0;
 }
 
-extern "C" int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *o, void *d_workspace, size_t workspace_bytes,
-                          float *d_coords, double *d_energy, uint8_t *d_ok, void *stream) {
-    if (!h || !o) return fail("null argument");
-    if (!h->has_bb) return fail("set_system/set_backbone first");
-    if (o->n_conf <= 0) return fail("n_conf must be positive");
-    CK(cudaSetDevice(h->device));
+// Enqueue the whole growth (environment init, input-atom energy, then K1/K2/K2s/K3 for every grown residue) on
+// `st` + `aux`.  `resync` allows the occasional read-back of the number of dead conformers (never while capturing).
+static int enqueue_growth(mcsce_handle h, const mcsce_grow_opts *o, const Workspace &w, cudaStream_t st, cudaStream_t aux,
+                          bool resync) {
     const SysDev &d = h->d;
-    Workspace w = carve(h, o->n_conf, h->max_trials, h->max_trial_atoms, d_workspace);
-    if (workspace_bytes < w.total) return fail("workspace too small: call mcsce_workspace_bytes");
-    cudaStream_t st = (cudaStream_t)stream;
     const int C = o->n_conf;
     const long long trial_stride = std::max(1, h->max_trial_atoms);
     const long long chi_set_stride = (long long)d.n_trials_total * MAX_CHI;
-
-    if (mcsce_init_env(h, C, (float *)w.env, stream)) return -1;
+    if (mcsce_init_env(h, C, (float *)w.env, (void *)st)) return -1;
     if (launch_input_energy(h, w.rows, w.pairs, h->d_input_energy, st)) return -1;
     init_state_kernel<<<(C + 255) / 256, 256, 0, st>>>(C, w.alive, w.e_acc, h->d_input_energy);
     h->launches += 1;
-
     // Two streams: `st` runs the generic-pair kernel and the selection of every residue in order; `aux` runs the
     // placement of the next residue (independent of the pending selection) and the special-pair kernel.
-    if (!h->aux) CK(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
-    if (!h->ev0) CK(cudaEventCreateWithFlags(&h->ev0, cudaEventDisableTiming));
-    while ((int)h->evP.size() < d.n_res) {
-        cudaEvent_t e;
-        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->evP.push_back(e);
-        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->evQ.push_back(e);
-        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->evS.push_back(e);
-    }
-    cudaStream_t aux = h->aux;
     CK(cudaEventRecord(h->ev0, st));
     CK(cudaStreamWaitEvent(aux, h->ev0, 0));
     int prev = -1, prev2 = -1, count = 0;
@@ -1377,13 +1383,13 @@ extern "C" int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *o, void *d_work
         // aux: K1 into the buffer last read by the residue before the previous one
         if (prev2 >= 0) CK(cudaStreamWaitEvent(aux, h->evS[prev2], 0));
         if (launch_place(h, i, C, T, o->d_chis, chi_set_stride, sd.trial_off, o->d_chis_out, trial, trial_stride,
-                         w.alive, o->seed, o->conf_id0, o->noise_deg, aux)) return -1;
+                         w.alive, aux)) return -1;
         CK(cudaEventRecord(h->evP[i], aux));
         // st: generic pairs
         CK(cudaStreamWaitEvent(st, h->evP[i], 0));
         // few conformers: the environment is split over blockIdx.z to fill the GPU; conformers that died leave empty
         // CTAs, so the number still alive is read back every 32 residues and the split re-derived from it
-        if (ms_alloc > 1 && o->env_split <= 0 && count > 0 && (count & 31) == 0) {
+        if (resync && ms_alloc > 1 && o->env_split <= 0 && count > 0 && (count & 31) == 0) {
             CK(cudaMemcpyAsync(h->h_n_dead, h->d_n_dead, sizeof(int), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             n_alive = std::max(1, C - *h->h_n_dead);
@@ -1400,8 +1406,8 @@ extern "C" int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *o, void *d_work
         SelectArgs a{};
         a.s = d; a.step = i; a.n_trials = T; a.n_split = split; a.partial = w.partial; a.sp_partial = w.sp_partial;
         a.dedup = dedup;
-        a.prob = d.prob + sd.trial_off; a.beta = o->beta; a.uniform = o->d_uniform; a.u_stride = d.n_res;
-        a.seed = o->seed; a.conf_id0 = o->conf_id0; a.env = w.env; a.trial = trial; a.trial_set_stride = trial_stride;
+        a.prob = d.prob + sd.trial_off; a.cp = h->d_call; a.uniform = o->d_uniform; a.u_stride = d.n_res;
+        a.env = w.env; a.trial = trial; a.trial_set_stride = trial_stride;
         a.alive = w.alive; a.e_acc = w.e_acc; a.selected = o->d_selected; a.trial_energy = o->d_trial_energy;
         a.pair_counter = h->d_pairs; a.n_dead = h->d_n_dead;
         long long n_active = 0;
@@ -1413,6 +1419,74 @@ extern "C" int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *o, void *d_work
         h->launches += 1;
         CK(cudaEventRecord(h->evS[i], st));
         prev2 = prev; prev = i; ++count;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *o, void *d_workspace, size_t workspace_bytes,
+                          float *d_coords, double *d_energy, uint8_t *d_ok, void *stream) {
+    if (!h || !o) return fail("null argument");
+    if (!h->has_bb) return fail("set_system/set_backbone first");
+    if (o->n_conf <= 0) return fail("n_conf must be positive");
+    CK(cudaSetDevice(h->device));
+    const SysDev &d = h->d;
+    Workspace w = carve(h, o->n_conf, h->max_trials, h->max_trial_atoms, d_workspace);
+    if (workspace_bytes < w.total) return fail("workspace too small: call mcsce_workspace_bytes");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int C = o->n_conf;
+    if (!h->aux) CK(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
+    if (!h->ev0) CK(cudaEventCreateWithFlags(&h->ev0, cudaEventDisableTiming));
+    while ((int)h->evP.size() < d.n_res) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->evP.push_back(e);
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->evQ.push_back(e);
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->evS.push_back(e);
+    }
+    // per-call scalars -> device parameter block (by-value kernel argument: no host buffer to keep alive)
+    CallParams cp{o->seed, o->conf_id0, o->beta, o->noise_deg};
+    set_call_params_kernel<<<1, 1, 0, st>>>(h->d_call, cp);
+    h->launches += 1;
+
+    // Launch-bound runs (little work per residue: few conformers and/or a small protein) replay a captured CUDA graph of
+    // the whole growth instead of ~4 launches + 7 event calls per residue; the graph is cached per (tables, n_conf,
+    // buffers, options).  Large runs enqueue directly and may re-derive the environment split while conformers die.
+    long long grow_steps = 0, pairs = 0;
+    for (int i = 0; i < d.n_res; ++i) {
+        const StepDev &sd = h->steps[i];
+        if (sd.kind != 2 || sd.n_trials <= 0) continue;
+        long long n_active = 0;
+        for (int c = 0; c < d.n_cls; ++c) n_active += h->cls_active[(size_t)i * d.n_cls + c];
+        pairs += (long long)sd.n_trials * sd.n_sc * n_active;
+        ++grow_steps;
+    }
+    const bool use_graph = !o->no_graph && !h->profiling && grow_steps > 0 && (pairs * C) / grow_steps < 300000000LL;
+    if (use_graph) {
+        std::vector<long long> key = {h->table_version, C, (long long)(size_t)d_workspace, (long long)workspace_bytes,
+                                      (long long)(size_t)o->d_chis, (long long)(size_t)o->d_uniform,
+                                      (long long)(size_t)o->d_trial_energy, (long long)(size_t)o->d_chis_out,
+                                      (long long)(size_t)o->d_selected, o->env_split, o->no_dedup};
+        if (!h->graph_exec || key != h->graph_key) {
+            if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+            if (!h->cap_stream) CK(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+            const long long before = h->launches;
+            CK(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeRelaxed));
+            const int rc = enqueue_growth(h, o, w, h->cap_stream, h->aux, false);
+            cudaGraph_t graph = nullptr;
+            cudaError_t e = cudaStreamEndCapture(h->cap_stream, &graph);
+            h->graph_launches = h->launches - before;
+            h->launches = before;
+            if (rc) { if (graph) cudaGraphDestroy(graph); return -1; }
+            if (e != cudaSuccess) return fail(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+            e = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess) { h->graph_exec = nullptr; return fail(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+            h->graph_key = key;
+        }
+        CK(cudaGraphLaunch(h->graph_exec, st));
+        h->launches += h->graph_launches;
+    } else {
+        if (enqueue_growth(h, o, w, st, h->aux, true)) return -1;
     }
     const long long n = (long long)C * d.n_atoms;
     gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d, C, w.env, d_coords);
