@@ -304,6 +304,10 @@ __global__ void __launch_bounds__(128) place_trials_kernel(PlaceArgs a) {
 #ifndef TILE_E
 #define TILE_E 1024                     // environment atoms staged per smem tile
 #endif
+#ifndef NO_RECIP_CORRECTION
+#define NO_RECIP_CORRECTION 1           // 1: 1/d2 = y*y of the raw rsqrt; 0: one Newton step on the reciprocal (2 more FMA-pipe ops per
+                                        // pair, -12 % speed).  Measured K2 error vs the reference: worst trial 0.21x (1) / 0.15x (0) of the tolerance
+#endif
 #ifndef PAIR_UNROLL
 #define PAIR_UNROLL 4                   // environment-atom pairs per unrolled iteration of the inner loop
 #endif
@@ -337,8 +341,9 @@ struct ScoreArgs {
 //   d   = e - a                                   3 FADD2
 //   d2  = fma(dz,dz,fma(dy,dy,dx*dx))             FMUL2 + 2 FFMA2   (fused: <= 4 ulp from the reference's unfused d2)
 //   dmin= min(dmin, d2.x, d2.y)                   clash decision deferred to the end of the segment
-//   y   = rsqrt.approx(d2)                        2 MUFU (<= 2 ulp): good enough for q/d
-//   w   = y*y ; w = w + w*(1 - d2*w)              FMUL2 + 2 FFMA2: one Newton step on the reciprocal, 1/d2 to ~1 ulp
+//   y   = rsqrt.approx(d2)                        2 MUFU (max rel. error 2^-22.9): used as is for q/d
+//   w   = y*y                                     FMUL2: 1/d2 to 3.2e-7, i.e. d^-12 to 2.2e-6 worst case, 0.22x the 1e-5 tolerance
+//                                                 (NO_RECIP_CORRECTION=0 adds the Newton step w += w*(1 - d2*w): 2 FFMA2)
 //   i3  = w*w*w ; a6 += i3*i3 ; a3 += i3          2 FMUL2 + FFMA2 + FADD2: sum d^-12, sum d^-6 (class constants at the flush)
 //   cq += q*y                                     FFMA2
 // The staged tile is stored pair-interleaved (x0 x1 y0 y1 | z0 z1 q0 q1) and every class segment is padded
@@ -383,8 +388,10 @@ __device__ __forceinline__ void score_segment(const float4 *__restrict__ s_env, 
 #endif
                 {
                     w = __fmul2_rn(y, y);
+#if !NO_RECIP_CORRECTION
                     const float2 nd2 = make_float2(-d2.x, -d2.y);
                     w = __ffma2_rn(w, __ffma2_rn(nd2, w, one2), w);
+#endif
                 }
                 const float2 i3 = __fmul2_rn(__fmul2_rn(w, w), w);
                 a6[r] = __ffma2_rn(i3, i3, a6[r]);
