@@ -29,6 +29,9 @@ from mcsce_b200.system import build_system
 _rotamer_library = None
 _ptm_rotamer_lib = None
 
+#: conformers grown per device launch sequence; larger ensembles are processed in chunks of this size
+MAX_CONFORMERS_PER_LAUNCH = 4096
+
 # kept for API compatibility: level 0 = the input structure, level i+1 = with residue i's side chain
 sidechain_placeholders = []
 energy_calculators = []
@@ -142,14 +145,23 @@ def _grow(backbone_coords, beta, n_conf):
     first = _state.get("next_conf", 0)
     _state["next_conf"] = first + n_conf
     single = sharding.world()[1] == 1
-    if hi > lo:
-        # one rank: results straight into pinned host memory; several ranks: keep them on the device for the gather
-        out = eng.grow(hi - lo, beta, seed=_state.get("seed", 0), conf_id0=first + lo, host_out=single)
-        local = (out["coords"], out["energy"], out["ok"])
-        if single:
-            local = tuple(x.copy() for x in local)
-    else:
+    parts = []
+    # one rank: results straight into pinned host memory; several ranks: keep them on the device for the gather.
+    # Big requests are grown in chunks so that the device workspace and the pinned staging stay bounded.
+    for c0 in range(lo, hi, MAX_CONFORMERS_PER_LAUNCH):
+        n = min(MAX_CONFORMERS_PER_LAUNCH, hi - c0)
+        out = eng.grow(n, beta, seed=_state.get("seed", 0), conf_id0=first + c0, host_out=single)
+        part = (out["coords"], out["energy"], out["ok"])
+        parts.append(tuple(x.copy() for x in part) if single else tuple(x.clone() for x in part))
+    if not parts:
         local = (np.zeros((0, sysm.n_atoms, 3), np.float32), np.zeros(0), np.zeros(0, np.uint8))
+    elif len(parts) == 1:
+        local = parts[0]
+    elif single:
+        local = tuple(np.concatenate([p[k] for p in parts]) for k in range(3))
+    else:
+        import torch
+        local = tuple(torch.cat([p[k] for p in parts]) for k in range(3))
     return sharding.gather_results(*local, n_total=n_conf)
 
 

@@ -146,6 +146,15 @@ __device__ __forceinline__ double u01_halfopen(unsigned a, unsigned b) {   // [0
 // through the pivot atom (libscbuild.py:44-54), applied to the atoms of the moving set.
 __device__ __forceinline__ void apply_chi_rotations(const TmplDev &tm, int n_rot, const double *chi, int lane, bool has,
                                                     float &x, float &y, float &z) {
+    // sin/cos of all half rotation angles at once: lane k handles rotation k (one float64 sincos per warp
+    // instead of one per rotation), then broadcast
+    double my_sn = 0.0, my_cs = 1.0;
+    if (lane < n_rot) {
+        double rot = tm.ori[lane] - chi[lane] * CUDART_PI / 180.0;      // measured - target (libscbuild.py:47)
+        if (rot > CUDART_PI) rot -= 2.0 * CUDART_PI;
+        else if (rot < -CUDART_PI) rot += 2.0 * CUDART_PI;
+        sincos(rot * 0.5, &my_sn, &my_cs);
+    }
     for (int k = 0; k < n_rot; ++k) {
         const int af = tm.axis_from[k], at = tm.axis_to[k];
         const float fx = __shfl_sync(0xffffffffu, x, af), fy = __shfl_sync(0xffffffffu, y, af), fz = __shfl_sync(0xffffffffu, z, af);
@@ -154,11 +163,7 @@ __device__ __forceinline__ void apply_chi_rotations(const TmplDev &tm, int n_rot
         const float ux = __fsub_rn(px, fx), uy = __fsub_rn(py, fy), uz = __fsub_rn(pz, fz);
         const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)), __fmul_rn(uz, uz)));
         const float ex = __fdiv_rn(ux, nrm), ey = __fdiv_rn(uy, nrm), ez = __fdiv_rn(uz, nrm);
-        double rot = tm.ori[k] - chi[k] * CUDART_PI / 180.0;          // measured - target (libscbuild.py:47)
-        if (rot > CUDART_PI) rot -= 2.0 * CUDART_PI;
-        else if (rot < -CUDART_PI) rot += 2.0 * CUDART_PI;
-        double sn, cs;
-        sincos(rot * 0.5, &sn, &cs);
+        const double sn = __shfl_sync(0xffffffffu, my_sn, k), cs = __shfl_sync(0xffffffffu, my_cs, k);
         const double b2 = sn * (double)(-ex), b3 = sn * (double)(-ey), b4 = sn * (double)(-ez);
         if (has && ((tm.move[k] >> lane) & 1u)) {
             const float dx = __fsub_rn(x, px), dy = __fsub_rn(y, py), dz = __fsub_rn(z, pz);   // float32 (libscbuild.py:44)

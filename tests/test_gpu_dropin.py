@@ -182,3 +182,25 @@ def test_cli_and_bridge(tmp_path):
     assert xyz is not None and xyz.shape[1] == 3 and xyz.shape[0] > len(s)
     with pytest.raises(RuntimeError):
         mcsce_sidechain("MQCKMD", s.coords, mode="nope")
+
+
+def test_large_ensembles_are_grown_in_chunks():
+    from functools import partial
+
+    from mcsce_b200.core import side_chain_builder as scb
+    from mcsce_b200.libs.libenergy import prepare_energy_function
+
+    case = GoldenCase("pep6")
+    s = case.structure()
+    scb.initialize_func_calc(partial(prepare_energy_function, batch_size=16, forcefield=None, terms=["lj", "clash", "coulomb"]), structure=s)
+    scb.set_seed(11)
+    whole = scb._grow(s.coords, case.beta, 13)
+    scb.set_seed(11)
+    old = scb.MAX_CONFORMERS_PER_LAUNCH
+    scb.MAX_CONFORMERS_PER_LAUNCH = 5
+    try:
+        chunked = scb._grow(s.coords, case.beta, 13)
+    finally:
+        scb.MAX_CONFORMERS_PER_LAUNCH = old
+    for a, b in zip(whole, chunked):
+        assert np.array_equal(a, b, equal_nan=True)
