@@ -340,3 +340,32 @@ def test_cuda_graph_replay_equals_direct_launches():
     eng.set_backbone(s.coords)
     back = eng.grow(16, case.beta, seed=1)
     assert np.array_equal(back["energy"].cpu().numpy(), ref[(1, 0)][0], equal_nan=True)
+
+
+@pytest.mark.parametrize("terms", [("lj", "coulomb"), ("coulomb", "clash"), ("lj",), ("clash",)])
+def test_term_subsets_match_oracle(terms):
+    """prepare_energy_function's `terms` switch (libenergy.py:63-70): any subset of lj / clash / coulomb."""
+    from mcsce_b200.chem.tables import load_tables
+    from mcsce_b200.engine import GrowthEngine
+    from mcsce_b200.system import build_system
+    from oracle import ref_numpy as O
+
+    case = GoldenCase("pep12")
+    lib, ptm = library()
+    s = case.structure()
+    sysm = build_system(s, terms=terms, rotamer_library=lib, ptm_library=ptm)
+    eng = GrowthEngine(0).set_system(sysm).set_backbone(s.coords)
+    envs = oracle_env_sequence(case, 0, s, build_system(s, terms=case.terms, rotamer_library=lib, ptm_library=ptm))
+    steps = case.steps_by_level(0)
+    efs = O.prepare_energy_functions(s, terms=terms)
+    for i in list(envs)[:4]:
+        trial = steps[i]["trial"]
+        got = eng.score_trials(i, trial[None], envs[i][None]).cpu().numpy()[0]
+        ref = efs[i + 1].calculate(trial, np.broadcast_to(envs[i][None], (len(trial),) + envs[i].shape))
+        assert np.array_equal(np.isinf(got), np.isinf(ref)), (terms, i)
+        if "clash" not in terms:
+            assert not np.isinf(got).any()
+        fin = np.isfinite(ref)
+        assert within_tol(got[fin], ref[fin]).all(), (terms, i, np.abs(got[fin] - ref[fin]).max())
+    e0 = efs[0].calculate(s.coords[None], s.coords[None, :0])[0]
+    assert abs(eng.input_energy() - e0) <= 1e-9 * max(1.0, abs(e0))
