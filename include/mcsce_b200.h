@@ -113,6 +113,8 @@ typedef struct {
     int32_t no_dedup;              /* 1: score the chi-independent side-chain atoms (HA, CB, ...) in every trial like the
                                       reference does, instead of once per residue (same result, more work) */
     int32_t no_graph;              /* 1: never replay a cached CUDA graph (launch-bound runs do by default) */
+    int32_t no_screen;             /* 1: score every trial against the whole environment; by default a short clash-only pass over
+                                      the atoms near the residue runs first and trials it rejects (+inf either way) are not scored */
 } mcsce_grow_opts;
 
 const char *mcsce_last_error(void);

@@ -47,7 +47,7 @@ class GrowOpts(C.Structure):
         ("n_conf", C.c_int32), ("conf_id0", C.c_int64), ("seed", C.c_uint64), ("beta", C.c_double),
         ("noise_deg", C.c_double), ("d_chis", C.c_void_p), ("d_uniform", C.c_void_p),
         ("d_trial_energy", C.c_void_p), ("d_chis_out", C.c_void_p), ("d_selected", C.c_void_p),
-        ("env_split", C.c_int32), ("no_dedup", C.c_int32), ("no_graph", C.c_int32),
+        ("env_split", C.c_int32), ("no_dedup", C.c_int32), ("no_graph", C.c_int32), ("no_screen", C.c_int32),
     ]
 
 

@@ -86,6 +86,9 @@ struct SysDev {
     const double *chi_mean, *chi_sigma, *prob;
     const float *input_xyz, *rigid_xyz;
     int n_trials_total;
+    // neighbour screen (per backbone): for every grown residue the active environment slots that can come near its
+    // side chain, class-major; scr_prefix[step*(n_cls+1)+c] = start of class c inside the residue's list
+    const int *scr_off, *scr_slot, *scr_prefix;
 };
 
 // Scalars that change from call to call live in device memory so that a captured CUDA graph of a growth can be
@@ -303,7 +306,7 @@ __global__ void __launch_bounds__(128) place_trials_kernel(PlaceArgs a) {
 #define SCORE_R 2                       // trial atoms per thread
 #endif
 #ifndef SCORE_MINB
-#define SCORE_MINB 1                    // min resident blocks per SM asked of the compiler
+#define SCORE_MINB 4                    // min resident blocks per SM asked of the compiler (keeps the kernel at <= 128 registers: 4 CTAs/SM)
 #endif
 #define TILE_A (SCORE_THREADS * SCORE_R)
 #ifndef TILE_E
@@ -337,6 +340,9 @@ struct ScoreArgs {
     const unsigned char *alive;
     int dedup;                         // 1: score chi-independent atoms once per residue (trial 0's copy)
     int fixed_extra_tile;              // 1: they get a tile of their own (the last one); 0: they ride in the last tile
+    unsigned char *screen;             // [set][n_trials] neighbour screen: 1 = the trial clashes with a nearby atom.  Written by
+                                       // the screen pass; the main pass (null = no screen) scores only the trials left
+    const double2 *sp_partial;         // screen pass: the special-pair kernel's results [set][n_trials]; its clash flags are merged in
 };
 
 // Inner loop over one class segment of the staged tile for RR trial atoms of this thread, two
@@ -426,10 +432,11 @@ template <int RR>
 __device__ __forceinline__ void score_tile(const ScoreArgs &a, const float4 *__restrict__ s_env, const int *s_seg, int c_first,
                                            int c_last, const float2 (&nx)[SCORE_R], const float2 (&ny)[SCORE_R],
                                            const float2 (&nz)[SCORE_R], const int (&ci)[SCORE_R], double (&e_lj)[SCORE_R],
-                                           double (&e_c)[SCORE_R], bool (&clash)[SCORE_R]) {
+                                           double (&e_c)[SCORE_R], bool (&clash)[SCORE_R], int part, int rep) {
     const int n_cls = a.s.n_cls;
     for (int c = c_first; c <= c_last; ++c) {
-        const int p0 = s_seg[c] >> 1, p1 = s_seg[c + 1] >> 1;          // padded, pair units
+        const int P0 = s_seg[c] >> 1, np = (s_seg[c + 1] >> 1) - P0;   // padded, pair units
+        const int p0 = P0 + np * part / rep, p1 = P0 + np * (part + 1) / rep;     // this replica's share of the segment
         if (p0 >= p1) continue;
         float thr2[SCORE_R];
         double E6[SCORE_R], E3[SCORE_R], EC[SCORE_R];
@@ -447,15 +454,79 @@ __device__ __forceinline__ void score_tile(const ScoreArgs &a, const float4 *__r
     }
 }
 
-#define TILE_SLOTS (TILE_E + 2 * MAX_CLS)      // staged atoms + one pad per class, even
+// Clash-only variants for the neighbour screen: distances and the running minimum, same decision rule.
+template <int RR>
+__device__ __forceinline__ void clash_segment(const float4 *__restrict__ s_env, int p0, int p1,
+                                              const float2 (&nx)[SCORE_R], const float2 (&ny)[SCORE_R], const float2 (&nz)[SCORE_R],
+                                              const float (&thr2)[SCORE_R], bool (&clash)[SCORE_R]) {
+    float dmin[RR];
+#pragma unroll
+    for (int r = 0; r < RR; ++r) dmin[r] = CUDART_INF_F;
+#pragma unroll kPairUnroll
+    for (int p = p0; p < p1; ++p) {
+        const float4 exy = s_env[2 * p], ezq = s_env[2 * p + 1];
+        const float2 ex = make_float2(exy.x, exy.y), ey = make_float2(exy.z, exy.w), ez = make_float2(ezq.x, ezq.y);
+#pragma unroll
+        for (int r = 0; r < RR; ++r) {
+            const float2 dx = __fadd2_rn(ex, nx[r]), dy = __fadd2_rn(ey, ny[r]), dz = __fadd2_rn(ez, nz[r]);
+            const float2 d2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+            dmin[r] = fminf(dmin[r], fminf(d2.x, d2.y));
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < RR; ++r) {
+        if (dmin[r] < thr2[r] * (1.0f - 1.0e-6f)) clash[r] = true;
+        else if (dmin[r] < thr2[r] * (1.0f + 1.0e-6f)) {
+            for (int p = p0; p < p1; ++p) {
+                const float4 exy = s_env[2 * p], ezq = s_env[2 * p + 1];
+                clash[r] |= dist2_ref(-nx[r].x, -ny[r].x, -nz[r].x, exy.x, exy.z, ezq.x) < thr2[r];
+                clash[r] |= dist2_ref(-nx[r].x, -ny[r].x, -nz[r].x, exy.y, exy.w, ezq.y) < thr2[r];
+            }
+        }
+    }
+}
 
+template <int RR>
+__device__ __forceinline__ void clash_tile(const ScoreArgs &a, const float4 *__restrict__ s_env, const int *s_seg, int c_first,
+                                           int c_last, const float2 (&nx)[SCORE_R], const float2 (&ny)[SCORE_R],
+                                           const float2 (&nz)[SCORE_R], const int (&ci)[SCORE_R], bool (&clash)[SCORE_R],
+                                           int part, int rep) {
+    const int n_cls = a.s.n_cls;
+    for (int c = c_first; c <= c_last; ++c) {
+        const int P0 = s_seg[c] >> 1, np = (s_seg[c + 1] >> 1) - P0;
+        const int p0 = P0 + np * part / rep, p1 = P0 + np * (part + 1) / rep;
+        if (p0 >= p1) continue;
+        float thr2[SCORE_R];
+#pragma unroll
+        for (int r = 0; r < RR; ++r) thr2[r] = __ldg(&a.s.cls_thr2f[ci[r] * n_cls + c]);
+        clash_segment<RR>(s_env, p0, p1, nx, ny, nz, thr2, clash);
+    }
+}
+
+#define TILE_SLOTS (TILE_E + 2 * MAX_CLS)      // staged atoms + one pad per class, even
+#ifndef TILE_REPLICATE
+#define TILE_REPLICATE 0                        // 1: warps a short tile leaves idle take shares of the environment.  Measured +1.5 % on
+                                                // cfg3; off because it makes a trial's float32 partial sums depend on how the tile
+                                                // was cut (1e-6 relative), which the bit-identity tests of screen/dedup rely on
+#endif
+#define SCREEN_WORDS 64                         // trials per residue the screen can index (32 per word)
+
+// SCREEN = false: the scoring pass (energies + clash against every active environment atom), over all trials or - with a
+//                 screen - over the trials the screen left, addressed through a compacted index.
+// SCREEN = true : the neighbour screen, clash test only against the residue's short list of nearby environment atoms
+//                 (grid (trial tiles, n_sets, 1)); a trial flagged here is +inf whatever else it touches, so the
+//                 scoring pass skips it.  A clash the list misses is still found by the scoring pass: the list only
+//                 has to be likely, not complete.
+template <bool SCREEN>
 __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MINB) score_generic_kernel(ScoreArgs a) {
     __shared__ float4 s_env[TILE_SLOTS / 2 * 2];     // pair p: [2p] = x0 x1 y0 y1, [2p+1] = z0 z1 q0 q1
     __shared__ int s_prefix[MAX_CLS + 1];
     __shared__ int s_seg[MAX_CLS + 1];                // padded start of every class segment inside the tile
     __shared__ int s_sp[MAX_SP_ENV];
-    __shared__ double s_e[TILE_A];
+    __shared__ double s_e[SCREEN ? 1 : TILE_A];
     __shared__ unsigned char s_clash[TILE_A];
+    __shared__ unsigned s_mask[SCREEN ? 1 : SCREEN_WORDS];     // surviving trials, one bit each
+    __shared__ int s_cnt[SCREEN ? 2 : SCREEN_WORDS + 1];       // exclusive prefix of their counts per word
 
     const int set = blockIdx.y;
     if (a.alive && !a.alive[set]) return;
@@ -463,42 +534,81 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MINB) score_generic_kerne
     const StepDev &st = a.s.steps[a.step];
     const int n_cls = a.s.n_cls;
     const int n_sc = st.n_sc;
+    const bool compact = !SCREEN && a.screen != nullptr;
 
-    if (tid == 0) {
+    if (SCREEN) {
+        if (tid <= n_cls) s_prefix[tid] = a.s.scr_prefix[a.step * (n_cls + 1) + tid];
+    } else if (tid == 0) {
         int acc = 0;
         for (int c = 0; c < n_cls; ++c) { s_prefix[c] = acc; acc += a.s.cls_active[a.step * n_cls + c]; }
         s_prefix[n_cls] = acc;
     }
     if (tid < MAX_SP_ENV) s_sp[tid] = (tid < st.n_sp_env) ? st.sp_env_slot[tid] : -1;
+    int n_keep = a.n_trials;
+    if (!SCREEN) {
+        if (compact) {
+            const unsigned char *flag = a.screen + (long long)set * a.n_trials;
+            const int n_words = (a.n_trials + 31) >> 5;
+            for (int wb = 0; wb < n_words; wb += SCORE_THREADS / 32) {
+                const int w = wb + (tid >> 5), t = w * 32 + (tid & 31);
+                const unsigned m = __ballot_sync(0xffffffffu, t < a.n_trials && flag[t] == 0);
+                if ((tid & 31) == 0 && w < n_words) s_mask[w] = m;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int acc = 0;
+                for (int w = 0; w < n_words; ++w) { s_cnt[w] = acc; acc += __popc(s_mask[w]); }
+                s_cnt[n_words] = acc;
+            }
+            __syncthreads();
+            n_keep = s_cnt[n_words];
+        }
+    }
     __syncthreads();
     const int n_active = s_prefix[n_cls];
+    // j-th trial this pass scores -> its index among the residue's trials
+    auto trial_of = [&](int j) -> int {
+        if (SCREEN || !compact) return j;
+        int w = 0;
+        while (s_cnt[w + 1] <= j) ++w;
+        return w * 32 + (int)__fns(s_mask[w], 0, j - s_cnt[w] + 1);
+    };
 
     // this block's trial atoms: atom la = r*SCORE_THREADS + tid of the tile.  With dedup the tiles hold only the
     // chi-dependent atoms of whole trials; the chi-independent atoms (trial 0's copy) ride in the free lanes of
     // the last tile, or in one extra tile when that one is full.
     const int n_per = a.dedup ? st.n_var : n_sc;                 // atoms per trial in a tile
     const bool last = blockIdx.x == gridDim.x - 1;
-    const bool extra = a.dedup && a.fixed_extra_tile && last;    // tile of chi-independent atoms only
+    const bool extra = !SCREEN && a.dedup && a.fixed_extra_tile && last;    // tile of chi-independent atoms only
     const int t0 = extra ? 0 : blockIdx.x * a.trials_per_tile;
-    const int nt = extra ? 0 : min(a.trials_per_tile, a.n_trials - t0);
+    const int nt = extra ? 0 : max(0, min(a.trials_per_tile, n_keep - t0));
     const int n_varatoms = nt * n_per;
-    const int n_fixatoms = (a.dedup && last) ? st.n_fix : 0;
+    const int n_fixatoms = (!SCREEN && a.dedup && last) ? st.n_fix : 0;
     const int n_local = n_varatoms + n_fixatoms;
+    if (n_local == 0) return;                                    // every trial of this tile was screened out
     const float4 *trial0 = a.trial + (long long)set * a.trial_set_stride;
-    const float4 *trial = trial0 + (long long)t0 * n_sc;
 
+    // Atom slots are warp-major: warp w owns slots [w*32R, (w+1)*32R), R per lane.  With TILE_REPLICATE a tile whose atoms
+    // fill only Wn of the NW warps is replicated: warp w scores the atoms of warp w % Wn against share w / Wn of every
+    // class segment, and the shares are added when the per-trial sums are formed.
+    constexpr int NW = SCORE_THREADS / 32, WA = 32 * SCORE_R;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int Wn = (n_local + WA - 1) / WA;
+    const int rep = TILE_REPLICATE ? NW / Wn : 1;
+    const bool busy = warp < rep * Wn;
+    const int aw = warp % Wn, part = warp / Wn;
     float2 nx[SCORE_R], ny[SCORE_R], nz[SCORE_R];     // minus the trial atom, duplicated into both halves
     int ci[SCORE_R], katom[SCORE_R];
     double e_lj[SCORE_R], e_c[SCORE_R];
     bool clash[SCORE_R];
 #pragma unroll
     for (int r = 0; r < SCORE_R; ++r) {
-        const int la = r * SCORE_THREADS + tid;
+        const int la = busy ? aw * WA + r * 32 + lane : n_local;
         int k = 0; float4 p = trial0[0];
         if (la < n_varatoms) {
             const int tl = la / n_per, kk = la % n_per;
             k = a.dedup ? st.var_k[kk] : kk;
-            p = trial[tl * n_sc + k];
+            p = trial0[(long long)trial_of(t0 + tl) * n_sc + k];
         } else if (la < n_local) {
             k = st.fix_k[la - n_varatoms];
             p = trial0[k];
@@ -509,16 +619,17 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MINB) score_generic_kerne
         e_lj[r] = 0.0; e_c[r] = 0.0; clash[r] = false;
     }
     // warp-uniform amount of work: rows of the tile this warp has atoms in
-    const int warp_base = tid & ~31;
     int rows = 0;
 #pragma unroll
-    for (int r = 0; r < SCORE_R; ++r) rows += (r * SCORE_THREADS + warp_base < n_local) ? 1 : 0;
+    for (int r = 0; r < SCORE_R; ++r) rows += (busy && aw * WA + r * 32 < n_local) ? 1 : 0;
 
     // environment chunk of this block (active order = class-major prefix order)
-    const int per = (n_active + a.n_split - 1) / a.n_split;
-    const int lo = blockIdx.z * per;
+    const int n_split = SCREEN ? 1 : a.n_split;
+    const int per = (n_active + n_split - 1) / n_split;
+    const int lo = SCREEN ? 0 : blockIdx.z * per;
     const int hi = min(n_active, lo + per);
     const float4 *env = a.env + (long long)set * a.s.n_atoms;
+    const int *scr_slot = SCREEN ? a.s.scr_slot + a.s.scr_off[a.step] : nullptr;
     float *s_flat = reinterpret_cast<float *>(s_env);
 
     for (int tile_lo = lo; tile_lo < hi; tile_lo += TILE_E) {
@@ -545,7 +656,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MINB) score_generic_kerne
             const int ae = tile_lo + e;
             int c_lo = 0, c_hi = n_cls;                     // largest c with prefix[c] <= ae
             while (c_hi - c_lo > 1) { int m = (c_lo + c_hi) >> 1; if (s_prefix[m] <= ae) c_lo = m; else c_hi = m; }
-            const int slot = a.s.cls_start[c_lo] + (ae - s_prefix[c_lo]);
+            const int slot = SCREEN ? scr_slot[ae] : a.s.cls_start[c_lo] + (ae - s_prefix[c_lo]);
             float4 v = env[slot];
             bool special = false;
 #pragma unroll
@@ -559,32 +670,53 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MINB) score_generic_kerne
         { int c_lo = 0, c_hi = n_cls; while (c_hi - c_lo > 1) { int m = (c_lo + c_hi) >> 1; if (s_prefix[m] <= tile_lo) c_lo = m; else c_hi = m; } c_first = c_lo; }
         { int c_lo = 0, c_hi = n_cls; const int last = tile_lo + tile_n - 1;
           while (c_hi - c_lo > 1) { int m = (c_lo + c_hi) >> 1; if (s_prefix[m] <= last) c_lo = m; else c_hi = m; } c_last = c_lo; }
-        if (rows == SCORE_R) score_tile<SCORE_R>(a, s_env, s_seg, c_first, c_last, nx, ny, nz, ci, e_lj, e_c, clash);
-        else if (SCORE_R > 2 && rows >= 2) score_tile<(SCORE_R > 2 ? SCORE_R - 1 : 1)>(a, s_env, s_seg, c_first, c_last, nx, ny, nz, ci, e_lj, e_c, clash);
-        else if (rows >= 1) score_tile<1>(a, s_env, s_seg, c_first, c_last, nx, ny, nz, ci, e_lj, e_c, clash);
+        if (SCREEN) {
+            if (rows == SCORE_R) clash_tile<SCORE_R>(a, s_env, s_seg, c_first, c_last, nx, ny, nz, ci, clash, part, rep);
+            else if (SCORE_R > 2 && rows >= 2) clash_tile<(SCORE_R > 2 ? SCORE_R - 1 : 1)>(a, s_env, s_seg, c_first, c_last, nx, ny, nz, ci, clash, part, rep);
+            else if (rows >= 1) clash_tile<1>(a, s_env, s_seg, c_first, c_last, nx, ny, nz, ci, clash, part, rep);
+        } else {
+            if (rows == SCORE_R) score_tile<SCORE_R>(a, s_env, s_seg, c_first, c_last, nx, ny, nz, ci, e_lj, e_c, clash, part, rep);
+            else if (SCORE_R > 2 && rows >= 2) score_tile<(SCORE_R > 2 ? SCORE_R - 1 : 1)>(a, s_env, s_seg, c_first, c_last, nx, ny, nz, ci, e_lj, e_c, clash, part, rep);
+            else if (rows >= 1) score_tile<1>(a, s_env, s_seg, c_first, c_last, nx, ny, nz, ci, e_lj, e_c, clash, part, rep);
+        }
     }
 
-    // per-atom totals -> per-trial partial sums (fixed order)
+    // per-atom totals -> per-trial partial sums (fixed order: atoms of the trial, then the replicas' shares)
     __syncthreads();
+    const int rstride = Wn * WA;                       // slots of one replica
 #pragma unroll
     for (int r = 0; r < SCORE_R; ++r) {
-        const int la = r * SCORE_THREADS + tid;
-        if (la < n_local) {
-            const double qi = a.s.charge[st.sc_start + katom[r]];
-            s_e[la] = e_lj[r] + COULOMB_PREF * qi * e_c[r];
-            s_clash[la] = clash[r] ? 1 : 0;
+        const int la = aw * WA + r * 32 + lane;
+        if (busy && la < n_local) {
+            if (!SCREEN) {
+                const double qi = a.s.charge[st.sc_start + katom[r]];
+                s_e[part * rstride + la] = e_lj[r] + COULOMB_PREF * qi * e_c[r];
+            }
+            s_clash[part * rstride + la] = clash[r] ? 1 : 0;
         }
     }
     __syncthreads();
+    if (SCREEN) {
+        for (int t = tid; t < nt; t += SCORE_THREADS) {
+            int cl = 0;
+            for (int q = 0; q < rep; ++q)
+                for (int k = 0; k < n_per; ++k) cl |= s_clash[q * rstride + t * n_per + k];
+            if (a.sp_partial[(long long)set * a.n_trials + t0 + t].y != 0.0) cl = 1;     // clash among the special pairs
+            a.screen[(long long)set * a.n_trials + t0 + t] = (unsigned char)cl;
+        }
+        return;
+    }
     const int stride = a.n_trials + (a.dedup ? 1 : 0);
     for (int t = tid; t < nt; t += SCORE_THREADS) {
         double e = 0.0; int cl = 0;
-        for (int k = 0; k < n_per; ++k) { e += s_e[t * n_per + k]; cl |= s_clash[t * n_per + k]; }
-        a.partial[((long long)set * stride + (t0 + t)) * a.n_split + blockIdx.z] = make_double2(e, cl ? 1.0 : 0.0);
+        for (int q = 0; q < rep; ++q)
+            for (int k = 0; k < n_per; ++k) { e += s_e[q * rstride + t * n_per + k]; cl |= s_clash[q * rstride + t * n_per + k]; }
+        a.partial[((long long)set * stride + trial_of(t0 + t)) * a.n_split + blockIdx.z] = make_double2(e, cl ? 1.0 : 0.0);
     }
     if (n_fixatoms > 0 && tid == SCORE_THREADS - 1) {
         double e = 0.0; int cl = 0;
-        for (int k = 0; k < n_fixatoms; ++k) { e += s_e[n_varatoms + k]; cl |= s_clash[n_varatoms + k]; }
+        for (int q = 0; q < rep; ++q)
+            for (int k = 0; k < n_fixatoms; ++k) { e += s_e[q * rstride + n_varatoms + k]; cl |= s_clash[q * rstride + n_varatoms + k]; }
         a.partial[((long long)set * stride + a.n_trials) * a.n_split + blockIdx.z] = make_double2(e, cl ? 1.0 : 0.0);
     }
 }
@@ -678,12 +810,15 @@ struct SelectArgs {
     int *n_dead;                        // conformers that failed so far (read back now and then to re-size the grids)
     unsigned long long *pair_counter;   // [0] algorithmic pairs (the reference's P), [1] pairs actually evaluated
     long long pairs_per_set, pairs_computed_per_set;
+    const unsigned char *screen;        // [set][n_trials] neighbour-screen flags (null = no screen): flagged trials are +inf and were not scored
+    long long pairs_computed_per_kept;  // executed pairs of one trial the screen left (pairs_computed_per_set then holds the rest)
 };
 
 __global__ void __launch_bounds__(128) select_kernel(SelectArgs a) {
     extern __shared__ double s_dyn[];
     double *s_E = s_dyn, *s_w = s_dyn + a.n_trials;
     __shared__ double s_red[4];
+    __shared__ int s_kept[4];
     __shared__ int s_sel;
     const int set = blockIdx.x, tid = threadIdx.x;
     if (a.alive && !a.alive[set]) {
@@ -699,27 +834,36 @@ __global__ void __launch_bounds__(128) select_kernel(SelectArgs a) {
             const double2 p = a.partial[((long long)set * stride + a.n_trials) * a.n_split + zz];
             e_fix += p.x; cl_fix |= (p.y != 0.0);
         }
+    int kept = 0;
     for (int t = tid; t < a.n_trials; t += 128) {
-        const double2 sp = a.sp_partial[(long long)set * a.n_trials + t];
-        double e = sp.x; bool cl = (sp.y != 0.0) || cl_fix;
-        for (int zz = 0; zz < a.n_split; ++zz) {
-            const double2 p = a.partial[((long long)set * stride + t) * a.n_split + zz];
-            e += p.x; cl |= (p.y != 0.0);
+        double e = CUDART_INF;
+        if (!(a.screen && a.screen[(long long)set * a.n_trials + t])) {
+            const double2 sp = a.sp_partial[(long long)set * a.n_trials + t];
+            e = sp.x; bool cl = (sp.y != 0.0) || cl_fix;
+            for (int zz = 0; zz < a.n_split; ++zz) {
+                const double2 p = a.partial[((long long)set * stride + t) * a.n_split + zz];
+                e += p.x; cl |= (p.y != 0.0);
+            }
+            e += e_fix;
+            if (cl) e = CUDART_INF;                           // energies[clash] = inf (libenergy.py:801)
+            ++kept;
         }
-        e += e_fix;
-        if (cl) e = CUDART_INF;                               // energies[clash] = inf (libenergy.py:801)
         s_E[t] = e;
         if (a.trial_energy) a.trial_energy[(long long)set * a.s.n_trials_total + st.trial_off + t] = e;
         mn = fmin(mn, e);
     }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, off));
-    if ((tid & 31) == 0) s_red[tid >> 5] = mn;
+    for (int off = 16; off > 0; off >>= 1) {
+        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+        kept += __shfl_xor_sync(0xffffffffu, kept, off);
+    }
+    if ((tid & 31) == 0) { s_red[tid >> 5] = mn; s_kept[tid >> 5] = kept; }
     __syncthreads();
     mn = fmin(fmin(s_red[0], s_red[1]), fmin(s_red[2], s_red[3]));
     if (tid == 0 && a.pair_counter) {
+        kept = s_kept[0] + s_kept[1] + s_kept[2] + s_kept[3];
         atomicAdd(a.pair_counter, (unsigned long long)a.pairs_per_set);
-        atomicAdd(a.pair_counter + 1, (unsigned long long)a.pairs_computed_per_set);
+        atomicAdd(a.pair_counter + 1, (unsigned long long)(a.pairs_computed_per_set + kept * a.pairs_computed_per_kept));
     }
     if (isinf(mn) || isnan(mn)) {                             // every trial clashes: growth fails (side_chain_builder.py:187)
         if (tid == 0) {
@@ -890,8 +1034,10 @@ struct mcsce_handle_s {
     // host mirrors needed for launch geometry
     std::vector<StepDev> steps;
     std::vector<TmplDev> tmpl_host;
-    std::vector<int> cls_active;
+    std::vector<int> cls_active, slot_of_atom, cls_of_atom, cls_start;
+    std::vector<double> cls_thr;
     std::vector<int> step_n_sp_env;
+    std::vector<int> scr_len;            // neighbour-screen list length per residue (0 = residue not screened)
     int max_trials = 0, max_trial_atoms = 0;
     StepDev *d_steps = nullptr;
     unsigned long long *d_pairs = nullptr;
@@ -1019,6 +1165,10 @@ extern "C" int mcsce_set_system(mcsce_handle h, const mcsce_system_desc *s) {
     if (upload(h, P, s2f.data(), nc2, &d.cls_s2f)) return -1;
     if (upload(h, P, thr2f.data(), nc2, &d.cls_thr2f)) return -1;
     h->cls_active.assign(s->cls_active, s->cls_active + (size_t)(s->n_res + 1) * s->n_cls);
+    h->slot_of_atom.assign(s->slot_of_atom, s->slot_of_atom + s->n_atoms);
+    h->cls_of_atom.assign(s->cls_of_atom, s->cls_of_atom + s->n_atoms);
+    h->cls_start.assign(s->cls_start, s->cls_start + s->n_cls + 1);
+    h->cls_thr.assign(s->cls_thr, s->cls_thr + nc2);
 
     std::vector<TmplDev> tm(s->n_types);
     for (int t = 0; t < s->n_types; ++t) {
@@ -1085,6 +1235,81 @@ __global__ void store_rigid_kernel(const float4 *src, int sc_start, int n_sc, fl
     if (k < n_sc) { rigid[(sc_start + k) * 3] = src[k].x; rigid[(sc_start + k) * 3 + 1] = src[k].y; rigid[(sc_start + k) * 3 + 2] = src[k].z; }
 }
 
+// Neighbour screen lists.  A trial that clashes with any atom is +inf no matter what else it touches, and most clashes
+// are with atoms a few angstrom away, so each grown residue gets a short list of environment slots that can come near
+// its side chain; K2 first tests every trial against that list (clash only) and scores just the survivors.  The list is
+// a heuristic: the scoring pass still tests every pair it evaluates, so a miss costs time, never correctness.
+//   input atoms: known position; side-chain atoms of earlier residues: within their template distance of their CA.
+static int build_screen_lists(mcsce_handle h, const mcsce_backbone_desc *b) {
+    SysDev &d = h->d;
+    const int n_cls = d.n_cls, n_res = d.n_res;
+    double scale = 1.0;
+    if (const char *e = getenv("MCSCE_B200_SCREEN_SCALE")) scale = atof(e);      // tuning knob; 0 disables the screen
+    std::vector<int> off(n_res + 1, 0), slots, prefix((size_t)n_res * (n_cls + 1), 0);
+    h->scr_len.assign(n_res, 0);
+    // every atom: a centre and a radius that bound where it can be
+    std::vector<float> cx((size_t)d.n_atoms * 3, 0.f), rad(d.n_atoms, 0.f);
+    for (int a = 0; a < d.n_input; ++a) for (int k = 0; k < 3; ++k) cx[(size_t)a * 3 + k] = b->input_xyz[(size_t)a * 3 + k];
+    std::vector<float> reach(n_res, 0.f);
+    for (int j = 0; j < n_res; ++j) {
+        const StepDev &sj = h->steps[j];
+        if (sj.kind == 0) continue;
+        const TmplDev &tm = h->tmpl_host[sj.type];
+        for (int p = 0; p < tm.n_atoms; ++p) {
+            const int k = tm.sc_rank[p];
+            if (k < 0 || k >= sj.n_sc) continue;
+            const float r = sqrtf(tm.xyz[p][0] * tm.xyz[p][0] + tm.xyz[p][1] * tm.xyz[p][1] + tm.xyz[p][2] * tm.xyz[p][2]);
+            const int a = sj.sc_start + k;
+            for (int q = 0; q < 3; ++q) cx[(size_t)a * 3 + q] = sj.ca[q];
+            rad[a] = (sj.kind == 2) ? 1.05f * r + 0.2f : r + 0.05f;      // chi rotations change the distance to CA a little
+            reach[j] = std::max(reach[j], rad[a]);
+        }
+    }
+    std::vector<double> thr_i(n_cls);
+    std::vector<std::vector<int>> bucket(n_cls);
+    for (int i = 0; i < n_res && scale > 0.0; ++i) {
+        off[i] = (int)slots.size();
+        const StepDev &si = h->steps[i];
+        if (si.kind != 2 || si.n_trials < 8 || si.n_trials > SCREEN_WORDS * 32) continue;
+        int n_active = 0;
+        for (int c = 0; c < n_cls; ++c) n_active += h->cls_active[(size_t)i * n_cls + c];
+        if (n_active < 256) continue;
+        std::fill(thr_i.begin(), thr_i.end(), 0.0);
+        for (int k = 0; k < si.n_sc; ++k) {
+            const int ck = h->cls_of_atom[si.sc_start + k];
+            for (int c = 0; c < n_cls; ++c) thr_i[c] = std::max(thr_i[c], h->cls_thr[(size_t)ck * n_cls + c]);
+        }
+        for (auto &v : bucket) v.clear();
+        int L = 0;
+        for (int a = 0; a < d.n_atoms; ++a) {
+            const int c = h->cls_of_atom[a], slot = h->slot_of_atom[a];
+            if (slot - h->cls_start[c] >= h->cls_active[(size_t)i * n_cls + c]) continue;        // not placed yet
+            if (!(thr_i[c] > 0.0)) continue;
+            bool special = false;
+            for (int q = 0; q < si.n_sp_env; ++q) special |= (si.sp_env_slot[q] == slot);
+            if (special) continue;
+            const float dx = cx[(size_t)a * 3] - si.ca[0], dy = cx[(size_t)a * 3 + 1] - si.ca[1], dz = cx[(size_t)a * 3 + 2] - si.ca[2];
+            const double lim = scale * (reach[i] + rad[a] + thr_i[c]);
+            if ((double)dx * dx + (double)dy * dy + (double)dz * dz < lim * lim) { bucket[c].push_back(slot); ++L; }
+        }
+        if (L == 0 || (long long)L * 5 > (long long)n_active * 2) continue;     // no gain when the list is most of the environment
+        for (int c = 0; c < n_cls; ++c) {
+            prefix[(size_t)i * (n_cls + 1) + c] = (int)slots.size() - off[i];
+            std::sort(bucket[c].begin(), bucket[c].end());
+            slots.insert(slots.end(), bucket[c].begin(), bucket[c].end());
+        }
+        prefix[(size_t)i * (n_cls + 1) + n_cls] = L;
+        h->scr_len[i] = L;
+    }
+    off[n_res] = (int)slots.size();
+    if (slots.empty()) slots.push_back(0);
+    auto &P = h->bb_allocs;
+    if (upload(h, P, off.data(), off.size(), &d.scr_off)) return -1;
+    if (upload(h, P, slots.data(), slots.size(), &d.scr_slot)) return -1;
+    if (upload(h, P, prefix.data(), prefix.size(), &d.scr_prefix)) return -1;
+    return 0;
+}
+
 extern "C" int mcsce_set_backbone(mcsce_handle h, const mcsce_backbone_desc *b) {
     if (!h || !b) return fail("null argument");
     if (!h->has_sys) return fail("mcsce_set_system must be called first");
@@ -1128,6 +1353,7 @@ extern "C" int mcsce_set_backbone(mcsce_handle h, const mcsce_backbone_desc *b) 
         }
     }
     CK(cudaMemcpy(h->d_steps, h->steps.data(), sizeof(StepDev) * d.n_res, cudaMemcpyHostToDevice));
+    if (build_screen_lists(h, b)) return -1;
     // GLY/ALA side chains have no chi: placed once per backbone with K1 (zero rotations) and shared
     // by every conformer (side_chain_builder.py:164-168)
     {
@@ -1154,10 +1380,11 @@ static inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a
 
 static int trials_per_tile_for(int n_per) { return std::max(1, TILE_A / std::max(1, n_per)); }
 
-static int choose_split(const mcsce_handle h, int step, int n_sets, int n_trials, int forced) {
+static int choose_split(const mcsce_handle h, int step, int n_sets, int n_trials, int forced, bool screened = false) {
     const StepDev &st = h->steps[step];
     int n_active = 0;
     for (int c = 0; c < h->d.n_cls; ++c) n_active += h->cls_active[(size_t)step * h->d.n_cls + c];
+    if (screened) n_trials = std::max(1, (n_trials * 5 + 7) / 8);      // the screen leaves about 5 trials in 8 (measured, cfg3/cfg5)
     const int tiles = (n_trials + trials_per_tile_for(st.n_sc) - 1) / trials_per_tile_for(st.n_sc);   // (upper bound with dedup)
     const long long ctas = (long long)tiles * n_sets;
     int max_split = std::max(1, std::min(32, (n_active + 255) / 256));
@@ -1176,7 +1403,7 @@ static int max_split_for(int n_sets, int sm_count) {
 struct Workspace {
     float4 *env, *trial, *trial2;
     double2 *partial, *sp_partial;
-    unsigned char *alive;
+    unsigned char *alive, *screen;
     double *e_acc;
     double2 *rows, *pairs;
     size_t total;
@@ -1193,6 +1420,7 @@ static Workspace carve(const mcsce_handle h, int n_conf, int max_trials, int max
     w.partial = (double2 *)take((size_t)n_conf * (std::max(1, max_trials) + 1) * ms * sizeof(double2));
     w.sp_partial = (double2 *)take((size_t)n_conf * std::max(1, max_trials) * sizeof(double2));
     w.alive = (unsigned char *)take((size_t)n_conf);
+    w.screen = (unsigned char *)take((size_t)n_conf * std::max(1, max_trials));
     w.e_acc = (double *)take((size_t)n_conf * sizeof(double));
     w.rows = (double2 *)take((size_t)std::max(1, h->d.n_input) * sizeof(double2));
     w.pairs = (double2 *)take((size_t)std::max(1, h->d.n_bb_pairs) * sizeof(double2));
@@ -1253,18 +1481,25 @@ static int launch_place(mcsce_handle h, int step, int n_sets, int n_rows, const 
 
 static int launch_generic(mcsce_handle h, int step, int n_sets, int n_trials, int n_split, const float4 *env,
                           const float4 *trial, long long trial_stride, double2 *partial, const unsigned char *alive,
-                          cudaStream_t st, int dedup = 0) {
+                          cudaStream_t st, int dedup = 0, unsigned char *screen = nullptr, const double2 *sp_partial = nullptr) {
     const StepDev &sd = h->steps[step];
     if (dedup && (sd.n_fix <= 0 || sd.n_var <= 0)) dedup = 0;
     ScoreArgs a{};
     a.s = h->d; a.step = step; a.n_trials = n_trials; a.trials_per_tile = trials_per_tile_for(dedup ? sd.n_var : sd.n_sc);
     a.n_split = n_split; a.env = env; a.trial = trial; a.trial_set_stride = trial_stride; a.partial = partial; a.alive = alive;
-    a.dedup = dedup;
+    a.dedup = dedup; a.screen = screen; a.sp_partial = sp_partial;
     const int tiles = (n_trials + a.trials_per_tile - 1) / a.trials_per_tile;
     const int last_atoms = (n_trials - (tiles - 1) * a.trials_per_tile) * (dedup ? sd.n_var : sd.n_sc);
     a.fixed_extra_tile = (dedup && last_atoms + sd.n_fix > TILE_A) ? 1 : 0;
     dim3 grid(tiles + a.fixed_extra_tile, n_sets, n_split);
-    { ProfScope ps(h, 1, st); score_generic_kernel<<<grid, SCORE_THREADS, 0, st>>>(a); }
+    {
+        ProfScope ps(h, 1, st);
+        if (screen) {      // neighbour screen first: flags the trials the scoring pass can skip
+            score_generic_kernel<true><<<dim3(tiles, n_sets, 1), SCORE_THREADS, 0, st>>>(a);
+            h->launches += 1;
+        }
+        score_generic_kernel<false><<<grid, SCORE_THREADS, 0, st>>>(a);
+    }
     h->launches += 1;
     CK(cudaGetLastError());
     return 0;
@@ -1406,13 +1641,20 @@ static int enqueue_growth(mcsce_handle h, const mcsce_grow_opts *o, const Worksp
             CK(cudaStreamSynchronize(st));
             n_alive = std::max(1, C - *h->h_n_dead);
         }
-        const int split = std::min(ms_alloc, choose_split(h, i, n_alive, T, o->env_split));
+        // neighbour screen: not in the launch-bound (graph) regime, where one more kernel per residue costs more than it saves
+        unsigned char *screen = (!o->no_screen && resync && h->scr_len[i] > 0) ? w.screen : nullptr;
+        const int split = std::min(ms_alloc, choose_split(h, i, n_alive, T, o->env_split, screen != nullptr));
         const int dedup = (sd.n_fix > 0 && sd.n_var > 0 && !o->no_dedup) ? 1 : 0;
-        if (launch_generic(h, i, C, T, split, w.env, trial, trial_stride, w.partial, w.alive, st, dedup)) return -1;
+        if (!screen && launch_generic(h, i, C, T, split, w.env, trial, trial_stride, w.partial, w.alive, st, dedup)) return -1;
         // aux: special pairs (need the environment as updated by the previous selection)
         if (prev >= 0) CK(cudaStreamWaitEvent(aux, h->evS[prev], 0));
         if (launch_special(h, i, C, T, w.env, trial, trial_stride, w.sp_partial, w.alive, aux)) return -1;
         CK(cudaEventRecord(h->evQ[i], aux));
+        // screened residue: the special pairs go first, their clash flags join the screen's, then the scoring pass
+        if (screen) {
+            CK(cudaStreamWaitEvent(st, h->evQ[i], 0));
+            if (launch_generic(h, i, C, T, split, w.env, trial, trial_stride, w.partial, w.alive, st, dedup, screen, w.sp_partial)) return -1;
+        }
         // st: selection
         CK(cudaStreamWaitEvent(st, h->evQ[i], 0));
         SelectArgs a{};
@@ -1425,8 +1667,13 @@ static int enqueue_growth(mcsce_handle h, const mcsce_grow_opts *o, const Worksp
         long long n_active = 0;
         for (int c = 0; c < d.n_cls; ++c) n_active += h->cls_active[(size_t)i * d.n_cls + c];
         a.pairs_per_set = (long long)T * ((long long)sd.n_sc * (sd.n_sc - 1) / 2 + (long long)sd.n_sc * n_active);
-        a.pairs_computed_per_set = dedup ? ((long long)T * sd.n_var + sd.n_fix) * n_active + (long long)T * sd.n_sp
-                                         : (long long)T * sd.n_sc * n_active + (long long)T * sd.n_sp;
+        // executed pairs: chi-independent atoms once, special pairs for every trial, the screen's clash-only pairs at half
+        // weight; plus, per trial the screen left, its chi-dependent atoms against the whole environment
+        const int n_per = dedup ? sd.n_var : sd.n_sc;
+        a.screen = screen;
+        a.pairs_computed_per_kept = (long long)n_per * n_active;
+        a.pairs_computed_per_set = (dedup ? (long long)sd.n_fix * n_active : 0) + (long long)T * sd.n_sp
+                                   + (screen ? (long long)T * n_per * h->scr_len[i] / 2 : 0);
         { ProfScope ps(h, 3, st); select_kernel<<<C, 128, sizeof(double) * 2 * T, st>>>(a); }
         h->launches += 1;
         CK(cudaEventRecord(h->evS[i], st));
@@ -1477,7 +1724,7 @@ extern "C" int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *o, void *d_work
         std::vector<long long> key = {h->table_version, C, (long long)(size_t)d_workspace, (long long)workspace_bytes,
                                       (long long)(size_t)o->d_chis, (long long)(size_t)o->d_uniform,
                                       (long long)(size_t)o->d_trial_energy, (long long)(size_t)o->d_chis_out,
-                                      (long long)(size_t)o->d_selected, o->env_split, o->no_dedup};
+                                      (long long)(size_t)o->d_selected, o->env_split, o->no_dedup, o->no_screen};
         if (!h->graph_exec || key != h->graph_key) {
             if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
             if (!h->cap_stream) CK(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));

@@ -189,7 +189,7 @@ class GrowthEngine:
         return int(self.lib.mcsce_workspace_bytes(self.h, int(n_conf)))
 
     def grow(self, n_conf, beta, seed=0, conf_id0=0, noise_deg=0.5, chis=None, uniforms=None, dump=False,
-             env_split=0, host_out=False, stream=None, no_dedup=False, no_graph=False):
+             env_split=0, host_out=False, stream=None, no_dedup=False, no_graph=False, no_screen=False):
         """Grow ``n_conf`` conformers.  Returns dict(coords (C,N,3) f32 growth order, energy (C,) f64,
         ok (C,) uint8 [, trial_energy, chis, selected]); torch CUDA tensors, or NumPy arrays (pinned
         staging inside the C call) with ``host_out``."""
@@ -203,6 +203,7 @@ class GrowthEngine:
         o.n_conf, o.conf_id0, o.seed, o.beta, o.noise_deg, o.env_split = C_, int(conf_id0), int(seed), float(beta), float(noise_deg), int(env_split)
         o.no_dedup = 1 if no_dedup else 0
         o.no_graph = 1 if no_graph else 0
+        o.no_screen = 1 if no_screen else 0
         keep = []
         if chis is not None:
             ch = torch.as_tensor(np.ascontiguousarray(chis, np.float64), device=self.device)

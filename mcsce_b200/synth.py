@@ -290,9 +290,19 @@ def config_backbone(cfg, spacing=None):
     if cfg in (4, "ptm150"):
         seq = random_sequence(150, 4)
         rng = np.random.default_rng(40)
-        pos = rng.permutation(np.arange(2, 148))[: 3 * len(PTM_SET)]
+        # HYP is a proline: inside an ideal helix its ring always hits the carbonyl O of residue i-4 / i-3 (every trial
+        # clashes, in the reference too), so it sits in the first turn of a helix; PRO is kept out of the interior likewise
+        first_turn = [1, 2, 51, 52, 101, 102]
+        n_each = 3
+        pos = [p for p in rng.permutation(np.arange(3, 148)) if p % 50 > 2][: n_each * (len(PTM_SET) - 1)]
+        others = [r for r in PTM_SET if r != "HYP"]
         for k, p in enumerate(pos):
-            seq[p] = PTM_SET[k % len(PTM_SET)]
+            seq[p] = others[k % len(others)]
+        for p in rng.permutation(first_turn)[:n_each]:
+            seq[p] = "HYP"
+        for p in range(150):
+            if seq[p] == "PRO" and p % 50 > 2:
+                seq[p] = "ALA"
         return helix_bundle_pdb([seq[i:i + 50] for i in range(0, 150, 50)], seed=4, one_chain=True,
                                 spacing=spacing or BUNDLE_SPACING)
     if cfg in (5, "2000"):

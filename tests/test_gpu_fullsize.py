@@ -66,12 +66,13 @@ def test_config3_300_residues_2048_conformers():
     assert not np.array_equal(c["energy"], energy[:64], equal_nan=True)
 
 
-def test_config3_whole_conformer_replay_through_c_oracle():
-    s, sysm, eng, co = _workload(3)
+def _replay_whole_conformers(cfg, n, seed, min_selections):
+    """Grow n conformers on the GPU, feed the chi rows it drew and the same uniforms to the C oracle: every selection
+    and clash decision must agree, per-trial energies within the north-star tolerance (bar the K1 float32 noise)."""
+    s, sysm, eng, co = _workload(cfg)
     rng = np.random.default_rng(5)
-    n = 6
     u = rng.random((n, sysm.n_res))
-    out = eng.grow(n, BETA, seed=11, uniforms=u, dump=True)
+    out = eng.grow(n, BETA, seed=seed, uniforms=u, dump=True)
     ref = co.grow(n, BETA, chis=out["chis"].cpu().numpy(), uniforms=u, dump=True)
     sel = out["selected"].cpu().numpy()
     assert np.array_equal(out["ok"].cpu().numpy(), ref["ok"])
@@ -83,15 +84,35 @@ def test_config3_whole_conformer_replay_through_c_oracle():
             if sel[c, i] < 0:
                 break
             n_sel += 1
-    assert n_sel > 1000
+    assert n_sel > min_selections
     te, tr = out["trial_energy"].cpu().numpy(), ref["trial_energy"]
     both = ~np.isnan(te) & ~np.isnan(tr)
     assert np.array_equal(np.isinf(te[both]), np.isinf(tr[both]))
     fin = both & np.isfinite(tr)
     bad = np.abs(te[fin] - tr[fin]) > np.maximum(1e-3, 1e-5 * np.abs(tr[fin]))
-    print("cfg3 replay: %d trials, %d selections, %d trials outside tolerance, worst %.2fx" % (
-        fin.sum(), n_sel, bad.sum(), (np.abs(te[fin] - tr[fin]) / np.maximum(1e-3, 1e-5 * np.abs(tr[fin]))).max()))
+    print("cfg%s replay: %d trials, %d selections, %d trials outside tolerance, worst %.2fx" % (
+        cfg, fin.sum(), n_sel, bad.sum(), (np.abs(te[fin] - tr[fin]) / np.maximum(1e-3, 1e-5 * np.abs(tr[fin]))).max()))
     assert bad.mean() < 0.03
+
+
+def test_config3_whole_conformer_replay_through_c_oracle():
+    _replay_whole_conformers(3, 6, 11, 1000)
+
+
+def test_config4_150_residues_with_ptm_residues():
+    """SEP, TPO, PTR, H2D, H2E, M3L, KCX, HYP (three of each) among 150 residues: extended rotamer / parameter tables."""
+    s, sysm, eng, co = _workload(4)
+    names = [st.resname for st in sysm.steps]
+    for r in ("SEP", "TPO", "PTR", "H2D", "H2E", "M3L", "KCX", "HYP"):
+        assert names.count(r) >= 3, r
+    n_grow = sum(st.kind == "grow" for st in sysm.steps)
+    a = eng.grow(512, BETA, seed=21, host_out=True)
+    coords, energy, ok = a["coords"].copy(), a["energy"].copy(), a["ok"].copy()
+    assert ok.mean() > 0.2 and np.isfinite(energy[ok == 1]).all()
+    assert _check_rescoring(sysm, co, coords, energy, ok, list(np.where(ok)[0][:8]), n_grow) == 8
+    b = eng.grow(512, BETA, seed=21, host_out=True)
+    assert np.array_equal(b["energy"], energy, equal_nan=True) and np.array_equal(b["coords"], coords)
+    _replay_whole_conformers(4, 8, 13, 400)
 
 
 def test_config5_2000_residues_8_chains():

@@ -318,6 +318,27 @@ def test_chi_independent_atoms_scored_once_equals_full_scoring():
         assert np.allclose(a["energy"].cpu().numpy(), b["energy"].cpu().numpy(), rtol=1e-12, atol=1e-9, equal_nan=True)
 
 
+def test_neighbour_screen_equals_scoring_every_trial():
+    """The clash-only pass over nearby atoms only removes trials that are +inf anyway: per-trial energies, selections,
+    coordinates and totals must be bit-identical with and without it."""
+    import os
+    for name, n in (("helix76", 6), ("std20", 6), ("twochain", 6), ("ptm14", 6)):
+        case, s, sysm, eng = engine_for(name)
+        a = eng.grow(n, case.beta, seed=31, dump=True, no_graph=True)
+        b = eng.grow(n, case.beta, seed=31, dump=True, no_graph=True, no_screen=True)
+        for key in ("selected", "trial_energy", "energy", "coords", "ok"):
+            assert np.array_equal(a[key].cpu().numpy(), b[key].cpu().numpy(), equal_nan=True), (name, key)
+    # the lists are really in use on the 76-residue case (otherwise this test proves nothing)
+    case, s, sysm, eng = engine_for("helix76")
+    eng.counters(reset=True)
+    eng.grow(4, case.beta, seed=5, no_graph=True)
+    with_screen = eng.counters(reset=True, computed=True)
+    eng.grow(4, case.beta, seed=5, no_graph=True, no_screen=True)
+    without = eng.counters(reset=True, computed=True)
+    assert with_screen[1] == without[1]                 # same algorithmic pairs
+    assert with_screen[2] < 0.9 * without[2]            # fewer executed
+
+
 def test_cuda_graph_replay_equals_direct_launches():
     """Launch-bound growths replay a cached CUDA graph; seeds, conformer offsets and beta are read from a device
     parameter block, so one graph serves every call with the same buffers."""
