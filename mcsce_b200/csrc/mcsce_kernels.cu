@@ -77,6 +77,7 @@ struct SysDev {
     const TmplDev *tmpl;
     const int *sp_k, *sp_partner;
     const double *sp_coef;
+    const double *sp_A, *sp_B, *sp_Q;   // the same coefficients, one array each (coalesced loads in the special-pair kernel)
     const float *sp_thr2f;
     const int *resnum;
     int n_bb_pairs;
@@ -144,20 +145,19 @@ __device__ __forceinline__ double u01_halfopen(unsigned a, unsigned b) {   // [0
     return (double)(v & ((1ull << 53) - 1)) * (1.0 / 9007199254740992.0);
 }
 
+// half-angle sine/cosine of chi rotation k: angle = wrap(template dihedral - target)   (libscbuild.py:44-54)
+__device__ __forceinline__ void chi_half_sincos(double ori, double chi_deg, double &sn, double &cs) {
+    double rot = ori - chi_deg * CUDART_PI / 180.0;                   // measured - target (libscbuild.py:47)
+    if (rot > CUDART_PI) rot -= 2.0 * CUDART_PI;
+    else if (rot < -CUDART_PI) rot += 2.0 * CUDART_PI;
+    sincos(rot * 0.5, &sn, &cs);
+}
+
 // chi rotations of one trial held one template atom per lane; float32 storage after every rotation
-// (libscbuild.py:108).  Rotation k: angle = wrap(template dihedral - target) about MINUS the unit axis
-// through the pivot atom (libscbuild.py:44-54), applied to the atoms of the moving set.
-__device__ __forceinline__ void apply_chi_rotations(const TmplDev &tm, int n_rot, const double *chi, int lane, bool has,
-                                                    float &x, float &y, float &z) {
-    // sin/cos of all half rotation angles at once: lane k handles rotation k (one float64 sincos per warp
-    // instead of one per rotation), then broadcast
-    double my_sn = 0.0, my_cs = 1.0;
-    if (lane < n_rot) {
-        double rot = tm.ori[lane] - chi[lane] * CUDART_PI / 180.0;      // measured - target (libscbuild.py:47)
-        if (rot > CUDART_PI) rot -= 2.0 * CUDART_PI;
-        else if (rot < -CUDART_PI) rot += 2.0 * CUDART_PI;
-        sincos(rot * 0.5, &my_sn, &my_cs);
-    }
+// (libscbuild.py:108).  Rotation k turns the atoms of the moving set about MINUS the unit axis through the
+// pivot atom; sn[k], cs[k] = sin, cos of half its angle (warp-uniform).
+__device__ __forceinline__ void apply_chi_rotations(const TmplDev &tm, int n_rot, const double *sn_k, const double *cs_k,
+                                                    int lane, bool has, float &x, float &y, float &z) {
     for (int k = 0; k < n_rot; ++k) {
         const int af = tm.axis_from[k], at = tm.axis_to[k];
         const float fx = __shfl_sync(0xffffffffu, x, af), fy = __shfl_sync(0xffffffffu, y, af), fz = __shfl_sync(0xffffffffu, z, af);
@@ -166,7 +166,7 @@ __device__ __forceinline__ void apply_chi_rotations(const TmplDev &tm, int n_rot
         const float ux = __fsub_rn(px, fx), uy = __fsub_rn(py, fy), uz = __fsub_rn(pz, fz);
         const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)), __fmul_rn(uz, uz)));
         const float ex = __fdiv_rn(ux, nrm), ey = __fdiv_rn(uy, nrm), ez = __fdiv_rn(uz, nrm);
-        const double sn = __shfl_sync(0xffffffffu, my_sn, k), cs = __shfl_sync(0xffffffffu, my_cs, k);
+        const double sn = sn_k[k], cs = cs_k[k];
         const double b2 = sn * (double)(-ex), b3 = sn * (double)(-ey), b4 = sn * (double)(-ez);
         if (has && ((tm.move[k] >> lane) & 1u)) {
             const float dx = __fsub_rn(x, px), dy = __fsub_rn(y, py), dz = __fsub_rn(z, pz);   // float32 (libscbuild.py:44)
@@ -181,16 +181,16 @@ __device__ __forceinline__ void apply_chi_rotations(const TmplDev &tm, int n_rot
 
 // stand-alone template rotation (C-ABI mcsce_rotate_template): all template atoms, template frame, no placement
 __global__ void __launch_bounds__(128) rotate_template_kernel(TmplDev tm, int n_rot, int n_rows, const double *chis, float *out) {
-    const int lane = threadIdx.x & 31;
-    const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
+    __shared__ double s_sn[4][MAX_ROT], s_cs[4][MAX_ROT];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t = blockIdx.x * 4 + warp;
     if (t >= n_rows) return;
     const bool has = lane < tm.n_atoms;
     float x = 0.f, y = 0.f, z = 0.f;
     if (has) { x = tm.xyz[lane][0]; y = tm.xyz[lane][1]; z = tm.xyz[lane][2]; }
-    double chi[MAX_ROT];
-#pragma unroll
-    for (int k = 0; k < MAX_ROT; ++k) chi[k] = (k < n_rot) ? chis[(long long)t * MAX_CHI + k] : 0.0;
-    apply_chi_rotations(tm, n_rot, chi, lane, has, x, y, z);
+    if (lane < n_rot) chi_half_sincos(tm.ori[lane], chis[(long long)t * MAX_CHI + lane], s_sn[warp][lane], s_cs[warp][lane]);
+    __syncwarp();
+    apply_chi_rotations(tm, n_rot, s_sn[warp], s_cs[warp], lane, has, x, y, z);
     if (has) { float *o = out + ((long long)t * tm.n_atoms + lane) * 3; o[0] = x; o[1] = y; o[2] = z; }
 }
 
@@ -207,7 +207,7 @@ __global__ void place_template_kernel(int n, const float *xyz, double q10, doubl
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1: chi -> xyz.   grid (ceil(n_trials/4), n_sets), block 128: one warp per trial row
+// K1: chi -> xyz.   grid (ceil(n_trials/K1_TRIALS), n_sets), block 128: K1_TRIALS trial rows per block
 // ------------------------------------------------------------------------------------------------
 struct PlaceArgs {
     SysDev s;
@@ -223,75 +223,78 @@ struct PlaceArgs {
     const CallParams *cp;     // seed, conformer offset, perturbation sigma (device memory)
 };
 
+#define K1_TRIALS 32          // trial rows per block: the scalar work per (row, chi) - Philox, Box-Muller, the half-angle
+                              // sincos - is done one thread per (row, chi) first, then each warp rotates/places 8 rows
 __global__ void __launch_bounds__(128) place_trials_kernel(PlaceArgs a) {
-    const int lane = threadIdx.x & 31;
-    const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
+    __shared__ double s_sn[K1_TRIALS][MAX_ROT], s_cs[K1_TRIALS][MAX_ROT];
     const int set = blockIdx.y;
-    if (t >= a.n_trials) return;
     if (a.alive && !a.alive[set]) return;
+    const int t0 = blockIdx.x * K1_TRIALS;
     const StepDev &st = a.s.steps[a.step];
     const TmplDev &tm = a.s.tmpl[st.type];
-    const bool has = lane < tm.n_atoms;
-    float x = 0.f, y = 0.f, z = 0.f;
-    if (has) { x = tm.xyz[lane][0]; y = tm.xyz[lane][1]; z = tm.xyz[lane][2]; }
 
-    // --- trial chi row (degrees) ---
-    double chi[MAX_ROT];
-    {
+    // --- phase 1: trial chi rows (degrees) and the rotations' half-angle sin/cos, one thread per (row, chi column) ---
+    for (int idx = threadIdx.x; idx < K1_TRIALS * 8; idx += 128) {
+        const int tl = idx >> 3, c = idx & 7, t = t0 + tl;
+        if (t >= a.n_trials || c >= MAX_CHI) continue;
         const long long row = a.chis_row_off + t;
+        const long long at = (long long)set * a.chis_set_stride + row * MAX_CHI + c;
+        double v = 0.0;
         if (a.chis_in) {
-#pragma unroll
-            for (int k = 0; k < MAX_ROT; ++k)
-                chi[k] = (k < st.n_chi) ? a.chis_in[(long long)set * a.chis_set_stride + row * MAX_CHI + k] : 0.0;
-            if (a.chis_out && lane < MAX_CHI)
-                a.chis_out[(long long)set * a.chis_set_stride + row * MAX_CHI + lane] =
-                    a.chis_in[(long long)set * a.chis_set_stride + row * MAX_CHI + lane];
+            v = a.chis_in[at];
+            if (a.chis_out) a.chis_out[at] = v;
         } else {
             // wrap(mean + sigma*z1) + noise*z2   (rotamer_library.py:155,165 ; side_chain_builder.py:173)
-            double mine = 0.0;
-            if (lane < st.n_chi_lib) {
+            if (c < st.n_chi_lib) {
                 const long long trow = (long long)st.trial_off + t;
                 const long long cid = a.cp->conf_id0 + set;
                 const unsigned long long seed = a.cp->seed;
                 uint4 r = philox4x32(make_uint4((unsigned)cid, (unsigned)(cid >> 32),
-                                                (unsigned)a.step, ((unsigned)t << 3) | (unsigned)lane),
+                                                (unsigned)a.step, ((unsigned)t << 3) | (unsigned)c),
                                      make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
                 double u1 = u01_open(r.x, r.y), u2 = u01_halfopen(r.z, r.w);
                 double rad = sqrt(-2.0 * log(u1)), sn, cs;
                 sincospi(2.0 * u2, &sn, &cs);
-                double v = a.s.chi_mean[trow * MAX_CHI + lane];
-                double sg = a.s.chi_sigma[trow * MAX_CHI + lane];
+                v = a.s.chi_mean[trow * MAX_CHI + c];
+                const double sg = a.s.chi_sigma[trow * MAX_CHI + c];
                 if (sg != 0.0) {
                     v = v + sg * (rad * cs);
                     if (v > 180.0) v -= 360.0;
                     if (v < -180.0) v += 360.0;
                 }
-                mine = v + a.cp->noise_deg * (rad * sn);
-                if (a.chis_out) a.chis_out[(long long)set * a.chis_set_stride + row * MAX_CHI + lane] = mine;
-            } else if (a.chis_out && lane < MAX_CHI) {
-                a.chis_out[(long long)set * a.chis_set_stride + row * MAX_CHI + lane] = 0.0;
+                v = v + a.cp->noise_deg * (rad * sn);
             }
-#pragma unroll
-            for (int k = 0; k < MAX_ROT; ++k) chi[k] = __shfl_sync(0xffffffffu, mine, k);
+            if (a.chis_out) a.chis_out[at] = v;
         }
+        if (c < st.n_chi) chi_half_sincos(tm.ori[c], v, s_sn[tl][c], s_cs[tl][c]);
     }
+    __syncthreads();
 
-    apply_chi_rotations(tm, st.n_chi, chi, lane, has, x, y, z);
-
-    // --- rigid placement: two rotations (first stored to float32) + CA (libcalc.py:465,480-482) ---
-    if (has) {
-        double ox, oy, oz;
-        quat_rotate(st.q1[0], st.q1[1], st.q1[2], st.q1[3], (double)x, (double)y, (double)z, ox, oy, oz);
-        const float rx = __double2float_rn(ox), ry = __double2float_rn(oy), rz = __double2float_rn(oz);
-        quat_rotate(st.q2[0], st.q2[1], st.q2[2], st.q2[3], (double)rx, (double)ry, (double)rz, ox, oy, oz);
-        const int rank = tm.sc_rank[lane];
+    // --- phase 2: one template atom per lane; each warp takes K1_TRIALS/4 rows ---
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool has = lane < tm.n_atoms;
+    float x0 = 0.f, y0 = 0.f, z0 = 0.f;
+    if (has) { x0 = tm.xyz[lane][0]; y0 = tm.xyz[lane][1]; z0 = tm.xyz[lane][2]; }
+    const int rank = has ? tm.sc_rank[lane] : -1;
+    const int n_rot = st.n_chi;
+    float4 *out = a.trial + (long long)set * a.trial_set_stride;
+    for (int j = 0; j < K1_TRIALS / 4; ++j) {
+        const int tl = warp * (K1_TRIALS / 4) + j, t = t0 + tl;
+        if (t >= a.n_trials) break;
+        float x = x0, y = y0, z = z0;
+        apply_chi_rotations(tm, n_rot, s_sn[tl], s_cs[tl], lane, has, x, y, z);
+        // rigid placement: two rotations (first stored to float32) + CA (libcalc.py:465,480-482)
         if (rank >= 0) {
+            double ox, oy, oz;
+            quat_rotate(st.q1[0], st.q1[1], st.q1[2], st.q1[3], (double)x, (double)y, (double)z, ox, oy, oz);
+            const float rx = __double2float_rn(ox), ry = __double2float_rn(oy), rz = __double2float_rn(oz);
+            quat_rotate(st.q2[0], st.q2[1], st.q2[2], st.q2[3], (double)rx, (double)ry, (double)rz, ox, oy, oz);
             float4 o;
             o.x = __double2float_rn(__dadd_rn(ox, (double)st.ca[0]));
             o.y = __double2float_rn(__dadd_rn(oy, (double)st.ca[1]));
             o.z = __double2float_rn(__dadd_rn(oz, (double)st.ca[2]));
             o.w = 0.f;
-            a.trial[(long long)set * a.trial_set_stride + (long long)t * st.n_sc + rank] = o;
+            out[(long long)t * st.n_sc + rank] = o;
         }
     }
 }
@@ -722,7 +725,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MINB) score_generic_kerne
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2s: special pairs in float64.  grid (ceil(n_trials/8), n_sets), block 256: one warp per trial
+// K2s: special pairs in float64.  grid (ceil(n_trials/(8*SP_TPW)), n_sets), block 256: one warp per SP_TPW trials
 // ------------------------------------------------------------------------------------------------
 struct SpecialArgs {
     SysDev s;
@@ -760,31 +763,49 @@ __device__ __forceinline__ double pair_energy_fast(float d2f, double A, double B
     return w3 * (A * w3 - B) + Q * y;
 }
 
+#define SP_TPW 4                        // trials per warp: the pair table entries a lane holds are reused for all of them
 __global__ void __launch_bounds__(256) score_special_kernel(SpecialArgs a) {
     const int lane = threadIdx.x & 31;
-    const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int tb = (blockIdx.x * 8 + (threadIdx.x >> 5)) * SP_TPW;
     const int set = blockIdx.y;
-    if (t >= a.n_trials) return;
+    if (tb >= a.n_trials) return;
     if (a.alive && !a.alive[set]) return;
     const StepDev &st = a.s.steps[a.step];
-    const float4 *trial = a.trial + (long long)set * a.trial_set_stride + (long long)t * st.n_sc;
+    const float4 *trial0 = a.trial + (long long)set * a.trial_set_stride;
     const float4 *env = a.env + (long long)set * a.s.n_atoms;
-    double e = 0.0; bool any = false;
+    const int n_sc = st.n_sc;
+    double e[SP_TPW]; bool any[SP_TPW];
+#pragma unroll
+    for (int i = 0; i < SP_TPW; ++i) { e[i] = 0.0; any[i] = false; }
     for (int p = lane; p < st.n_sp; p += 32) {
-        const int k = a.s.sp_k[st.sp_off + p];
-        const int pa = a.s.sp_partner[st.sp_off + p];
-        const double *cf = a.s.sp_coef + (long long)(st.sp_off + p) * 4;
-        const float4 an = trial[k];
-        const float4 bo = (pa >= 0) ? env[st.sp_env_slot[pa]] : trial[-pa - 1];
-        const float d2 = dist2_ref(an.x, an.y, an.z, bo.x, bo.y, bo.z);
-        any |= d2 < a.s.sp_thr2f[st.sp_off + p];
-        const double A = cf[0], B = cf[1], Q = cf[2];
-        if (A != 0.0 || B != 0.0 || Q != 0.0) e += pair_energy_fast(d2, A, B, Q);
+        const int q = st.sp_off + p;
+        const int k = a.s.sp_k[q];
+        const int pa = a.s.sp_partner[q];
+        const double A = a.s.sp_A[q], B = a.s.sp_B[q], Q = a.s.sp_Q[q];
+        const float thr2 = a.s.sp_thr2f[q];
+        const bool live = (A != 0.0 || B != 0.0 || Q != 0.0);
+        float4 bo_env = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pa >= 0) bo_env = env[st.sp_env_slot[pa]];          // environment partner: the same for every trial
+#pragma unroll
+        for (int i = 0; i < SP_TPW; ++i) {
+            if (tb + i < a.n_trials) {
+                const float4 *trial = trial0 + (long long)(tb + i) * n_sc;
+                const float4 an = trial[k];
+                const float4 bo = (pa >= 0) ? bo_env : trial[-pa - 1];
+                const float d2 = dist2_ref(an.x, an.y, an.z, bo.x, bo.y, bo.z);
+                any[i] |= d2 < thr2;
+                if (live) e[i] += pair_energy_fast(d2, A, B, Q);
+            }
+        }
     }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) e += __shfl_xor_sync(0xffffffffu, e, off);
-    any = __any_sync(0xffffffffu, any);
-    if (lane == 0) a.sp_partial[(long long)set * a.n_trials + t] = make_double2(e, any ? 1.0 : 0.0);
+    for (int i = 0; i < SP_TPW; ++i) {
+        double v = e[i];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        const bool cl = __any_sync(0xffffffffu, any[i]);
+        if (lane == 0 && tb + i < a.n_trials) a.sp_partial[(long long)set * a.n_trials + tb + i] = make_double2(v, cl ? 1.0 : 0.0);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1036,6 +1057,7 @@ struct mcsce_handle_s {
     std::vector<TmplDev> tmpl_host;
     std::vector<int> cls_active, slot_of_atom, cls_of_atom, cls_start;
     std::vector<double> cls_thr;
+    std::vector<int> resnum;
     std::vector<int> step_n_sp_env;
     std::vector<int> scr_len;            // neighbour-screen list length per residue (0 = residue not screened)
     int max_trials = 0, max_trial_atoms = 0;
@@ -1169,6 +1191,7 @@ extern "C" int mcsce_set_system(mcsce_handle h, const mcsce_system_desc *s) {
     h->cls_of_atom.assign(s->cls_of_atom, s->cls_of_atom + s->n_atoms);
     h->cls_start.assign(s->cls_start, s->cls_start + s->n_cls + 1);
     h->cls_thr.assign(s->cls_thr, s->cls_thr + nc2);
+    h->resnum.assign(s->resnum, s->resnum + s->n_atoms);
 
     std::vector<TmplDev> tm(s->n_types);
     for (int t = 0; t < s->n_types; ++t) {
@@ -1210,6 +1233,11 @@ extern "C" int mcsce_set_system(mcsce_handle h, const mcsce_system_desc *s) {
     if (upload(h, P, s->sp_k, s->n_sp_total, &d.sp_k)) return -1;
     if (upload(h, P, s->sp_partner, s->n_sp_total, &d.sp_partner)) return -1;
     if (upload(h, P, s->sp_coef, (size_t)s->n_sp_total * 4, &d.sp_coef)) return -1;
+    for (int c = 0; c < 3; ++c) {
+        std::vector<double> col((size_t)s->n_sp_total);
+        for (int i = 0; i < s->n_sp_total; ++i) col[i] = s->sp_coef[(size_t)i * 4 + c];
+        if (upload(h, P, col.data(), col.size(), c == 0 ? &d.sp_A : c == 1 ? &d.sp_B : &d.sp_Q)) return -1;
+    }
     {
         std::vector<float> t2((size_t)s->n_sp_total);
         for (int i = 0; i < s->n_sp_total; ++i) t2[i] = exact_thr2(s->sp_coef[(size_t)i * 4 + 3]);
@@ -1265,6 +1293,25 @@ static int build_screen_lists(mcsce_handle h, const mcsce_backbone_desc *b) {
             reach[j] = std::max(reach[j], rad[a]);
         }
     }
+    // atom groups with a bounding sphere each (runs of input atoms with one residue number, one side chain per
+    // residue), so that a residue only looks at the atoms of groups that can reach it
+    struct Group { int a0, a1; float c[3], r; };
+    std::vector<Group> groups;
+    auto close_group = [&](int a0, int a1) {
+        Group g{a0, a1, {0.f, 0.f, 0.f}, 0.f};
+        for (int a = a0; a < a1; ++a) for (int k = 0; k < 3; ++k) g.c[k] += cx[(size_t)a * 3 + k] / (float)(a1 - a0);
+        for (int a = a0; a < a1; ++a) {
+            const float dx = cx[(size_t)a * 3] - g.c[0], dy = cx[(size_t)a * 3 + 1] - g.c[1], dz = cx[(size_t)a * 3 + 2] - g.c[2];
+            g.r = std::max(g.r, sqrtf(dx * dx + dy * dy + dz * dz) + rad[a]);
+        }
+        groups.push_back(g);
+    };
+    for (int a = 0, a0 = 0; a <= d.n_input; ++a)
+        if (a == d.n_input || (a > a0 && h->resnum[a] != h->resnum[a0]) || a - a0 >= 64) { if (a > a0) close_group(a0, a); a0 = a; }
+    for (int j = 0; j < n_res; ++j)
+        if (h->steps[j].kind != 0 && h->steps[j].n_sc > 0) close_group(h->steps[j].sc_start, h->steps[j].sc_start + h->steps[j].n_sc);
+    double thr_max = 0.0;
+    for (double v : h->cls_thr) thr_max = std::max(thr_max, v);
     std::vector<double> thr_i(n_cls);
     std::vector<std::vector<int>> bucket(n_cls);
     for (int i = 0; i < n_res && scale > 0.0; ++i) {
@@ -1281,16 +1328,21 @@ static int build_screen_lists(mcsce_handle h, const mcsce_backbone_desc *b) {
         }
         for (auto &v : bucket) v.clear();
         int L = 0;
-        for (int a = 0; a < d.n_atoms; ++a) {
-            const int c = h->cls_of_atom[a], slot = h->slot_of_atom[a];
-            if (slot - h->cls_start[c] >= h->cls_active[(size_t)i * n_cls + c]) continue;        // not placed yet
-            if (!(thr_i[c] > 0.0)) continue;
-            bool special = false;
-            for (int q = 0; q < si.n_sp_env; ++q) special |= (si.sp_env_slot[q] == slot);
-            if (special) continue;
-            const float dx = cx[(size_t)a * 3] - si.ca[0], dy = cx[(size_t)a * 3 + 1] - si.ca[1], dz = cx[(size_t)a * 3 + 2] - si.ca[2];
-            const double lim = scale * (reach[i] + rad[a] + thr_i[c]);
-            if ((double)dx * dx + (double)dy * dy + (double)dz * dz < lim * lim) { bucket[c].push_back(slot); ++L; }
+        for (const Group &g : groups) {
+            const float gx = g.c[0] - si.ca[0], gy = g.c[1] - si.ca[1], gz = g.c[2] - si.ca[2];
+            const double glim = scale * (reach[i] + thr_max) + g.r;
+            if ((double)gx * gx + (double)gy * gy + (double)gz * gz >= glim * glim) continue;
+            for (int a = g.a0; a < g.a1; ++a) {
+                const int c = h->cls_of_atom[a], slot = h->slot_of_atom[a];
+                if (slot - h->cls_start[c] >= h->cls_active[(size_t)i * n_cls + c]) continue;        // not placed yet
+                if (!(thr_i[c] > 0.0)) continue;
+                bool special = false;
+                for (int q = 0; q < si.n_sp_env; ++q) special |= (si.sp_env_slot[q] == slot);
+                if (special) continue;
+                const float dx = cx[(size_t)a * 3] - si.ca[0], dy = cx[(size_t)a * 3 + 1] - si.ca[1], dz = cx[(size_t)a * 3 + 2] - si.ca[2];
+                const double lim = scale * (reach[i] + rad[a] + thr_i[c]);
+                if ((double)dx * dx + (double)dy * dy + (double)dz * dz < lim * lim) { bucket[c].push_back(slot); ++L; }
+            }
         }
         if (L == 0 || (long long)L * 5 > (long long)n_active * 2) continue;     // no gain when the list is most of the environment
         for (int c = 0; c < n_cls; ++c) {
@@ -1302,6 +1354,15 @@ static int build_screen_lists(mcsce_handle h, const mcsce_backbone_desc *b) {
         h->scr_len[i] = L;
     }
     off[n_res] = (int)slots.size();
+    if (getenv("MCSCE_B200_SCREEN_DEBUG")) {
+        long long sl = 0, sa = 0; int ns = 0;
+        for (int i = 0; i < n_res; ++i) if (h->scr_len[i] > 0) {
+            ++ns; sl += h->scr_len[i];
+            for (int c = 0; c < n_cls; ++c) sa += h->cls_active[(size_t)i * n_cls + c];
+        }
+        fprintf(stderr, "[mcsce_b200] neighbour screen: %d residues screened, mean list %.0f of %.0f active atoms\n", ns,
+                ns ? (double)sl / ns : 0.0, ns ? (double)sa / ns : 0.0);
+    }
     if (slots.empty()) slots.push_back(0);
     auto &P = h->bb_allocs;
     if (upload(h, P, off.data(), off.size(), &d.scr_off)) return -1;
@@ -1472,7 +1533,7 @@ static int launch_place(mcsce_handle h, int step, int n_sets, int n_rows, const 
     a.s = h->d; a.step = step; a.n_trials = n_rows; a.chis_in = chis_in; a.chis_set_stride = set_stride;
     a.chis_row_off = row_off; a.chis_out = chis_out; a.trial = trial; a.trial_set_stride = trial_stride;
     a.alive = alive; a.cp = h->d_call;
-    dim3 grid((n_rows + 3) / 4, n_sets);
+    dim3 grid((n_rows + K1_TRIALS - 1) / K1_TRIALS, n_sets);
     { ProfScope ps(h, 0, st); place_trials_kernel<<<grid, 128, 0, st>>>(a); }
     h->launches += 1;
     CK(cudaGetLastError());
@@ -1510,7 +1571,7 @@ static int launch_special(mcsce_handle h, int step, int n_sets, int n_trials, co
     SpecialArgs b{};
     b.s = h->d; b.step = step; b.n_trials = n_trials; b.env = env; b.trial = trial; b.trial_set_stride = trial_stride;
     b.sp_partial = sp_partial; b.alive = alive;
-    dim3 grid2((n_trials + 7) / 8, n_sets);
+    dim3 grid2((n_trials + 8 * SP_TPW - 1) / (8 * SP_TPW), n_sets);
     { ProfScope ps(h, 2, st); score_special_kernel<<<grid2, 256, 0, st>>>(b); }
     h->launches += 1;
     CK(cudaGetLastError());
