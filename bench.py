@@ -199,6 +199,8 @@ def run_ours(args, rank, world, local_rank):
     # ---- end-to-end through the public call with host buffers: set_backbone (H2D of the step's inputs)
     #      + grow_host (D2H of coordinates, energies, flags), every step ----
     e2e_steps = max(1, min(args.steps, 3))
+    eng.set_backbone(s.coords)
+    step(9_999, host=True)               # untimed: first use of the host-buffer path allocates its pinned staging
     barrier()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -257,9 +259,12 @@ def run_ours(args, rank, world, local_rank):
         "flops_per_pair": FLOPS_PER_PAIR, "pairs_per_launch_avg": prof_pairs / max(1, k2_n),
         "launch_ms_avg": k2_ms / max(1, k2_n), "launches": k2_n, "share_of_step": k2_ms / prof_step_ms if prof_step_ms else None,
         "kernel_ms": {k: v[0] for k, v in prof.items()}, "step_ms_in_this_pass": prof_step_ms,
-        "note": "achieved counts ALGORITHMIC pairs (the reference's P, libcalc.py:56); the kernel executes fewer because "
-                "chi-independent atoms (HA, CB) are scored once per residue - see achieved_executed. K1/K2s run on a second "
-                "stream beside K2, so kernel_ms do not add up to the step",
+        "note": "achieved counts ALGORITHMIC pairs (the reference's P, libcalc.py:56) over the K2 launches (neighbour screen + "
+                "scoring pass of a residue, one event pair). The kernel executes fewer: chi-independent atoms (HA, CB) are scored "
+                "once per residue and trials that the clash-only screen rejects (+inf either way) are not scored - "
+                "achieved_executed / frac_executed count the pair evaluations actually done (screen pairs at half weight) and "
+                "are the figure to judge the kernel by. In this pass all kernels are serialised on one stream, so kernel_ms are "
+                "per-kernel times; in the timed steps K1/K2s overlap K2 on a second stream",
         "achieved_executed": executed, "frac_executed": executed / peak_tflops,
         "frac_at_observed_clock": (achieved / (sm_count * 128 * 2 * clocks["sm_mhz"] * 1e6 / 1e12)) if clocks.get("sm_mhz") else None,
     }

@@ -70,6 +70,7 @@ struct TmplDev {
 struct SysDev {
     int n_atoms, n_input, n_res, n_cls, n_types;
     const int *slot_of_atom, *cls_of_atom, *cls_start, *cls_active;
+    const int *cls_prefix;              // [(n_res+1)*(n_cls+1)] exclusive prefix of cls_active per residue
     const double *charge;
     const float *cls_s2f, *cls_thr2f;
     const double *cls_e4, *cls_s2d, *cls_thrd;
@@ -346,6 +347,7 @@ struct ScoreArgs {
     unsigned char *screen;             // [set][n_trials] neighbour screen: 1 = the trial clashes with a nearby atom.  Written by
                                        // the screen pass; the main pass (null = no screen) scores only the trials left
     const double2 *sp_partial;         // screen pass: the special-pair kernel's results [set][n_trials]; its clash flags are merged in
+    int *n_keep;                       // [set] trials the screen left (added up by the screen pass, zeroed again by the selection)
 };
 
 // Inner loop over one class segment of the staged tile for RR trial atoms of this thread, two
@@ -525,7 +527,8 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MINB) score_generic_kerne
     __shared__ float4 s_env[TILE_SLOTS / 2 * 2];     // pair p: [2p] = x0 x1 y0 y1, [2p+1] = z0 z1 q0 q1
     __shared__ int s_prefix[MAX_CLS + 1];
     __shared__ int s_seg[MAX_CLS + 1];                // padded start of every class segment inside the tile
-    __shared__ int s_sp[MAX_SP_ENV];
+    __shared__ int s_chunk[MAX_CLS + 1];              // 32-atom staging chunks before every class segment
+    __shared__ int s_sp[MAX_SP_ENV], s_sp_c[MAX_SP_ENV];
     __shared__ double s_e[SCREEN ? 1 : TILE_A];
     __shared__ unsigned char s_clash[TILE_A];
     __shared__ unsigned s_mask[SCREEN ? 1 : SCREEN_WORDS];     // surviving trials, one bit each
@@ -533,20 +536,31 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MINB) score_generic_kerne
 
     const int set = blockIdx.y;
     if (a.alive && !a.alive[set]) return;
+    const bool compact = !SCREEN && a.screen != nullptr;
+    // tiles beyond the trials the screen left have nothing to do (the last tile may still carry the chi-independent atoms)
+    if (compact && !(a.dedup && blockIdx.x == gridDim.x - 1) && blockIdx.x * a.trials_per_tile >= a.n_keep[set]) return;
     const int tid = threadIdx.x;
     const StepDev &st = a.s.steps[a.step];
     const int n_cls = a.s.n_cls;
     const int n_sc = st.n_sc;
-    const bool compact = !SCREEN && a.screen != nullptr;
 
-    if (SCREEN) {
-        if (tid <= n_cls) s_prefix[tid] = a.s.scr_prefix[a.step * (n_cls + 1) + tid];
-    } else if (tid == 0) {
-        int acc = 0;
-        for (int c = 0; c < n_cls; ++c) { s_prefix[c] = acc; acc += a.s.cls_active[a.step * n_cls + c]; }
-        s_prefix[n_cls] = acc;
+    const int warp = tid >> 5, lane = tid & 31;
+    {   // start of every class in the order the pass walks: the residue's screen list, or the active environment
+        const int *src = (SCREEN ? a.s.scr_prefix : a.s.cls_prefix) + a.step * (n_cls + 1);
+        for (int c = tid; c <= n_cls; c += SCORE_THREADS) s_prefix[c] = src[c];
     }
-    if (tid < MAX_SP_ENV) s_sp[tid] = (tid < st.n_sp_env) ? st.sp_env_slot[tid] : -1;
+    __syncthreads();
+    if (!SCREEN && tid < MAX_SP_ENV) {      // special environment atoms: where they sit in that order (-1: not active)
+        int ae = -1, cc = 0;
+        if (tid < st.n_sp_env) {
+            const int slot = st.sp_env_slot[tid];
+            int c_lo = 0, c_hi = n_cls;       // largest c with cls_start[c] <= slot
+            while (c_hi - c_lo > 1) { int m = (c_lo + c_hi) >> 1; if (a.s.cls_start[m] <= slot) c_lo = m; else c_hi = m; }
+            const int r = slot - a.s.cls_start[c_lo];
+            if (r < s_prefix[c_lo + 1] - s_prefix[c_lo]) { ae = s_prefix[c_lo] + r; cc = c_lo; }
+        }
+        s_sp[tid] = ae; s_sp_c[tid] = cc;
+    }
     int n_keep = a.n_trials;
     if (!SCREEN) {
         if (compact) {
@@ -595,7 +609,6 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MINB) score_generic_kerne
     // fill only Wn of the NW warps is replicated: warp w scores the atoms of warp w % Wn against share w / Wn of every
     // class segment, and the shares are added when the per-trial sums are formed.
     constexpr int NW = SCORE_THREADS / 32, WA = 32 * SCORE_R;
-    const int warp = tid >> 5, lane = tid & 31;
     const int Wn = (n_local + WA - 1) / WA;
     const int rep = TILE_REPLICATE ? NW / Wn : 1;
     const bool busy = warp < rep * Wn;
@@ -636,37 +649,55 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MINB) score_generic_kerne
     float *s_flat = reinterpret_cast<float *>(s_env);
 
     for (int tile_lo = lo; tile_lo < hi; tile_lo += TILE_E) {
-        const int tile_n = min(TILE_E, hi - tile_lo);
+        const int tile_n = min(TILE_E, hi - tile_lo), tile_hi = tile_lo + tile_n;
         __syncthreads();
-        if (tid == 0) {       // padded (even) segment starts of the classes intersecting the tile
-            int acc = 0;
-            for (int c = 0; c < n_cls; ++c) {
-                s_seg[c] = acc;
-                const int len = max(0, min(s_prefix[c + 1], tile_lo + tile_n) - max(s_prefix[c], tile_lo));
-                acc += (len + 1) & ~1;
-            }
-            s_seg[n_cls] = acc;
-        }
-        __syncthreads();
-        if (tid < n_cls) {    // park a dummy in the pad slot of odd-length segments
-            const int len = max(0, min(s_prefix[tid + 1], tile_lo + tile_n) - max(s_prefix[tid], tile_lo));
-            if (len & 1) {
-                const int P = s_seg[tid] + len, pp = P >> 1, hh = P & 1;
-                s_flat[8 * pp + hh] = 1.0e15f; s_flat[8 * pp + 2 + hh] = 1.0e15f; s_flat[8 * pp + 4 + hh] = 1.0e15f; s_flat[8 * pp + 6 + hh] = 0.f;
-            }
-        }
-        for (int e = tid; e < tile_n; e += SCORE_THREADS) {
-            const int ae = tile_lo + e;
-            int c_lo = 0, c_hi = n_cls;                     // largest c with prefix[c] <= ae
-            while (c_hi - c_lo > 1) { int m = (c_lo + c_hi) >> 1; if (s_prefix[m] <= ae) c_lo = m; else c_hi = m; }
-            const int slot = SCREEN ? scr_slot[ae] : a.s.cls_start[c_lo] + (ae - s_prefix[c_lo]);
-            float4 v = env[slot];
-            bool special = false;
+        // Layout of the tile: per class the atoms of [tile_lo, tile_hi) that belong to it, padded to an even count.
+        // Warp 0 scans the padded lengths (s_seg) and the number of 32-atom staging chunks (s_chunk) of the classes.
+        if (tid < 32) {
+            int carry_seg = 0, carry_chunk = 0;
+            for (int c0 = 0; c0 < n_cls; c0 += 32) {
+                const int c = c0 + tid;
+                int len = 0;
+                if (c < n_cls) len = max(0, min(s_prefix[c + 1], tile_hi) - max(s_prefix[c], tile_lo));
+                const int even = (len + 1) & ~1, chunks = (even + 31) >> 5;
+                int xs = even, xc = chunks;
 #pragma unroll
-            for (int q = 0; q < MAX_SP_ENV; ++q) special |= (s_sp[q] == slot);
-            if (special) v = make_float4(1.0e15f, 1.0e15f, 1.0e15f, 0.f);   // scored by the special-pair kernel
-            const int P = s_seg[c_lo] + (ae - max(s_prefix[c_lo], tile_lo)), pp = P >> 1, hh = P & 1;
-            s_flat[8 * pp + hh] = v.x; s_flat[8 * pp + 2 + hh] = v.y; s_flat[8 * pp + 4 + hh] = v.z; s_flat[8 * pp + 6 + hh] = v.w;
+                for (int off = 1; off < 32; off <<= 1) {
+                    const int ys = __shfl_up_sync(0xffffffffu, xs, off), yc = __shfl_up_sync(0xffffffffu, xc, off);
+                    if (tid >= off) { xs += ys; xc += yc; }
+                }
+                if (c < n_cls) { s_seg[c] = carry_seg + xs - even; s_chunk[c] = carry_chunk + xc - chunks; }
+                carry_seg += __shfl_sync(0xffffffffu, xs, 31);
+                carry_chunk += __shfl_sync(0xffffffffu, xc, 31);
+            }
+            if (tid == 0) { s_seg[n_cls] = carry_seg; s_chunk[n_cls] = carry_chunk; }
+        }
+        __syncthreads();
+        {   // staging: a warp takes whole chunks, so the class of a chunk is found once per 32 atoms
+            const int n_chunks = s_chunk[n_cls];
+            int c = 0;
+            for (int q = warp; q < n_chunks; q += SCORE_THREADS / 32) {
+                while (s_chunk[c + 1] <= q) ++c;
+                const int first = max(s_prefix[c], tile_lo);              // position of the class's first atom of this tile
+                const int len = min(s_prefix[c + 1], tile_hi) - first;
+                const int e = ((q - s_chunk[c]) << 5) + lane;
+                if (e < ((len + 1) & ~1)) {
+                    float4 v = make_float4(1.0e15f, 1.0e15f, 1.0e15f, 0.f);  // pad slot of an odd segment: a parked dummy
+                    if (e < len) v = env[SCREEN ? scr_slot[first + e] : a.s.cls_start[c] + (first - s_prefix[c]) + e];
+                    const int P = s_seg[c] + e, pp = P >> 1, hh = P & 1;
+                    s_flat[8 * pp + hh] = v.x; s_flat[8 * pp + 2 + hh] = v.y; s_flat[8 * pp + 4 + hh] = v.z; s_flat[8 * pp + 6 + hh] = v.w;
+                }
+            }
+        }
+        if (!SCREEN && st.n_sp_env > 0) {      // the special environment atoms are scored by the special-pair kernel: park them
+            __syncthreads();
+            if (tid < st.n_sp_env) {
+                const int ae = s_sp[tid], c = s_sp_c[tid];
+                if (ae >= tile_lo && ae < tile_hi) {
+                    const int P = s_seg[c] + (ae - max(s_prefix[c], tile_lo)), pp = P >> 1, hh = P & 1;
+                    s_flat[8 * pp + hh] = 1.0e15f; s_flat[8 * pp + 2 + hh] = 1.0e15f; s_flat[8 * pp + 4 + hh] = 1.0e15f; s_flat[8 * pp + 6 + hh] = 0.f;
+                }
+            }
         }
         __syncthreads();
         int c_first, c_last;
@@ -700,13 +731,17 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MINB) score_generic_kerne
     }
     __syncthreads();
     if (SCREEN) {
+        int kept = 0;
         for (int t = tid; t < nt; t += SCORE_THREADS) {
             int cl = 0;
             for (int q = 0; q < rep; ++q)
                 for (int k = 0; k < n_per; ++k) cl |= s_clash[q * rstride + t * n_per + k];
             if (a.sp_partial[(long long)set * a.n_trials + t0 + t].y != 0.0) cl = 1;     // clash among the special pairs
             a.screen[(long long)set * a.n_trials + t0 + t] = (unsigned char)cl;
+            kept += cl ? 0 : 1;
         }
+        kept = __reduce_add_sync(0xffffffffu, kept);
+        if (lane == 0 && kept) atomicAdd(a.n_keep + set, kept);
         return;
     }
     const int stride = a.n_trials + (a.dedup ? 1 : 0);
@@ -833,6 +868,7 @@ struct SelectArgs {
     long long pairs_per_set, pairs_computed_per_set;
     const unsigned char *screen;        // [set][n_trials] neighbour-screen flags (null = no screen): flagged trials are +inf and were not scored
     long long pairs_computed_per_kept;  // executed pairs of one trial the screen left (pairs_computed_per_set then holds the rest)
+    int *n_keep;                        // [set] the screen's survivor counter, reset here for the next residue
 };
 
 __global__ void __launch_bounds__(128) select_kernel(SelectArgs a) {
@@ -847,6 +883,7 @@ __global__ void __launch_bounds__(128) select_kernel(SelectArgs a) {
         return;
     }
     const StepDev &st = a.s.steps[a.step];
+    if (a.n_keep && tid == 0) a.n_keep[set] = 0;
     double mn = CUDART_INF;
     const int stride = a.n_trials + (a.dedup ? 1 : 0);
     double e_fix = 0.0; bool cl_fix = false;
@@ -1187,6 +1224,13 @@ extern "C" int mcsce_set_system(mcsce_handle h, const mcsce_system_desc *s) {
     if (upload(h, P, s2f.data(), nc2, &d.cls_s2f)) return -1;
     if (upload(h, P, thr2f.data(), nc2, &d.cls_thr2f)) return -1;
     h->cls_active.assign(s->cls_active, s->cls_active + (size_t)(s->n_res + 1) * s->n_cls);
+    {
+        std::vector<int> pre((size_t)(s->n_res + 1) * (s->n_cls + 1), 0);
+        for (int i = 0; i <= s->n_res; ++i)
+            for (int c = 0; c < s->n_cls; ++c)
+                pre[(size_t)i * (s->n_cls + 1) + c + 1] = pre[(size_t)i * (s->n_cls + 1) + c] + s->cls_active[(size_t)i * s->n_cls + c];
+        if (upload(h, P, pre.data(), pre.size(), &d.cls_prefix)) return -1;
+    }
     h->slot_of_atom.assign(s->slot_of_atom, s->slot_of_atom + s->n_atoms);
     h->cls_of_atom.assign(s->cls_of_atom, s->cls_of_atom + s->n_atoms);
     h->cls_start.assign(s->cls_start, s->cls_start + s->n_cls + 1);
@@ -1441,6 +1485,9 @@ static inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a
 
 static int trials_per_tile_for(int n_per) { return std::max(1, TILE_A / std::max(1, n_per)); }
 
+// Environment split of the scoring pass: 1 when the conformers (x trial tiles) fill the GPU, otherwise enough shares of the
+// environment to reach about one resident round of CTAs.  (A rule that also balanced the last round of big launches
+// was measured: no gain on cfg3/cfg5, and it makes the float32 partial sums depend on the number of conformers per GPU.)
 static int choose_split(const mcsce_handle h, int step, int n_sets, int n_trials, int forced, bool screened = false) {
     const StepDev &st = h->steps[step];
     int n_active = 0;
@@ -1465,6 +1512,7 @@ struct Workspace {
     float4 *env, *trial, *trial2;
     double2 *partial, *sp_partial;
     unsigned char *alive, *screen;
+    int *n_keep;
     double *e_acc;
     double2 *rows, *pairs;
     size_t total;
@@ -1482,6 +1530,7 @@ static Workspace carve(const mcsce_handle h, int n_conf, int max_trials, int max
     w.sp_partial = (double2 *)take((size_t)n_conf * std::max(1, max_trials) * sizeof(double2));
     w.alive = (unsigned char *)take((size_t)n_conf);
     w.screen = (unsigned char *)take((size_t)n_conf * std::max(1, max_trials));
+    w.n_keep = (int *)take((size_t)n_conf * sizeof(int));
     w.e_acc = (double *)take((size_t)n_conf * sizeof(double));
     w.rows = (double2 *)take((size_t)std::max(1, h->d.n_input) * sizeof(double2));
     w.pairs = (double2 *)take((size_t)std::max(1, h->d.n_bb_pairs) * sizeof(double2));
@@ -1542,13 +1591,14 @@ static int launch_place(mcsce_handle h, int step, int n_sets, int n_rows, const 
 
 static int launch_generic(mcsce_handle h, int step, int n_sets, int n_trials, int n_split, const float4 *env,
                           const float4 *trial, long long trial_stride, double2 *partial, const unsigned char *alive,
-                          cudaStream_t st, int dedup = 0, unsigned char *screen = nullptr, const double2 *sp_partial = nullptr) {
+                          cudaStream_t st, int dedup = 0, unsigned char *screen = nullptr, const double2 *sp_partial = nullptr,
+                          int *n_keep = nullptr) {
     const StepDev &sd = h->steps[step];
     if (dedup && (sd.n_fix <= 0 || sd.n_var <= 0)) dedup = 0;
     ScoreArgs a{};
     a.s = h->d; a.step = step; a.n_trials = n_trials; a.trials_per_tile = trials_per_tile_for(dedup ? sd.n_var : sd.n_sc);
     a.n_split = n_split; a.env = env; a.trial = trial; a.trial_set_stride = trial_stride; a.partial = partial; a.alive = alive;
-    a.dedup = dedup; a.screen = screen; a.sp_partial = sp_partial;
+    a.dedup = dedup; a.screen = screen; a.sp_partial = sp_partial; a.n_keep = n_keep;
     const int tiles = (n_trials + a.trials_per_tile - 1) / a.trials_per_tile;
     const int last_atoms = (n_trials - (tiles - 1) * a.trials_per_tile) * (dedup ? sd.n_var : sd.n_sc);
     a.fixed_extra_tile = (dedup && last_atoms + sd.n_fix > TILE_A) ? 1 : 0;
@@ -1683,6 +1733,7 @@ static int enqueue_growth(mcsce_handle h, const mcsce_grow_opts *o, const Worksp
     const int ms_alloc = max_split_for(C, h->sm_count);
     int n_alive = C;
     CK(cudaMemsetAsync(h->d_n_dead, 0, sizeof(int), st));
+    CK(cudaMemsetAsync(w.n_keep, 0, sizeof(int) * (size_t)C, st));
     for (int i = 0; i < d.n_res; ++i) {
         const StepDev &sd = h->steps[i];
         if (sd.kind != 2 || sd.n_trials <= 0) continue;
@@ -1704,8 +1755,8 @@ static int enqueue_growth(mcsce_handle h, const mcsce_grow_opts *o, const Worksp
         }
         // neighbour screen: not in the launch-bound (graph) regime, where one more kernel per residue costs more than it saves
         unsigned char *screen = (!o->no_screen && resync && h->scr_len[i] > 0) ? w.screen : nullptr;
-        const int split = std::min(ms_alloc, choose_split(h, i, n_alive, T, o->env_split, screen != nullptr));
         const int dedup = (sd.n_fix > 0 && sd.n_var > 0 && !o->no_dedup) ? 1 : 0;
+        const int split = std::min(ms_alloc, choose_split(h, i, n_alive, T, o->env_split, screen != nullptr));
         if (!screen && launch_generic(h, i, C, T, split, w.env, trial, trial_stride, w.partial, w.alive, st, dedup)) return -1;
         // aux: special pairs (need the environment as updated by the previous selection)
         if (prev >= 0) CK(cudaStreamWaitEvent(aux, h->evS[prev], 0));
@@ -1714,7 +1765,8 @@ static int enqueue_growth(mcsce_handle h, const mcsce_grow_opts *o, const Worksp
         // screened residue: the special pairs go first, their clash flags join the screen's, then the scoring pass
         if (screen) {
             CK(cudaStreamWaitEvent(st, h->evQ[i], 0));
-            if (launch_generic(h, i, C, T, split, w.env, trial, trial_stride, w.partial, w.alive, st, dedup, screen, w.sp_partial)) return -1;
+            if (launch_generic(h, i, C, T, split, w.env, trial, trial_stride, w.partial, w.alive, st, dedup, screen, w.sp_partial,
+                               w.n_keep)) return -1;
         }
         // st: selection
         CK(cudaStreamWaitEvent(st, h->evQ[i], 0));
@@ -1731,7 +1783,7 @@ static int enqueue_growth(mcsce_handle h, const mcsce_grow_opts *o, const Worksp
         // executed pairs: chi-independent atoms once, special pairs for every trial, the screen's clash-only pairs at half
         // weight; plus, per trial the screen left, its chi-dependent atoms against the whole environment
         const int n_per = dedup ? sd.n_var : sd.n_sc;
-        a.screen = screen;
+        a.screen = screen; a.n_keep = w.n_keep;
         a.pairs_computed_per_kept = (long long)n_per * n_active;
         a.pairs_computed_per_set = (dedup ? (long long)sd.n_fix * n_active : 0) + (long long)T * sd.n_sp
                                    + (screen ? (long long)T * n_per * h->scr_len[i] / 2 : 0);
@@ -1806,7 +1858,8 @@ extern "C" int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *o, void *d_work
         CK(cudaGraphLaunch(h->graph_exec, st));
         h->launches += h->graph_launches;
     } else {
-        if (enqueue_growth(h, o, w, st, h->aux, true)) return -1;
+        // while the per-class event timing is on, everything goes to one stream so that each kernel is timed alone
+        if (enqueue_growth(h, o, w, st, h->profiling ? st : h->aux, true)) return -1;
     }
     const long long n = (long long)C * d.n_atoms;
     gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d, C, w.env, d_coords);

@@ -1,20 +1,19 @@
-"""Tile fragmentation of the scoring pass after the screen: lanes and warps doing work in the CTAs that run."""
+"""Tile occupancy of the scoring pass after the screen: how full the CTAs that run are (cfg3 by default)."""
 import sys
 from pathlib import Path
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
 import numpy as np, bench
 from mcsce_b200.engine import GrowthEngine
+from mcsce_b200.chem.tables import load_tables
 wl = sys.argv[1] if len(sys.argv) > 1 else "cfg3"
 s, sysm, n_conf, desc = bench.build_workload(wl)
 eng = GrowthEngine(0).set_system(sysm).set_backbone(s.coords)
 out = eng.grow(64, bench.BETA, seed=1, dump=True)
 te = out["trial_energy"].cpu().numpy()
-tmpl_fix = {}
-tot_atoms = tot_rows = tot_ctas = 0; w_atoms = w_rows = w_cta = 0.0
-hist = np.zeros(9)
-from mcsce_b200.chem.tables import load_tables
 t = load_tables()
+hist_after = np.zeros(5); hist_before = np.zeros(5)       # work-weighted CTAs by warps in use (64 atoms per warp)
+cta_after = cta_before = 0.0; pairs_after = pairs_before = 0.0
 for st in sysm.steps:
     if st.kind != "grow": continue
     o = eng.trial_off[st.index]; T = len(st.prob)
@@ -23,23 +22,20 @@ for st in sysm.steps:
     alive = ~np.isnan(blk).all(axis=1)
     keep = np.isfinite(blk).sum(axis=1)[alive]
     tm = t.templates[st.resname]
-    # chi-dependent atoms: moved by some rotation, except the first pivot
-    mv = set()
-    for prog in tm.chis[:tm.n_sound]:
-        mv |= set(int(x) for x in prog["moving"]) if isinstance(prog, dict) else set()
-    n_var = getattr(st, "n_var", None)
-    if n_var is None:
-        n_var = max(1, st.n_sc - 2)      # HA + CB fixed (approximation)
-    n_fix = st.n_sc - n_var
-    for k in keep:
-        atoms = int(k) * n_var + n_fix
-        ctas = max(1, -(-atoms // 256))
-        for c in range(ctas):
-            a = min(256, atoms - c * 256)
-            # row-major layout: row r = atoms r*128..; warp w has lanes in row r if r*128 + 32w < a
-            rows = sum(1 for r in range(2) for w in range(4) if r * 128 + 32 * w < a)
-            tot_atoms += a; tot_rows += rows; tot_ctas += 1
-            w_atoms += a * n_env; w_rows += rows * n_env; w_cta += n_env
-            hist[rows] += n_env
-print(wl, "lane utilisation (atoms / warp-rows*32): %.3f   warp-row utilisation (rows / CTAs*8): %.3f" % (w_atoms / (w_rows * 32), w_rows / (w_cta * 8)))
-print("work-weighted share of CTAs by active warp-rows (0..8):", np.round(hist / hist.sum(), 3))
+    moved = set()
+    for prog in tm.chis[:min(tm.n_sound, st.n_chi)]:
+        moved |= set(int(x) for x in prog["moving"])
+    if st.n_chi > 0: moved.discard(int(tm.chis[0]["axis"][1]))
+    n_var = sum(1 for p in tm.sc_idx if int(p) in moved); n_fix = st.n_sc - n_var
+    for label, ks in (("after", keep), ("before", np.full(len(keep), T))):
+        for k in ks:
+            atoms = int(k) * n_var + n_fix
+            full, rem = divmod(atoms, 256)
+            tiles = [256] * full + ([rem] if rem else [])
+            for a in tiles:
+                w = -(-a // 64)
+                if label == "after": hist_after[w] += n_env; cta_after += n_env; pairs_after += a * n_env
+                else: hist_before[w] += n_env; cta_before += n_env; pairs_before += a * n_env
+print(wl, "CTA-time share by warps in use (1..4): before", np.round(hist_before[1:] / hist_before.sum(), 3), " after", np.round(hist_after[1:] / hist_after.sum(), 3))
+print("mean atoms per running CTA: before %.0f after %.0f;  CTA-time after/before %.3f; pairs after/before %.3f" % (
+    pairs_before / cta_before, pairs_after / cta_after, cta_after / cta_before, pairs_after / pairs_before))
