@@ -605,21 +605,23 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MINB) score_generic_kerne
     if (n_local == 0) return;                                    // every trial of this tile was screened out
     const float4 *trial0 = a.trial + (long long)set * a.trial_set_stride;
 
-    // Atom slots are warp-major: warp w owns slots [w*32R, (w+1)*32R), R per lane.  With TILE_REPLICATE a tile whose atoms
-    // fill only Wn of the NW warps is replicated: warp w scores the atoms of warp w % Wn against share w / Wn of every
-    // class segment, and the shares are added when the per-trial sums are formed.
+    // Atom slots: row-major, atom la = r*SCORE_THREADS + tid, so a short tile keeps every warp at the same (smaller) number
+    // of rows.  With TILE_REPLICATE they are warp-major instead (warp w owns slots [w*32R, (w+1)*32R)) and a tile whose
+    // atoms fill only Wn of the NW warps is replicated: warp w scores the atoms of warp w % Wn against share w / Wn of
+    // every class segment, and the shares are added when the per-trial sums are formed.
     constexpr int NW = SCORE_THREADS / 32, WA = 32 * SCORE_R;
-    const int Wn = (n_local + WA - 1) / WA;
+    const int Wn = TILE_REPLICATE ? (n_local + WA - 1) / WA : NW;
     const int rep = TILE_REPLICATE ? NW / Wn : 1;
     const bool busy = warp < rep * Wn;
     const int aw = warp % Wn, part = warp / Wn;
+    auto slot_of = [&](int r) -> int { return TILE_REPLICATE ? aw * WA + r * 32 + lane : r * SCORE_THREADS + tid; };
     float2 nx[SCORE_R], ny[SCORE_R], nz[SCORE_R];     // minus the trial atom, duplicated into both halves
     int ci[SCORE_R], katom[SCORE_R];
     double e_lj[SCORE_R], e_c[SCORE_R];
     bool clash[SCORE_R];
 #pragma unroll
     for (int r = 0; r < SCORE_R; ++r) {
-        const int la = busy ? aw * WA + r * 32 + lane : n_local;
+        const int la = busy ? slot_of(r) : n_local;
         int k = 0; float4 p = trial0[0];
         if (la < n_varatoms) {
             const int tl = la / n_per, kk = la % n_per;
@@ -637,7 +639,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MINB) score_generic_kerne
     // warp-uniform amount of work: rows of the tile this warp has atoms in
     int rows = 0;
 #pragma unroll
-    for (int r = 0; r < SCORE_R; ++r) rows += (busy && aw * WA + r * 32 < n_local) ? 1 : 0;
+    for (int r = 0; r < SCORE_R; ++r) rows += (busy && slot_of(r) - lane < n_local) ? 1 : 0;
 
     // environment chunk of this block (active order = class-major prefix order)
     const int n_split = SCREEN ? 1 : a.n_split;
@@ -717,10 +719,10 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MINB) score_generic_kerne
 
     // per-atom totals -> per-trial partial sums (fixed order: atoms of the trial, then the replicas' shares)
     __syncthreads();
-    const int rstride = Wn * WA;                       // slots of one replica
+    const int rstride = TILE_REPLICATE ? Wn * WA : TILE_A;   // slots of one replica
 #pragma unroll
     for (int r = 0; r < SCORE_R; ++r) {
-        const int la = aw * WA + r * 32 + lane;
+        const int la = slot_of(r);
         if (busy && la < n_local) {
             if (!SCREEN) {
                 const double qi = a.s.charge[st.sc_start + katom[r]];
