@@ -526,8 +526,8 @@ template <bool SCREEN>
 __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MINB) score_generic_kernel(ScoreArgs a) {
     __shared__ float4 s_env[TILE_SLOTS / 2 * 2];     // pair p: [2p] = x0 x1 y0 y1, [2p+1] = z0 z1 q0 q1
     __shared__ int s_prefix[MAX_CLS + 1];
-    __shared__ int s_seg[MAX_CLS + 1];                // padded start of every class segment inside the tile
-    __shared__ int s_chunk[MAX_CLS + 1];              // 32-atom staging chunks before every class segment
+    __shared__ int s_seg2[2][MAX_CLS + 1];            // padded start of every class segment inside the tile (this tile, next tile)
+    __shared__ int s_chunk2[2][MAX_CLS + 1];          // 32-atom staging chunks before every class segment
     __shared__ int s_sp[MAX_SP_ENV], s_sp_c[MAX_SP_ENV];
     __shared__ double s_e[SCREEN ? 1 : TILE_A];
     __shared__ unsigned char s_clash[TILE_A];
@@ -650,31 +650,34 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MINB) score_generic_kerne
     const int *scr_slot = SCREEN ? a.s.scr_slot + a.s.scr_off[a.step] : nullptr;
     float *s_flat = reinterpret_cast<float *>(s_env);
 
-    for (int tile_lo = lo; tile_lo < hi; tile_lo += TILE_E) {
-        const int tile_n = min(TILE_E, hi - tile_lo), tile_hi = tile_lo + tile_n;
-        __syncthreads();
-        // Layout of the tile: per class the atoms of [tile_lo, tile_hi) that belong to it, padded to an even count.
-        // Warp 0 scans the padded lengths (s_seg) and the number of 32-atom staging chunks (s_chunk) of the classes.
-        if (tid < 32) {
-            int carry_seg = 0, carry_chunk = 0;
-            for (int c0 = 0; c0 < n_cls; c0 += 32) {
-                const int c = c0 + tid;
-                int len = 0;
-                if (c < n_cls) len = max(0, min(s_prefix[c + 1], tile_hi) - max(s_prefix[c], tile_lo));
-                const int even = (len + 1) & ~1, chunks = (even + 31) >> 5;
-                int xs = even, xc = chunks;
+    // Layout of a tile: per class the atoms of [tile_lo, tile_hi) that belong to it, padded to an even count.  Warp 0
+    // scans the padded lengths (s_seg) and the number of 32-atom staging chunks (s_chunk) of the classes - for the first
+    // tile here, for every later tile while the other warps already score the current one (two buffers).
+    auto scan_tile = [&](int buf, int t_lo, int t_hi) {
+        int carry_seg = 0, carry_chunk = 0;
+        for (int c0 = 0; c0 < n_cls; c0 += 32) {
+            const int c = c0 + lane;
+            int len = 0;
+            if (c < n_cls) len = max(0, min(s_prefix[c + 1], t_hi) - max(s_prefix[c], t_lo));
+            const int even = (len + 1) & ~1, chunks = (even + 31) >> 5;
+            int xs = even, xc = chunks;
 #pragma unroll
-                for (int off = 1; off < 32; off <<= 1) {
-                    const int ys = __shfl_up_sync(0xffffffffu, xs, off), yc = __shfl_up_sync(0xffffffffu, xc, off);
-                    if (tid >= off) { xs += ys; xc += yc; }
-                }
-                if (c < n_cls) { s_seg[c] = carry_seg + xs - even; s_chunk[c] = carry_chunk + xc - chunks; }
-                carry_seg += __shfl_sync(0xffffffffu, xs, 31);
-                carry_chunk += __shfl_sync(0xffffffffu, xc, 31);
+            for (int off = 1; off < 32; off <<= 1) {
+                const int ys = __shfl_up_sync(0xffffffffu, xs, off), yc = __shfl_up_sync(0xffffffffu, xc, off);
+                if (lane >= off) { xs += ys; xc += yc; }
             }
-            if (tid == 0) { s_seg[n_cls] = carry_seg; s_chunk[n_cls] = carry_chunk; }
+            if (c < n_cls) { s_seg2[buf][c] = carry_seg + xs - even; s_chunk2[buf][c] = carry_chunk + xc - chunks; }
+            carry_seg += __shfl_sync(0xffffffffu, xs, 31);
+            carry_chunk += __shfl_sync(0xffffffffu, xc, 31);
         }
-        __syncthreads();
+        if (lane == 0) { s_seg2[buf][n_cls] = carry_seg; s_chunk2[buf][n_cls] = carry_chunk; }
+    };
+    if (warp == 0 && lo < hi) scan_tile(0, lo, min(lo + TILE_E, hi));
+    int buf = 0;
+    for (int tile_lo = lo; tile_lo < hi; tile_lo += TILE_E, buf ^= 1) {
+        const int tile_n = min(TILE_E, hi - tile_lo), tile_hi = tile_lo + tile_n;
+        const int *s_seg = s_seg2[buf], *s_chunk = s_chunk2[buf];
+        __syncthreads();          // the scan of this tile is visible; nobody reads the previous tile any more
         {   // staging: a warp takes whole chunks, so the class of a chunk is found once per 32 atoms
             const int n_chunks = s_chunk[n_cls];
             int c = 0;
@@ -690,18 +693,20 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MINB) score_generic_kerne
                     s_flat[8 * pp + hh] = v.x; s_flat[8 * pp + 2 + hh] = v.y; s_flat[8 * pp + 4 + hh] = v.z; s_flat[8 * pp + 6 + hh] = v.w;
                 }
             }
-        }
-        if (!SCREEN && st.n_sp_env > 0) {      // the special environment atoms are scored by the special-pair kernel: park them
-            __syncthreads();
-            if (tid < st.n_sp_env) {
-                const int ae = s_sp[tid], c = s_sp_c[tid];
-                if (ae >= tile_lo && ae < tile_hi) {
-                    const int P = s_seg[c] + (ae - max(s_prefix[c], tile_lo)), pp = P >> 1, hh = P & 1;
-                    s_flat[8 * pp + hh] = 1.0e15f; s_flat[8 * pp + 2 + hh] = 1.0e15f; s_flat[8 * pp + 4 + hh] = 1.0e15f; s_flat[8 * pp + 6 + hh] = 0.f;
+            // the special environment atoms are scored by the special-pair kernel: the thread that staged one parks it
+            if (!SCREEN)
+                for (int j = 0; j < st.n_sp_env; ++j) {
+                    const int ae = s_sp[j], cj = s_sp_c[j];
+                    if (ae < tile_lo || ae >= tile_hi) continue;
+                    const int e = ae - max(s_prefix[cj], tile_lo);
+                    if ((s_chunk[cj] + (e >> 5)) % (SCORE_THREADS / 32) == warp && (e & 31) == lane) {
+                        const int P = s_seg[cj] + e, pp = P >> 1, hh = P & 1;
+                        s_flat[8 * pp + hh] = 1.0e15f; s_flat[8 * pp + 2 + hh] = 1.0e15f; s_flat[8 * pp + 4 + hh] = 1.0e15f; s_flat[8 * pp + 6 + hh] = 0.f;
+                    }
                 }
-            }
         }
-        __syncthreads();
+        __syncthreads();          // tile staged
+        if (warp == 0 && tile_hi < hi) scan_tile(buf ^ 1, tile_hi, min(tile_hi + TILE_E, hi));
         int c_first, c_last;
         { int c_lo = 0, c_hi = n_cls; while (c_hi - c_lo > 1) { int m = (c_lo + c_hi) >> 1; if (s_prefix[m] <= tile_lo) c_lo = m; else c_hi = m; } c_first = c_lo; }
         { int c_lo = 0, c_hi = n_cls; const int last = tile_lo + tile_n - 1;
