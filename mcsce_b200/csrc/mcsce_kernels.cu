@@ -437,11 +437,10 @@ template <int RR>
 __device__ __forceinline__ void score_tile(const ScoreArgs &a, const float4 *__restrict__ s_env, const int *s_seg, int c_first,
                                            int c_last, const float2 (&nx)[SCORE_R], const float2 (&ny)[SCORE_R],
                                            const float2 (&nz)[SCORE_R], const int (&ci)[SCORE_R], double (&e_lj)[SCORE_R],
-                                           double (&e_c)[SCORE_R], bool (&clash)[SCORE_R], int part, int rep) {
+                                           double (&e_c)[SCORE_R], bool (&clash)[SCORE_R]) {
     const int n_cls = a.s.n_cls;
     for (int c = c_first; c <= c_last; ++c) {
-        const int P0 = s_seg[c] >> 1, np = (s_seg[c + 1] >> 1) - P0;   // padded, pair units
-        const int p0 = P0 + np * part / rep, p1 = P0 + np * (part + 1) / rep;     // this replica's share of the segment
+        const int p0 = s_seg[c] >> 1, p1 = s_seg[c + 1] >> 1;          // padded, pair units
         if (p0 >= p1) continue;
         float thr2[SCORE_R];
         double E6[SCORE_R], E3[SCORE_R], EC[SCORE_R];
@@ -494,12 +493,10 @@ __device__ __forceinline__ void clash_segment(const float4 *__restrict__ s_env, 
 template <int RR>
 __device__ __forceinline__ void clash_tile(const ScoreArgs &a, const float4 *__restrict__ s_env, const int *s_seg, int c_first,
                                            int c_last, const float2 (&nx)[SCORE_R], const float2 (&ny)[SCORE_R],
-                                           const float2 (&nz)[SCORE_R], const int (&ci)[SCORE_R], bool (&clash)[SCORE_R],
-                                           int part, int rep) {
+                                           const float2 (&nz)[SCORE_R], const int (&ci)[SCORE_R], bool (&clash)[SCORE_R]) {
     const int n_cls = a.s.n_cls;
     for (int c = c_first; c <= c_last; ++c) {
-        const int P0 = s_seg[c] >> 1, np = (s_seg[c + 1] >> 1) - P0;
-        const int p0 = P0 + np * part / rep, p1 = P0 + np * (part + 1) / rep;
+        const int p0 = s_seg[c] >> 1, p1 = s_seg[c + 1] >> 1;
         if (p0 >= p1) continue;
         float thr2[SCORE_R];
 #pragma unroll
@@ -509,11 +506,6 @@ __device__ __forceinline__ void clash_tile(const ScoreArgs &a, const float4 *__r
 }
 
 #define TILE_SLOTS (TILE_E + 2 * MAX_CLS)      // staged atoms + one pad per class, even
-#ifndef TILE_REPLICATE
-#define TILE_REPLICATE 0                        // 1: warps a short tile leaves idle take shares of the environment.  Measured +1.5 % on
-                                                // cfg3; off because it makes a trial's float32 partial sums depend on how the tile
-                                                // was cut (1e-6 relative), which the bit-identity tests of screen/dedup rely on
-#endif
 #define SCREEN_WORDS 64                         // trials per residue the screen can index (32 per word)
 
 // SCREEN = false: the scoring pass (energies + clash against every active environment atom), over all trials or - with a
@@ -605,23 +597,16 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MINB) score_generic_kerne
     if (n_local == 0) return;                                    // every trial of this tile was screened out
     const float4 *trial0 = a.trial + (long long)set * a.trial_set_stride;
 
-    // Atom slots: row-major, atom la = r*SCORE_THREADS + tid, so a short tile keeps every warp at the same (smaller) number
-    // of rows.  With TILE_REPLICATE they are warp-major instead (warp w owns slots [w*32R, (w+1)*32R)) and a tile whose
-    // atoms fill only Wn of the NW warps is replicated: warp w scores the atoms of warp w % Wn against share w / Wn of
-    // every class segment, and the shares are added when the per-trial sums are formed.
-    constexpr int NW = SCORE_THREADS / 32, WA = 32 * SCORE_R;
-    const int Wn = TILE_REPLICATE ? (n_local + WA - 1) / WA : NW;
-    const int rep = TILE_REPLICATE ? NW / Wn : 1;
-    const bool busy = warp < rep * Wn;
-    const int aw = warp % Wn, part = warp / Wn;
-    auto slot_of = [&](int r) -> int { return TILE_REPLICATE ? aw * WA + r * 32 + lane : r * SCORE_THREADS + tid; };
+    // Atom slots are row-major, atom la = r*SCORE_THREADS + tid, so a short tile keeps every warp at the same (smaller)
+    // number of rows.  (Handing the idle warps of a short tile shares of the environment was measured twice - per class
+    // segment and per quarter of the staged tile - and gained 0-1.5 %: not kept.)
     float2 nx[SCORE_R], ny[SCORE_R], nz[SCORE_R];     // minus the trial atom, duplicated into both halves
     int ci[SCORE_R], katom[SCORE_R];
     double e_lj[SCORE_R], e_c[SCORE_R];
     bool clash[SCORE_R];
 #pragma unroll
     for (int r = 0; r < SCORE_R; ++r) {
-        const int la = busy ? slot_of(r) : n_local;
+        const int la = r * SCORE_THREADS + tid;
         int k = 0; float4 p = trial0[0];
         if (la < n_varatoms) {
             const int tl = la / n_per, kk = la % n_per;
@@ -639,7 +624,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MINB) score_generic_kerne
     // warp-uniform amount of work: rows of the tile this warp has atoms in
     int rows = 0;
 #pragma unroll
-    for (int r = 0; r < SCORE_R; ++r) rows += (busy && slot_of(r) - lane < n_local) ? 1 : 0;
+    for (int r = 0; r < SCORE_R; ++r) rows += (r * SCORE_THREADS + (tid & ~31) < n_local) ? 1 : 0;
 
     // environment chunk of this block (active order = class-major prefix order)
     const int n_split = SCREEN ? 1 : a.n_split;
@@ -712,28 +697,27 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MINB) score_generic_kerne
         { int c_lo = 0, c_hi = n_cls; const int last = tile_lo + tile_n - 1;
           while (c_hi - c_lo > 1) { int m = (c_lo + c_hi) >> 1; if (s_prefix[m] <= last) c_lo = m; else c_hi = m; } c_last = c_lo; }
         if (SCREEN) {
-            if (rows == SCORE_R) clash_tile<SCORE_R>(a, s_env, s_seg, c_first, c_last, nx, ny, nz, ci, clash, part, rep);
-            else if (SCORE_R > 2 && rows >= 2) clash_tile<(SCORE_R > 2 ? SCORE_R - 1 : 1)>(a, s_env, s_seg, c_first, c_last, nx, ny, nz, ci, clash, part, rep);
-            else if (rows >= 1) clash_tile<1>(a, s_env, s_seg, c_first, c_last, nx, ny, nz, ci, clash, part, rep);
+            if (rows == SCORE_R) clash_tile<SCORE_R>(a, s_env, s_seg, c_first, c_last, nx, ny, nz, ci, clash);
+            else if (SCORE_R > 2 && rows >= 2) clash_tile<(SCORE_R > 2 ? SCORE_R - 1 : 1)>(a, s_env, s_seg, c_first, c_last, nx, ny, nz, ci, clash);
+            else if (rows >= 1) clash_tile<1>(a, s_env, s_seg, c_first, c_last, nx, ny, nz, ci, clash);
         } else {
-            if (rows == SCORE_R) score_tile<SCORE_R>(a, s_env, s_seg, c_first, c_last, nx, ny, nz, ci, e_lj, e_c, clash, part, rep);
-            else if (SCORE_R > 2 && rows >= 2) score_tile<(SCORE_R > 2 ? SCORE_R - 1 : 1)>(a, s_env, s_seg, c_first, c_last, nx, ny, nz, ci, e_lj, e_c, clash, part, rep);
-            else if (rows >= 1) score_tile<1>(a, s_env, s_seg, c_first, c_last, nx, ny, nz, ci, e_lj, e_c, clash, part, rep);
+            if (rows == SCORE_R) score_tile<SCORE_R>(a, s_env, s_seg, c_first, c_last, nx, ny, nz, ci, e_lj, e_c, clash);
+            else if (SCORE_R > 2 && rows >= 2) score_tile<(SCORE_R > 2 ? SCORE_R - 1 : 1)>(a, s_env, s_seg, c_first, c_last, nx, ny, nz, ci, e_lj, e_c, clash);
+            else if (rows >= 1) score_tile<1>(a, s_env, s_seg, c_first, c_last, nx, ny, nz, ci, e_lj, e_c, clash);
         }
     }
 
-    // per-atom totals -> per-trial partial sums (fixed order: atoms of the trial, then the replicas' shares)
+    // per-atom totals -> per-trial partial sums (fixed order)
     __syncthreads();
-    const int rstride = TILE_REPLICATE ? Wn * WA : TILE_A;   // slots of one replica
 #pragma unroll
     for (int r = 0; r < SCORE_R; ++r) {
-        const int la = slot_of(r);
-        if (busy && la < n_local) {
+        const int la = r * SCORE_THREADS + tid;
+        if (la < n_local) {
             if (!SCREEN) {
                 const double qi = a.s.charge[st.sc_start + katom[r]];
-                s_e[part * rstride + la] = e_lj[r] + COULOMB_PREF * qi * e_c[r];
+                s_e[la] = e_lj[r] + COULOMB_PREF * qi * e_c[r];
             }
-            s_clash[part * rstride + la] = clash[r] ? 1 : 0;
+            s_clash[la] = clash[r] ? 1 : 0;
         }
     }
     __syncthreads();
@@ -741,8 +725,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MINB) score_generic_kerne
         int kept = 0;
         for (int t = tid; t < nt; t += SCORE_THREADS) {
             int cl = 0;
-            for (int q = 0; q < rep; ++q)
-                for (int k = 0; k < n_per; ++k) cl |= s_clash[q * rstride + t * n_per + k];
+            for (int k = 0; k < n_per; ++k) cl |= s_clash[t * n_per + k];
             if (a.sp_partial[(long long)set * a.n_trials + t0 + t].y != 0.0) cl = 1;     // clash among the special pairs
             a.screen[(long long)set * a.n_trials + t0 + t] = (unsigned char)cl;
             kept += cl ? 0 : 1;
@@ -754,14 +737,12 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MINB) score_generic_kerne
     const int stride = a.n_trials + (a.dedup ? 1 : 0);
     for (int t = tid; t < nt; t += SCORE_THREADS) {
         double e = 0.0; int cl = 0;
-        for (int q = 0; q < rep; ++q)
-            for (int k = 0; k < n_per; ++k) { e += s_e[q * rstride + t * n_per + k]; cl |= s_clash[q * rstride + t * n_per + k]; }
+        for (int k = 0; k < n_per; ++k) { e += s_e[t * n_per + k]; cl |= s_clash[t * n_per + k]; }
         a.partial[((long long)set * stride + trial_of(t0 + t)) * a.n_split + blockIdx.z] = make_double2(e, cl ? 1.0 : 0.0);
     }
     if (n_fixatoms > 0 && tid == SCORE_THREADS - 1) {
         double e = 0.0; int cl = 0;
-        for (int q = 0; q < rep; ++q)
-            for (int k = 0; k < n_fixatoms; ++k) { e += s_e[q * rstride + n_varatoms + k]; cl |= s_clash[q * rstride + n_varatoms + k]; }
+        for (int k = 0; k < n_fixatoms; ++k) { e += s_e[n_varatoms + k]; cl |= s_clash[n_varatoms + k]; }
         a.partial[((long long)set * stride + a.n_trials) * a.n_split + blockIdx.z] = make_double2(e, cl ? 1.0 : 0.0);
     }
 }
