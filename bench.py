@@ -152,6 +152,7 @@ def run_ours(args, rank, world, local_rank):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's version/debug lines must not land on stdout (one JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
