@@ -1,10 +1,13 @@
 // mcsce_b200 — hand-written sm_100a kernels + C ABI for the MCSCE side-chain growth path.
 //
 // Kernels (one launch each per grown residue, all conformers at once):
-//   place_trials_kernel   K1  chi angles -> placed trial side chains          (warp = one trial, lane = one template atom)
-//   score_generic_kernel  K2  trial atoms x environment atoms, generic pairs  (thread = R trial atoms, env tiles in smem)
-//   score_special_kernel  K2s pairs within three bonds + intra-side-chain     (warp = one trial, exact float64)
-//   select_kernel         K3  clash mask + Boltzmann selection + append       (block = one conformer)
+//   place_trials_kernel      K1  chi angles -> placed trial side chains       (block = 32 trial rows, lane = one template atom)
+//   score_special_kernel     K2s pairs within three bonds + intra-side-chain  (warp = 4 trials, exact float64)
+//   score_generic_kernel<1>  K2  neighbour screen: clash test against the atoms near the residue; flags the trials that
+//                                are +inf anyway                               (thread = R trial atoms, list tile in smem)
+//   score_generic_kernel<0>  K2  trial atoms x environment atoms, generic pairs, over the trials the screen left
+//                                                                               (thread = R trial atoms, env tiles in smem)
+//   select_kernel            K3  clash mask + Boltzmann selection + append    (block = one conformer)
 // plus init_env / input_energy / gather kernels.  Reference file:line citations are in
 // include/mcsce_b200.h and DESIGN.md.
 //
