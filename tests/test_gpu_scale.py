@@ -23,10 +23,10 @@ def _setup(pdb_text, retain=()):
     return s, sysm, eng, COracle(sysm, s.coords)
 
 
-def _replay_and_compare(sysm, eng, co, n_conf, seed, env_split=0, max_out_frac=0.03):
+def _replay_and_compare(sysm, eng, co, n_conf, seed, env_split=0, max_out_frac=0.03, no_graph=False):
     rng = np.random.default_rng(seed)
     u = rng.random((n_conf, sysm.n_res))
-    out = eng.grow(n_conf, BETA, seed=seed, uniforms=u, dump=True, env_split=env_split)
+    out = eng.grow(n_conf, BETA, seed=seed, uniforms=u, dump=True, env_split=env_split, no_graph=no_graph)
     chis = out["chis"].cpu().numpy()
     ref = co.grow(n_conf, BETA, chis=chis, uniforms=u, dump=True)
     sel, ok, te = out["selected"].cpu().numpy(), out["ok"].cpu().numpy(), out["trial_energy"].cpu().numpy()
@@ -103,6 +103,50 @@ def test_retained_residues_fix_mode():
     eng = GrowthEngine(0).set_system(sysm).set_backbone(s.coords)
     co = COracle(sysm, s.coords)
     _replay_and_compare(sysm, eng, co, 5, seed=12)
+
+
+def test_direct_launch_regime_with_neighbour_screen_against_oracle():
+    """Small systems replay a CUDA graph without the neighbour screen; with ``no_graph`` they take the path big runs
+    take (screen + compaction of the surviving trials).  Same parity bar against the C oracle: a bundle, a three-chain
+    complex, and a helix with retained residues (their side chains are input atoms of the screen lists)."""
+    from mcsce_b200 import synth
+    from mcsce_b200.chem.tables import load_tables
+    from mcsce_b200.engine import GrowthEngine
+    from mcsce_b200.structure import Structure
+    from mcsce_b200.system import build_system
+    from oracle.growth_c import COracle
+
+    seq = synth.random_sequence(60, 21)
+    s, sysm, eng, co = _setup(synth.helix_bundle_pdb([seq[:30], seq[30:]], seed=21, one_chain=True, spacing=12.0))
+    eng.counters(reset=True)
+    _replay_and_compare(sysm, eng, co, 6, seed=5, no_graph=True)
+    _, alg, done = eng.counters(reset=True, computed=True)
+    assert done < 0.85 * alg                                   # the screen really removed trials
+    seq = synth.random_sequence(45, 33, chain_starts=(0, 15, 30))
+    s, sysm, eng, co = _setup(synth.helix_bundle_pdb([seq[:15], seq[15:30], seq[30:]], seed=33, one_chain=False, spacing=14.0))
+    _replay_and_compare(sysm, eng, co, 4, seed=8, no_graph=True)
+
+    lib, ptm = library()
+    seq = synth.random_sequence(40, 7)
+    bb = Structure(synth.helix_bundle_pdb([seq], seed=7, one_chain=True)).build().remove_side_chains([])
+    sysm0 = build_system(bb, rotamer_library=lib, ptm_library=ptm)
+    eng0 = GrowthEngine(0).set_system(sysm0).set_backbone(bb.coords)
+    out = eng0.grow(16, BETA, seed=4, host_out=True)
+    c = int(np.argmax(out["ok"]))
+    assert out["ok"][c]
+    t = load_tables()
+    full = bb.copy()
+    for st in sysm0.steps:
+        tm = t.templates[st.resname]
+        full.append_atoms([tm.names[k] for k in tm.sc_idx], tm.resname, "A", st.resnum,
+                          out["coords"][c][st.sc_start:st.sc_start + st.n_sc])
+    full.reorder_with_resnum()
+    retain = [5, 6, 20, 21, 33]
+    s = full.remove_side_chains(retain)
+    sysm = build_system(s, retain_idxs=tuple(retain), rotamer_library=lib, ptm_library=ptm)
+    eng = GrowthEngine(0).set_system(sysm).set_backbone(s.coords)
+    co = COracle(sysm, s.coords)
+    _replay_and_compare(sysm, eng, co, 5, seed=12, no_graph=True)
 
 
 def test_all_rigid_and_tiny_cases():
