@@ -110,6 +110,18 @@ def cpu_baseline(s, sysm, n_steps=1, warmup=0, conformers_per_core=1):
             "succeeded_fraction": float(np.mean(ok))}
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+    """The one JSON line of the run, to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def pairs_per_conformer(sysm):
     total = 0
     for st in sysm.steps:
@@ -140,7 +152,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "conformers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_ours(args, rank, world, local_rank):
@@ -297,7 +309,7 @@ def run_ours(args, rank, world, local_rank):
     }
     if cpu:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -312,6 +324,12 @@ def main():
     ap.add_argument("--conformers", type=int, default=0, help="conformers per GPU per step (default: the workload's)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: anything libraries print there (NCCL's version banner, ...) is sent to stderr
+    # by pointing fd 1 at fd 2 for the whole run; the line itself goes to the saved descriptor
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
