@@ -15,7 +15,7 @@ from mcsce_b200._lib import (MAX_CHI, MAX_CHI_ROT, MAX_SC, MAX_SP_ENV, MAX_TMPL,
                              SystemDesc, check, load_library)
 from mcsce_b200.chem.tables import load_tables
 from mcsce_b200.libs.placement import placement_quaternions
-from mcsce_b200.system import placement_backbone
+from mcsce_b200.system import assign_trials, placement_backbone
 
 
 def _ptr(a, typ):
@@ -137,6 +137,8 @@ class GrowthEngine:
         backbone_coords = np.asarray(backbone_coords, dtype=np.float32)
         assert backbone_coords.shape == (sysm.n_input, 3), "backbone atom count mismatch"
         L = sysm.n_res
+        if sysm.rotamer_library is not None:
+            assign_trials(sysm, backbone_coords, t)      # trial sets follow the backbone's phi/psi (side_chain_builder.py:144-147,171)
         bb = placement_backbone(backbone_coords, sysm)
         q1 = np.zeros((L, 4)); q2 = np.zeros((L, 4)); ca = np.zeros((L, 3), np.float32)
         q1[:, 0] = q2[:, 0] = 1.0

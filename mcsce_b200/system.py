@@ -100,6 +100,9 @@ class GrowthSystem:
     cls_start: np.ndarray = None   # (n_cls+1,) slot offsets
     cls_active: np.ndarray = None  # (L+1, n_cls) active atoms of each class when residue i is grown
     bb_pairs: tuple = None       # backbone self-energy special pairs (i, j, coef)
+    rotamer_library: object = None   # libraries the trial sets come from (None: scoring-only system)
+    ptm_library: object = None
+    trial_key: bytes = None          # N/CA/C coordinates the current trial sets were made for
 
     @property
     def n_atoms(self):
@@ -223,16 +226,37 @@ def build_system(structure, retain_idxs=(), terms=("lj", "clash", "coulomb"), ro
         ch_mask = sysm.chains == ch
         sysm.is_nterm |= ch_mask & (sysm.resnums == keys[0])
         sysm.is_cterm |= ch_mask & (sysm.resnums == keys[-1])
+    sysm.rotamer_library, sysm.ptm_library = rotamer_library, ptm_library
     if rotamer_library is not None:
-        for st in steps:
-            if st.kind != "grow":
-                continue
-            mean, sig, prob = rotamer_library.trial_distribution(st.resname, st.phi, st.psi, ptm_library)
-            st.chi_mean, st.chi_sigma, st.prob = np.asarray(mean, float), np.asarray(sig, float), np.asarray(prob, float)
-            st.n_chi_lib = st.chi_mean.shape[1]
-            st.n_chi = min(st.n_chi_lib, tables.templates[st.resname].n_sound)
+        assign_trials(sysm, structure.xyz[:n_input], tables)
     _finalize(sysm, tables)
     return sysm
+
+
+def assign_trials(sysm, input_coords, tables=None):
+    """phi/psi and the trial set of every grown residue for these input-atom coordinates.  The reference derives both
+    from the coordinates handed to every ``create_side_chain_structure`` call (side_chain_builder.py:143-147, 171), so
+    one prepared sequence serves any backbone conformation; ``GrowthEngine.set_backbone`` calls this when the backbone
+    torsion atoms differ from the ones the current tables were made for.  Returns True if anything was recomputed."""
+    tables = tables or load_tables()
+    rounded = _round3_f32(np.asarray(input_coords, dtype=np.float32))     # read back from the 3-decimal table (:143-144)
+    ncac = np.zeros((3 * sysm.n_res, 3), dtype=np.float32)
+    for st in sysm.steps:
+        ncac[3 * st.index:3 * st.index + 3] = rounded[list(st.bb_rows)]
+    key = ncac.tobytes()
+    if sysm.trial_key == key:
+        return False
+    phi, psi = backbone_torsions_deg(ncac)
+    for st in sysm.steps:
+        st.phi, st.psi = float(phi[st.index]), float(psi[st.index])
+        if st.kind != "grow":
+            continue
+        mean, sig, prob = sysm.rotamer_library.trial_distribution(st.resname, st.phi, st.psi, sysm.ptm_library)
+        st.chi_mean, st.chi_sigma, st.prob = np.asarray(mean, float), np.asarray(sig, float), np.asarray(prob, float)
+        st.n_chi_lib = st.chi_mean.shape[1]
+        st.n_chi = min(st.n_chi_lib, tables.templates[st.resname].n_sound)
+    sysm.trial_key = key
+    return True
 
 
 def _finalize(sysm, tables):

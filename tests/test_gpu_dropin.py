@@ -162,6 +162,37 @@ def test_side_chain_builder_entry_points(tmp_path):
     assert callable(f)
 
 
+def test_one_preparation_serves_other_backbone_conformations():
+    """``create_side_chain_structure`` takes the backbone per call (side_chain_builder.py:143-147): growing conformation B
+    after preparing the sequence on conformation A equals preparing on B."""
+    from functools import partial
+
+    from mcsce_b200 import synth
+    from mcsce_b200.core import side_chain_builder as scb
+    from mcsce_b200.libs.libenergy import prepare_energy_function
+    from mcsce_b200.structure import Structure
+
+    seq = ["MET", "LYS", "PHE", "GLU", "LEU", "SER", "ARG", "ASP", "TRP", "GLN", "VAL", "ASN"]
+    a = Structure(synth.small_peptide_pdb(seq, seed=2)).build().remove_side_chains([])
+    b = Structure(synth.small_peptide_pdb(seq, seed=2, phi=-120.0, psi=130.0)).build().remove_side_chains([])
+    creator = partial(prepare_energy_function, batch_size=16, forcefield=None, terms=["lj", "clash", "coulomb"])
+    beta = 1.0 / (300 * 0.008314462)
+
+    def grow_b(prepare_on):
+        scb.initialize_func_calc(creator, structure=prepare_on)
+        scb.set_seed(11)
+        out = [scb.create_side_chain_structure([b.coords, beta, [], None]) for _ in range(4)]
+        return [(ok, e, None if st is None else st.coords.copy()) for st, ok, e, _ in out]
+
+    fresh, reused = grow_b(b), grow_b(a)
+    assert any(ok for ok, _, _ in fresh)
+    for (ok1, e1, x1), (ok2, e2, x2) in zip(fresh, reused):
+        assert ok1 == ok2
+        if ok1:
+            assert e1 == e2 and np.array_equal(x1, x2)
+            assert np.abs(x1[:4] - b.coords[:4]).max() == 0          # grown on B's backbone
+
+
 def test_cli_and_bridge(tmp_path):
     from mcsce_b200 import cli
     from mcsce_b200.mcsce_sidechain import mcsce_sidechain

@@ -151,3 +151,28 @@ def test_engine_refuses_to_run_without_cuda():
 
     with pytest.raises(RuntimeError):
         GrowthEngine(0)
+
+
+def test_trial_sets_follow_the_backbone_handed_in():
+    """The reference derives phi/psi and with them the trial sets from the coordinates of every
+    ``create_side_chain_structure`` call (side_chain_builder.py:143-147, 171): a sequence prepared on one conformation
+    must give, for another conformation, the tables a fresh preparation on that conformation gives."""
+    from mcsce_b200 import synth
+    from mcsce_b200.structure import Structure
+    from mcsce_b200.system import assign_trials, build_system
+
+    lib, ptm = library()
+    seq = ["MET", "LYS", "PHE", "GLU", "LEU", "SER", "ARG", "ASP", "TRP", "GLN", "VAL", "ASN", "SEP", "ILE"]
+    a = Structure(synth.small_peptide_pdb(seq, seed=2)).build().remove_side_chains([])                    # helix
+    b = Structure(synth.small_peptide_pdb(seq, seed=2, phi=-120.0, psi=130.0)).build().remove_side_chains([])   # strand
+    sys_a = build_system(a, rotamer_library=lib, ptm_library=ptm)
+    sys_b = build_system(b, rotamer_library=lib, ptm_library=ptm)
+    assert any(len(x.prob) != len(y.prob) or not np.array_equal(x.chi_mean, y.chi_mean)
+               for x, y in zip(sys_a.steps, sys_b.steps) if x.kind == "grow")
+    assert not assign_trials(sys_a, a.coords)             # same conformation: nothing to do
+    assert assign_trials(sys_a, b.coords)
+    for x, y in zip(sys_a.steps, sys_b.steps):
+        assert (x.phi == y.phi or (np.isnan(x.phi) and np.isnan(y.phi))) and (x.psi == y.psi or (np.isnan(x.psi) and np.isnan(y.psi)))
+        if x.kind == "grow":
+            assert np.array_equal(x.chi_mean, y.chi_mean) and np.array_equal(x.chi_sigma, y.chi_sigma)
+            assert np.array_equal(x.prob, y.prob) and x.n_chi == y.n_chi
