@@ -1091,23 +1091,29 @@ struct mcsce_handle_s {
     int max_trials = 0, max_trial_atoms = 0;
     StepDev *d_steps = nullptr;
     unsigned long long *d_pairs = nullptr;
-    int *d_n_dead = nullptr, *h_n_dead = nullptr;      // device counter + pinned host copy
-    CallParams *d_call = nullptr;
+    int *h_n_dead = nullptr;                           // pinned host copy of a lane's dead-conformer counter
     // cached CUDA graph of one growth (small, launch-bound runs)
     cudaStream_t cap_stream = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
     std::vector<long long> graph_key;
     long long graph_launches = 0;
     long long table_version = 0;
-    double *d_input_energy = nullptr;
     long long launches = 0;
-    // second stream + events: placement (K1, FP64 pipe) and the special-pair kernel of a residue run
-    // beside the generic-pair kernel (FP32 pipe) of the same / previous residue
-    cudaStream_t aux = nullptr;
-    std::vector<cudaEvent_t> evP, evQ, evS;
-    cudaEvent_t ev0 = nullptr;
+    // A lane = what one group of conformers in flight needs: a main stream (lane 0: the caller's), a second stream for
+    // the placement of the next residue and the special-pair kernel, their events, the call's parameter block.  Big calls
+    // run two groups side by side so that the launch tails and the small kernels of one hide under the other's scoring pass.
+    struct Lane {
+        cudaStream_t main = nullptr, aux = nullptr;
+        std::vector<cudaEvent_t> evP, evQ, evS;
+        cudaEvent_t ev0 = nullptr, done = nullptr;
+        CallParams *d_call = nullptr;
+        int *d_n_dead = nullptr;
+        double *d_input_energy = nullptr;
+    } lane[2];
+    const CallParams *cur_call = nullptr;     // parameter block of the lane being enqueued (read by launch_place)
     // optional per-kernel-class device timing (CUDA events on the launch stream)
     bool profiling = false;
+    bool capturing = false;
     std::vector<cudaEvent_t> ev[4];     // 0 place, 1 score_generic, 2 score_special, 3 select: begin/end pairs
 };
 
@@ -1159,10 +1165,13 @@ extern "C" int mcsce_create(mcsce_handle *out, int device) {
     h->sm_count = prop.multiProcessorCount;
     CK(cudaMalloc((void **)&h->d_pairs, 2 * sizeof(unsigned long long)));
     CK(cudaMemset(h->d_pairs, 0, 2 * sizeof(unsigned long long)));
-    CK(cudaMalloc((void **)&h->d_input_energy, sizeof(double)));
-    CK(cudaMalloc((void **)&h->d_n_dead, sizeof(int)));
-    CK(cudaMalloc((void **)&h->d_call, sizeof(CallParams)));
-    CK(cudaMemset(h->d_call, 0, sizeof(CallParams)));
+    for (auto &ln : h->lane) {
+        CK(cudaMalloc((void **)&ln.d_input_energy, sizeof(double)));
+        CK(cudaMalloc((void **)&ln.d_n_dead, sizeof(int)));
+        CK(cudaMalloc((void **)&ln.d_call, sizeof(CallParams)));
+        CK(cudaMemset(ln.d_call, 0, sizeof(CallParams)));
+    }
+    h->cur_call = h->lane[0].d_call;
     CK(cudaMallocHost((void **)&h->h_n_dead, sizeof(int)));
     *out = h;
     return 0;
@@ -1172,16 +1181,20 @@ extern "C" int mcsce_destroy(mcsce_handle h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     free_pool(h->sys_allocs); free_pool(h->bb_allocs);
-    for (auto e : h->evP) cudaEventDestroy(e);
-    for (auto e : h->evQ) cudaEventDestroy(e);
-    for (auto e : h->evS) cudaEventDestroy(e);
-    if (h->ev0) cudaEventDestroy(h->ev0);
-    if (h->aux) cudaStreamDestroy(h->aux);
+    for (auto &ln : h->lane) {
+        for (auto e : ln.evP) cudaEventDestroy(e);
+        for (auto e : ln.evQ) cudaEventDestroy(e);
+        for (auto e : ln.evS) cudaEventDestroy(e);
+        if (ln.ev0) cudaEventDestroy(ln.ev0);
+        if (ln.done) cudaEventDestroy(ln.done);
+        if (ln.aux) cudaStreamDestroy(ln.aux);
+        if (ln.main) cudaStreamDestroy(ln.main);
+        if (ln.d_input_energy) cudaFree(ln.d_input_energy);
+        if (ln.d_n_dead) cudaFree(ln.d_n_dead);
+        if (ln.d_call) cudaFree(ln.d_call);
+    }
     if (h->d_steps) cudaFree(h->d_steps);
     if (h->d_pairs) cudaFree(h->d_pairs);
-    if (h->d_input_energy) cudaFree(h->d_input_energy);
-    if (h->d_n_dead) cudaFree(h->d_n_dead);
-    if (h->d_call) cudaFree(h->d_call);
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
     if (h->h_n_dead) cudaFreeHost(h->h_n_dead);
@@ -1529,9 +1542,17 @@ static Workspace carve(const mcsce_handle h, int n_conf, int max_trials, int max
     return w;
 }
 
+static int lane_count(const mcsce_handle h, int n_conf);
+
 extern "C" size_t mcsce_workspace_bytes(mcsce_handle h, int n_conf) {
     if (!h || !h->has_bb || n_conf <= 0) return 0;
-    return carve(h, n_conf, h->max_trials, h->max_trial_atoms, nullptr).total;
+    size_t whole = carve(h, n_conf, h->max_trials, h->max_trial_atoms, nullptr).total;
+    if (lane_count(h, n_conf) == 2) {        // two conformer groups, each with a complete workspace
+        const int c0 = n_conf / 2;
+        whole = std::max(whole, carve(h, c0, h->max_trials, h->max_trial_atoms, nullptr).total +
+                                carve(h, n_conf - c0, h->max_trials, h->max_trial_atoms, nullptr).total);
+    }
+    return whole;
 }
 
 static int launch_input_energy(mcsce_handle h, double2 *rows, double2 *pairs, double *out, cudaStream_t st) {
@@ -1572,7 +1593,7 @@ static int launch_place(mcsce_handle h, int step, int n_sets, int n_rows, const 
     PlaceArgs a{};
     a.s = h->d; a.step = step; a.n_trials = n_rows; a.chis_in = chis_in; a.chis_set_stride = set_stride;
     a.chis_row_off = row_off; a.chis_out = chis_out; a.trial = trial; a.trial_set_stride = trial_stride;
-    a.alive = alive; a.cp = h->d_call;
+    a.alive = alive; a.cp = h->cur_call;
     dim3 grid((n_rows + K1_TRIALS - 1) / K1_TRIALS, n_sets);
     { ProfScope ps(h, 0, st); place_trials_kernel<<<grid, 128, 0, st>>>(a); }
     h->launches += 1;
@@ -1706,24 +1727,32 @@ extern "C" int mcsce_select(mcsce_handle h, int n_sets, int n_trials, const doub
 
 // Enqueue the whole growth (environment init, input-atom energy, then K1/K2/K2s/K3 for every grown residue) on
 // `st` + `aux`.  `resync` allows the occasional read-back of the number of dead conformers (never while capturing).
-static int enqueue_growth(mcsce_handle h, const mcsce_grow_opts *o, const Workspace &w, cudaStream_t st, cudaStream_t aux,
-                          bool resync) {
+static int enqueue_growth(mcsce_handle h, const mcsce_grow_opts *o, const Workspace &w, mcsce_handle_s::Lane &ln,
+                          cudaStream_t st, cudaStream_t aux, bool resync) {
     const SysDev &d = h->d;
+    h->cur_call = ln.d_call;
+    // per-call scalars -> device parameter block (by-value kernel argument: no host buffer to keep alive)
+    // (not while capturing: a replayed graph must read the values of the call that replays it, written by mcsce_grow)
+    if (!h->capturing) {
+        CallParams cp{o->seed, o->conf_id0, o->beta, o->noise_deg};
+        set_call_params_kernel<<<1, 1, 0, st>>>(ln.d_call, cp);
+        h->launches += 1;
+    }
     const int C = o->n_conf;
     const long long trial_stride = std::max(1, h->max_trial_atoms);
     const long long chi_set_stride = (long long)d.n_trials_total * MAX_CHI;
     if (mcsce_init_env(h, C, (float *)w.env, (void *)st)) return -1;
-    if (launch_input_energy(h, w.rows, w.pairs, h->d_input_energy, st)) return -1;
-    init_state_kernel<<<(C + 255) / 256, 256, 0, st>>>(C, w.alive, w.e_acc, h->d_input_energy);
+    if (launch_input_energy(h, w.rows, w.pairs, ln.d_input_energy, st)) return -1;
+    init_state_kernel<<<(C + 255) / 256, 256, 0, st>>>(C, w.alive, w.e_acc, ln.d_input_energy);
     h->launches += 1;
     // Two streams: `st` runs the generic-pair kernel and the selection of every residue in order; `aux` runs the
     // placement of the next residue (independent of the pending selection) and the special-pair kernel.
-    CK(cudaEventRecord(h->ev0, st));
-    CK(cudaStreamWaitEvent(aux, h->ev0, 0));
+    CK(cudaEventRecord(ln.ev0, st));
+    CK(cudaStreamWaitEvent(aux, ln.ev0, 0));
     int prev = -1, prev2 = -1, count = 0;
     const int ms_alloc = max_split_for(C, h->sm_count);
     int n_alive = C;
-    CK(cudaMemsetAsync(h->d_n_dead, 0, sizeof(int), st));
+    CK(cudaMemsetAsync(ln.d_n_dead, 0, sizeof(int), st));
     CK(cudaMemsetAsync(w.n_keep, 0, sizeof(int) * (size_t)C, st));
     for (int i = 0; i < d.n_res; ++i) {
         const StepDev &sd = h->steps[i];
@@ -1731,16 +1760,16 @@ static int enqueue_growth(mcsce_handle h, const mcsce_grow_opts *o, const Worksp
         const int T = sd.n_trials;
         float4 *trial = (count & 1) ? w.trial2 : w.trial;
         // aux: K1 into the buffer last read by the residue before the previous one
-        if (prev2 >= 0) CK(cudaStreamWaitEvent(aux, h->evS[prev2], 0));
+        if (prev2 >= 0) CK(cudaStreamWaitEvent(aux, ln.evS[prev2], 0));
         if (launch_place(h, i, C, T, o->d_chis, chi_set_stride, sd.trial_off, o->d_chis_out, trial, trial_stride,
                          w.alive, aux)) return -1;
-        CK(cudaEventRecord(h->evP[i], aux));
+        CK(cudaEventRecord(ln.evP[i], aux));
         // st: generic pairs
-        CK(cudaStreamWaitEvent(st, h->evP[i], 0));
+        CK(cudaStreamWaitEvent(st, ln.evP[i], 0));
         // few conformers: the environment is split over blockIdx.z to fill the GPU; conformers that died leave empty
         // CTAs, so the number still alive is read back every 32 residues and the split re-derived from it
         if (resync && ms_alloc > 1 && o->env_split <= 0 && count > 0 && (count & 31) == 0) {
-            CK(cudaMemcpyAsync(h->h_n_dead, h->d_n_dead, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(h->h_n_dead, ln.d_n_dead, sizeof(int), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             n_alive = std::max(1, C - *h->h_n_dead);
         }
@@ -1750,24 +1779,24 @@ static int enqueue_growth(mcsce_handle h, const mcsce_grow_opts *o, const Worksp
         const int split = std::min(ms_alloc, choose_split(h, i, n_alive, T, o->env_split, screen != nullptr));
         if (!screen && launch_generic(h, i, C, T, split, w.env, trial, trial_stride, w.partial, w.alive, st, dedup)) return -1;
         // aux: special pairs (need the environment as updated by the previous selection)
-        if (prev >= 0) CK(cudaStreamWaitEvent(aux, h->evS[prev], 0));
+        if (prev >= 0) CK(cudaStreamWaitEvent(aux, ln.evS[prev], 0));
         if (launch_special(h, i, C, T, w.env, trial, trial_stride, w.sp_partial, w.alive, aux)) return -1;
-        CK(cudaEventRecord(h->evQ[i], aux));
+        CK(cudaEventRecord(ln.evQ[i], aux));
         // screened residue: the special pairs go first, their clash flags join the screen's, then the scoring pass
         if (screen) {
-            CK(cudaStreamWaitEvent(st, h->evQ[i], 0));
+            CK(cudaStreamWaitEvent(st, ln.evQ[i], 0));
             if (launch_generic(h, i, C, T, split, w.env, trial, trial_stride, w.partial, w.alive, st, dedup, screen, w.sp_partial,
                                w.n_keep)) return -1;
         }
         // st: selection
-        CK(cudaStreamWaitEvent(st, h->evQ[i], 0));
+        CK(cudaStreamWaitEvent(st, ln.evQ[i], 0));
         SelectArgs a{};
         a.s = d; a.step = i; a.n_trials = T; a.n_split = split; a.partial = w.partial; a.sp_partial = w.sp_partial;
         a.dedup = dedup;
-        a.prob = d.prob + sd.trial_off; a.cp = h->d_call; a.uniform = o->d_uniform; a.u_stride = d.n_res;
+        a.prob = d.prob + sd.trial_off; a.cp = ln.d_call; a.uniform = o->d_uniform; a.u_stride = d.n_res;
         a.env = w.env; a.trial = trial; a.trial_set_stride = trial_stride;
         a.alive = w.alive; a.e_acc = w.e_acc; a.selected = o->d_selected; a.trial_energy = o->d_trial_energy;
-        a.pair_counter = h->d_pairs; a.n_dead = h->d_n_dead;
+        a.pair_counter = h->d_pairs; a.n_dead = ln.d_n_dead;
         long long n_active = 0;
         for (int c = 0; c < d.n_cls; ++c) n_active += h->cls_active[(size_t)i * d.n_cls + c];
         a.pairs_per_set = (long long)T * ((long long)sd.n_sc * (sd.n_sc - 1) / 2 + (long long)sd.n_sc * n_active);
@@ -1780,9 +1809,37 @@ static int enqueue_growth(mcsce_handle h, const mcsce_grow_opts *o, const Worksp
                                    + (screen ? (long long)T * n_per * h->scr_len[i] / 2 : 0);
         { ProfScope ps(h, 3, st); select_kernel<<<C, 128, sizeof(double) * 2 * T, st>>>(a); }
         h->launches += 1;
-        CK(cudaEventRecord(h->evS[i], st));
+        CK(cudaEventRecord(ln.evS[i], st));
         prev2 = prev; prev = i; ++count;
     }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// conformer groups in flight for one call: two when each half alone still fills the GPU (>= 4 CTAs per SM with one tile
+// per conformer, so that both halves keep the environment split of the whole: results do not depend on the grouping)
+static int lane_count(const mcsce_handle h, int n_conf) { return (n_conf / 2 >= 4 * h->sm_count) ? 2 : 1; }
+
+static int prepare_lane(mcsce_handle h, mcsce_handle_s::Lane &ln, bool own_main) {
+    if (own_main && !ln.main) CK(cudaStreamCreateWithFlags(&ln.main, cudaStreamNonBlocking));
+    if (!ln.aux) CK(cudaStreamCreateWithFlags(&ln.aux, cudaStreamNonBlocking));
+    if (!ln.ev0) CK(cudaEventCreateWithFlags(&ln.ev0, cudaEventDisableTiming));
+    if (!ln.done) CK(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
+    while ((int)ln.evP.size() < h->d.n_res) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ln.evP.push_back(e);
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ln.evQ.push_back(e);
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ln.evS.push_back(e);
+    }
+    return 0;
+}
+
+static int finish_growth(mcsce_handle h, int C, const Workspace &w, float *d_coords, double *d_energy, uint8_t *d_ok,
+                         cudaStream_t st) {
+    const long long n = (long long)C * h->d.n_atoms;
+    gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->d, C, w.env, d_coords);
+    finish_kernel<<<(C + 255) / 256, 256, 0, st>>>(C, w.alive, w.e_acc, d_energy, d_ok);
+    h->launches += 2;
     CK(cudaGetLastError());
     return 0;
 }
@@ -1794,22 +1851,10 @@ extern "C" int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *o, void *d_work
     if (o->n_conf <= 0) return fail("n_conf must be positive");
     CK(cudaSetDevice(h->device));
     const SysDev &d = h->d;
-    Workspace w = carve(h, o->n_conf, h->max_trials, h->max_trial_atoms, d_workspace);
-    if (workspace_bytes < w.total) return fail("workspace too small: call mcsce_workspace_bytes");
+    if (workspace_bytes < mcsce_workspace_bytes(h, o->n_conf)) return fail("workspace too small: call mcsce_workspace_bytes");
     cudaStream_t st = (cudaStream_t)stream;
     const int C = o->n_conf;
-    if (!h->aux) CK(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
-    if (!h->ev0) CK(cudaEventCreateWithFlags(&h->ev0, cudaEventDisableTiming));
-    while ((int)h->evP.size() < d.n_res) {
-        cudaEvent_t e;
-        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->evP.push_back(e);
-        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->evQ.push_back(e);
-        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->evS.push_back(e);
-    }
-    // per-call scalars -> device parameter block (by-value kernel argument: no host buffer to keep alive)
-    CallParams cp{o->seed, o->conf_id0, o->beta, o->noise_deg};
-    set_call_params_kernel<<<1, 1, 0, st>>>(h->d_call, cp);
-    h->launches += 1;
+    if (prepare_lane(h, h->lane[0], false)) return -1;
 
     // Launch-bound runs (little work per residue: few conformers and/or a small protein) replay a captured CUDA graph of
     // the whole growth instead of ~4 launches + 7 event calls per residue; the graph is cached per (tables, n_conf,
@@ -1825,6 +1870,7 @@ extern "C" int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *o, void *d_work
     }
     const bool use_graph = !o->no_graph && !h->profiling && grow_steps > 0 && (pairs * C) / grow_steps < 300000000LL;
     if (use_graph) {
+        Workspace w = carve(h, C, h->max_trials, h->max_trial_atoms, d_workspace);
         std::vector<long long> key = {h->table_version, C, (long long)(size_t)d_workspace, (long long)workspace_bytes,
                                       (long long)(size_t)o->d_chis, (long long)(size_t)o->d_uniform,
                                       (long long)(size_t)o->d_trial_energy, (long long)(size_t)o->d_chis_out,
@@ -1833,10 +1879,12 @@ extern "C" int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *o, void *d_work
             if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
             if (!h->cap_stream) CK(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
             const long long before = h->launches;
+            h->capturing = true;
             CK(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeRelaxed));
-            const int rc = enqueue_growth(h, o, w, h->cap_stream, h->aux, false);
+            const int rc = enqueue_growth(h, o, w, h->lane[0], h->cap_stream, h->lane[0].aux, false);
             cudaGraph_t graph = nullptr;
             cudaError_t e = cudaStreamEndCapture(h->cap_stream, &graph);
+            h->capturing = false;
             h->graph_launches = h->launches - before;
             h->launches = before;
             if (rc) { if (graph) cudaGraphDestroy(graph); return -1; }
@@ -1846,17 +1894,43 @@ extern "C" int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *o, void *d_work
             if (e != cudaSuccess) { h->graph_exec = nullptr; return fail(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
             h->graph_key = key;
         }
+        CallParams cp{o->seed, o->conf_id0, o->beta, o->noise_deg};
+        set_call_params_kernel<<<1, 1, 0, st>>>(h->lane[0].d_call, cp);
+        h->launches += 1;
         CK(cudaGraphLaunch(h->graph_exec, st));
         h->launches += h->graph_launches;
-    } else {
-        // while the per-class event timing is on, everything goes to one stream so that each kernel is timed alone
-        if (enqueue_growth(h, o, w, st, h->profiling ? st : h->aux, true)) return -1;
+        return finish_growth(h, C, w, d_coords, d_energy, d_ok, st);
     }
-    const long long n = (long long)C * d.n_atoms;
-    gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d, C, w.env, d_coords);
-    finish_kernel<<<(C + 255) / 256, 256, 0, st>>>(C, w.alive, w.e_acc, d_energy, d_ok);
-    h->launches += 2;
-    CK(cudaGetLastError());
+
+    const int G = h->profiling ? 1 : lane_count(h, C);
+    if (G == 1) {
+        Workspace w = carve(h, C, h->max_trials, h->max_trial_atoms, d_workspace);
+        // while the per-class event timing is on, everything goes to one stream so that each kernel is timed alone
+        if (enqueue_growth(h, o, w, h->lane[0], st, h->profiling ? st : h->lane[0].aux, true)) return -1;
+        return finish_growth(h, C, w, d_coords, d_energy, d_ok, st);
+    }
+    // two groups of conformers, each a complete growth on its own pair of streams; group 0 on the caller's stream
+    if (prepare_lane(h, h->lane[1], true)) return -1;
+    const int C0 = C / 2, C1 = C - C0;
+    Workspace w0 = carve(h, C0, h->max_trials, h->max_trial_atoms, d_workspace);
+    Workspace w1 = carve(h, C1, h->max_trials, h->max_trial_atoms, (char *)d_workspace + w0.total);
+    mcsce_grow_opts o0 = *o, o1 = *o;
+    o0.n_conf = C0; o1.n_conf = C1; o1.conf_id0 = o->conf_id0 + C0;
+    const long long chi_stride = (long long)d.n_trials_total * MAX_CHI;
+    if (o->d_chis) o1.d_chis = o->d_chis + (long long)C0 * chi_stride;
+    if (o->d_chis_out) o1.d_chis_out = o->d_chis_out + (long long)C0 * chi_stride;
+    if (o->d_uniform) o1.d_uniform = o->d_uniform + (long long)C0 * d.n_res;
+    if (o->d_selected) o1.d_selected = o->d_selected + (long long)C0 * d.n_res;
+    if (o->d_trial_energy) o1.d_trial_energy = o->d_trial_energy + (long long)C0 * d.n_trials_total;
+    cudaStream_t st1 = h->lane[1].main;
+    CK(cudaEventRecord(h->lane[1].ev0, st));                 // group 1 starts after whatever precedes the call on `st`
+    CK(cudaStreamWaitEvent(st1, h->lane[1].ev0, 0));
+    if (enqueue_growth(h, &o0, w0, h->lane[0], st, h->lane[0].aux, true)) return -1;
+    if (enqueue_growth(h, &o1, w1, h->lane[1], st1, h->lane[1].aux, true)) return -1;
+    if (finish_growth(h, C1, w1, d_coords + (size_t)C0 * d.n_atoms * 3, d_energy + C0, d_ok + C0, st1)) return -1;
+    CK(cudaEventRecord(h->lane[1].done, st1));
+    if (finish_growth(h, C0, w0, d_coords, d_energy, d_ok, st)) return -1;
+    CK(cudaStreamWaitEvent(st, h->lane[1].done, 0));
     return 0;
 }
 
