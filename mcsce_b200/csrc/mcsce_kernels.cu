@@ -1074,6 +1074,13 @@ __global__ void finish_kernel(int n_sets, const unsigned char *alive, const doub
 // ------------------------------------------------------------------------------------------------
 // host side: handle, table upload, launch logic
 // ------------------------------------------------------------------------------------------------
+#ifndef MAX_LANES
+#define MAX_LANES 4
+#endif
+#ifndef LANE_LIMIT
+#define LANE_LIMIT 2                    // conformer groups in flight at most (3 and 4 measured: see DESIGN)
+#endif
+
 struct mcsce_handle_s {
     int device = 0;
     int sm_count = 148;
@@ -1109,7 +1116,7 @@ struct mcsce_handle_s {
         CallParams *d_call = nullptr;
         int *d_n_dead = nullptr;
         double *d_input_energy = nullptr;
-    } lane[2];
+    } lane[MAX_LANES];
     const CallParams *cur_call = nullptr;     // parameter block of the lane being enqueued (read by launch_place)
     // optional per-kernel-class device timing (CUDA events on the launch stream)
     bool profiling = false;
@@ -1547,10 +1554,14 @@ static int lane_count(const mcsce_handle h, int n_conf);
 extern "C" size_t mcsce_workspace_bytes(mcsce_handle h, int n_conf) {
     if (!h || !h->has_bb || n_conf <= 0) return 0;
     size_t whole = carve(h, n_conf, h->max_trials, h->max_trial_atoms, nullptr).total;
-    if (lane_count(h, n_conf) == 2) {        // two conformer groups, each with a complete workspace
-        const int c0 = n_conf / 2;
-        whole = std::max(whole, carve(h, c0, h->max_trials, h->max_trial_atoms, nullptr).total +
-                                carve(h, n_conf - c0, h->max_trials, h->max_trial_atoms, nullptr).total);
+    const int G = lane_count(h, n_conf);
+    if (G > 1) {                             // conformer groups, each with a complete workspace
+        size_t sum = 0;
+        for (int g = 0; g < G; ++g) {
+            const int c0 = (int)((long long)n_conf * g / G), c1 = (int)((long long)n_conf * (g + 1) / G);
+            sum += carve(h, c1 - c0, h->max_trials, h->max_trial_atoms, nullptr).total;
+        }
+        whole = std::max(whole, sum);
     }
     return whole;
 }
@@ -1818,7 +1829,13 @@ static int enqueue_growth(mcsce_handle h, const mcsce_grow_opts *o, const Worksp
 
 // conformer groups in flight for one call: two when each half alone still fills the GPU (>= 4 CTAs per SM with one tile
 // per conformer, so that both halves keep the environment split of the whole: results do not depend on the grouping)
-static int lane_count(const mcsce_handle h, int n_conf) { return (n_conf / 2 >= 4 * h->sm_count) ? 2 : 1; }
+static int lane_count(const mcsce_handle h, int n_conf) {
+    int g = 1;
+    if (const char *e = getenv("MCSCE_B200_LANES")) { g = atoi(e); g = std::max(1, std::min(g, MAX_LANES)); }   // tuning knob
+    else g = LANE_LIMIT;
+    while (g > 1 && n_conf / g < 4 * h->sm_count) --g;
+    return g;
+}
 
 static int prepare_lane(mcsce_handle h, mcsce_handle_s::Lane &ln, bool own_main) {
     if (own_main && !ln.main) CK(cudaStreamCreateWithFlags(&ln.main, cudaStreamNonBlocking));
@@ -1909,28 +1926,36 @@ extern "C" int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *o, void *d_work
         if (enqueue_growth(h, o, w, h->lane[0], st, h->profiling ? st : h->lane[0].aux, true)) return -1;
         return finish_growth(h, C, w, d_coords, d_energy, d_ok, st);
     }
-    // two groups of conformers, each a complete growth on its own pair of streams; group 0 on the caller's stream
-    if (prepare_lane(h, h->lane[1], true)) return -1;
-    const int C0 = C / 2, C1 = C - C0;
-    Workspace w0 = carve(h, C0, h->max_trials, h->max_trial_atoms, d_workspace);
-    Workspace w1 = carve(h, C1, h->max_trials, h->max_trial_atoms, (char *)d_workspace + w0.total);
-    mcsce_grow_opts o0 = *o, o1 = *o;
-    o0.n_conf = C0; o1.n_conf = C1; o1.conf_id0 = o->conf_id0 + C0;
+    // G groups of conformers, each a complete growth on its own pair of streams; group 0 on the caller's stream
     const long long chi_stride = (long long)d.n_trials_total * MAX_CHI;
-    if (o->d_chis) o1.d_chis = o->d_chis + (long long)C0 * chi_stride;
-    if (o->d_chis_out) o1.d_chis_out = o->d_chis_out + (long long)C0 * chi_stride;
-    if (o->d_uniform) o1.d_uniform = o->d_uniform + (long long)C0 * d.n_res;
-    if (o->d_selected) o1.d_selected = o->d_selected + (long long)C0 * d.n_res;
-    if (o->d_trial_energy) o1.d_trial_energy = o->d_trial_energy + (long long)C0 * d.n_trials_total;
-    cudaStream_t st1 = h->lane[1].main;
-    CK(cudaEventRecord(h->lane[1].ev0, st));                 // group 1 starts after whatever precedes the call on `st`
-    CK(cudaStreamWaitEvent(st1, h->lane[1].ev0, 0));
-    if (enqueue_growth(h, &o0, w0, h->lane[0], st, h->lane[0].aux, true)) return -1;
-    if (enqueue_growth(h, &o1, w1, h->lane[1], st1, h->lane[1].aux, true)) return -1;
-    if (finish_growth(h, C1, w1, d_coords + (size_t)C0 * d.n_atoms * 3, d_energy + C0, d_ok + C0, st1)) return -1;
-    CK(cudaEventRecord(h->lane[1].done, st1));
-    if (finish_growth(h, C0, w0, d_coords, d_energy, d_ok, st)) return -1;
-    CK(cudaStreamWaitEvent(st, h->lane[1].done, 0));
+    size_t ws_off = 0;
+    Workspace w0{};
+    for (int g = 1; g < G; ++g) {                               // fork: the other groups start after whatever precedes the call on `st`
+        auto &ln = h->lane[g];
+        if (prepare_lane(h, ln, true)) return -1;
+        CK(cudaEventRecord(ln.ev0, st));
+        CK(cudaStreamWaitEvent(ln.main, ln.ev0, 0));
+    }
+    for (int g = 0; g < G; ++g) {
+        auto &ln = h->lane[g];
+        const int c0 = (int)((long long)C * g / G), cg = (int)((long long)C * (g + 1) / G) - c0;
+        Workspace w = carve(h, cg, h->max_trials, h->max_trial_atoms, (char *)d_workspace + ws_off);
+        ws_off += w.total;
+        mcsce_grow_opts og = *o;
+        og.n_conf = cg; og.conf_id0 = o->conf_id0 + c0;
+        if (o->d_chis) og.d_chis = o->d_chis + (long long)c0 * chi_stride;
+        if (o->d_chis_out) og.d_chis_out = o->d_chis_out + (long long)c0 * chi_stride;
+        if (o->d_uniform) og.d_uniform = o->d_uniform + (long long)c0 * d.n_res;
+        if (o->d_selected) og.d_selected = o->d_selected + (long long)c0 * d.n_res;
+        if (o->d_trial_energy) og.d_trial_energy = o->d_trial_energy + (long long)c0 * d.n_trials_total;
+        cudaStream_t sg = g == 0 ? st : ln.main;
+        if (enqueue_growth(h, &og, w, ln, sg, ln.aux, true)) return -1;
+        if (g == 0) { w0 = w; continue; }
+        if (finish_growth(h, cg, w, d_coords + (size_t)c0 * d.n_atoms * 3, d_energy + c0, d_ok + c0, sg)) return -1;
+        CK(cudaEventRecord(ln.done, sg));
+    }
+    if (finish_growth(h, (int)((long long)C / G), w0, d_coords, d_energy, d_ok, st)) return -1;
+    for (int g = 1; g < G; ++g) CK(cudaStreamWaitEvent(st, h->lane[g].done, 0));
     return 0;
 }
 
