@@ -1115,8 +1115,8 @@ struct mcsce_handle_s {
         cudaEvent_t ev0 = nullptr, done = nullptr;
         CallParams *d_call = nullptr;
         int *d_n_dead = nullptr;
-        double *d_input_energy = nullptr;
     } lane[MAX_LANES];
+    double *d_input_energy = nullptr;         // energy of the input atoms alone: a constant of the backbone, computed in set_backbone
     const CallParams *cur_call = nullptr;     // parameter block of the lane being enqueued (read by launch_place)
     // optional per-kernel-class device timing (CUDA events on the launch stream)
     bool profiling = false;
@@ -1173,12 +1173,12 @@ extern "C" int mcsce_create(mcsce_handle *out, int device) {
     CK(cudaMalloc((void **)&h->d_pairs, 2 * sizeof(unsigned long long)));
     CK(cudaMemset(h->d_pairs, 0, 2 * sizeof(unsigned long long)));
     for (auto &ln : h->lane) {
-        CK(cudaMalloc((void **)&ln.d_input_energy, sizeof(double)));
         CK(cudaMalloc((void **)&ln.d_n_dead, sizeof(int)));
         CK(cudaMalloc((void **)&ln.d_call, sizeof(CallParams)));
         CK(cudaMemset(ln.d_call, 0, sizeof(CallParams)));
     }
     h->cur_call = h->lane[0].d_call;
+    CK(cudaMalloc((void **)&h->d_input_energy, sizeof(double)));
     CK(cudaMallocHost((void **)&h->h_n_dead, sizeof(int)));
     *out = h;
     return 0;
@@ -1196,11 +1196,11 @@ extern "C" int mcsce_destroy(mcsce_handle h) {
         if (ln.done) cudaEventDestroy(ln.done);
         if (ln.aux) cudaStreamDestroy(ln.aux);
         if (ln.main) cudaStreamDestroy(ln.main);
-        if (ln.d_input_energy) cudaFree(ln.d_input_energy);
         if (ln.d_n_dead) cudaFree(ln.d_n_dead);
         if (ln.d_call) cudaFree(ln.d_call);
     }
     if (h->d_steps) cudaFree(h->d_steps);
+    if (h->d_input_energy) cudaFree(h->d_input_energy);
     if (h->d_pairs) cudaFree(h->d_pairs);
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
@@ -1323,6 +1323,8 @@ __global__ void store_rigid_kernel(const float4 *src, int sc_start, int n_sc, fl
 // its side chain; K2 first tests every trial against that list (clash only) and scores just the survivors.  The list is
 // a heuristic: the scoring pass still tests every pair it evaluates, so a miss costs time, never correctness.
 //   input atoms: known position; side-chain atoms of earlier residues: within their template distance of their CA.
+static int launch_input_energy(mcsce_handle h, double2 *rows, double2 *pairs, double *out, cudaStream_t st);
+
 static int build_screen_lists(mcsce_handle h, const mcsce_backbone_desc *b) {
     SysDev &d = h->d;
     const int n_cls = d.n_cls, n_res = d.n_res;
@@ -1488,6 +1490,15 @@ extern "C" int mcsce_set_backbone(mcsce_handle h, const mcsce_backbone_desc *b) 
         CK(cudaDeviceSynchronize());
         cudaFree(tmp);
     }
+    {   // energy of the input atoms alone (side_chain_builder.py:149): a constant of the backbone, every conformer starts from it
+        double2 *rows = nullptr, *pairs = nullptr;
+        CK(cudaMalloc((void **)&rows, sizeof(double2) * std::max(1, d.n_input)));
+        CK(cudaMalloc((void **)&pairs, sizeof(double2) * std::max(1, d.n_bb_pairs)));
+        const int rc = launch_input_energy(h, rows, pairs, h->d_input_energy, 0);
+        cudaDeviceSynchronize();
+        cudaFree(rows); cudaFree(pairs);
+        if (rc) return -1;
+    }
     h->has_bb = true;
     return 0;
 }
@@ -1525,7 +1536,6 @@ struct Workspace {
     unsigned char *alive, *screen;
     int *n_keep;
     double *e_acc;
-    double2 *rows, *pairs;
     size_t total;
 };
 
@@ -1543,8 +1553,6 @@ static Workspace carve(const mcsce_handle h, int n_conf, int max_trials, int max
     w.screen = (unsigned char *)take((size_t)n_conf * std::max(1, max_trials));
     w.n_keep = (int *)take((size_t)n_conf * sizeof(int));
     w.e_acc = (double *)take((size_t)n_conf * sizeof(double));
-    w.rows = (double2 *)take((size_t)std::max(1, h->d.n_input) * sizeof(double2));
-    w.pairs = (double2 *)take((size_t)std::max(1, h->d.n_bb_pairs) * sizeof(double2));
     w.total = off;
     return w;
 }
@@ -1753,8 +1761,7 @@ static int enqueue_growth(mcsce_handle h, const mcsce_grow_opts *o, const Worksp
     const long long trial_stride = std::max(1, h->max_trial_atoms);
     const long long chi_set_stride = (long long)d.n_trials_total * MAX_CHI;
     if (mcsce_init_env(h, C, (float *)w.env, (void *)st)) return -1;
-    if (launch_input_energy(h, w.rows, w.pairs, ln.d_input_energy, st)) return -1;
-    init_state_kernel<<<(C + 255) / 256, 256, 0, st>>>(C, w.alive, w.e_acc, ln.d_input_energy);
+    init_state_kernel<<<(C + 255) / 256, 256, 0, st>>>(C, w.alive, w.e_acc, h->d_input_energy);   // starts from the input atoms' energy (:149)
     h->launches += 1;
     // Two streams: `st` runs the generic-pair kernel and the selection of every residue in order; `aux` runs the
     // placement of the next residue (independent of the pending selection) and the special-pair kernel.
