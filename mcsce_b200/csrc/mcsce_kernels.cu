@@ -1900,7 +1900,6 @@ extern "C" int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *o, void *d_work
                                       (long long)(size_t)o->d_trial_energy, (long long)(size_t)o->d_chis_out,
                                       (long long)(size_t)o->d_selected, o->env_split, o->no_dedup, o->no_screen};
         if (!h->graph_exec || key != h->graph_key) {
-            if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
             if (!h->cap_stream) CK(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
             const long long before = h->launches;
             h->capturing = true;
@@ -1913,7 +1912,15 @@ extern "C" int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *o, void *d_work
             h->launches = before;
             if (rc) { if (graph) cudaGraphDestroy(graph); return -1; }
             if (e != cudaSuccess) return fail(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
-            e = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+            // a new backbone of the same sequence gives the same graph topology with other launch sizes and table
+            // pointers: update the instantiated graph in place (much cheaper than instantiating), else start over
+            bool updated = false;
+            if (h->graph_exec) {
+                cudaGraphExecUpdateResultInfo info;
+                updated = cudaGraphExecUpdate(h->graph_exec, graph, &info) == cudaSuccess;
+                if (!updated) { cudaGetLastError(); cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+            }
+            if (!updated) e = cudaGraphInstantiate(&h->graph_exec, graph, 0);
             cudaGraphDestroy(graph);
             if (e != cudaSuccess) { h->graph_exec = nullptr; return fail(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
             h->graph_key = key;
