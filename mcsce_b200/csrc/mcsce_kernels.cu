@@ -532,12 +532,20 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MINB) score_generic_kerne
     const int set = blockIdx.y;
     if (a.alive && !a.alive[set]) return;
     const bool compact = !SCREEN && a.screen != nullptr;
-    // tiles beyond the trials the screen left have nothing to do (the last tile may still carry the chi-independent atoms)
-    if (compact && !(a.dedup && blockIdx.x == gridDim.x - 1) && blockIdx.x * a.trials_per_tile >= a.n_keep[set]) return;
     const int tid = threadIdx.x;
     const StepDev &st = a.s.steps[a.step];
     const int n_cls = a.s.n_cls;
     const int n_sc = st.n_sc;
+    // The chi-independent atoms ride in the last tile that has trials (the next one if that tile is full): without a screen
+    // that is the last tile of the grid, with a screen it follows from the number of trials the screen left - and the
+    // tiles beyond have nothing to do.
+    int fix_tile = gridDim.x - 1;
+    if (compact) {
+        const int nk = a.n_keep[set], tpt = a.trials_per_tile, n_per0 = a.dedup ? st.n_var : n_sc;
+        const int lt = nk > 0 ? (nk - 1) / tpt : 0;
+        fix_tile = ((nk - lt * tpt) * n_per0 + st.n_fix <= TILE_A) ? lt : lt + 1;
+        if (blockIdx.x * tpt >= nk && !(a.dedup && (int)blockIdx.x == fix_tile)) return;
+    }
 
     const int warp = tid >> 5, lane = tid & 31;
     {   // start of every class in the order the pass walks: the residue's screen list, or the active environment
@@ -590,8 +598,8 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MINB) score_generic_kerne
     // chi-dependent atoms of whole trials; the chi-independent atoms (trial 0's copy) ride in the free lanes of
     // the last tile, or in one extra tile when that one is full.
     const int n_per = a.dedup ? st.n_var : n_sc;                 // atoms per trial in a tile
-    const bool last = blockIdx.x == gridDim.x - 1;
-    const bool extra = !SCREEN && a.dedup && a.fixed_extra_tile && last;    // tile of chi-independent atoms only
+    const bool last = (int)blockIdx.x == fix_tile;
+    const bool extra = !SCREEN && !compact && a.dedup && a.fixed_extra_tile && last;    // tile of chi-independent atoms only
     const int t0 = extra ? 0 : blockIdx.x * a.trials_per_tile;
     const int nt = extra ? 0 : max(0, min(a.trials_per_tile, n_keep - t0));
     const int n_varatoms = nt * n_per;
