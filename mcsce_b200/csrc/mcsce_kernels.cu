@@ -25,6 +25,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <chrono>
 
 #include "../../include/mcsce_b200.h"
 
@@ -1092,7 +1093,9 @@ __global__ void finish_kernel(int n_sets, const unsigned char *alive, const doub
 struct mcsce_handle_s {
     int device = 0;
     int sm_count = 148;
-    std::vector<void *> sys_allocs, bb_allocs;
+    std::vector<void *> sys_allocs;
+    char *bb_slab = nullptr;              // backbone-dependent tables: one grow-only device allocation, refilled by set_backbone
+    size_t bb_cap = 0;
     SysDev d{};
     bool has_sys = false, has_bb = false;
     // host mirrors needed for launch geometry
@@ -1195,7 +1198,8 @@ extern "C" int mcsce_create(mcsce_handle *out, int device) {
 extern "C" int mcsce_destroy(mcsce_handle h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
-    free_pool(h->sys_allocs); free_pool(h->bb_allocs);
+    free_pool(h->sys_allocs);
+    if (h->bb_slab) cudaFree(h->bb_slab);
     for (auto &ln : h->lane) {
         for (auto e : ln.evP) cudaEventDestroy(e);
         for (auto e : ln.evQ) cudaEventDestroy(e);
@@ -1221,7 +1225,7 @@ extern "C" int mcsce_set_system(mcsce_handle h, const mcsce_system_desc *s) {
     if (!h || !s) return fail("null argument");
     CK(cudaSetDevice(h->device));
     if (s->n_cls > MAX_CLS) return fail("too many atom classes");
-    free_pool(h->sys_allocs); free_pool(h->bb_allocs);
+    free_pool(h->sys_allocs);
     h->has_sys = h->has_bb = false;
     h->table_version++;
     SysDev &d = h->d;
@@ -1333,12 +1337,13 @@ __global__ void store_rigid_kernel(const float4 *src, int sc_start, int n_sc, fl
 //   input atoms: known position; side-chain atoms of earlier residues: within their template distance of their CA.
 static int launch_input_energy(mcsce_handle h, double2 *rows, double2 *pairs, double *out, cudaStream_t st);
 
-static int build_screen_lists(mcsce_handle h, const mcsce_backbone_desc *b) {
+static int build_screen_lists(mcsce_handle h, const mcsce_backbone_desc *b, std::vector<int> &off, std::vector<int> &slots,
+                              std::vector<int> &prefix) {
     SysDev &d = h->d;
     const int n_cls = d.n_cls, n_res = d.n_res;
     double scale = 1.0;
     if (const char *e = getenv("MCSCE_B200_SCREEN_SCALE")) scale = atof(e);      // tuning knob; 0 disables the screen
-    std::vector<int> off(n_res + 1, 0), slots, prefix((size_t)n_res * (n_cls + 1), 0);
+    off.assign(n_res + 1, 0); slots.clear(); prefix.assign((size_t)n_res * (n_cls + 1), 0);
     h->scr_len.assign(n_res, 0);
     // every atom: a centre and a radius that bound where it can be
     std::vector<float> cx((size_t)d.n_atoms * 3, 0.f), rad(d.n_atoms, 0.f);
@@ -1429,10 +1434,6 @@ static int build_screen_lists(mcsce_handle h, const mcsce_backbone_desc *b) {
                 ns ? (double)sl / ns : 0.0, ns ? (double)sa / ns : 0.0);
     }
     if (slots.empty()) slots.push_back(0);
-    auto &P = h->bb_allocs;
-    if (upload(h, P, off.data(), off.size(), &d.scr_off)) return -1;
-    if (upload(h, P, slots.data(), slots.size(), &d.scr_slot)) return -1;
-    if (upload(h, P, prefix.data(), prefix.size(), &d.scr_prefix)) return -1;
     return 0;
 }
 
@@ -1440,16 +1441,15 @@ extern "C" int mcsce_set_backbone(mcsce_handle h, const mcsce_backbone_desc *b) 
     if (!h || !b) return fail("null argument");
     if (!h->has_sys) return fail("mcsce_set_system must be called first");
     CK(cudaSetDevice(h->device));
+    const bool dbg = getenv("MCSCE_B200_SCREEN_DEBUG") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); };
+    auto t_start = now();
     CK(cudaDeviceSynchronize());          // a growth still in flight reads these tables
-    free_pool(h->bb_allocs);
+    if (dbg) fprintf(stderr, "[mcsce_b200] set_backbone: sync %.2f ms\n", ms_since(t_start));
     h->table_version++;
     SysDev &d = h->d;
-    auto &P = h->bb_allocs;
     d.n_trials_total = b->n_trials_total;
-    if (upload(h, P, b->chi_mean, (size_t)b->n_trials_total * MAX_CHI, &d.chi_mean)) return -1;
-    if (upload(h, P, b->chi_sigma, (size_t)b->n_trials_total * MAX_CHI, &d.chi_sigma)) return -1;
-    if (upload(h, P, b->prob, b->n_trials_total, &d.prob)) return -1;
-    if (upload(h, P, b->input_xyz, (size_t)d.n_input * 3, &d.input_xyz)) return -1;
     h->max_trials = 0; h->max_trial_atoms = 0;
     for (int i = 0; i < d.n_res; ++i) {
         StepDev &o = h->steps[i];
@@ -1479,14 +1479,46 @@ extern "C" int mcsce_set_backbone(mcsce_handle h, const mcsce_backbone_desc *b) 
         }
     }
     CK(cudaMemcpy(h->d_steps, h->steps.data(), sizeof(StepDev) * d.n_res, cudaMemcpyHostToDevice));
-    if (build_screen_lists(h, b)) return -1;
+    std::vector<int> scr_off, scr_slots, scr_prefix;
+    if (build_screen_lists(h, b, scr_off, scr_slots, scr_prefix)) return -1;
+    if (dbg) fprintf(stderr, "[mcsce_b200] set_backbone: +screen lists (host) %.2f ms\n", ms_since(t_start));
+    // all backbone-dependent device tables live in one grow-only allocation (no cudaMalloc/cudaFree per backbone)
+    float *rigid = nullptr;
+    {
+        std::vector<float> nanv((size_t)d.n_atoms * 3, NAN);
+        struct Item { const void *src; size_t bytes; const void **dst; };
+        const size_t nt6 = (size_t)b->n_trials_total * MAX_CHI;
+        const Item items[] = {
+            {b->chi_mean, nt6 * sizeof(double), (const void **)&d.chi_mean},
+            {b->chi_sigma, nt6 * sizeof(double), (const void **)&d.chi_sigma},
+            {b->prob, (size_t)b->n_trials_total * sizeof(double), (const void **)&d.prob},
+            {b->input_xyz, (size_t)d.n_input * 3 * sizeof(float), (const void **)&d.input_xyz},
+            {scr_off.data(), scr_off.size() * sizeof(int), (const void **)&d.scr_off},
+            {scr_slots.data(), scr_slots.size() * sizeof(int), (const void **)&d.scr_slot},
+            {scr_prefix.data(), scr_prefix.size() * sizeof(int), (const void **)&d.scr_prefix},
+            {nanv.data(), nanv.size() * sizeof(float), (const void **)&d.rigid_xyz},
+        };
+        size_t need = 0;
+        for (const Item &it : items) need += (std::max<size_t>(it.bytes, 1) + 255) / 256 * 256;
+        if (need > h->bb_cap) {
+            if (h->bb_slab) cudaFree(h->bb_slab);
+            h->bb_slab = nullptr; h->bb_cap = 0;
+            CK(cudaMalloc((void **)&h->bb_slab, need + need / 4));
+            h->bb_cap = need + need / 4;
+        }
+        size_t used = 0;
+        for (const Item &it : items) {
+            char *p = h->bb_slab + used;
+            used += (std::max<size_t>(it.bytes, 1) + 255) / 256 * 256;
+            if (it.bytes) CK(cudaMemcpy(p, it.src, it.bytes, cudaMemcpyHostToDevice));
+            *it.dst = p;
+        }
+        rigid = const_cast<float *>(d.rigid_xyz);
+    }
+    if (dbg) fprintf(stderr, "[mcsce_b200] set_backbone: +tables %.2f ms\n", ms_since(t_start));
     // GLY/ALA side chains have no chi: placed once per backbone with K1 (zero rotations) and shared
     // by every conformer (side_chain_builder.py:164-168)
     {
-        std::vector<float> nanv((size_t)d.n_atoms * 3, NAN);
-        float *rigid = nullptr;
-        if (upload(h, P, nanv.data(), nanv.size(), (const float **)&rigid)) return -1;
-        d.rigid_xyz = rigid;
         float4 *tmp = nullptr;
         CK(cudaMalloc((void **)&tmp, sizeof(float4) * MAX_SC));
         for (int i = 0; i < d.n_res; ++i) {
@@ -1498,6 +1530,7 @@ extern "C" int mcsce_set_backbone(mcsce_handle h, const mcsce_backbone_desc *b) 
         CK(cudaDeviceSynchronize());
         cudaFree(tmp);
     }
+    if (dbg) fprintf(stderr, "[mcsce_b200] set_backbone: +rigid side chains %.2f ms\n", ms_since(t_start));
     {   // energy of the input atoms alone (side_chain_builder.py:149): a constant of the backbone, every conformer starts from it
         double2 *rows = nullptr, *pairs = nullptr;
         CK(cudaMalloc((void **)&rows, sizeof(double2) * std::max(1, d.n_input)));
@@ -1507,6 +1540,7 @@ extern "C" int mcsce_set_backbone(mcsce_handle h, const mcsce_backbone_desc *b) 
         cudaFree(rows); cudaFree(pairs);
         if (rc) return -1;
     }
+    if (dbg) fprintf(stderr, "[mcsce_b200] set_backbone: +input energy %.2f ms\n", ms_since(t_start));
     h->has_bb = true;
     return 0;
 }

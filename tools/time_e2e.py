@@ -4,7 +4,8 @@ ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
 import bench, torch
 from mcsce_b200.engine import GrowthEngine
-s, sysm, n_conf, desc = bench.build_workload("cfg3")
+wl = sys.argv[2] if len(sys.argv) > 2 else "cfg3"
+s, sysm, n_conf, desc = bench.build_workload(wl)
 eng = GrowthEngine(0).set_system(sysm).set_backbone(s.coords)
 C = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 eng.grow(C, bench.BETA, seed=0); torch.cuda.synchronize()

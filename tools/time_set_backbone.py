@@ -5,7 +5,7 @@ ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
 import bench, torch
 from mcsce_b200.engine import GrowthEngine
-for wl in ("cfg2", "cfg3"):
+for wl in (sys.argv[1:] or ["cfg2", "cfg3"]):
     s, sysm, n_conf, desc = bench.build_workload(wl)
     eng = GrowthEngine(0).set_system(sysm).set_backbone(s.coords)
     t0 = time.perf_counter()
