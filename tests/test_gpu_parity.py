@@ -339,6 +339,22 @@ def test_neighbour_screen_equals_scoring_every_trial():
     assert with_screen[2] < 0.9 * without[2]            # fewer executed
 
 
+def test_one_engine_serves_systems_of_different_size_in_turn():
+    """The handle keeps grow-only device tables (backbone slab, workspace, cached graph): switching to a bigger system
+    and back must not leave anything of the other system behind."""
+    case_a, s_a, sys_a, eng = engine_for("pep12")
+    first = eng.grow(6, case_a.beta, seed=3, dump=True)
+    ref = {k: first[k].cpu().numpy().copy() for k in ("energy", "coords", "selected", "ok")}
+    case_b, s_b, sys_b, _ = engine_for("helix76")
+    eng.set_system(sys_b).set_backbone(s_b.coords)
+    big = eng.grow(6, case_b.beta, seed=3, no_graph=True)
+    assert big["coords"].shape[1] == sys_b.n_atoms and big["ok"].any()
+    eng.set_system(sys_a).set_backbone(s_a.coords)
+    again = eng.grow(6, case_a.beta, seed=3, dump=True)
+    for k, v in ref.items():
+        assert np.array_equal(again[k].cpu().numpy(), v, equal_nan=True), k
+
+
 def test_cuda_graph_replay_equals_direct_launches():
     """Launch-bound growths replay a cached CUDA graph; seeds, conformer offsets and beta are read from a device
     parameter block, so one graph serves every call with the same buffers."""
