@@ -302,7 +302,19 @@ int oracle_grow(const oracle_system *s, int n_conf, double beta, double noise_de
  * against everything placed before it) and the smallest ratio distance / clash distance over all scored pairs.
  * Size-independent check for full-size runs: must equal the energy the growth accumulated, and the ratio must
  * be >= 1 for a conformer reported as grown without clashes. */
+static double rescore_impl(const oracle_system *s, const float *xyz, double *min_clash_ratio, double *level_energy);
+
 double oracle_rescore(const oracle_system *s, const float *xyz, double *min_clash_ratio) {
+    return rescore_impl(s, xyz, min_clash_ratio, NULL);
+}
+
+/* Same, and level_energy[i] = energy of residue i's side chain against everything placed before it (NaN for
+ * residues that are not grown): the per-trial quantity of libenergy.py:786-810 for the trial that was selected. */
+double oracle_rescore_levels(const oracle_system *s, const float *xyz, double *min_clash_ratio, double *level_energy) {
+    return rescore_impl(s, xyz, min_clash_ratio, level_energy);
+}
+
+static double rescore_impl(const oracle_system *s, const float *xyz, double *min_clash_ratio, double *level_energy) {
     const int nc = s->n_cls;
     double *clsA = (double *)malloc(sizeof(double) * nc * nc), *clsB = (double *)malloc(sizeof(double) * nc * nc);
     for (int i = 0; i < nc * nc; ++i) {
@@ -315,10 +327,13 @@ double oracle_rescore(const oracle_system *s, const float *xyz, double *min_clas
     double ratio = INFINITY;
     unsigned char *is_special = (unsigned char *)calloc(s->n_atoms, 1);
     for (int i = 0; i < s->n_res; ++i) {
+        if (level_energy) level_energy[i] = NAN;
         if (s->step_kind[i] != 2) continue;
         const int n_sc = s->step_n_sc[i], sc0 = s->step_sc_start[i];
         for (int q = 0; q < s->step_n_sp_env[i]; ++q) is_special[s->step_sp_env[(size_t)i * MAX_SP_ENV + q]] = 1;
-        total += trial_energy(s, i, xyz + (size_t)sc0 * 3, xyz, sc0, is_special, clsA, clsB);
+        const double e_level = trial_energy(s, i, xyz + (size_t)sc0 * 3, xyz, sc0, is_special, clsA, clsB);
+        if (level_energy) level_energy[i] = e_level;
+        total += e_level;
         for (int k = 0; k < n_sc; ++k) {
             const int ci = s->cls_of_atom[sc0 + k];
             for (int j = 0; j < sc0; ++j) {

@@ -66,6 +66,8 @@ def load():
     lib.oracle_max_threads.restype = C.c_int
     lib.oracle_rescore.restype = C.c_double
     lib.oracle_rescore.argtypes = [C.POINTER(_System), C.c_void_p, C.POINTER(C.c_double)]
+    lib.oracle_rescore_levels.restype = C.c_double
+    lib.oracle_rescore_levels.argtypes = [C.POINTER(_System), C.c_void_p, C.POINTER(C.c_double), C.c_void_p]
     return lib
 
 
@@ -152,6 +154,17 @@ class COracle:
         r = C.c_double(0.0)
         e = self.lib.oracle_rescore(C.byref(self.desc), xyz.ctypes.data_as(C.c_void_p), C.byref(r))
         return float(e), float(r.value)
+
+    def rescore_levels(self, coords):
+        """(total, ratio, per-residue energies): like ``rescore`` plus the energy of every grown residue's side chain
+        against everything placed before it - what the growth scored for the trial it selected."""
+        xyz = np.ascontiguousarray(coords, np.float32)
+        assert xyz.shape == (self.sysm.n_atoms, 3)
+        r = C.c_double(0.0)
+        lev = np.zeros(self.sysm.n_res)
+        e = self.lib.oracle_rescore_levels(C.byref(self.desc), xyz.ctypes.data_as(C.c_void_p), C.byref(r),
+                                           lev.ctypes.data_as(C.c_void_p))
+        return float(e), float(r.value), lev
 
     def grow(self, n_conf, beta, seed=0, noise_deg=0.5, chis=None, uniforms=None, dump=False, n_threads=0):
         N = self.sysm.n_atoms
