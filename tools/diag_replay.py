@@ -10,9 +10,10 @@ wl = sys.argv[1] if len(sys.argv) > 1 else "cfg3"
 s, sysm, n_conf, desc = bench.build_workload(wl)
 eng = GrowthEngine(0).set_system(sysm).set_backbone(s.coords)
 co = COracle(sysm, s.coords)
-n = 6
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 6
+seed = int(sys.argv[3]) if len(sys.argv) > 3 else 11
 u = np.random.default_rng(5).random((n, sysm.n_res))
-out = eng.grow(n, bench.BETA, seed=11, uniforms=u, dump=True)
+out = eng.grow(n, bench.BETA, seed=seed, uniforms=u, dump=True)
 ref = co.grow(n, bench.BETA, chis=out["chis"].cpu().numpy(), uniforms=u, dump=True)
 te, tr = out["trial_energy"].cpu().numpy(), ref["trial_energy"]
 fin = ~np.isnan(te) & ~np.isnan(tr) & np.isfinite(tr) & np.isfinite(te)
