@@ -46,6 +46,8 @@ CASES = {
                        "LEU", "LYS", "MET", "PHE", "PRO", "SER", "THR", "TRP", "TYR", "VAL", "HIP", "ASN"],
                   n_conf=1, seed=16, full=False),
     "helix76": dict(cfg=1, n_conf=1, seed=17, full=False),
+    # --fix mode (cli.py:118-147): residues 3, 4 and 9 keep the side chains of an earlier growth of pep12
+    "fix12": dict(base="pep12", retain=[3, 4, 9], n_conf=2, seed=18, full=True),
 }
 
 
@@ -81,18 +83,40 @@ def run_case(name, spec, out_dir):
             out[i] = np.random.random()
         return out
 
-    pdb_text = case_pdb(name, spec)
     terms = spec.get("terms", ["lj", "clash", "coulomb"])
+    retain = list(spec.get("retain", []))
     tmp = tempfile.mkdtemp()
     pdb_path = os.path.join(tmp, name + ".pdb")
-    Path(pdb_path).write_text(pdb_text)
     ff = forcefields["Amberff14SB"](Cterminal="OXT", Nterminal="HN")
+    if spec.get("base"):
+        # input of a --fix run: a complete structure, grown here by the reference from the base case's backbone
+        base_path = os.path.join(tmp, "base.pdb")
+        Path(base_path).write_text(case_pdb(spec["base"], CASES[spec["base"]]))
+        b = Structure(base_path)
+        b.build()
+        b = b.remove_side_chains([])
+        scb.initialize_func_calc(partial(prepare_energy_function, batch_size=16, forcefield=ff, terms=terms), structure=b)
+        np.random.seed(spec["seed"]); nb_seed(spec["seed"])
+        pristine0 = copy.deepcopy(scb._rotamer_library._data)
+        full_structure = None
+        for _ in range(20):
+            full_structure, ok, _, _ = scb.create_side_chain_structure([b.coords, 1 / (300 * 0.008314462), [], None])
+            if ok:
+                break
+        scb._rotamer_library._data = pristine0
+        assert full_structure is not None
+        full_structure.write_PDB(pdb_path)
+        pdb_text = Path(pdb_path).read_text()
+    else:
+        pdb_text = case_pdb(name, spec)
+        Path(pdb_path).write_text(pdb_text)
     s = Structure(pdb_path)
     s.build()
     assert s.check_backbone_atom_completeness() == []
-    s = s.remove_side_chains([])
+    s = s.remove_side_chains(retain)
     t0 = time.time()
-    scb.initialize_func_calc(partial(prepare_energy_function, batch_size=16, forcefield=ff, terms=terms), structure=s)
+    scb.initialize_func_calc(partial(prepare_energy_function, batch_size=16, forcefield=ff, terms=terms), structure=s,
+                             retain_idxs=retain)
     print("[%s] reference init %.1fs" % (name, time.time() - t0))
 
     # ---- recorders (wrap, never edit) ----
@@ -131,7 +155,7 @@ def run_case(name, spec, out_dir):
     pristine = copy.deepcopy(scb._rotamer_library._data)
     beta = 1 / (300 * 0.008314462)
     out = dict(pdb=np.array(pdb_text), terms=np.array(terms), beta=np.float64(beta),
-               n_conf=np.int64(spec["n_conf"]), full=np.bool_(spec["full"]))
+               n_conf=np.int64(spec["n_conf"]), full=np.bool_(spec["full"]), retain=np.array(retain, dtype=np.int64))
     n_grow = sum(1 for f in orig_efuncs[1:] if f is not None)
     try:
         for c in range(spec["n_conf"]):
@@ -142,7 +166,7 @@ def run_case(name, spec, out_dir):
             np.random.seed(seed)
             rec.clear()
             rec.update(chis=[], weights=[], selected=[], steps=[])
-            structure, ok, energy, _ = scb.create_side_chain_structure([s.coords, beta, [], None])
+            structure, ok, energy, _ = scb.create_side_chain_structure([s.coords, beta, retain, None])
             scb._rotamer_library._data = copy.deepcopy(pristine)
             # regroup the flat chi rows per growth step
             pos = 0

@@ -15,12 +15,14 @@ class GoldenCase:
         self.beta = float(self.z["beta"])
         self.n_conf = int(self.z["n_conf"])
         self.full = bool(self.z["full"])
+        # residue numbers that keep the side chains of the input structure (--fix mode, cli.py:118-147)
+        self.retain = tuple(int(r) for r in self.z["retain"]) if "retain" in self.z.files else ()
 
     def structure(self):
         from mcsce_b200.structure import Structure
 
         s = Structure(self.pdb).build()
-        return s.remove_side_chains([])
+        return s.remove_side_chains(list(self.retain))
 
     def n_steps(self, c):
         return int(self.z["c%d_nsteps" % c])

@@ -14,7 +14,7 @@ from golden_utils import GoldenCase, library
 
 pytestmark = pytest.mark.gpu
 
-FULL_CASES = ["pep6", "pep6_ljclash", "pep12", "ptm14", "twochain"]
+FULL_CASES = ["pep6", "pep6_ljclash", "pep12", "ptm14", "twochain", "fix12"]
 ALL_CASES = FULL_CASES + ["std20", "helix76"]
 _ENG = {}
 
@@ -28,7 +28,7 @@ def engine_for(name):
     case = GoldenCase(name)
     lib, ptm = library()
     s = case.structure()
-    sysm = build_system(s, terms=case.terms, rotamer_library=lib, ptm_library=ptm)
+    sysm = build_system(s, retain_idxs=case.retain, terms=case.terms, rotamer_library=lib, ptm_library=ptm)
     eng = GrowthEngine(0).set_system(sysm).set_backbone(s.coords)
     _ENG[name] = (case, s, sysm, eng)
     return _ENG[name]

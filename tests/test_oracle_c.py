@@ -13,11 +13,11 @@ def _setup(name):
     case = GoldenCase(name)
     lib, ptm = library()
     s = case.structure()
-    sysm = build_system(s, terms=case.terms, rotamer_library=lib, ptm_library=ptm)
+    sysm = build_system(s, retain_idxs=case.retain, terms=case.terms, rotamer_library=lib, ptm_library=ptm)
     return case, s, sysm, COracle(sysm, s.coords)
 
 
-@pytest.mark.parametrize("name", ["pep6", "pep6_ljclash", "pep12", "ptm14", "twochain", "std20", "helix76"])
+@pytest.mark.parametrize("name", ["pep6", "pep6_ljclash", "pep12", "ptm14", "twochain", "std20", "helix76", "fix12"])
 def test_c_oracle_replays_reference(name):
     from mcsce_b200._lib import MAX_CHI
 

@@ -11,7 +11,7 @@ import pytest
 from golden_utils import GoldenCase, library
 from oracle import ref_numpy as O
 
-FULL_CASES = ["pep6", "pep6_ljclash", "pep12", "ptm14", "twochain"]
+FULL_CASES = ["pep6", "pep6_ljclash", "pep12", "ptm14", "twochain", "fix12"]
 LIGHT_CASES = ["std20", "helix76"]
 
 
@@ -29,7 +29,8 @@ def _replay(case, c, record):
     def u_for_step(i):
         return float(steps[i]["u"])
 
-    return O.grow_conformer(s, s.coords, case.beta, chi_for_step, u_for_step, terms=case.terms, record=record)
+    return O.grow_conformer(s, s.coords, case.beta, chi_for_step, u_for_step, retain_idxs=case.retain, terms=case.terms,
+                            record=record)
 
 
 def _check_case(name, max_conf=None, check_trial=True):
