@@ -46,6 +46,9 @@ CASES = {
                        "LEU", "LYS", "MET", "PHE", "PRO", "SER", "THR", "TRP", "TYR", "VAL", "HIP", "ASN"],
                   n_conf=1, seed=16, full=False),
     "helix76": dict(cfg=1, n_conf=1, seed=17, full=False),
+    # the eleven other PTM residues the reference can grow: S1P H1D H1E AGM ALY MEN BHD SMC MGN CGU LYZ
+    "ptm18": dict(seq=["SER", "S1P", "ALA", "H1D", "GLY", "H1E", "AGM", "LEU", "ALY", "MEN", "VAL", "BHD", "SMC", "ALA",
+                       "MGN", "CGU", "LYZ", "GLU"], n_conf=2, seed=19, full=True),
     # --fix mode (cli.py:118-147): residues 3, 4 and 9 keep the side chains of an earlier growth of pep12
     "fix12": dict(base="pep12", retain=[3, 4, 9], n_conf=2, seed=18, full=True),
 }

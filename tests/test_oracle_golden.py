@@ -11,7 +11,7 @@ import pytest
 from golden_utils import GoldenCase, library
 from oracle import ref_numpy as O
 
-FULL_CASES = ["pep6", "pep6_ljclash", "pep12", "ptm14", "twochain", "fix12"]
+FULL_CASES = ["pep6", "pep6_ljclash", "pep12", "ptm14", "twochain", "fix12", "ptm18"]
 LIGHT_CASES = ["std20", "helix76"]
 
 

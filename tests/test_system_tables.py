@@ -18,7 +18,7 @@ def _system(name):
     return case, s, build_system(s, retain_idxs=case.retain, terms=case.terms, rotamer_library=lib, ptm_library=ptm)
 
 
-@pytest.mark.parametrize("name", ["pep12", "ptm14", "twochain", "pep6_ljclash", "fix12"])
+@pytest.mark.parametrize("name", ["pep12", "ptm14", "twochain", "pep6_ljclash", "fix12", "ptm18"])
 def test_pair_coefficients_match_oracle(name):
     from mcsce_b200.chem.tables import load_tables
 
