@@ -49,6 +49,8 @@ CASES = {
     # the eleven other PTM residues the reference can grow: S1P H1D H1E AGM ALY MEN BHD SMC MGN CGU LYZ
     "ptm18": dict(seq=["SER", "S1P", "ALA", "H1D", "GLY", "H1E", "AGM", "LEU", "ALY", "MEN", "VAL", "BHD", "SMC", "ALA",
                        "MGN", "CGU", "LYZ", "GLU"], n_conf=2, seed=19, full=True),
+    # two 20-residue helices 11 A apart in one chain: trials meet atoms of the other helix (clashes that are not local in sequence)
+    "bundle40": dict(seq=None, n_conf=1, seed=20, full=False),
     # --fix mode (cli.py:118-147): residues 3, 4 and 9 keep the side chains of an earlier growth of pep12
     "fix12": dict(base="pep12", retain=[3, 4, 9], n_conf=2, seed=18, full=True),
 }
@@ -59,6 +61,9 @@ def case_pdb(name, spec):
 
     if spec.get("cfg"):
         return synth.config_backbone(spec["cfg"])
+    if name == "bundle40":
+        seq = synth.random_sequence(40, 20)
+        return synth.helix_bundle_pdb([seq[:20], seq[20:]], seed=20, one_chain=True, spacing=11.0)
     if name == "twochain":
         a = ["LYS", "GLU", "PHE", "SER", "TRP", "ASN"]
         b = ["ARG", "LEU", "ASP", "TYR", "MET", "VAL"]

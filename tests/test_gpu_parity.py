@@ -15,7 +15,7 @@ from golden_utils import GoldenCase, library
 pytestmark = pytest.mark.gpu
 
 FULL_CASES = ["pep6", "pep6_ljclash", "pep12", "ptm14", "twochain", "fix12", "ptm18"]
-ALL_CASES = FULL_CASES + ["std20", "helix76"]
+ALL_CASES = FULL_CASES + ["std20", "helix76", "bundle40"]
 _ENG = {}
 
 

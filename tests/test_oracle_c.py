@@ -17,7 +17,7 @@ def _setup(name):
     return case, s, sysm, COracle(sysm, s.coords)
 
 
-@pytest.mark.parametrize("name", ["pep6", "pep6_ljclash", "pep12", "ptm14", "twochain", "std20", "helix76", "fix12", "ptm18"])
+@pytest.mark.parametrize("name", ["pep6", "pep6_ljclash", "pep12", "ptm14", "twochain", "std20", "helix76", "fix12", "ptm18", "bundle40"])
 def test_c_oracle_replays_reference(name):
     from mcsce_b200._lib import MAX_CHI
 

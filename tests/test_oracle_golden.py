@@ -12,7 +12,7 @@ from golden_utils import GoldenCase, library
 from oracle import ref_numpy as O
 
 FULL_CASES = ["pep6", "pep6_ljclash", "pep12", "ptm14", "twochain", "fix12", "ptm18"]
-LIGHT_CASES = ["std20", "helix76"]
+LIGHT_CASES = ["std20", "helix76", "bundle40"]
 
 
 def _replay(case, c, record):
