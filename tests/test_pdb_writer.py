@@ -54,3 +54,17 @@ def test_round3_matches_reference_text_route():
     assert np.array_equal(_round3_f32(x), want)
     big = np.array([[-1234.5678, 10000.1234, 5.0]], np.float32)
     assert np.array_equal(_round3_f32(big), np.round(big, decimals=3).astype("<U8").astype(np.float32))
+
+
+def test_pdb_text_written_by_the_reference_round_trips_byte_for_byte(tmp_path):
+    """``fix12.npz`` carries a complete structure as the reference's own ``write_PDB`` wrote it (libpdb.py:178-195);
+    reading it and writing it back with this package's ``Structure`` must give the same file."""
+    from golden_utils import GoldenCase
+    from mcsce_b200.structure import Structure
+
+    text = GoldenCase("fix12").pdb
+    s = Structure(text).build()
+    out = tmp_path / "again.pdb"
+    s.write_PDB(str(out))
+    assert out.read_text() == text
+    assert len(s) == 201 and "HD13" in text
