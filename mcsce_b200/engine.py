@@ -14,7 +14,7 @@ from mcsce_b200 import _lib
 from mcsce_b200._lib import (MAX_CHI, MAX_CHI_ROT, MAX_SC, MAX_SP_ENV, MAX_TMPL, BackboneDesc, GrowOpts,
                              SystemDesc, check, load_library)
 from mcsce_b200.chem.tables import load_tables
-from mcsce_b200.libs.placement import placement_quaternions
+from mcsce_b200.libs.placement import placement_quaternions_batch
 from mcsce_b200.system import assign_trials, placement_backbone
 
 
@@ -146,13 +146,14 @@ class GrowthEngine:
         n_lib = np.zeros(L, np.int32); n_chi = np.zeros(L, np.int32)
         means, sigmas, probs = [], [], []
         off = 0
-        for st in sysm.steps:
-            if st.kind == "skip":
-                continue
-            if st.kind == "grow" and st.chi_mean is None:     # no trial sets: scoring-only use (energy closures)
-                continue
-            tm = t.templates[st.resname]
-            q1[st.index], q2[st.index], ca[st.index] = placement_quaternions(bb[st.index], tm.coords[0], tm.coords[2])
+        placed = [st for st in sysm.steps
+                  if st.kind != "skip" and not (st.kind == "grow" and st.chi_mean is None)]   # (no trial sets: scoring-only use)
+        if placed:      # template placement of all residues at once (same arithmetic as the per-residue routine)
+            idx = np.array([st.index for st in placed])
+            tn = np.stack([t.templates[st.resname].coords[0] for st in placed])
+            tc = np.stack([t.templates[st.resname].coords[2] for st in placed])
+            q1[idx], q2[idx], ca[idx] = placement_quaternions_batch(bb[idx], tn, tc)
+        for st in placed:
             if st.kind != "grow":
                 continue
             T = len(st.prob)

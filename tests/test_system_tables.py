@@ -178,3 +178,21 @@ def test_trial_sets_follow_the_backbone_handed_in():
         if x.kind == "grow":
             assert np.array_equal(x.chi_mean, y.chi_mean) and np.array_equal(x.chi_sigma, y.chi_sigma)
             assert np.array_equal(x.prob, y.prob) and x.n_chi == y.n_chi
+
+
+def test_batched_placement_quaternions_are_bit_identical_to_the_per_residue_routine():
+    from mcsce_b200.libs.placement import placement_quaternions, placement_quaternions_batch
+
+    rng = np.random.default_rng(4)
+    tn = np.array([-0.527, 1.359, 0.0], np.float32); tc = np.array([1.526, 0.0, 0.0], np.float32)
+    for L in (1, 2, 3, 7, 16, 33, 257):
+        bb = np.zeros((L, 3, 3), np.float32)
+        for i in range(L):
+            a = np.linalg.qr(rng.standard_normal((3, 3)))[0]
+            bb[i] = np.round(np.stack([tn, np.zeros(3), tc]) @ a.T + rng.normal(0, 0.05, (3, 3)) + rng.uniform(-90, 90, 3), 3)
+        TN = (np.tile(tn, (L, 1)) + rng.normal(0, 0.01, (L, 3))).astype(np.float32)
+        TC = (np.tile(tc, (L, 1)) + rng.normal(0, 0.01, (L, 3))).astype(np.float32)
+        q1, q2, ca = placement_quaternions_batch(bb, TN, TC)
+        for i in range(L):
+            r1, r2, rc = placement_quaternions(bb[i], TN[i], TC[i])
+            assert np.array_equal(r1, q1[i]) and np.array_equal(r2, q2[i]) and np.array_equal(rc, ca[i]), (L, i)
