@@ -240,9 +240,7 @@ def assign_trials(sysm, input_coords, tables=None):
     torsion atoms differ from the ones the current tables were made for.  Returns True if anything was recomputed."""
     tables = tables or load_tables()
     rounded = _round3_f32(np.asarray(input_coords, dtype=np.float32))     # read back from the 3-decimal table (:143-144)
-    ncac = np.zeros((3 * sysm.n_res, 3), dtype=np.float32)
-    for st in sysm.steps:
-        ncac[3 * st.index:3 * st.index + 3] = rounded[list(st.bb_rows)]
+    ncac = np.ascontiguousarray(rounded[_bb_rows(sysm)].reshape(-1, 3))
     key = ncac.tobytes()
     if sysm.trial_key == key:
         return False
@@ -413,7 +411,13 @@ def placement_backbone(backbone_coords, sysm):
     """(L, 3, 3) float32 N,CA,C per residue as the reference sees them for template placement:
     read back from the 3-decimal structure table (side_chain_builder.py:143-144)."""
     rounded = _round3_f32(np.asarray(backbone_coords))
-    out = np.zeros((sysm.n_res, 3, 3), dtype=np.float32)
-    for st in sysm.steps:
-        out[st.index] = rounded[list(st.bb_rows)]
-    return out
+    return np.ascontiguousarray(rounded[_bb_rows(sysm)], dtype=np.float32)
+
+
+def _bb_rows(sysm):
+    """(L, 3) growth-order indices of every residue's N, CA, C (cached on the system)."""
+    rows = getattr(sysm, "_bb_rows_arr", None)
+    if rows is None:
+        rows = np.array([st.bb_rows for st in sysm.steps], dtype=np.int64).reshape(sysm.n_res, 3)
+        sysm._bb_rows_arr = rows
+    return rows
