@@ -136,7 +136,8 @@ size_t mcsce_workspace_bytes(mcsce_handle h, int n_conf);
  * Replaces create_side_chain_structure (core/side_chain_builder.py:109-205) for a batch.
  *   d_coords  [n_conf*n_atoms*3] float32, growth order (out)
  *   d_energy  [n_conf] float64 accumulated energy incl. the input-atom self energy (out)
- *   d_ok      [n_conf] uint8, 0 = every trial of some residue clashed (out)                  */
+ *   d_ok      [n_conf] uint8, 0 = every trial of some residue clashed (out)
+ * n_conf <= 65535 per call (the Python side chunks larger requests).                          */
 int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *opts, void *d_workspace, size_t workspace_bytes,
                float *d_coords, double *d_energy, uint8_t *d_ok, void *stream);
 

@@ -1915,6 +1915,7 @@ extern "C" int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *o, void *d_work
     if (!h || !o) return fail("null argument");
     if (!h->has_bb) return fail("set_system/set_backbone first");
     if (o->n_conf <= 0) return fail("n_conf must be positive");
+    if (o->n_conf > 65535) return fail("n_conf too large: at most 65535 conformers per call (conformers are the grid's y dimension); split the call");
     CK(cudaSetDevice(h->device));
     const SysDev &d = h->d;
     if (workspace_bytes < mcsce_workspace_bytes(h, o->n_conf)) return fail("workspace too small: call mcsce_workspace_bytes");
