@@ -520,10 +520,10 @@ __device__ __forceinline__ void clash_tile(const ScoreArgs &a, const float4 *__r
 //                 has to be likely, not complete.
 template <bool SCREEN>
 __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MINB) score_generic_kernel(ScoreArgs a) {
-    __shared__ float4 s_env[TILE_SLOTS / 2 * 2];     // pair p: [2p] = x0 x1 y0 y1, [2p+1] = z0 z1 q0 q1
+    __shared__ float4 s_env2[2][TILE_SLOTS / 2 * 2];  // two tile buffers; pair p: [2p] = x0 x1 y0 y1, [2p+1] = z0 z1 q0 q1
     __shared__ int s_prefix[MAX_CLS + 1];
-    __shared__ int s_seg2[2][MAX_CLS + 1];            // padded start of every class segment inside the tile (this tile, next tile)
-    __shared__ int s_chunk2[2][MAX_CLS + 1];          // 32-atom staging chunks before every class segment
+    __shared__ int s_seg3[3][MAX_CLS + 1];            // padded start of every class segment inside the tile: tiles t, t+1, t+2
+    __shared__ int s_chunk3[3][MAX_CLS + 1];          // 32-atom staging chunks before every class segment
     __shared__ int s_sp[MAX_SP_ENV], s_sp_c[MAX_SP_ENV];
     __shared__ double s_e[SCREEN ? 1 : TILE_A];
     __shared__ unsigned char s_clash[TILE_A];
@@ -645,11 +645,10 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MINB) score_generic_kerne
     const int hi = min(n_active, lo + per);
     const float4 *env = a.env + (long long)set * a.s.n_atoms;
     const int *scr_slot = SCREEN ? a.s.scr_slot + a.s.scr_off[a.step] : nullptr;
-    float *s_flat = reinterpret_cast<float *>(s_env);
 
     // Layout of a tile: per class the atoms of [tile_lo, tile_hi) that belong to it, padded to an even count.  Warp 0
-    // scans the padded lengths (s_seg) and the number of 32-atom staging chunks (s_chunk) of the classes - for the first
-    // tile here, for every later tile while the other warps already score the current one (two buffers).
+    // scans the padded lengths (s_seg) and the number of 32-atom staging chunks (s_chunk) of the classes, two tiles ahead
+    // of the one being scored (three buffers).
     auto scan_tile = [&](int buf, int t_lo, int t_hi) {
         int carry_seg = 0, carry_chunk = 0;
         for (int c0 = 0; c0 < n_cls; c0 += 32) {
@@ -663,47 +662,74 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MINB) score_generic_kerne
                 const int ys = __shfl_up_sync(0xffffffffu, xs, off), yc = __shfl_up_sync(0xffffffffu, xc, off);
                 if (lane >= off) { xs += ys; xc += yc; }
             }
-            if (c < n_cls) { s_seg2[buf][c] = carry_seg + xs - even; s_chunk2[buf][c] = carry_chunk + xc - chunks; }
+            if (c < n_cls) { s_seg3[buf][c] = carry_seg + xs - even; s_chunk3[buf][c] = carry_chunk + xc - chunks; }
             carry_seg += __shfl_sync(0xffffffffu, xs, 31);
             carry_chunk += __shfl_sync(0xffffffffu, xc, 31);
         }
-        if (lane == 0) { s_seg2[buf][n_cls] = carry_seg; s_chunk2[buf][n_cls] = carry_chunk; }
+        if (lane == 0) { s_seg3[buf][n_cls] = carry_seg; s_chunk3[buf][n_cls] = carry_chunk; }
     };
-    if (warp == 0 && lo < hi) scan_tile(0, lo, min(lo + TILE_E, hi));
-    int buf = 0;
-    for (int tile_lo = lo; tile_lo < hi; tile_lo += TILE_E, buf ^= 1) {
-        const int tile_n = min(TILE_E, hi - tile_lo), tile_hi = tile_lo + tile_n;
-        const int *s_seg = s_seg2[buf], *s_chunk = s_chunk2[buf];
-        __syncthreads();          // the scan of this tile is visible; nobody reads the previous tile any more
-        {   // staging: a warp takes whole chunks, so the class of a chunk is found once per 32 atoms
-            const int n_chunks = s_chunk[n_cls];
-            int c = 0;
-            for (int q = warp; q < n_chunks; q += SCORE_THREADS / 32) {
-                while (s_chunk[c + 1] <= q) ++c;
-                const int first = max(s_prefix[c], tile_lo);              // position of the class's first atom of this tile
-                const int len = min(s_prefix[c + 1], tile_hi) - first;
-                const int e = ((q - s_chunk[c]) << 5) + lane;
-                if (e < ((len + 1) & ~1)) {
-                    float4 v = make_float4(1.0e15f, 1.0e15f, 1.0e15f, 0.f);  // pad slot of an odd segment: a parked dummy
-                    if (e < len) v = env[SCREEN ? scr_slot[first + e] : a.s.cls_start[c] + (first - s_prefix[c]) + e];
-                    const int P = s_seg[c] + e, pp = P >> 1, hh = P & 1;
-                    s_flat[8 * pp + hh] = v.x; s_flat[8 * pp + 2 + hh] = v.y; s_flat[8 * pp + 4 + hh] = v.z; s_flat[8 * pp + 6 + hh] = v.w;
+    // Staging of one tile, asynchronous (LDGSTS: global -> shared without registers, four 4-byte copies per atom into the
+    // pair-interleaved layout): a warp takes whole chunks, so the class of a chunk is found once per 32 atoms.  The copies
+    // of tile t+1 are issued before tile t is scored, so their latency hides under the pair loop.
+    auto stage_tile = [&](int t, int t_lo, int t_hi) {
+        const int *seg = s_seg3[t % 3], *chunk = s_chunk3[t % 3];
+        float *flat = reinterpret_cast<float *>(s_env2[t & 1]);
+        const int n_chunks = chunk[n_cls];
+        int c = 0;
+        for (int q = warp; q < n_chunks; q += SCORE_THREADS / 32) {
+            while (chunk[c + 1] <= q) ++c;
+            const int first = max(s_prefix[c], t_lo);                 // position of the class's first atom of this tile
+            const int len = min(s_prefix[c + 1], t_hi) - first;
+            const int e = ((q - chunk[c]) << 5) + lane;
+            if (e < ((len + 1) & ~1)) {
+                const int P = seg[c] + e, pp = P >> 1, hh = P & 1;
+                float *dst = flat + 8 * pp + hh;
+                if (e < len) {
+                    const float *src = reinterpret_cast<const float *>(env + (SCREEN ? scr_slot[first + e] : a.s.cls_start[c] + (first - s_prefix[c]) + e));
+                    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(d), "l"(src));
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(d + 8), "l"(src + 1));
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(d + 16), "l"(src + 2));
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(d + 24), "l"(src + 3));
+                } else {                                               // pad slot of an odd segment: a parked dummy
+                    dst[0] = 1.0e15f; dst[2] = 1.0e15f; dst[4] = 1.0e15f; dst[6] = 0.f;
                 }
             }
-            // the special environment atoms are scored by the special-pair kernel: the thread that staged one parks it
-            if (!SCREEN)
-                for (int j = 0; j < st.n_sp_env; ++j) {
-                    const int ae = s_sp[j], cj = s_sp_c[j];
-                    if (ae < tile_lo || ae >= tile_hi) continue;
-                    const int e = ae - max(s_prefix[cj], tile_lo);
-                    if ((s_chunk[cj] + (e >> 5)) % (SCORE_THREADS / 32) == warp && (e & 31) == lane) {
-                        const int P = s_seg[cj] + e, pp = P >> 1, hh = P & 1;
-                        s_flat[8 * pp + hh] = 1.0e15f; s_flat[8 * pp + 2 + hh] = 1.0e15f; s_flat[8 * pp + 4 + hh] = 1.0e15f; s_flat[8 * pp + 6 + hh] = 0.f;
-                    }
-                }
         }
-        __syncthreads();          // tile staged
-        if (warp == 0 && tile_hi < hi) scan_tile(buf ^ 1, tile_hi, min(tile_hi + TILE_E, hi));
+        asm volatile("cp.async.commit_group;");
+    };
+    const int n_tiles = (hi - lo + TILE_E - 1) / TILE_E;
+    if (warp == 0) {
+        if (n_tiles > 0) scan_tile(0, lo, min(lo + TILE_E, hi));
+        if (n_tiles > 1) scan_tile(1, lo + TILE_E, min(lo + 2 * TILE_E, hi));
+    }
+    __syncthreads();
+    if (n_tiles > 0) stage_tile(0, lo, min(lo + TILE_E, hi));
+    for (int t = 0; t < n_tiles; ++t) {
+        const int tile_lo = lo + t * TILE_E;
+        const int tile_n = min(TILE_E, hi - tile_lo), tile_hi = tile_lo + tile_n;
+        const int *s_seg = s_seg3[t % 3], *s_chunk = s_chunk3[t % 3];
+        const float4 *s_env = s_env2[t & 1];
+        float *s_flat = reinterpret_cast<float *>(s_env2[t & 1]);
+        if (t + 1 < n_tiles) {                                            // prefetch the next tile into the other buffer
+            stage_tile(t + 1, tile_hi, min(tile_hi + TILE_E, hi));
+            asm volatile("cp.async.wait_group 1;" ::: "memory");          // this thread's copies of tile t have landed
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        // the special environment atoms are scored by the special-pair kernel: the thread that staged one parks it
+        if (!SCREEN)
+            for (int j = 0; j < st.n_sp_env; ++j) {
+                const int ae = s_sp[j], cj = s_sp_c[j];
+                if (ae < tile_lo || ae >= tile_hi) continue;
+                const int e = ae - max(s_prefix[cj], tile_lo);
+                if ((s_chunk[cj] + (e >> 5)) % (SCORE_THREADS / 32) == warp && (e & 31) == lane) {
+                    const int P = s_seg[cj] + e, pp = P >> 1, hh = P & 1;
+                    s_flat[8 * pp + hh] = 1.0e15f; s_flat[8 * pp + 2 + hh] = 1.0e15f; s_flat[8 * pp + 4 + hh] = 1.0e15f; s_flat[8 * pp + 6 + hh] = 0.f;
+                }
+            }
+        __syncthreads();          // tile t staged by everybody
+        if (warp == 0 && t + 2 < n_tiles) scan_tile((t + 2) % 3, tile_lo + 2 * TILE_E, min(tile_lo + 3 * TILE_E, hi));
         int c_first, c_last;
         { int c_lo = 0, c_hi = n_cls; while (c_hi - c_lo > 1) { int m = (c_lo + c_hi) >> 1; if (s_prefix[m] <= tile_lo) c_lo = m; else c_hi = m; } c_first = c_lo; }
         { int c_lo = 0, c_hi = n_cls; const int last = tile_lo + tile_n - 1;
@@ -717,6 +743,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MINB) score_generic_kerne
             else if (SCORE_R > 2 && rows >= 2) score_tile<(SCORE_R > 2 ? SCORE_R - 1 : 1)>(a, s_env, s_seg, c_first, c_last, nx, ny, nz, ci, e_lj, e_c, clash);
             else if (rows >= 1) score_tile<1>(a, s_env, s_seg, c_first, c_last, nx, ny, nz, ci, e_lj, e_c, clash);
         }
+        if (t + 2 < n_tiles) __syncthreads();     // tile t's buffer is overwritten by the prefetch of tile t+2; its scan is visible
     }
 
     // per-atom totals -> per-trial partial sums (fixed order)
