@@ -78,6 +78,7 @@ struct SysDev {
     const double *charge;
     const float *cls_s2f, *cls_thr2f;
     const double *cls_e4, *cls_s2d, *cls_thrd;
+    const double *cls_A, *cls_B;         // [n_cls*n_cls] e4*s2^6 and e4*s2^3: A/d^12 - B/d^6
     const StepDev *steps;
     const TmplDev *tmpl;
     const int *sp_k, *sp_partner;
@@ -447,16 +448,20 @@ __device__ __forceinline__ void score_tile(const ScoreArgs &a, const float4 *__r
         const int p0 = s_seg[c] >> 1, p1 = s_seg[c + 1] >> 1;          // padded, pair units
         if (p0 >= p1) continue;
         float thr2[SCORE_R];
+        double A[SCORE_R], B[SCORE_R];
         double E6[SCORE_R], E3[SCORE_R], EC[SCORE_R];
+        // class-pair constants, loaded before the pair loop so that their latency hides under it:
+        // A/d^12 - B/d^6 with A = e4*s2^6, B = e4*s2^3 (libenergy.py:478-481), float64, products formed on the host
 #pragma unroll
-        for (int r = 0; r < RR; ++r) { thr2[r] = __ldg(&a.s.cls_thr2f[ci[r] * n_cls + c]); E6[r] = 0.0; E3[r] = 0.0; EC[r] = 0.0; }
+        for (int r = 0; r < RR; ++r) {
+            const int idx = ci[r] * n_cls + c;
+            thr2[r] = __ldg(&a.s.cls_thr2f[idx]); A[r] = __ldg(&a.s.cls_A[idx]); B[r] = __ldg(&a.s.cls_B[idx]);
+            E6[r] = 0.0; E3[r] = 0.0; EC[r] = 0.0;
+        }
         score_segment<RR>(s_env, p0, p1, nx, ny, nz, thr2, E6, E3, EC, clash);
 #pragma unroll
         for (int r = 0; r < RR; ++r) {
-            // A/d^12 - B/d^6 with A = e4*s2^6, B = e4*s2^3 (libenergy.py:478-481), class constants in float64
-            const double s2 = __ldg(&a.s.cls_s2d[ci[r] * n_cls + c]), e4 = __ldg(&a.s.cls_e4[ci[r] * n_cls + c]);
-            const double s6 = s2 * s2 * s2;
-            e_lj[r] += e4 * s6 * (s6 * E6[r] - E3[r]);
+            e_lj[r] += A[r] * E6[r] - B[r] * E3[r];
             e_c[r] += EC[r];
         }
     }
@@ -1271,6 +1276,15 @@ extern "C" int mcsce_set_system(mcsce_handle h, const mcsce_system_desc *s) {
     if (upload(h, P, s->cls_thr, nc2, &d.cls_thrd)) return -1;
     std::vector<float> s2f(nc2), thr2f(nc2);
     for (size_t i = 0; i < nc2; ++i) { s2f[i] = (float)s->cls_s2[i]; thr2f[i] = exact_thr2(s->cls_thr[i]); }
+    {
+        std::vector<double> cA(nc2), cB(nc2);
+        for (size_t i = 0; i < nc2; ++i) {
+            const double s6 = s->cls_s2[i] * s->cls_s2[i] * s->cls_s2[i];
+            cA[i] = s->cls_e4[i] * s6 * s6; cB[i] = s->cls_e4[i] * s6;
+        }
+        if (upload(h, P, cA.data(), nc2, &d.cls_A)) return -1;
+        if (upload(h, P, cB.data(), nc2, &d.cls_B)) return -1;
+    }
     if (upload(h, P, s2f.data(), nc2, &d.cls_s2f)) return -1;
     if (upload(h, P, thr2f.data(), nc2, &d.cls_thr2f)) return -1;
     h->cls_active.assign(s->cls_active, s->cls_active + (size_t)(s->n_res + 1) * s->n_cls);
