@@ -210,6 +210,51 @@ int mcsce_write_pdbs(int n_conf, int n_atoms, const float *h_coords, const uint8
  * milliseconds / launch counts for [place, score_generic, score_special, select]. */
 int mcsce_profile(mcsce_handle h, int enable, double *ms_by_class, int64_t *launches_by_class);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * A7 - hydrophobic potential of mean force (libs/libhpmf.py) on the Hasel-Hendrickson-Still approximate
+ * solvent-accessible surface (libs/libsasa.py), evaluated for batches of whole structures.
+ * The reference cannot reach this term through prepare_energy_function (libs/libenergy.py:110-113 vs :217,
+ * :807 vs libhpmf.py:92); the entry points mirror the two closures that do run when called directly.
+ * ------------------------------------------------------------------------------------------------ */
+#define MCSCE_SASA_MAX_BONDS 4   /* covalent neighbours that carry a SASA type (N-terminal N: CA H1 H2 H3) */
+
+typedef struct {
+    int32_t n_atoms;               /* atoms per structure (typed or not)                          */
+    int32_t n_typed;               /* atoms with a SASA type (libhpmf.py:22-68: carbon-bound H have none) */
+    int32_t n_types;
+    const int32_t *typed_atom;     /* [n_typed] index of the typed atom within the structure      */
+    const int32_t *type_of;        /* [n_typed] SASA type index                                   */
+    const int32_t *bonded;         /* [n_typed*MCSCE_SASA_MAX_BONDS] typed indices of the covalent neighbours, -1 = none
+                                      (the bond_connectivities matrix of libsasa.py:76, row by row) */
+    const double *type_R;          /* [n_types] radius, A   (libsasa.py:46-70)                     */
+    const double *type_P;          /* [n_types] P_i         (libsasa.py:21-45)                     */
+    const uint8_t *type_is_carbon; /* [n_types] type name starts with "C" (libhpmf.py:90)          */
+    double r_solvent;              /* 1.4 A (libsasa.py:76)                                        */
+    double pij_bonded, pij_non_bonded;   /* 0.8875, 0.3516 (libsasa.py:73-74)                      */
+    double hpmf_c[3], hpmf_w[3], hpmf_h[3];  /* Gaussian centres, widths, heights (libhpmf.py:17-19) */
+    double sa_threshold;           /* carbons with SA <= threshold drop out (libhpmf.py:20, 98)    */
+} mcsce_hpmf_desc;
+
+typedef struct mcsce_hpmf_s *mcsce_hpmf;
+
+/* replaces libsasa.calc_sasa(...) / libhpmf.init_hpmf_calculator(...): everything that does not depend on coordinates */
+int mcsce_hpmf_create(mcsce_hpmf *out, int device, const mcsce_hpmf_desc *h_desc);
+int mcsce_hpmf_destroy(mcsce_hpmf h);
+
+/* replaces the closure of calc_sasa (libsasa.py:89-108) for n_struct structures:
+ *   d_coords [n_struct*n_atoms*3] float32  ->  d_sasa [n_struct*n_typed] float64, A^2            */
+int mcsce_sasa(mcsce_hpmf h, int n_struct, const float *d_coords, double *d_sasa, void *stream);
+
+/* replaces the closure of init_hpmf_calculator (libhpmf.py:92-109) for n_struct structures:
+ *   d_coords [n_struct*n_atoms*3] float32  ->  d_v [n_struct] float64;
+ *   d_sasa [n_struct*n_typed] float64: caller-provided scratch, holds the surface areas on return  */
+int mcsce_hpmf_energy(mcsce_hpmf h, int n_struct, const float *d_coords, double *d_sasa, double *d_v, void *stream);
+
+/* per-kernel device time of the last mcsce_hpmf_energy call: ms[0] = SASA kernel, ms[1] = carbon-pair kernel
+ * (CUDA events on the launch stream; synchronises) */
+int mcsce_hpmf_last_ms(mcsce_hpmf h, double *ms);
+
 #ifdef __cplusplus
 }
 #endif

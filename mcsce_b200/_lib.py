@@ -51,6 +51,20 @@ class GrowOpts(C.Structure):
     ]
 
 
+SASA_MAX_BONDS = 4
+
+
+class HpmfDesc(C.Structure):
+    _fields_ = [
+        ("n_atoms", C.c_int32), ("n_typed", C.c_int32), ("n_types", C.c_int32),
+        ("typed_atom", _i32p), ("type_of", _i32p), ("bonded", _i32p),
+        ("type_R", _f64p), ("type_P", _f64p), ("type_is_carbon", C.POINTER(C.c_uint8)),
+        ("r_solvent", C.c_double), ("pij_bonded", C.c_double), ("pij_non_bonded", C.c_double),
+        ("hpmf_c", C.c_double * 3), ("hpmf_w", C.c_double * 3), ("hpmf_h", C.c_double * 3),
+        ("sa_threshold", C.c_double),
+    ]
+
+
 #: every symbol include/mcsce_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "mcsce_last_error": (C.c_char_p, []),
@@ -78,6 +92,11 @@ SYMBOLS = {
     "mcsce_write_pdbs": (C.c_int, [C.c_int, C.c_int, _f32p, C.c_void_p, _i32p, C.c_char_p, C.c_int, C.c_int, C.c_char_p,
                                    C.c_int, _i32p]),
     "mcsce_profile": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "mcsce_hpmf_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(HpmfDesc)]),
+    "mcsce_hpmf_destroy": (C.c_int, [C.c_void_p]),
+    "mcsce_sasa": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mcsce_hpmf_energy": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mcsce_hpmf_last_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "mcsce_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int]),
 }
 

@@ -15,7 +15,7 @@ from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
 ROOT = PKG.parent
-CU_SOURCES = [PKG / "csrc" / "mcsce_kernels.cu", PKG / "csrc" / "pdb_writer.cpp"]
+CU_SOURCES = [PKG / "csrc" / "mcsce_kernels.cu", PKG / "csrc" / "hpmf_kernels.cu", PKG / "csrc" / "pdb_writer.cpp"]
 LIB = PKG / "libmcsce_b200.so"
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

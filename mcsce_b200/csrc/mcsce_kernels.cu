@@ -38,6 +38,8 @@
 
 static thread_local std::string g_err;
 static int fail(const std::string &m) { g_err = m; return -1; }
+// error text of the other translation units of the library (hpmf_kernels.cu)
+int mcsce_fail_shared(const std::string &m) { return fail(m); }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
     return fail(std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
 
