@@ -242,7 +242,10 @@ typedef struct mcsce_hpmf_s *mcsce_hpmf;
 int mcsce_hpmf_create(mcsce_hpmf *out, int device, const mcsce_hpmf_desc *h_desc);
 int mcsce_hpmf_destroy(mcsce_hpmf h);
 
-/* replaces the closure of calc_sasa (libsasa.py:89-108) for n_struct structures:
+/* Atoms with x > 1e14 count as absent (the growth parks unplaced atoms at 1e15): surface area 0, no pair terms -
+ * a partially grown structure is evaluated as if it held only the atoms placed so far.
+ *
+ * replaces the closure of calc_sasa (libsasa.py:89-108) for n_struct structures:
  *   d_coords [n_struct*n_atoms*3] float32  ->  d_sasa [n_struct*n_typed] float64, A^2            */
 int mcsce_sasa(mcsce_hpmf h, int n_struct, const float *d_coords, double *d_sasa, void *stream);
 

@@ -31,6 +31,8 @@ _ptm_rotamer_lib = None
 
 #: conformers grown per device launch sequence; larger ensembles are processed in chunks of this size
 MAX_CONFORMERS_PER_LAUNCH = 4096
+#: the same for the step-by-step growth that carries the ``hpmf`` term (one whole-structure evaluation per trial)
+MAX_CONFORMERS_PER_STEPWISE_CALL = 64
 
 # kept for API compatibility: level 0 = the input structure, level i+1 = with residue i's side chain
 sidechain_placeholders = []
@@ -103,6 +105,11 @@ def initialize_func_calc(efunc_creator, aa_seq=None, structure=None, retain_idxs
     lib, ptm = _libraries()
     t = load_tables()
     terms = _terms_of(efunc_creator)
+    from mcsce_b200.libs.libenergy import _SUPPORTED
+    bad = [x for x in terms if x not in _SUPPORTED]
+    if bad:
+        raise NotImplementedError("energy terms %s are not runnable in the reference either; supported: %s"
+                                  % (bad, list(_SUPPORTED)))
     sysm = build_system(structure, retain_idxs=tuple(retain_idxs), terms=terms, rotamer_library=lib, ptm_library=ptm, tables=t)
     eng = _state.get("engine")
     if eng is None:
@@ -121,6 +128,11 @@ def initialize_func_calc(efunc_creator, aa_seq=None, structure=None, retain_idxs
     energy_calculators = _LazyCalculators(efunc_creator, placeholders, [st.kind for st in sysm.steps])
     _state.pop("final", None)
     _state.update(engine=eng, system=sysm, structure=structure, retain=tuple(retain_idxs), backbone=None, seed=_state.get("seed", 0))
+    _state["extra_term"] = None
+    if "hpmf" in terms:
+        # coordinate-based term (libenergy.py:213-220, 806-808): not in the fused loop, grown step by step
+        from mcsce_b200.hpmf import growth_term
+        _state["extra_term"] = growth_term(eng)
     print("Finished preparing all energy functions. Now start conformer generation")
 
 
@@ -148,11 +160,19 @@ def _grow(backbone_coords, beta, n_conf):
     parts = []
     # one rank: results straight into pinned host memory; several ranks: keep them on the device for the gather.
     # Big requests are grown in chunks so that the device workspace and the pinned staging stay bounded.
-    for c0 in range(lo, hi, MAX_CONFORMERS_PER_LAUNCH):
-        n = min(MAX_CONFORMERS_PER_LAUNCH, hi - c0)
-        out = eng.grow(n, beta, seed=_state.get("seed", 0), conf_id0=first + c0, host_out=single)
-        part = (out["coords"], out["energy"], out["ok"])
-        parts.append(tuple(x.copy() for x in part) if single else tuple(x.clone() for x in part))
+    extra = _state.get("extra_term")
+    chunk = MAX_CONFORMERS_PER_LAUNCH if extra is None else MAX_CONFORMERS_PER_STEPWISE_CALL
+    for c0 in range(lo, hi, chunk):
+        n = min(chunk, hi - c0)
+        if extra is None:
+            out = eng.grow(n, beta, seed=_state.get("seed", 0), conf_id0=first + c0, host_out=single)
+            part = (out["coords"], out["energy"], out["ok"])
+            parts.append(tuple(x.copy() for x in part) if single else tuple(x.clone() for x in part))
+        else:
+            # generator keyed by (seed, first conformer id) so that results do not depend on the sharding
+            out = eng.grow_stepwise(n, beta, seed=[_state.get("seed", 0), first + c0], extra_term=extra)
+            part = (out["coords"], out["energy"], out["ok"])
+            parts.append(tuple(x.cpu().numpy() for x in part) if single else part)
     if not parts:
         local = (np.zeros((0, sysm.n_atoms, 3), np.float32), np.zeros(0), np.zeros(0, np.uint8))
     elif len(parts) == 1:

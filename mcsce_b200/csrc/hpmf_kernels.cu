@@ -26,6 +26,7 @@ int mcsce_fail_shared(const std::string &m);
 #define MAXB MCSCE_SASA_MAX_BONDS
 #define MAX_SASA_TYPES 32
 #define HPMF_CUTOFF 18.0f
+#define ABSENT_X 1.0e14f       // x beyond this = atom not placed (the growth parks unplaced atoms at 1e15)
 
 struct HpmfDev {
     int n_atoms, n_typed, n_types, n_carbon;
@@ -98,7 +99,8 @@ __global__ void __launch_bounds__(HT) sasa_kernel(HpmfDev s, const float *__rest
             }
         }
     }
-    if (live) sasa[(long long)blockIdx.y * s.n_typed + i] = __dmul_rn(Si, prod);
+    // an atom parked at 1e15 (not placed yet, the growth's convention) has no surface and no partners
+    if (live) sasa[(long long)blockIdx.y * s.n_typed + i] = xi > ABSENT_X ? 0.0 : __dmul_rn(Si, prod);
 }
 
 __global__ void __launch_bounds__(HT) hpmf_pair_kernel(HpmfDev s, const float *__restrict__ coords,
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(HT) hpmf_pair_kernel(HpmfDev s, const float *_
         const float *p = coords + (base + s.typed_atom[c]) * 3;
         xi = p[0]; yi = p[1]; zi = p[2];
         const double a = sa[c];
-        wi = a > s.sa_threshold ? tanh(a) : 0.0;
+        wi = (a > s.sa_threshold && xi <= ABSENT_X) ? tanh(a) : 0.0;
     }
     const double C0 = s.C[0], C1 = s.C[1], C2 = s.C[2], W0 = s.W[0], W1 = s.W[1], W2 = s.W[2];
     const double H0 = s.H[0], H1 = s.H[1], H2 = s.H[2];
@@ -130,7 +132,7 @@ __global__ void __launch_bounds__(HT) hpmf_pair_kernel(HpmfDev s, const float *_
             const float *p = coords + (base + s.typed_atom[c]) * 3;
             sx[tid] = p[0]; sy[tid] = p[1]; sz[tid] = p[2];
             const double a = sa[c];
-            sw[tid] = a > s.sa_threshold ? tanh(a) : 0.0;
+            sw[tid] = (a > s.sa_threshold && p[0] <= ABSENT_X) ? tanh(a) : 0.0;
         }
         __syncthreads();
         if (wi == 0.0) continue;

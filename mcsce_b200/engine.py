@@ -304,6 +304,77 @@ class GrowthEngine:
                                     self._stream_ptr()))
         return sel, es
 
+    # -- step-by-step growth through the single-kernel entry points ------------------
+    def initial_coords(self, n_conf):
+        """(n_conf, n_atoms, 3) float32 growth-order coordinates before any residue is grown: input atoms and the
+        conformer-independent GLY/ALA side chains in place, everything else parked at 1e15 (mcsce_init_env)."""
+        torch = self.torch
+        N = self.system.n_atoms
+        env = torch.empty((1, N, 4), dtype=torch.float32, device=self.device)
+        check(self.lib.mcsce_init_env(self.h, 1, C.c_void_p(env.data_ptr()), self._stream_ptr()))
+        slot = torch.as_tensor(np.asarray(self.system.slot_of_atom, dtype=np.int64), device=self.device)
+        return env[0, slot, :3].unsqueeze(0).repeat(int(n_conf), 1, 1).contiguous()
+
+    def grow_stepwise(self, n_conf, beta, seed=0, noise_deg=0.5, chis=None, uniforms=None, extra_term=None,
+                      record=None):
+        """The growth loop of ``mcsce_grow`` driven from the host, one residue at a time, through the single-kernel
+        entry points (K1 ``mcsce_place_trials``, K2 ``mcsce_score_trials``, K3 ``mcsce_select``).  It exists for
+        energy terms that the fused loop does not carry: ``extra_term(step, coords, trial_xyz, finite) -> (C, T)``
+        float64 is added to the energy of every trial that passed the clash filter, and
+        ``extra_term(None, coords, None, None) -> (C,)`` to the starting energy - how the reference treats its
+        coordinate-based terms (``efuncs_coords``, libenergy.py:806-808; side_chain_builder.py:149).
+
+        ``chis`` (C, n_trials_total, MAX_CHI) / ``uniforms`` (C, n_res) replay given trial rows and draws; otherwise
+        they come from a NumPy generator seeded with ``seed`` (not the Philox streams of the fused path).
+        Returns dict(coords, energy, ok) as ``grow`` does, plus ``selected`` (C, n_res)."""
+        torch = self.torch
+        assert self._has_backbone, "set_backbone first"
+        sysm = self.system
+        C_, L = int(n_conf), sysm.n_res
+        rng = np.random.default_rng(seed)
+        if uniforms is None:
+            uniforms = rng.random((C_, L))
+        uniforms = np.asarray(uniforms, dtype=np.float64).reshape(C_, L)
+        if chis is not None:
+            chis = np.asarray(chis, dtype=np.float64).reshape(C_, self.n_trials_total, MAX_CHI)
+        coords = self.initial_coords(C_)
+        energy = torch.full((C_,), self.input_energy(), dtype=torch.float64, device=self.device)
+        if extra_term is not None:
+            energy = energy + extra_term(None, coords, None, None)
+        alive = torch.ones(C_, dtype=torch.bool, device=self.device)
+        selected = torch.full((C_, L), -2, dtype=torch.int32, device=self.device)
+        rows_c = torch.arange(C_, device=self.device)
+        for st in sysm.steps:
+            if st.kind != "grow":
+                continue
+            i, T, o = st.index, len(st.prob), int(self.trial_off[st.index])
+            if chis is not None:
+                rows = chis[:, o:o + T, :]
+            else:
+                rows = np.zeros((C_, T, MAX_CHI))
+                k = st.n_chi_lib
+                mean = st.chi_mean[None] + st.chi_sigma[None] * rng.standard_normal((C_, T, k))
+                mean = np.where(st.chi_sigma[None] > 0, (mean + 180.0) % 360.0 - 180.0, mean)
+                rows[:, :, :k] = mean + noise_deg * rng.standard_normal((C_, T, k))
+            xyz = self.place_trials(i, rows.reshape(C_ * T, MAX_CHI)).reshape(C_, T, st.n_sc, 3).contiguous()
+            e = self.score_trials(i, xyz, coords[:, :st.sc_start])
+            if extra_term is not None:
+                finite = torch.isfinite(e) & alive[:, None]
+                e = torch.where(finite, e + extra_term(st, coords, xyz, finite), e)
+            sel, e_sel = self.select(e, st.prob, beta, uniforms[:, i])
+            if record is not None:
+                record.append(dict(step=i, chis=rows.copy(), energies=e.cpu().numpy(), selected=sel.cpu().numpy()))
+            ok_now = sel >= 0
+            selected[:, i] = torch.where(alive, sel, torch.full_like(sel, -1))
+            pick = sel.clamp(min=0).long()
+            new_xyz = xyz[rows_c, pick]
+            keep = (alive & ok_now)[:, None, None]
+            coords[:, st.sc_start:st.sc_start + st.n_sc] = torch.where(keep, new_xyz, coords[:, st.sc_start:st.sc_start + st.n_sc])
+            energy = torch.where(alive & ok_now, energy + e_sel, energy)
+            alive = alive & ok_now
+        nan = torch.full_like(energy, float("nan"))
+        return dict(coords=coords, energy=torch.where(alive, energy, nan), ok=alive.to(torch.uint8), selected=selected)
+
     def input_energy(self):
         torch = self.torch
         out = torch.empty(1, dtype=torch.float64, device=self.device)

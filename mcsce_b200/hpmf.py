@@ -210,3 +210,41 @@ def calculator_for_labels(atom_labels, residue_numbers, residue_labels, device=0
 
 def calculator_for_structure(structure, device=0):
     return calculator_for_labels(structure.atom_labels, structure.res_nums, structure.res_labels, device=device)
+
+
+def growth_term(engine, calc=None, max_bytes=1 << 30):
+    """``extra_term`` for :meth:`GrowthEngine.grow_stepwise`: V_hpmf of every partially grown structure a trial
+    would produce - the input atoms, the side chains placed so far and the trial's - which is what the reference's
+    coordinate-based energy terms receive (libenergy.py:806-808 with the level's atom list, side_chain_builder.py:
+    93-104), evaluated by ``mcsce_hpmf_energy`` on structures whose later atoms are parked (absent).
+
+    Brute force: one whole-structure evaluation per (conformer, trial), O(T N^2) per residue and conformer.  Fine
+    for the reference's own problem sizes (a 76-residue chain: ~5e3 structures of 1.2e3 atoms per conformer); an
+    incremental form (only surface areas within reach of the trial change) is what a fused version needs."""
+    torch = engine.torch
+    sysm = engine.system
+    if calc is None:
+        calc = calculator_for_labels([str(a) for a in sysm.names], [int(r) for r in sysm.resnums],
+                                     [str(r) for r in sysm.resnames], device=engine.device_index)
+    N = sysm.n_atoms
+    per = max(1, int(max_bytes // (N * 12)))
+    parked = 1.0e15
+
+    def term(st, coords, xyz, finite):
+        if st is None:                                     # level 0: the input atoms alone
+            s0 = coords.clone()
+            s0[:, sysm.n_input:] = parked
+            return calc.energy(s0)
+        out = torch.zeros(finite.shape, dtype=torch.float64, device=coords.device)
+        idx = finite.nonzero()
+        end = st.sc_start + st.n_sc
+        for lo in range(0, idx.shape[0], per):
+            c, t = idx[lo:lo + per, 0], idx[lo:lo + per, 1]
+            s = coords[c]
+            s[:, st.sc_start:end] = xyz[c, t]
+            s[:, end:] = parked
+            out[c, t] = calc.energy(s)
+        return out
+
+    term.calculator = calc
+    return term

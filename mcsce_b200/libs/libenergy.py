@@ -6,16 +6,22 @@ coords_old (T, n_old, 3)) -> (T,) float64`` with ``inf`` where the clash filter 
 ``libmcsce_b200.so``.  No O(N^2) masks are built: the labels are turned into per-atom classes and
 the exact special-pair list of the new side chain (mcsce_b200.system).
 
-Terms: ``lj``, ``clash``, ``coulomb`` - the set the reference CLI uses (cli.py:149-151).  The
-reference's angle / dihedral / gb / hpmf switches cannot run in the reference itself
-(``connectivity_matrix`` is commented out at libenergy.py:110-113, keras is absent); asking for them
-here raises ``NotImplementedError`` instead of ``UnboundLocalError``.
+Terms: ``lj``, ``clash``, ``coulomb`` - the set the reference CLI uses (cli.py:149-151) - and ``hpmf``.
+The reference's angle / dihedral / gb / hpmf switches cannot run in the reference itself
+(``connectivity_matrix`` is commented out at libenergy.py:110-113, keras is absent); asking for
+angle / dihedral / gb here raises ``NotImplementedError`` instead of ``UnboundLocalError``.
+
+``hpmf`` is the one of them whose building blocks run in the reference when called directly
+(libhpmf.py, libsasa.py).  It is wired the way the reference's code reads once its two slips are
+repaired: the bond connectivity is the 1-bond mask (the commented-out lines), and the closure gets the
+level's whole structure, new and old atoms in label order (``efuncs_coords``, libenergy.py:806-808):
+every trial that passes the clash filter gets ``V_hpmf`` of (old atoms + its new atoms) added.
 """
 from __future__ import annotations
 
 import numpy as np
 
-_SUPPORTED = ("lj", "clash", "coulomb")
+_SUPPORTED = ("lj", "clash", "coulomb", "hpmf")
 
 
 def _device():
@@ -42,8 +48,31 @@ def prepare_energy_function(atom_labels, residue_numbers, residue_labels, N_term
                                     C_terminal_indicators, partial_indices, terms=tuple(terms))
     eng = GrowthEngine(_device()).set_system(sysm)
     eng.set_backbone(np.zeros((sysm.n_input, 3), dtype=np.float32))
+    hpmf = None
+    if "hpmf" in terms:
+        from mcsce_b200.hpmf import calculator_for_labels
+        hpmf = calculator_for_labels(atom_labels, residue_numbers, residue_labels, device=_device())
+
+    def add_hpmf(out, coords_new, coords_old):
+        ok = np.isfinite(out)
+        if hpmf is None or not ok.any():
+            return out
+        if partial_indices is None:
+            full = coords_new[ok]
+        else:
+            new_idx, old_idx = (np.asarray(x, dtype=np.int64) for x in partial_indices)
+            full = np.empty((int(ok.sum()), len(atom_labels), 3), dtype=np.float32)
+            full[:, new_idx] = coords_new[ok]
+            full[:, old_idx] = coords_old[ok]
+        out[ok] += hpmf.energy(full).cpu().numpy()
+        return out
 
     def calculate(coords_new, coords_old):
+        coords_new = np.asarray(coords_new, dtype=np.float32)
+        coords_old = np.asarray(coords_old, dtype=np.float32)
+        return add_hpmf(_pair_terms(coords_new, coords_old), coords_new, coords_old)
+
+    def _pair_terms(coords_new, coords_old):
         coords_new = np.asarray(coords_new, dtype=np.float32)
         coords_old = np.asarray(coords_old, dtype=np.float32)
         assert len(coords_new.shape) == 3

@@ -310,7 +310,7 @@ def prepare_energy_functions(structure, retain_idxs=(), terms=("lj", "clash", "c
 
 
 def grow_conformer(structure, backbone_coords, beta, chi_for_step, uniform_for_step, retain_idxs=(),
-                   terms=("lj", "clash", "coulomb"), tables=None, efuncs=None, record=None):
+                   terms=("lj", "clash", "coulomb"), tables=None, efuncs=None, record=None, extra_term=None):
     """One conformer of the growth loop (side_chain_builder.py:109-205).
 
     ``structure``: backbone-only ``mcsce_b200.structure.Structure`` (atom bookkeeping only).
@@ -318,6 +318,9 @@ def grow_conformer(structure, backbone_coords, beta, chi_for_step, uniform_for_s
     trial set of residue ordinal i (library rows + noise, supplied by the caller so that the
     oracle, the reference and the GPU path see identical trials).
     ``uniform_for_step(i) -> u`` in [0,1).
+    ``extra_term(atom_labels, res_nums, res_labels, coords) -> float``: a coordinate-based term on the
+    level's whole structure (the reference's ``efuncs_coords``, libenergy.py:806-808), added to every trial
+    that passed the clash filter and to the starting energy.
     Returns dict(ok, energy, coords (growth order, float32), records).
     """
     from mcsce_b200.structure import _round3_f32
@@ -344,6 +347,8 @@ def grow_conformer(structure, backbone_coords, beta, chi_for_step, uniform_for_s
 
     coords = backbone_coords.copy()
     energy = efunc(0).calculate(coords[None], coords[None, :0])[0]
+    if extra_term is not None:
+        energy = energy + extra_term(work.atom_labels, work.res_nums, work.res_labels, coords)
     for i, res in enumerate(res_types):
         num = first + i
         if num in retain_idxs:
@@ -366,6 +371,11 @@ def grow_conformer(structure, backbone_coords, beta, chi_for_step, uniform_for_s
         trial = np.stack([trial_side_chain(tmpl, bb, chis[k]) for k in range(T)])
         env = np.broadcast_to(coords[None], (T,) + coords.shape)
         e = ef.calculate(trial, env)
+        if extra_term is not None:
+            for k in range(T):
+                if np.isfinite(e[k]):
+                    e[k] += extra_term(work.atom_labels, work.res_nums, work.res_labels,
+                                       np.concatenate([coords, trial[k]]))
         if record is not None:
             record.append(dict(step=i, res=res, chis=np.array(chis, dtype=F64), probs=np.array(probs),
                                trial=trial.copy(), energies=e.copy(), n_env=len(coords)))

@@ -94,7 +94,7 @@ def test_prepare_energy_function_closure(name):
         assert np.array_equal(np.isinf(got2[1:]), np.isinf(g["energies"][1:8]))
         checked += 1
     with pytest.raises(NotImplementedError):
-        prepare_energy_function(s.atom_labels, s.res_nums, s.res_labels, n_term[:len(s)], c_term[:len(s)], None, terms=["lj", "hpmf"])
+        prepare_energy_function(s.atom_labels, s.res_nums, s.res_labels, n_term[:len(s)], c_term[:len(s)], None, terms=["lj", "gb"])
     with pytest.raises(AssertionError):
         f0(s.coords, s.coords)
 

@@ -154,3 +154,164 @@ def test_config3_grown_conformers_against_oracle():
         vo, sao = O.hpmf(xs[c], keep, types, bonded, load_sasa_tables())
         np.testing.assert_allclose(sa[c], sao, rtol=1e-9, atol=1e-9)
         assert abs(v[c] - vo) <= _tol(vo), (c, v[c], vo)
+
+
+# ---------------------------------------------------------------------------------------------
+# the term inside the growth (step-by-step loop through the single-kernel entry points)
+# ---------------------------------------------------------------------------------------------
+
+def _oracle_hpmf_term():
+    from mcsce_b200.hpmf import bond_pairs, load_sasa_tables
+    from oracle import hpmf_numpy as O
+
+    cache = {}
+
+    def term(labels, nums, reslabels, coords):
+        n = len(labels)
+        if n not in cache:
+            names, rn, rl = [str(a) for a in labels], [int(x) for x in nums], [str(x) for x in reslabels]
+            keep, types = O.convert_atom_types(names, rn, rl, load_sasa_tables()["atom_types"])
+            bi, bj = bond_pairs(names, rn, rl)
+            idx = np.cumsum(keep) - 1
+            sel = keep[bi] & keep[bj]
+            bonded = np.zeros((keep.sum(), keep.sum()), bool)
+            bonded[idx[bi[sel]], idx[bj[sel]]] = True
+            cache[n] = (keep, types, bonded | bonded.T)
+        keep, types, bonded = cache[n]
+        return O.hpmf(np.asarray(coords, np.float32), keep, types, bonded, load_sasa_tables())[0]
+
+    return term
+
+
+def _pep12():
+    from golden_utils import GoldenCase
+    from mcsce_b200.engine import GrowthEngine
+    from mcsce_b200.system import build_system
+
+    case = GoldenCase("pep12")
+    lib, ptm = library()
+    s = case.structure()
+    sysm = build_system(s, terms=case.terms, rotamer_library=lib, ptm_library=ptm)
+    return case, s, sysm, GrowthEngine(0).set_system(sysm).set_backbone(s.coords)
+
+
+def test_stepwise_growth_equals_fused_growth():
+    """Same trial rows and uniforms through ``mcsce_grow`` and through the host-driven K1/K2/K3 loop: same
+    selections, same coordinates, energies within the per-trial tolerance summed over the residues."""
+    case, s, sysm, eng = _pep12()
+    u = np.random.default_rng(3).random((8, sysm.n_res))
+    a = eng.grow(8, case.beta, seed=11, uniforms=u, dump=True)
+    chis = a["chis"].cpu().numpy()
+    b = eng.grow_stepwise(8, case.beta, chis=chis, uniforms=u)
+    sel_a, sel_b = a["selected"].cpu().numpy(), b["selected"].cpu().numpy()
+    grown = [st.index for st in sysm.steps if st.kind == "grow"]
+    ok = a["ok"].cpu().numpy().astype(bool)
+    assert np.array_equal(sel_a[ok][:, grown], sel_b[ok][:, grown])
+    assert np.array_equal(ok, b["ok"].cpu().numpy().astype(bool)) and ok.sum() >= 4
+    assert np.array_equal(a["coords"].cpu().numpy()[ok], b["coords"].cpu().numpy()[ok])
+    ea, eb = a["energy"].cpu().numpy()[ok], b["energy"].cpu().numpy()[ok]
+    assert (np.abs(ea - eb) <= 1e-3 * len(grown) + 1e-5 * np.abs(ea)).all()
+    # own generator: deterministic in the seed, different between seeds
+    c1 = eng.grow_stepwise(4, case.beta, seed=5)
+    c2 = eng.grow_stepwise(4, case.beta, seed=5)
+    c3 = eng.grow_stepwise(4, case.beta, seed=6)
+    assert np.array_equal(c1["coords"].cpu().numpy(), c2["coords"].cpu().numpy())
+    assert not np.array_equal(c1["selected"].cpu().numpy(), c3["selected"].cpu().numpy())
+
+
+def test_growth_with_hpmf_term_against_oracle_growth():
+    """lj + clash + coulomb + hpmf: the GPU's step-by-step growth against the NumPy oracle's growth loop carrying
+    the same coordinate-based term, on identical trial rows and uniforms - per-trial energies within tolerance,
+    every selection identical."""
+    from mcsce_b200.hpmf import growth_term
+    from oracle import ref_numpy as O
+
+    case, s, sysm, eng = _pep12()
+    term = growth_term(eng)
+    u = np.random.default_rng(4).random((3, sysm.n_res))
+    rec = []
+    out = eng.grow_stepwise(3, case.beta, seed=9, uniforms=u, extra_term=term, record=rec)
+    plain = eng.grow_stepwise(3, case.beta, seed=9, uniforms=u)
+    sel = out["selected"].cpu().numpy()
+    assert not np.array_equal(sel, plain["selected"].cpu().numpy())          # the term changes the growth
+    by_step = {r["step"]: r for r in rec}
+    oterm = _oracle_hpmf_term()
+    worst, outliers, n_trials = 0.0, 0, 0
+    for c in range(3):
+        def chi_for_step(i, res, phi, psi):
+            st = sysm.steps[i]
+            return by_step[i]["chis"][c, :, :st.n_chi_lib], st.prob
+
+        orec = []
+        ref = O.grow_conformer(s, s.coords, case.beta, chi_for_step, lambda i: u[c, i], terms=case.terms, record=orec,
+                               extra_term=oterm)
+        assert bool(out["ok"][c].item()) == ref["ok"]
+        for r in orec:
+            got = by_step[r["step"]]["energies"][c]
+            assert np.array_equal(np.isinf(got), np.isinf(r["energies"])), r["step"]
+            fin = np.isfinite(r["energies"])
+            tol = np.maximum(1e-3, 1e-5 * np.abs(r["energies"][fin]))
+            ratio = np.abs(got[fin] - r["energies"][fin]) / tol
+            # a carbon whose surface area sits on the 6 A^2 exposure threshold switches all its pair terms with a
+            # 1e-6 A coordinate difference (K1 fidelity): such trials are counted, not bounded
+            outliers += int((ratio > 4.0).sum()); n_trials += int(fin.sum())
+            if (ratio <= 4.0).any():
+                worst = max(worst, float(ratio[ratio <= 4.0].max()))
+            if "selected" in r:
+                assert sel[c, r["step"]] == r["selected"], (c, r["step"])
+        if ref["ok"]:
+            e = float(out["energy"][c].item())
+            assert abs(e - ref["energy"]) <= 1e-3 * sysm.n_res + 1e-5 * abs(ref["energy"]), (e, ref["energy"])
+    assert n_trials > 500 and outliers <= 2, (outliers, n_trials, worst)
+
+
+def test_hpmf_through_the_reference_entry_points(tmp_path):
+    """terms=[..., "hpmf"] through prepare_energy_function's closure and initialize_func_calc /
+    create_side_chain_ensemble."""
+    from functools import partial
+
+    from mcsce_b200.core import side_chain_builder as scb
+    from mcsce_b200.libs.libenergy import prepare_energy_function
+    from oracle import ref_numpy as O
+
+    case, s, sysm, eng = _pep12()
+    terms = ["lj", "clash", "coulomb", "hpmf"]
+    oterm = _oracle_hpmf_term()
+    # closure of a level: residue 1 (ARG) grown on top of MET
+    out = eng.grow_stepwise(1, case.beta, seed=2)
+    xyz = out["coords"][0].cpu().numpy()
+    st = [x for x in sysm.steps if x.kind == "grow"][1]
+    n_all = st.sc_start + st.n_sc
+    names, nums, labels = sysm.names[:n_all], sysm.resnums[:n_all], sysm.resnames[:n_all]
+    idx = np.arange(n_all)
+    f = prepare_energy_function(names, nums, labels, sysm.is_nterm[:n_all], sysm.is_cterm[:n_all], None,
+                                partial_indices=[idx[-st.n_sc:], idx[:-st.n_sc]], terms=terms)
+    f_plain = prepare_energy_function(names, nums, labels, sysm.is_nterm[:n_all], sysm.is_cterm[:n_all], None,
+                                      partial_indices=[idx[-st.n_sc:], idx[:-st.n_sc]], terms=terms[:3])
+    rows = np.zeros((6, 6)); rows[:, :st.n_chi_lib] = st.chi_mean[:6]
+    trial = eng.place_trials(st.index, rows).cpu().numpy()
+    env = np.repeat(xyz[None, :st.sc_start], 6, axis=0)
+    got, base = f(trial, env), f_plain(trial, env)
+    assert np.array_equal(np.isinf(got), np.isinf(base))
+    for k in np.nonzero(np.isfinite(base))[0]:
+        v = oterm(names, nums, labels, np.concatenate([env[k], trial[k]]))
+        assert abs((got[k] - base[k]) - v) <= max(1e-3, 1e-5 * abs(v)), (k, got[k] - base[k], v)
+    # whole-structure closure (level 0)
+    n_term, c_term = s.get_terminal_res_atom_arr()
+    f0 = prepare_energy_function(s.atom_labels, s.res_nums, s.res_labels, n_term, c_term, None, terms=terms)
+    f0p = prepare_energy_function(s.atom_labels, s.res_nums, s.res_labels, n_term, c_term, None, terms=terms[:3])
+    v0 = oterm(s.atom_labels, s.res_nums, s.res_labels, s.coords)
+    assert abs((f0(s.coords[None], s.coords[None, :0])[0] - f0p(s.coords[None], s.coords[None, :0])[0]) - v0) <= 1e-3
+    # growth entry points
+    scb.set_seed(3)
+    scb.initialize_func_calc(partial(prepare_energy_function, batch_size=16, forcefield=None, terms=terms), structure=s)
+    confs, success = scb.create_side_chain_ensemble(s, 6, 300, str(tmp_path))
+    assert len(success) == 6 and sum(success) >= 3
+    lines = (tmp_path / "energies.csv").read_text().strip().splitlines()
+    assert len(lines) == 1 + sum(success)
+    structure, ok, energy, _ = scb.create_side_chain_structure([s.coords, case.beta, [], None])
+    assert ok and np.isfinite(energy)
+    with pytest.raises(NotImplementedError):
+        scb.initialize_func_calc(partial(prepare_energy_function, terms=["lj", "gb"]), structure=s)
+    # leave the module prepared for the plain terms (other tests share it)
+    scb.initialize_func_calc(partial(prepare_energy_function, batch_size=16, forcefield=None, terms=terms[:3]), structure=s)
