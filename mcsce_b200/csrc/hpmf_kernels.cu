@@ -43,9 +43,14 @@ __device__ __forceinline__ float norm2_f32(float ax, float ay, float az, float b
     return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
 }
 
+// fused form for range tests only: never feeds a result
+__device__ __forceinline__ float dist2_fast(float ax, float ay, float az, float bx, float by, float bz) {
+    const float x = ax - bx, y = ay - by, z = az - bz;
+    return fmaf(z, z, fmaf(y, y, x * x));
+}
+
 __global__ void __launch_bounds__(HT) sasa_kernel(HpmfDev s, const float *__restrict__ coords, double *__restrict__ sasa) {
-    __shared__ float sx[HT], sy[HT], sz[HT];
-    __shared__ int st[HT];
+    __shared__ float4 sp[HT];               // x, y, z, type (int bits): one 16-byte load per partner
     __shared__ double s_thr[MAX_SASA_TYPES * MAX_SASA_TYPES];
     __shared__ double s_R[MAX_SASA_TYPES], s_piRRs[MAX_SASA_TYPES];
     const int tid = threadIdx.x, nt = s.n_types;
@@ -71,8 +76,7 @@ __global__ void __launch_bounds__(HT) sasa_kernel(HpmfDev s, const float *__rest
         const int jl = j0 + tid;
         if (jl < s.n_typed) {
             const float *p = coords + (base + s.typed_atom[jl]) * 3;
-            sx[tid] = p[0]; sy[tid] = p[1]; sz[tid] = p[2];
-            st[tid] = s.type_of[jl];
+            sp[tid] = make_float4(p[0], p[1], p[2], __int_as_float(s.type_of[jl]));
         }
         __syncthreads();
         if (!live) continue;
@@ -80,12 +84,12 @@ __global__ void __launch_bounds__(HT) sasa_kernel(HpmfDev s, const float *__rest
         const double *thr_row = s_thr + ti * nt;
 #pragma unroll 4
         for (int jj = 0; jj < n; ++jj) {
-            const float d2 = norm2_f32(xi, yi, zi, sx[jj], sy[jj], sz[jj]);
-            if (d2 < s.pre2) {
+            const float4 q = sp[jj];
+            if (dist2_fast(xi, yi, zi, q.x, q.y, q.z) < s.pre2) {     // superset test (pre2 is padded by 1e-3)
                 const int j = j0 + jj;
                 if (j == i) continue;
-                const float d = __fsqrt_rn(d2);
-                const int tj = st[jj];
+                const float d = __fsqrt_rn(norm2_f32(xi, yi, zi, q.x, q.y, q.z));
+                const int tj = __float_as_int(q.w);
                 const double thr = thr_row[tj];
                 if ((double)d < thr) {
                     const double pij = (j == b0 || j == b1 || j == b2 || j == b3) ? s.pij_bonded : s.pij_non_bonded;
@@ -105,7 +109,7 @@ __global__ void __launch_bounds__(HT) sasa_kernel(HpmfDev s, const float *__rest
 
 __global__ void __launch_bounds__(HT) hpmf_pair_kernel(HpmfDev s, const float *__restrict__ coords,
                                                        const double *__restrict__ sasa, double *__restrict__ partial) {
-    __shared__ float sx[HT], sy[HT], sz[HT];
+    __shared__ float4 sp[HT];
     __shared__ double sw[HT];
     __shared__ double red[HT];
     const int tid = threadIdx.x;
@@ -130,20 +134,21 @@ __global__ void __launch_bounds__(HT) hpmf_pair_kernel(HpmfDev s, const float *_
         if (jl < s.n_carbon) {
             const int c = s.carbon[jl];
             const float *p = coords + (base + s.typed_atom[c]) * 3;
-            sx[tid] = p[0]; sy[tid] = p[1]; sz[tid] = p[2];
             const double a = sa[c];
-            sw[tid] = (a > s.sa_threshold && p[0] <= ABSENT_X) ? tanh(a) : 0.0;
+            const double w = (a > s.sa_threshold && p[0] <= ABSENT_X) ? tanh(a) : 0.0;
+            sw[tid] = w;
+            sp[tid] = make_float4(p[0], p[1], p[2], w == 0.0 ? 0.f : 1.f);
         }
         __syncthreads();
         if (wi == 0.0) continue;
         const int n = min(HT, s.n_carbon - j0);
 #pragma unroll 4
         for (int jj = 0; jj < n; ++jj) {
-            const float d2 = norm2_f32(xi, yi, zi, sx[jj], sy[jj], sz[jj]);
-            if (d2 < HPMF_CUTOFF * HPMF_CUTOFF) {
+            const float4 q = sp[jj];
+            if (q.w != 0.f && dist2_fast(xi, yi, zi, q.x, q.y, q.z) < HPMF_CUTOFF * HPMF_CUTOFF) {
+                if (j0 + jj == i) continue;
                 const double wj = sw[jj];
-                if (wj == 0.0 || j0 + jj == i) continue;
-                const double r = (double)__fsqrt_rn(d2);
+                const double r = (double)__fsqrt_rn(norm2_f32(xi, yi, zi, q.x, q.y, q.z));
                 const double t0 = (r - C0) / W0, t1 = (r - C1) / W1, t2 = (r - C2) / W2;
                 const double g = H0 * exp(-(t0 * t0)) + H1 * exp(-(t1 * t1)) + H2 * exp(-(t2 * t2));
                 acc += wj * g;
