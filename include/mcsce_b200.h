@@ -254,6 +254,16 @@ int mcsce_sasa(mcsce_hpmf h, int n_struct, const float *d_coords, double *d_sasa
  *   d_sasa [n_struct*n_typed] float64: caller-provided scratch, holds the surface areas on return  */
 int mcsce_hpmf_energy(mcsce_hpmf h, int n_struct, const float *d_coords, double *d_sasa, double *d_v, void *stream);
 
+/* The term inside the growth (libenergy.py:806-808: coordinate-based terms are added to every trial that passed the
+ * clash filter, evaluated on the level's whole structure): V_hpmf of (the atoms before first_new + one trial's new
+ * atoms) for every (conformer, trial) with d_mask != 0, without re-evaluating the environment per trial.
+ *   d_coords [n_conf*n_atoms*3] float32: the conformers so far; atoms from first_new on are ignored
+ *   d_trial  [n_conf*n_trials*n_new*3] float32: the trials' coordinates of atoms [first_new, first_new+n_new)
+ *   d_mask   [n_conf*n_trials] uint8 or NULL (= all);  d_v [n_conf*n_trials] float64 out, 0 where masked
+ * Synchronises the stream (reads back an overflow flag).  n_conf <= 65535.                               */
+int mcsce_hpmf_trials(mcsce_hpmf h, int n_conf, const float *d_coords, int first_new, int n_new, int n_trials,
+                      const float *d_trial, const uint8_t *d_mask, double *d_v, void *stream);
+
 /* per-kernel device time of the last mcsce_hpmf_energy call: ms[0] = SASA kernel, ms[1] = carbon-pair kernel
  * (CUDA events on the launch stream; synchronises) */
 int mcsce_hpmf_last_ms(mcsce_hpmf h, double *ms);

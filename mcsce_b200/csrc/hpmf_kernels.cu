@@ -15,6 +15,7 @@
 #include <stdint.h>
 #include <string>
 #include <vector>
+#include <algorithm>
 
 #include "../../include/mcsce_b200.h"
 
@@ -49,16 +50,33 @@ __device__ __forceinline__ float dist2_fast(float ax, float ay, float az, float 
     return fmaf(z, z, fmaf(y, y, x * x));
 }
 
-__global__ void __launch_bounds__(HT) sasa_kernel(HpmfDev s, const float *__restrict__ coords, double *__restrict__ sasa) {
+// one factor of the product: atom i (P_i, S_i, R_i) shadowed by partner j (pi (R_j + R_s), R_j) at distance d < thr
+__device__ __forceinline__ double sasa_term(double Pi, double Si, double Ri, double piRRs_j, double Rj, double thr, float d,
+                                            double pij) {
+    // dij + 1e-8 stays float32 in the reference (float32 array + Python scalar)
+    const double dd = (double)__fadd_rn(d, 1e-8f);
+    const double bij = __dmul_rn(__dmul_rn(piRRs_j, __dsub_rn(thr, (double)d)),
+                                 __dadd_rn(1.0, __ddiv_rn(__dsub_rn(Rj, Ri), dd)));
+    return __dsub_rn(1.0, __ddiv_rn(__dmul_rn(__dmul_rn(Pi, pij), bij), Si));
+}
+
+// nt_lim: only the first nt_lim typed atoms exist (a partially grown structure); n_typed for a whole one
+__global__ void __launch_bounds__(HT) sasa_kernel(HpmfDev s, const float *__restrict__ coords, double *__restrict__ sasa,
+                                                  int nt_lim) {
     __shared__ float4 sp[HT];               // x, y, z, type (int bits): one 16-byte load per partner
     __shared__ double s_thr[MAX_SASA_TYPES * MAX_SASA_TYPES];
     __shared__ double s_R[MAX_SASA_TYPES], s_piRRs[MAX_SASA_TYPES];
     const int tid = threadIdx.x, nt = s.n_types;
     const long long base = (long long)blockIdx.y * s.n_atoms;
+    if (blockIdx.x * HT >= nt_lim) {            // whole block beyond the atoms that exist
+        const int i0 = blockIdx.x * HT + tid;
+        if (i0 < s.n_typed) sasa[(long long)blockIdx.y * s.n_typed + i0] = 0.0;
+        return;
+    }
     for (int k = tid; k < nt * nt; k += HT) s_thr[k] = s.thr[k];
     if (tid < nt) { s_R[tid] = s.R[tid]; s_piRRs[tid] = s.piRRs[tid]; }
     const int i = blockIdx.x * HT + tid;
-    const bool live = i < s.n_typed;
+    const bool live = i < nt_lim;
     float xi = 0.f, yi = 0.f, zi = 0.f;
     int ti = 0, b0 = -1, b1 = -1, b2 = -1, b3 = -1;
     double Ri = 0., Pi = 0., Si = 1.;
@@ -71,16 +89,16 @@ __global__ void __launch_bounds__(HT) sasa_kernel(HpmfDev s, const float *__rest
         Ri = s.R[ti]; Pi = s.P[ti]; Si = s.S[ti];
     }
     double prod = 1.0;
-    for (int j0 = 0; j0 < s.n_typed; j0 += HT) {
+    for (int j0 = 0; j0 < nt_lim; j0 += HT) {
         __syncthreads();
         const int jl = j0 + tid;
-        if (jl < s.n_typed) {
+        if (jl < nt_lim) {
             const float *p = coords + (base + s.typed_atom[jl]) * 3;
             sp[tid] = make_float4(p[0], p[1], p[2], __int_as_float(s.type_of[jl]));
         }
         __syncthreads();
         if (!live) continue;
-        const int n = min(HT, s.n_typed - j0);
+        const int n = min(HT, nt_lim - j0);
         const double *thr_row = s_thr + ti * nt;
 #pragma unroll 4
         for (int jj = 0; jj < n; ++jj) {
@@ -93,22 +111,26 @@ __global__ void __launch_bounds__(HT) sasa_kernel(HpmfDev s, const float *__rest
                 const double thr = thr_row[tj];
                 if ((double)d < thr) {
                     const double pij = (j == b0 || j == b1 || j == b2 || j == b3) ? s.pij_bonded : s.pij_non_bonded;
-                    // dij + 1e-8 stays float32 in the reference (float32 array + Python scalar)
-                    const double dd = (double)__fadd_rn(d, 1e-8f);
-                    const double bij = __dmul_rn(__dmul_rn(s_piRRs[tj], __dsub_rn(thr, (double)d)),
-                                                 __dadd_rn(1.0, __ddiv_rn(__dsub_rn(s_R[tj], Ri), dd)));
-                    const double term = __dsub_rn(1.0, __ddiv_rn(__dmul_rn(__dmul_rn(Pi, pij), bij), Si));
-                    prod = __dmul_rn(prod, term);
+                    prod = __dmul_rn(prod, sasa_term(Pi, Si, Ri, s_piRRs[tj], s_R[tj], thr, d, pij));
                 }
             }
         }
     }
     // an atom parked at 1e15 (not placed yet, the growth's convention) has no surface and no partners
     if (live) sasa[(long long)blockIdx.y * s.n_typed + i] = xi > ABSENT_X ? 0.0 : __dmul_rn(Si, prod);
+    else if (i < s.n_typed) sasa[(long long)blockIdx.y * s.n_typed + i] = 0.0;
 }
 
+__device__ __forceinline__ double gauss3(const HpmfDev &s, double r) {
+    const double t0 = (r - s.C[0]) / s.W[0], t1 = (r - s.C[1]) / s.W[1], t2 = (r - s.C[2]) / s.W[2];
+    return s.H[0] * exp(-(t0 * t0)) + s.H[1] * exp(-(t1 * t1)) + s.H[2] * exp(-(t2 * t2));
+}
+
+// nc_lim: only the first nc_lim carbons exist.  w_out / f_out (optional, [n_struct*n_carbon]): the weight of every
+// carbon and its field F_i = sum_{j != i} w_j G_ij - what the per-trial kernel builds its increments on.
 __global__ void __launch_bounds__(HT) hpmf_pair_kernel(HpmfDev s, const float *__restrict__ coords,
-                                                       const double *__restrict__ sasa, double *__restrict__ partial) {
+                                                       const double *__restrict__ sasa, double *__restrict__ partial,
+                                                       int nc_lim, double *__restrict__ w_out, double *__restrict__ f_out) {
     __shared__ float4 sp[HT];
     __shared__ double sw[HT];
     __shared__ double red[HT];
@@ -118,20 +140,19 @@ __global__ void __launch_bounds__(HT) hpmf_pair_kernel(HpmfDev s, const float *_
     const int i = blockIdx.x * HT + tid;
     float xi = 0.f, yi = 0.f, zi = 0.f;
     double wi = 0.0;
-    if (i < s.n_carbon) {
+    if (i < nc_lim) {
         const int c = s.carbon[i];
         const float *p = coords + (base + s.typed_atom[c]) * 3;
         xi = p[0]; yi = p[1]; zi = p[2];
         const double a = sa[c];
         wi = (a > s.sa_threshold && xi <= ABSENT_X) ? tanh(a) : 0.0;
     }
-    const double C0 = s.C[0], C1 = s.C[1], C2 = s.C[2], W0 = s.W[0], W1 = s.W[1], W2 = s.W[2];
-    const double H0 = s.H[0], H1 = s.H[1], H2 = s.H[2];
+    const bool want_field = f_out != nullptr && i < nc_lim;
     double acc = 0.0;
-    for (int j0 = 0; j0 < s.n_carbon; j0 += HT) {
+    for (int j0 = 0; j0 < nc_lim; j0 += HT) {
         __syncthreads();
         const int jl = j0 + tid;
-        if (jl < s.n_carbon) {
+        if (jl < nc_lim) {
             const int c = s.carbon[jl];
             const float *p = coords + (base + s.typed_atom[c]) * 3;
             const double a = sa[c];
@@ -140,8 +161,8 @@ __global__ void __launch_bounds__(HT) hpmf_pair_kernel(HpmfDev s, const float *_
             sp[tid] = make_float4(p[0], p[1], p[2], w == 0.0 ? 0.f : 1.f);
         }
         __syncthreads();
-        if (wi == 0.0) continue;
-        const int n = min(HT, s.n_carbon - j0);
+        if (wi == 0.0 && !want_field) continue;
+        const int n = min(HT, nc_lim - j0);
 #pragma unroll 4
         for (int jj = 0; jj < n; ++jj) {
             const float4 q = sp[jj];
@@ -149,11 +170,13 @@ __global__ void __launch_bounds__(HT) hpmf_pair_kernel(HpmfDev s, const float *_
                 if (j0 + jj == i) continue;
                 const double wj = sw[jj];
                 const double r = (double)__fsqrt_rn(norm2_f32(xi, yi, zi, q.x, q.y, q.z));
-                const double t0 = (r - C0) / W0, t1 = (r - C1) / W1, t2 = (r - C2) / W2;
-                const double g = H0 * exp(-(t0 * t0)) + H1 * exp(-(t1 * t1)) + H2 * exp(-(t2 * t2));
-                acc += wj * g;
+                acc += wj * gauss3(s, r);
             }
         }
+    }
+    if (i < s.n_carbon && w_out) {
+        const long long o = (long long)blockIdx.y * s.n_carbon + i;
+        w_out[o] = wi; f_out[o] = i < nc_lim ? acc : 0.0;
     }
     red[tid] = wi * acc;
     __syncthreads();
@@ -172,6 +195,191 @@ __global__ void hpmf_finish_kernel(int n_struct, int n_tiles, const double *__re
     v[c] = 0.5 * sum;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// per-trial V_hpmf of (environment + one trial side chain) without re-evaluating the environment
+// ------------------------------------------------------------------------------------------------
+// The surface area is a product over partners, so adding the trial's atoms multiplies the environment's areas:
+//   SA_k(env + trial) = SA_k(env) * prod_{n in trial, in range} term_kn ,
+// and with w = tanh(SA) [SA > A_c], delta_k = w_k(env + trial) - w_k(env), F_k = sum_{j != k} w_j(env) G_kj :
+//   V(env + trial) = V(env) + sum_k delta_k F_k + sum_{k < l} delta_k delta_l G_kl
+//                  + sum_{n, e} w_n (w_e + delta_e) G_ne + sum_{n < m} w_n w_m G_nm
+// (k, l, e: environment carbons, delta != 0 only within reach of the trial; n, m: the trial's carbons).  Exact - the
+// same pair terms as the whole-structure evaluation, grouped differently.  One block per (trial, conformer).
+#define MAX_NEW_T 16           // typed atoms of one side chain (ARG: 12)
+#define MAX_NEW_C 12           // carbons of one side chain (TRP: 9)
+#define MAX_LIST 512           // environment carbons whose weight a trial changes
+
+__global__ void __launch_bounds__(HT) hpmf_trial_kernel(
+        HpmfDev s, const float *__restrict__ coords, const float *__restrict__ trial, const unsigned char *__restrict__ mask,
+        int first_new, int n_new, int n_trials, int e1, int m, int c1, int mc, const int *__restrict__ carbon_ord,
+        const double *__restrict__ sa_env, const double *__restrict__ w0, const double *__restrict__ f0,
+        const double *__restrict__ v0, double *__restrict__ out, int *__restrict__ overflow) {
+    const int t = blockIdx.x, c = blockIdx.y, tid = threadIdx.x, nt = s.n_types;
+    const long long ct = (long long)c * n_trials + t;
+    if (mask && !mask[ct]) { if (tid == 0) out[ct] = 0.0; return; }
+    __shared__ float4 ta[MAX_NEW_T];                  // trial typed atoms: x, y, z, type
+    __shared__ int tbond[MAX_NEW_T][MAXB];
+    __shared__ double s_thr[MAX_SASA_TYPES * MAX_SASA_TYPES];
+    __shared__ double s_R[MAX_SASA_TYPES], s_piRRs[MAX_SASA_TYPES], s_P[MAX_SASA_TYPES], s_S[MAX_SASA_TYPES];
+    __shared__ double tprod[HT / 32][MAX_NEW_T];
+    __shared__ float4 tc[MAX_NEW_C];                  // trial carbons
+    __shared__ double tw[MAX_NEW_C];
+    __shared__ float4 lpos[MAX_LIST];
+    __shared__ double ldel[MAX_LIST];
+    __shared__ int ln;
+    __shared__ double red[HT];
+    for (int k = tid; k < nt * nt; k += HT) s_thr[k] = s.thr[k];
+    if (tid < nt) { s_R[tid] = s.R[tid]; s_piRRs[tid] = s.piRRs[tid]; s_P[tid] = s.P[tid]; s_S[tid] = s.S[tid]; }
+    if (tid < m) {
+        const int g = e1 + tid;
+        const float *p = trial + (ct * n_new + (s.typed_atom[g] - first_new)) * 3;
+        ta[tid] = make_float4(p[0], p[1], p[2], __int_as_float(s.type_of[g]));
+#pragma unroll
+        for (int b = 0; b < MAXB; ++b) tbond[tid][b] = s.bonded[g * MAXB + b];
+    }
+    if (tid < MAX_NEW_C) { tw[tid] = 0.0; tc[tid] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    if (tid == 0) ln = 0;
+    __syncthreads();
+
+    // phase 1: environment atoms x trial atoms - factors of both surface products
+    double tp[MAX_NEW_T];
+#pragma unroll
+    for (int n = 0; n < MAX_NEW_T; ++n) tp[n] = 1.0;
+    double acc = 0.0;                                  // sum_k delta_k F_k, later the Gaussian sums
+    const float *cbase = coords + (long long)c * s.n_atoms * 3;
+    const double *sa = sa_env + (long long)c * s.n_typed;
+    const double *w0c = w0 + (long long)c * s.n_carbon, *f0c = f0 + (long long)c * s.n_carbon;
+    for (int k = tid; k < e1; k += HT) {
+        const float *p = cbase + (long long)s.typed_atom[k] * 3;
+        const float xk = p[0], yk = p[1], zk = p[2];
+        if (xk > ABSENT_X) continue;
+        int tk = -1, b0 = -1, b1 = -1, b2 = -1, b3 = -1;
+        double f = 1.0;
+#pragma unroll
+        for (int n = 0; n < MAX_NEW_T; ++n) {
+            if (n < m) {
+                const float4 q = ta[n];
+                if (dist2_fast(xk, yk, zk, q.x, q.y, q.z) < s.pre2) {
+                    const float d = __fsqrt_rn(norm2_f32(xk, yk, zk, q.x, q.y, q.z));
+                    if (tk < 0) {
+                        tk = s.type_of[k];
+                        b0 = s.bonded[k * MAXB]; b1 = s.bonded[k * MAXB + 1]; b2 = s.bonded[k * MAXB + 2]; b3 = s.bonded[k * MAXB + 3];
+                    }
+                    const int tn = __float_as_int(q.w);
+                    const double thr = s_thr[tk * nt + tn];
+                    if ((double)d < thr) {
+                        const int g = e1 + n;
+                        const double pij = (g == b0 || g == b1 || g == b2 || g == b3) ? s.pij_bonded : s.pij_non_bonded;
+                        f = __dmul_rn(f, sasa_term(s_P[tk], s_S[tk], s_R[tk], s_piRRs[tn], s_R[tn], thr, d, pij));
+                        tp[n] = __dmul_rn(tp[n], sasa_term(s_P[tn], s_S[tn], s_R[tn], s_piRRs[tk], s_R[tk], thr, d, pij));
+                    }
+                }
+            }
+        }
+        if (f != 1.0) {
+            const int ck = carbon_ord[k];
+            if (ck >= 0) {
+                const double a = sa[k] * f;
+                const double w = a > s.sa_threshold ? tanh(a) : 0.0;
+                const double del = w - w0c[ck];
+                if (del != 0.0) {
+                    acc += del * f0c[ck];
+                    const int idx = atomicAdd(&ln, 1);
+                    if (idx < MAX_LIST) { lpos[idx] = make_float4(xk, yk, zk, 0.f); ldel[idx] = del; }
+                }
+            }
+        }
+    }
+    // block-wide products for the trial atoms
+#pragma unroll
+    for (int n = 0; n < MAX_NEW_T; ++n) {
+        if (n < m) {
+            double v = tp[n];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v *= __shfl_xor_sync(0xffffffffu, v, off);
+            if ((tid & 31) == 0) tprod[tid >> 5][n] = v;
+        }
+    }
+    __syncthreads();
+    // phase 2: trial atoms among themselves -> their surface areas and weights
+    if (tid < m) {
+        double prod = 1.0;
+#pragma unroll
+        for (int w = 0; w < HT / 32; ++w) prod *= tprod[w][tid];
+        const float4 me = ta[tid];
+        const int ti = __float_as_int(me.w);
+        for (int n = 0; n < m; ++n) {
+            if (n == tid) continue;
+            const float4 q = ta[n];
+            const float d = __fsqrt_rn(norm2_f32(me.x, me.y, me.z, q.x, q.y, q.z));
+            const int tn = __float_as_int(q.w);
+            const double thr = s_thr[ti * nt + tn];
+            if ((double)d < thr) {
+                const int g = e1 + n;
+                const bool bonded = g == tbond[tid][0] || g == tbond[tid][1] || g == tbond[tid][2] || g == tbond[tid][3];
+                prod = __dmul_rn(prod, sasa_term(s_P[ti], s_S[ti], s_R[ti], s_piRRs[tn], s_R[tn], thr, d,
+                                                 bonded ? s.pij_bonded : s.pij_non_bonded));
+            }
+        }
+        const int ck = carbon_ord[e1 + tid];
+        if (ck >= 0) {
+            const double a = __dmul_rn(s_S[ti], prod);
+            tw[ck - c1] = a > s.sa_threshold ? tanh(a) : 0.0;
+            tc[ck - c1] = make_float4(me.x, me.y, me.z, 0.f);
+        }
+    }
+    __syncthreads();
+    const int L = min(ln, MAX_LIST);
+    if (tid == 0 && ln > MAX_LIST) atomicExch(overflow, 1);
+    const float cut2 = HPMF_CUTOFF * HPMF_CUTOFF;
+    // phase 3a: trial carbons x environment carbons (weights of the environment alone)
+    for (int ck = tid; ck < c1; ck += HT) {
+        const double wk = w0c[ck];
+        if (wk == 0.0) continue;
+        const float *p = cbase + (long long)s.typed_atom[s.carbon[ck]] * 3;
+        const float xk = p[0], yk = p[1], zk = p[2];
+        for (int n = 0; n < mc; ++n) {
+            const double wn = tw[n];
+            const float4 q = tc[n];
+            if (wn != 0.0 && dist2_fast(xk, yk, zk, q.x, q.y, q.z) < cut2)
+                acc += wn * wk * gauss3(s, (double)__fsqrt_rn(norm2_f32(xk, yk, zk, q.x, q.y, q.z)));
+        }
+    }
+    // phase 3b: the changed environment carbons: with the trial carbons, and among themselves
+    for (int a = tid; a < L; a += HT) {
+        const float4 pa = lpos[a];
+        const double da = ldel[a];
+        for (int n = 0; n < mc; ++n) {
+            const double wn = tw[n];
+            const float4 q = tc[n];
+            if (wn != 0.0 && dist2_fast(pa.x, pa.y, pa.z, q.x, q.y, q.z) < cut2)
+                acc += wn * da * gauss3(s, (double)__fsqrt_rn(norm2_f32(pa.x, pa.y, pa.z, q.x, q.y, q.z)));
+        }
+        for (int b = a + 1; b < L; ++b) {
+            const float4 pb = lpos[b];
+            if (dist2_fast(pa.x, pa.y, pa.z, pb.x, pb.y, pb.z) < cut2)
+                acc += da * ldel[b] * gauss3(s, (double)__fsqrt_rn(norm2_f32(pa.x, pa.y, pa.z, pb.x, pb.y, pb.z)));
+        }
+    }
+    // phase 3c: trial carbons among themselves
+    if (tid < mc) {
+        const float4 pa = tc[tid];
+        for (int b = tid + 1; b < mc; ++b) {
+            const float4 pb = tc[b];
+            if (tw[tid] != 0.0 && tw[b] != 0.0 && dist2_fast(pa.x, pa.y, pa.z, pb.x, pb.y, pb.z) < cut2)
+                acc += tw[tid] * tw[b] * gauss3(s, (double)__fsqrt_rn(norm2_f32(pa.x, pa.y, pa.z, pb.x, pb.y, pb.z)));
+        }
+    }
+    red[tid] = acc;
+    __syncthreads();
+    for (int k = HT / 2; k > 0; k >>= 1) {
+        if (tid < k) red[tid] += red[tid + k];
+        __syncthreads();
+    }
+    if (tid == 0) out[ct] = v0[c] + red[0];
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -181,6 +389,12 @@ struct mcsce_hpmf_s {
     std::vector<void *> owned;
     double *d_partial = nullptr;
     size_t partial_cap = 0;
+    // per-trial evaluation: host copies of the index tables, per-conformer environment state (grow-only)
+    std::vector<int> h_typed_atom, h_carbon;
+    const int *d_carbon_ord = nullptr;
+    double *d_env_state = nullptr;          // sa_env [C*n_typed] | w0 [C*n_carbon] | f0 [C*n_carbon] | v0 [C]
+    size_t env_state_cap = 0;
+    int *d_overflow = nullptr;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     bool timed = false;
 };
@@ -228,6 +442,20 @@ extern "C" int mcsce_hpmf_create(mcsce_hpmf *out, int device, const mcsce_hpmf_d
     if (upload(h, d->type_of, (size_t)d->n_typed, &v.type_of)) return -1;
     if (upload(h, d->bonded, (size_t)d->n_typed * MAXB, &v.bonded)) return -1;
     if (upload(h, carbon.data(), carbon.size(), &v.carbon)) return -1;
+    {
+        std::vector<int> ord((size_t)d->n_typed, -1);
+        for (size_t k = 0; k < carbon.size(); ++k) ord[carbon[k]] = (int)k;
+        if (upload(h, ord.data(), ord.size(), &h->d_carbon_ord)) return -1;
+        h->h_typed_atom.assign(d->typed_atom, d->typed_atom + d->n_typed);
+        h->h_carbon = carbon;
+        for (int i = 1; i < d->n_typed; ++i)
+            if (d->typed_atom[i] <= d->typed_atom[i - 1]) { delete h; return mcsce_fail_shared("mcsce_hpmf_create: typed_atom must be ascending"); }
+        void *po = nullptr;
+        HCK(cudaMalloc(&po, sizeof(int)));
+        HCK(cudaMemset(po, 0, sizeof(int)));
+        h->owned.push_back(po);
+        h->d_overflow = (int *)po;
+    }
     if (upload(h, thr.data(), thr.size(), &v.thr)) return -1;
     if (upload(h, d->type_R, (size_t)nt, &v.R)) return -1;
     if (upload(h, d->type_P, (size_t)nt, &v.P)) return -1;
@@ -247,18 +475,21 @@ extern "C" int mcsce_hpmf_destroy(mcsce_hpmf h) {
     cudaSetDevice(h->device);
     for (void *p : h->owned) cudaFree(p);
     if (h->d_partial) cudaFree(h->d_partial);
+    if (h->d_env_state) cudaFree(h->d_env_state);
     for (int k = 0; k < 3; ++k) if (h->ev[k]) cudaEventDestroy(h->ev[k]);
     delete h;
     return 0;
 }
 
-static int launch_sasa(mcsce_hpmf h, int n_struct, const float *d_coords, double *d_sasa, cudaStream_t st) {
+static int launch_sasa(mcsce_hpmf h, int n_struct, const float *d_coords, double *d_sasa, cudaStream_t st, int nt_lim = -1) {
+    if (nt_lim < 0) nt_lim = h->dev.n_typed;
     const HpmfDev &v = h->dev;
     if (v.n_typed == 0) return 0;
     const int tiles = (v.n_typed + HT - 1) / HT;
     for (int c0 = 0; c0 < n_struct; c0 += 65535) {
         const int nc = n_struct - c0 < 65535 ? n_struct - c0 : 65535;
-        sasa_kernel<<<dim3(tiles, nc), HT, 0, st>>>(v, d_coords + (size_t)c0 * v.n_atoms * 3, d_sasa + (size_t)c0 * v.n_typed);
+        sasa_kernel<<<dim3(tiles, nc), HT, 0, st>>>(v, d_coords + (size_t)c0 * v.n_atoms * 3, d_sasa + (size_t)c0 * v.n_typed,
+                                                    nt_lim);
     }
     HCK(cudaGetLastError());
     return 0;
@@ -293,13 +524,71 @@ extern "C" int mcsce_hpmf_energy(mcsce_hpmf h, int n_struct, const float *d_coor
     for (int c0 = 0; c0 < n_struct; c0 += 65535) {
         const int nc = n_struct - c0 < 65535 ? n_struct - c0 : 65535;
         hpmf_pair_kernel<<<dim3(tiles, nc), HT, 0, st>>>(v, d_coords + (size_t)c0 * v.n_atoms * 3,
-                                                         d_sasa + (size_t)c0 * v.n_typed, h->d_partial + (size_t)c0 * tiles);
+                                                         d_sasa + (size_t)c0 * v.n_typed, h->d_partial + (size_t)c0 * tiles,
+                                                         v.n_carbon, nullptr, nullptr);
     }
     HCK(cudaGetLastError());
     HCK(cudaEventRecord(h->ev[2], st));
     hpmf_finish_kernel<<<(n_struct + 127) / 128, 128, 0, st>>>(n_struct, tiles, h->d_partial, d_v);
     HCK(cudaGetLastError());
     h->timed = true;
+    return 0;
+}
+
+
+extern "C" int mcsce_hpmf_trials(mcsce_hpmf h, int n_conf, const float *d_coords, int first_new, int n_new, int n_trials,
+                                 const float *d_trial, const uint8_t *d_mask, double *d_v, void *stream) {
+    if (!h || !d_coords || !d_trial || !d_v) return mcsce_fail_shared("mcsce_hpmf_trials: null argument");
+    if (n_conf <= 0 || n_trials <= 0) return 0;
+    if (n_conf > 65535) return mcsce_fail_shared("mcsce_hpmf_trials: at most 65535 conformers per call");
+    const HpmfDev &v = h->dev;
+    if (first_new < 0 || n_new <= 0 || first_new + n_new > v.n_atoms) return mcsce_fail_shared("mcsce_hpmf_trials: new-atom range out of bounds");
+    HCK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const std::vector<int> &ta = h->h_typed_atom;
+    const int e1 = (int)(std::lower_bound(ta.begin(), ta.end(), first_new) - ta.begin());
+    const int e2 = (int)(std::lower_bound(ta.begin(), ta.end(), first_new + n_new) - ta.begin());
+    const int c1 = (int)(std::lower_bound(h->h_carbon.begin(), h->h_carbon.end(), e1) - h->h_carbon.begin());
+    const int c2 = (int)(std::lower_bound(h->h_carbon.begin(), h->h_carbon.end(), e2) - h->h_carbon.begin());
+    const int m = e2 - e1, mc = c2 - c1;
+    if (m > MAX_NEW_T || mc > MAX_NEW_C) return mcsce_fail_shared("mcsce_hpmf_trials: too many typed atoms in the new residue");
+    const int tiles = c1 > 0 ? (c1 + HT - 1) / HT : 1;
+    const size_t n_state = (size_t)n_conf * ((size_t)v.n_typed + 2 * (size_t)v.n_carbon + 1);
+    if (n_state > h->env_state_cap || (size_t)n_conf * tiles > h->partial_cap) {
+        HCK(cudaStreamSynchronize(st));
+        if (n_state > h->env_state_cap) {
+            if (h->d_env_state) HCK(cudaFree(h->d_env_state));
+            h->d_env_state = nullptr; h->env_state_cap = 0;
+            HCK(cudaMalloc(&h->d_env_state, n_state * sizeof(double)));
+            h->env_state_cap = n_state;
+        }
+        const size_t need = (size_t)n_conf * ((v.n_carbon + HT - 1) / HT + 1);
+        if (need > h->partial_cap) {
+            if (h->d_partial) HCK(cudaFree(h->d_partial));
+            h->d_partial = nullptr; h->partial_cap = 0;
+            HCK(cudaMalloc(&h->d_partial, need * sizeof(double)));
+            h->partial_cap = need;
+        }
+    }
+    double *sa_env = h->d_env_state;
+    double *w0 = sa_env + (size_t)n_conf * v.n_typed;
+    double *f0 = w0 + (size_t)n_conf * v.n_carbon;
+    double *v0 = f0 + (size_t)n_conf * v.n_carbon;
+    // the environment alone (atoms before first_new), once per conformer
+    if (launch_sasa(h, n_conf, d_coords, sa_env, st, e1)) return -1;
+    hpmf_pair_kernel<<<dim3(tiles, n_conf), HT, 0, st>>>(v, d_coords, sa_env, h->d_partial, c1, w0, f0);
+    hpmf_finish_kernel<<<(n_conf + 127) / 128, 128, 0, st>>>(n_conf, tiles, h->d_partial, v0);
+    // every trial on top of it
+    hpmf_trial_kernel<<<dim3(n_trials, n_conf), HT, 0, st>>>(v, d_coords, d_trial, d_mask, first_new, n_new, n_trials, e1, m,
+                                                             c1, mc, h->d_carbon_ord, sa_env, w0, f0, v0, d_v, h->d_overflow);
+    HCK(cudaGetLastError());
+    int over = 0;
+    HCK(cudaMemcpyAsync(&over, h->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
+    HCK(cudaStreamSynchronize(st));
+    if (over) {
+        HCK(cudaMemset(h->d_overflow, 0, sizeof(int)));
+        return mcsce_fail_shared("mcsce_hpmf_trials: more than 512 environment carbons change weight under one trial");
+    }
     return 0;
 }
 

@@ -192,6 +192,26 @@ class HpmfCalculator:
             v, sasa = v[0], sasa[0]
         return (v, sasa) if return_sasa else v
 
+    def trial_energies(self, coords, first_new, n_new, trial_xyz, mask=None):
+        """V_hpmf of (atoms before ``first_new`` + each trial's ``n_new`` new atoms): ``coords`` (C, n_atoms, 3),
+        ``trial_xyz`` (C, T, n_new, 3), ``mask`` (C, T) bool or None -> (C, T) float64 device tensor, 0 where masked.
+        The environment's surface areas and pair fields are evaluated once per conformer; every trial only adds its
+        own factors and pair terms (``mcsce_hpmf_trials``)."""
+        torch = self.torch
+        x = coords.to(device=self.device, dtype=torch.float32).contiguous()
+        t = trial_xyz.to(device=self.device, dtype=torch.float32).contiguous()
+        C_, T = int(t.shape[0]), int(t.shape[1])
+        assert x.shape == (C_, self.n_atoms, 3) and t.shape[2] == n_new and t.shape[3] == 3
+        out = torch.empty((C_, T), dtype=torch.float64, device=self.device)
+        m = None
+        if mask is not None:
+            m = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            assert m.shape == (C_, T)
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        check(self.lib.mcsce_hpmf_trials(self.h, C_, x.data_ptr(), int(first_new), int(n_new), T, t.data_ptr(),
+                                         m.data_ptr() if m is not None else None, out.data_ptr(), st))
+        return out
+
     def last_ms(self):
         ms = (C.c_double * 2)()
         check(self.lib.mcsce_hpmf_last_ms(self.h, ms))
@@ -212,15 +232,15 @@ def calculator_for_structure(structure, device=0):
     return calculator_for_labels(structure.atom_labels, structure.res_nums, structure.res_labels, device=device)
 
 
-def growth_term(engine, calc=None, max_bytes=1 << 30):
+def growth_term(engine, calc=None, max_bytes=1 << 30, brute_force=False):
     """``extra_term`` for :meth:`GrowthEngine.grow_stepwise`: V_hpmf of every partially grown structure a trial
     would produce - the input atoms, the side chains placed so far and the trial's - which is what the reference's
     coordinate-based energy terms receive (libenergy.py:806-808 with the level's atom list, side_chain_builder.py:
     93-104), evaluated by ``mcsce_hpmf_energy`` on structures whose later atoms are parked (absent).
 
-    Brute force: one whole-structure evaluation per (conformer, trial), O(T N^2) per residue and conformer.  Fine
-    for the reference's own problem sizes (a 76-residue chain: ~5e3 structures of 1.2e3 atoms per conformer); an
-    incremental form (only surface areas within reach of the trial change) is what a fused version needs."""
+    Default: ``mcsce_hpmf_trials`` - the environment once per conformer and residue, O(N^2), then every trial adds
+    its own factors and pair terms, O(n_new N).  ``brute_force=True``: one whole-structure evaluation per
+    (conformer, trial), O(T N^2) per residue and conformer; same numbers, kept as the check of the first."""
     torch = engine.torch
     sysm = engine.system
     if calc is None:
@@ -231,10 +251,12 @@ def growth_term(engine, calc=None, max_bytes=1 << 30):
     parked = 1.0e15
 
     def term(st, coords, xyz, finite):
-        if st is None:                                     # level 0: the input atoms alone
-            s0 = coords.clone()
+        if st is None:                                     # level 0: the input atoms alone, the same for every conformer
+            s0 = coords[:1].clone()
             s0[:, sysm.n_input:] = parked
-            return calc.energy(s0)
+            return calc.energy(s0).expand(coords.shape[0])
+        if not brute_force:
+            return calc.trial_energies(coords, st.sc_start, st.n_sc, xyz, finite)
         out = torch.zeros(finite.shape, dtype=torch.float64, device=coords.device)
         idx = finite.nonzero()
         end = st.sc_start + st.n_sc

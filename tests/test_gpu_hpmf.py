@@ -229,8 +229,16 @@ def test_growth_with_hpmf_term_against_oracle_growth():
     case, s, sysm, eng = _pep12()
     term = growth_term(eng)
     u = np.random.default_rng(4).random((3, sysm.n_res))
-    rec = []
+    rec, rec_bf = [], []
     out = eng.grow_stepwise(3, case.beta, seed=9, uniforms=u, extra_term=term, record=rec)
+    # the brute-force form of the term (one whole structure per trial) gives the same growth
+    bf = eng.grow_stepwise(3, case.beta, seed=9, uniforms=u, extra_term=growth_term(eng, term.calculator, brute_force=True),
+                           record=rec_bf)
+    assert np.array_equal(bf["selected"].cpu().numpy(), out["selected"].cpu().numpy())
+    for a, b in zip(rec, rec_bf):
+        fin = np.isfinite(a["energies"])
+        assert np.array_equal(fin, np.isfinite(b["energies"]))
+        assert np.allclose(a["energies"][fin], b["energies"][fin], rtol=1e-11, atol=1e-9)
     plain = eng.grow_stepwise(3, case.beta, seed=9, uniforms=u)
     sel = out["selected"].cpu().numpy()
     assert not np.array_equal(sel, plain["selected"].cpu().numpy())          # the term changes the growth
@@ -315,3 +323,50 @@ def test_hpmf_through_the_reference_entry_points(tmp_path):
         scb.initialize_func_calc(partial(prepare_energy_function, terms=["lj", "gb"]), structure=s)
     # leave the module prepared for the plain terms (other tests share it)
     scb.initialize_func_calc(partial(prepare_energy_function, batch_size=16, forcefield=None, terms=terms[:3]), structure=s)
+
+
+@pytest.mark.parametrize("cfg,n_conf", [(2, 6), (3, 3)])
+def test_per_trial_increments_equal_whole_structure_evaluation(cfg, n_conf):
+    """``mcsce_hpmf_trials`` (environment once, every trial adds its own factors and pair terms) against one
+    whole-structure ``mcsce_hpmf_energy`` per trial, on partially grown conformers of configs 2 and 3 at an early,
+    a middle and a late residue, with and without a mask."""
+    import torch
+
+    from mcsce_b200 import synth
+    from mcsce_b200.engine import GrowthEngine
+    from mcsce_b200.hpmf import calculator_for_labels
+    from mcsce_b200.structure import Structure
+    from mcsce_b200.system import build_system
+
+    lib, ptm = library()
+    s = Structure(synth.config_backbone(cfg)).build().remove_side_chains([])
+    sysm = build_system(s, rotamer_library=lib, ptm_library=ptm)
+    eng = GrowthEngine(0).set_system(sysm).set_backbone(s.coords)
+    out = eng.grow(4 * n_conf, 1.0 / (300 * 0.008314462), seed=8)
+    full = out["coords"][out["ok"].bool()][:n_conf].contiguous()
+    C_ = full.shape[0]
+    assert C_ >= 2
+    calc = calculator_for_labels([str(a) for a in sysm.names], [int(r) for r in sysm.resnums], [str(r) for r in sysm.resnames])
+    grown = [st for st in sysm.steps if st.kind == "grow"]
+    rng = np.random.default_rng(1)
+    worst = 0.0
+    for st in (grown[1], grown[len(grown) // 2], grown[-1]):
+        T = min(len(st.prob), 24)
+        rows = np.zeros((C_ * T, 6))
+        rows[:, :st.n_chi_lib] = np.tile(st.chi_mean[:T], (C_, 1)) + rng.normal(0, 5.0, (C_ * T, st.n_chi_lib))
+        xyz = eng.place_trials(st.index, rows).reshape(C_, T, st.n_sc, 3).contiguous()
+        got = calc.trial_energies(full, st.sc_start, st.n_sc, xyz).cpu().numpy()
+        end = st.sc_start + st.n_sc
+        structs = full[:, None].repeat(1, T, 1, 1)
+        structs[:, :, st.sc_start:end] = xyz
+        structs[:, :, end:] = 1.0e15
+        ref = calc.energy(structs.reshape(C_ * T, -1, 3)).cpu().numpy().reshape(C_, T)
+        err = np.abs(got - ref) / np.maximum(1.0, np.abs(ref))
+        worst = max(worst, float(err.max()))
+        assert err.max() <= 1e-10, (st.index, st.resname, err.max())
+        assert len(np.unique(np.round(ref, 9))) > T            # trials and conformers differ
+        mask = torch.as_tensor(rng.random((C_, T)) < 0.5, device=full.device)
+        got_m = calc.trial_energies(full, st.sc_start, st.n_sc, xyz, mask).cpu().numpy()
+        mk = mask.cpu().numpy()
+        assert np.array_equal(got_m[mk], got[mk]) and (got_m[~mk] == 0).all()
+    print("worst relative difference", worst)
