@@ -254,18 +254,24 @@ class GrowthEngine:
     def _stream_ptr(self):
         return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
 
-    def place_trials(self, residue, chis):
-        """K1: chis (rows, nchi) degrees -> (rows, n_sc, 3) float32 torch tensor."""
+    def place_trials(self, residue, chis, keep4=False):
+        """K1: chis (rows, nchi) degrees -> (rows, n_sc, 3) float32 torch tensor (``keep4``: the kernel's own
+        (rows, n_sc, 4) buffer).  ``chis`` may be a float64 device tensor of MAX_CHI columns."""
         torch = self.torch
         st = self.system.steps[residue]
-        rows = np.zeros((len(chis), MAX_CHI))
-        chis = np.asarray(chis, dtype=np.float64).reshape(len(chis), -1)
-        rows[:, :chis.shape[1]] = chis[:, :MAX_CHI]
-        d_ch = torch.as_tensor(rows, device=self.device)
+        if torch.is_tensor(chis):
+            d_ch = chis.to(device=self.device, dtype=torch.float64).contiguous()
+            assert d_ch.dim() == 2 and d_ch.shape[1] == MAX_CHI
+            rows = d_ch
+        else:
+            rows = np.zeros((len(chis), MAX_CHI))
+            chis = np.asarray(chis, dtype=np.float64).reshape(len(chis), -1)
+            rows[:, :chis.shape[1]] = chis[:, :MAX_CHI]
+            d_ch = torch.as_tensor(rows, device=self.device)
         out = torch.empty((len(rows), st.n_sc, 4), dtype=torch.float32, device=self.device)
         check(self.lib.mcsce_place_trials(self.h, int(residue), len(rows), C.c_void_p(d_ch.data_ptr()),
                                           C.c_void_p(out.data_ptr()), self._stream_ptr()))
-        return out[:, :, :3]
+        return out if keep4 else out[:, :, :3]
 
     def score_trials(self, residue, trial_xyz, old_xyz, env_split=0):
         """K2: trial_xyz (S, T, n_sc, 3), old_xyz (S, n_old, 3) growth order -> (S, T) float64 energies
@@ -278,8 +284,11 @@ class GrowthEngine:
         assert trial_xyz.shape[2] == st.n_sc and old_xyz.shape[0] == S
         n_old = old_xyz.shape[1]
         assert n_old == st.sc_start, "environment must be the %d atoms that precede this side chain" % st.sc_start
-        t4 = torch.zeros((S, T, st.n_sc, 4), dtype=torch.float32, device=self.device)
-        t4[..., :3] = trial_xyz
+        if trial_xyz.shape[-1] == 4 and trial_xyz.is_contiguous():
+            t4 = trial_xyz                                   # K1's own buffer
+        else:
+            t4 = torch.zeros((S, T, st.n_sc, 4), dtype=torch.float32, device=self.device)
+            t4[..., :3] = trial_xyz
         env = torch.empty((S, self.system.n_atoms, 4), dtype=torch.float32, device=self.device)
         sp = self._stream_ptr()
         check(self.lib.mcsce_pack_env(self.h, S, n_old, C.c_void_p(old_xyz.data_ptr()), C.c_void_p(env.data_ptr()), sp))
@@ -325,18 +334,25 @@ class GrowthEngine:
         coordinate-based terms (``efuncs_coords``, libenergy.py:806-808; side_chain_builder.py:149).
 
         ``chis`` (C, n_trials_total, MAX_CHI) / ``uniforms`` (C, n_res) replay given trial rows and draws; otherwise
-        they come from a NumPy generator seeded with ``seed`` (not the Philox streams of the fused path).
+        they come from torch's device generator seeded with ``seed`` (not the Philox streams of the fused path).
         Returns dict(coords, energy, ok) as ``grow`` does, plus ``selected`` (C, n_res)."""
         torch = self.torch
         assert self._has_backbone, "set_backbone first"
         sysm = self.system
         C_, L = int(n_conf), sysm.n_res
-        rng = np.random.default_rng(seed)
+        gen = torch.Generator(device=self.device)
+        words = [int(x) for x in np.atleast_1d(seed)]
+        gen.manual_seed(int(np.random.SeedSequence(words).generate_state(1, dtype=np.uint64)[0] >> 1))
         if uniforms is None:
-            uniforms = rng.random((C_, L))
-        uniforms = np.asarray(uniforms, dtype=np.float64).reshape(C_, L)
+            uniforms = torch.rand((C_, L), dtype=torch.float64, device=self.device, generator=gen)
+        else:
+            uniforms = torch.as_tensor(np.asarray(uniforms, dtype=np.float64).reshape(C_, L), device=self.device)
         if chis is not None:
-            chis = np.asarray(chis, dtype=np.float64).reshape(C_, self.n_trials_total, MAX_CHI)
+            chis = torch.as_tensor(np.asarray(chis, dtype=np.float64).reshape(C_, self.n_trials_total, MAX_CHI),
+                                   device=self.device)
+        if getattr(self, "_step_cache_key", None) != (id(sysm), sysm.trial_key):
+            self._step_cache = {}
+            self._step_cache_key = (id(sysm), sysm.trial_key)
         coords = self.initial_coords(C_)
         energy = torch.full((C_,), self.input_energy(), dtype=torch.float64, device=self.device)
         if extra_term is not None:
@@ -348,22 +364,29 @@ class GrowthEngine:
             if st.kind != "grow":
                 continue
             i, T, o = st.index, len(st.prob), int(self.trial_off[st.index])
+            if i not in self._step_cache:                    # library rows of the residue on the device, once per backbone
+                pad = lambda a: np.pad(np.asarray(a, dtype=np.float64), ((0, 0), (0, MAX_CHI - a.shape[1])))  # noqa: E731
+                self._step_cache[i] = tuple(torch.as_tensor(x, device=self.device) for x in
+                                            (pad(st.chi_mean), pad(st.chi_sigma), np.asarray(st.prob, dtype=np.float64)))
+            mean_d, sigma_d, prob_d = self._step_cache[i]
             if chis is not None:
-                rows = chis[:, o:o + T, :]
+                rows = chis[:, o:o + T, :].contiguous()
             else:
-                rows = np.zeros((C_, T, MAX_CHI))
-                k = st.n_chi_lib
-                mean = st.chi_mean[None] + st.chi_sigma[None] * rng.standard_normal((C_, T, k))
-                mean = np.where(st.chi_sigma[None] > 0, (mean + 180.0) % 360.0 - 180.0, mean)
-                rows[:, :, :k] = mean + noise_deg * rng.standard_normal((C_, T, k))
-            xyz = self.place_trials(i, rows.reshape(C_ * T, MAX_CHI)).reshape(C_, T, st.n_sc, 3).contiguous()
-            e = self.score_trials(i, xyz, coords[:, :st.sc_start])
+                z = torch.randn((2, C_, T, MAX_CHI), dtype=torch.float64, device=self.device, generator=gen)
+                drawn = mean_d[None] + sigma_d[None] * z[0]
+                drawn = torch.where(drawn > 180.0, drawn - 360.0, drawn)        # wrap_angles (rotamer_library.py:20-25)
+                drawn = torch.where(drawn < -180.0, drawn + 360.0, drawn)
+                rows = drawn + noise_deg * z[1]
+                rows[:, :, st.n_chi_lib:] = 0.0
+            xyz4 = self.place_trials(i, rows.reshape(C_ * T, MAX_CHI), keep4=True).reshape(C_, T, st.n_sc, 4)
+            xyz = xyz4[..., :3]
+            e = self.score_trials(i, xyz4, coords[:, :st.sc_start])
             if extra_term is not None:
                 finite = torch.isfinite(e) & alive[:, None]
                 e = torch.where(finite, e + extra_term(st, coords, xyz, finite), e)
-            sel, e_sel = self.select(e, st.prob, beta, uniforms[:, i])
+            sel, e_sel = self.select(e, prob_d, beta, uniforms[:, i])
             if record is not None:
-                record.append(dict(step=i, chis=rows.copy(), energies=e.cpu().numpy(), selected=sel.cpu().numpy()))
+                record.append(dict(step=i, chis=rows.cpu().numpy(), energies=e.cpu().numpy(), selected=sel.cpu().numpy()))
             ok_now = sel >= 0
             selected[:, i] = torch.where(alive, sel, torch.full_like(sel, -1))
             pick = sel.clamp(min=0).long()

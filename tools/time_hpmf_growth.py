@@ -40,9 +40,13 @@ def timed(fn, reps=2):
 t_fused, a = timed(lambda: eng.grow(n_conf, beta, seed=1))
 t_step, b = timed(lambda: eng.grow_stepwise(n_conf, beta, seed=1))
 t_hpmf, c = timed(lambda: eng.grow_stepwise(n_conf, beta, seed=1, extra_term=term), reps=1)
+t_bf = None
+if "--brute" in sys.argv:
+    bf = growth_term(eng, term.calculator, brute_force=True)
+    t_bf, _ = timed(lambda: eng.grow_stepwise(n_conf, beta, seed=1, extra_term=bf), reps=1)
 n_trials = int(eng.n_trials_total)
 print(json.dumps({"workload": "cfg%d" % cfg, "conformers": n_conf, "atoms": sysm.n_atoms, "trials_per_conformer": n_trials,
-                  "fused_s": t_fused, "stepwise_s": t_step, "stepwise_hpmf_s": t_hpmf,
-                  "hpmf_structures_per_s": n_conf * n_trials / max(1e-9, t_hpmf - t_step),
+                  "fused_s": t_fused, "stepwise_s": t_step, "stepwise_hpmf_s": t_hpmf, "stepwise_hpmf_brute_force_s": t_bf,
+                  "hpmf_trials_per_s": n_conf * n_trials / max(1e-9, t_hpmf - t_step),
                   "ok": [float(x["ok"].float().mean()) for x in (a, b, c)],
                   "mean_energy": [float(x["energy"][x["ok"].bool()].mean()) for x in (a, b, c)]}))
