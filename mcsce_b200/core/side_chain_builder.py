@@ -31,8 +31,8 @@ _ptm_rotamer_lib = None
 
 #: conformers grown per device launch sequence; larger ensembles are processed in chunks of this size
 MAX_CONFORMERS_PER_LAUNCH = 4096
-#: the same for the step-by-step growth that carries the ``hpmf`` term (one whole-structure evaluation per trial)
-MAX_CONFORMERS_PER_STEPWISE_CALL = 64
+#: the same for the step-by-step growth that carries the ``hpmf`` term
+MAX_CONFORMERS_PER_STEPWISE_CALL = 1024
 
 # kept for API compatibility: level 0 = the input structure, level i+1 = with residue i's side chain
 sidechain_placeholders = []
