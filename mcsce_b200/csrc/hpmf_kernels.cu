@@ -13,6 +13,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string>
 #include <vector>
 #include <algorithm>
@@ -209,8 +210,10 @@ __global__ void hpmf_finish_kernel(int n_struct, int n_tiles, const double *__re
 #define MAX_NEW_T 16           // typed atoms of one side chain (ARG: 12)
 #define MAX_NEW_C 12           // carbons of one side chain (TRP: 9)
 #define MAX_LIST 512           // environment carbons whose weight a trial changes
+#define TRIAL_MINB_DEFAULT 4
 
-__global__ void __launch_bounds__(HT) hpmf_trial_kernel(
+template <int MINB>
+__global__ void __launch_bounds__(HT, MINB) hpmf_trial_kernel(
         HpmfDev s, const float *__restrict__ coords, const float *__restrict__ trial, const unsigned char *__restrict__ mask,
         int first_new, int n_new, int n_trials, int e1, int m, int c1, int mc, const int *__restrict__ carbon_ord,
         const double *__restrict__ sa_env, const double *__restrict__ w0, const double *__restrict__ f0,
@@ -579,8 +582,15 @@ extern "C" int mcsce_hpmf_trials(mcsce_hpmf h, int n_conf, const float *d_coords
     hpmf_pair_kernel<<<dim3(tiles, n_conf), HT, 0, st>>>(v, d_coords, sa_env, h->d_partial, c1, w0, f0);
     hpmf_finish_kernel<<<(n_conf + 127) / 128, 128, 0, st>>>(n_conf, tiles, h->d_partial, v0);
     // every trial on top of it
-    hpmf_trial_kernel<<<dim3(n_trials, n_conf), HT, 0, st>>>(v, d_coords, d_trial, d_mask, first_new, n_new, n_trials, e1, m,
-                                                             c1, mc, h->d_carbon_ord, sa_env, w0, f0, v0, d_v, h->d_overflow);
+    {
+        static int minb = -1;                 // tuning knob: resident blocks per SM the kernel is compiled for
+        if (minb < 0) { const char *e = getenv("MCSCE_B200_HPMF_MINB"); minb = e ? atoi(e) : TRIAL_MINB_DEFAULT; }
+        const dim3 grid(n_trials, n_conf);
+#define LAUNCH_TRIAL(B) hpmf_trial_kernel<B><<<grid, HT, 0, st>>>(v, d_coords, d_trial, d_mask, first_new, n_new, n_trials, \
+            e1, m, c1, mc, h->d_carbon_ord, sa_env, w0, f0, v0, d_v, h->d_overflow)
+        if (minb >= 8) LAUNCH_TRIAL(8); else if (minb >= 6) LAUNCH_TRIAL(6); else LAUNCH_TRIAL(4);
+#undef LAUNCH_TRIAL
+    }
     HCK(cudaGetLastError());
     int over = 0;
     HCK(cudaMemcpyAsync(&over, h->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
