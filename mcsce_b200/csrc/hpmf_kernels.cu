@@ -4,6 +4,8 @@
 //   hpmf_pair_kernel   V = 1/2 sum_{i != j carbons, SA > A_c} tanh(SA_i) tanh(SA_j) sum_k H_k exp(-((r - C_k)/W_k)^2)
 //                                                                                                          (libhpmf.py:92-109)
 //   hpmf_finish_kernel fixed-order sum of the per-block partial sums
+//   hpmf_trial_kernel  V(environment + one trial side chain) for every (trial, conformer) of a growth step from the
+//                      environment's areas, weights and pair fields - the environment is evaluated once, not per trial
 //
 // One structure per blockIdx.y, 128 atoms (carbons) per block, partner atoms staged through shared memory in tiles
 // of 128.  Numerics follow the reference: pair difference, squared norm and square root in float32 (np.linalg.norm

@@ -70,3 +70,63 @@ def test_bonded_table_limits():
     m = np.zeros((6, 6)); m[0, 1:] = 1; m += m.T
     with pytest.raises(ValueError):
         _bonded_table(6, m)
+
+
+def test_oracle_properties():
+    """Size-independent properties of the restatement itself: atom order does not matter, two copies far apart
+    give twice the energy, an isolated atom keeps its whole sphere, a huge threshold leaves no pairs."""
+    from mcsce_b200.hpmf import load_sasa_tables
+
+    tb = load_sasa_tables()
+    g = _case("pep12")
+    types = [str(t) for t in g["types"]]
+    f = g["atom_filter"]
+    x = g["coords"][0]
+    v, sa = O.hpmf(x, f, types, g["bonded"], tb)
+    # permutation of the typed atoms
+    rng = np.random.default_rng(0)
+    xt = x[f]
+    perm = rng.permutation(len(types))
+    vp, sap = O.hpmf(xt[perm], np.ones(len(types), bool), [types[k] for k in perm], g["bonded"][np.ix_(perm, perm)], tb)
+    np.testing.assert_allclose(sap, sa[perm], rtol=1e-12)
+    assert abs(vp - v) <= 1e-10 * abs(v)
+    # two copies 512 A apart (coordinates on a 2^-10 grid so that the shift is exact in float32)
+    xq = (np.round(xt * 1024) / 1024).astype(np.float32)
+    v1, _ = O.hpmf(xq, np.ones(len(types), bool), types, g["bonded"], tb)
+    n = len(types)
+    both = np.zeros((2 * n, 2 * n), bool); both[:n, :n] = g["bonded"]; both[n:, n:] = g["bonded"]
+    v2, _ = O.hpmf(np.concatenate([xq, xq + np.float32(512)]), np.ones(2 * n, bool), types + types, both, tb)
+    assert abs(v2 - 2 * v1) <= 1e-10 * abs(v1)
+    lone = O.sasa(np.zeros((1, 3), np.float32), ["CH3-SP3"], np.zeros((1, 1), bool), tb["P"], tb["R"], tb["pij_bonded"],
+                  tb["pij_non_bonded"])
+    assert lone[0] == 4 * np.pi * (tb["R"]["CH3-SP3"] + 1.4) ** 2
+    assert O.hpmf(x, f, types, g["bonded"], tb, threshold=1e9)[0] == 0.0
+
+
+def test_oracle_growth_hook_is_neutral_when_the_term_is_zero():
+    """``extra_term`` of the oracle's growth loop: a zero term reproduces the fixture's growth, a constant one only
+    shifts the accumulated energy by (grown residues + 1) x constant."""
+    from golden_utils import GoldenCase, library
+    from oracle import ref_numpy as R
+
+    lib, ptm = library()
+    case = GoldenCase("pep6")
+    s = case.structure()
+    steps = {k: case.step(0, k) for k in range(case.n_steps(0))}
+    by_level = case.steps_by_level(0)
+
+    def chi_for_step(i, res, phi, psi):
+        return by_level[i]["chis"], lib.trial_distribution(res, phi, psi, ptm)[2]
+
+    runs = []
+    for const in (None, 0.0, 2.5):
+        term = None if const is None else (lambda labels, nums, rl, xyz, c=const: c)
+        rec = []
+        out = R.grow_conformer(s, s.coords, case.beta, chi_for_step, lambda i: float(by_level[i]["u"]), terms=case.terms,
+                               record=rec, extra_term=term)
+        runs.append((out, rec))
+    (a, ra), (b, rb), (c, rc) = runs
+    assert a["ok"] and b["ok"] and c["ok"] and len(steps) > 0
+    assert a["energy"] == b["energy"] and np.array_equal(a["coords"], b["coords"])
+    assert [r["selected"] for r in ra] == [r["selected"] for r in rc]
+    assert abs(c["energy"] - a["energy"] - 2.5 * (len(rc) + 1)) <= 1e-9
