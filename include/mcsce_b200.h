@@ -264,6 +264,13 @@ int mcsce_hpmf_energy(mcsce_hpmf h, int n_struct, const float *d_coords, double 
 int mcsce_hpmf_trials(mcsce_hpmf h, int n_conf, const float *d_coords, int first_new, int n_new, int n_trials,
                       const float *d_trial, const uint8_t *d_mask, double *d_v, void *stream);
 
+/* Growth loops call mcsce_hpmf_trials residue after residue on the same d_coords buffer, each call's environment
+ * being the previous one's plus the atoms placed since.  enable=1 lets the handle keep the environment's areas,
+ * weights and pair fields between such calls and extend them by the new atoms instead of re-deriving them (the
+ * caller promises: same buffer and n_conf, first_new never decreases, atoms below the previous first_new unchanged);
+ * every call of this function - with 0 or 1 - forgets the kept state, so a new growth starts with one.  */
+int mcsce_hpmf_carry(mcsce_hpmf h, int enable);
+
 /* per-kernel device time of the last mcsce_hpmf_energy call: ms[0] = SASA kernel, ms[1] = carbon-pair kernel
  * (CUDA events on the launch stream; synchronises) */
 int mcsce_hpmf_last_ms(mcsce_hpmf h, double *ms);

@@ -385,6 +385,191 @@ __global__ void __launch_bounds__(HT, MINB) hpmf_trial_kernel(
     if (tid == 0) out[ct] = v0[c] + red[0];
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// carrying the environment state from one growth step to the next
+// ------------------------------------------------------------------------------------------------
+// Between two steps the environment only gains the atoms [L, F): the side chain selected at the previous step (and
+// conformer-independent GLY/ALA side chains in between).  Instead of re-deriving areas, weights and fields of the
+// whole environment, the state of level L is extended: the new atoms multiply the areas of the atoms in their reach
+// (hpmf_extend_kernel, one block per conformer - the trial kernel's first two phases with the results written
+// back), then every carbon's field gains the changed weights' and the new carbons' terms and the new carbons get
+// their full sums (hpmf_field_update_kernel).
+#define EXT_LIST 1024          // environment carbons whose weight one extension changes
+
+__global__ void __launch_bounds__(HT) hpmf_extend_kernel(
+        HpmfDev s, const float *__restrict__ coords, int eL, int m, const int *__restrict__ carbon_ord,
+        double *__restrict__ sa_env, double *__restrict__ w0, float4 *__restrict__ ext_pos, double *__restrict__ ext_del,
+        int *__restrict__ ext_ck, int *__restrict__ ext_n, int *__restrict__ overflow) {
+    const int c = blockIdx.x, tid = threadIdx.x, nt = s.n_types;
+    __shared__ float4 ta[MAX_NEW_T];
+    __shared__ int tbond[MAX_NEW_T][MAXB];
+    __shared__ double s_thr[MAX_SASA_TYPES * MAX_SASA_TYPES];
+    __shared__ double s_R[MAX_SASA_TYPES], s_piRRs[MAX_SASA_TYPES], s_P[MAX_SASA_TYPES], s_S[MAX_SASA_TYPES];
+    __shared__ double tprod[HT / 32][MAX_NEW_T];
+    __shared__ int ln;
+    const float *cbase = coords + (long long)c * s.n_atoms * 3;
+    double *sa = sa_env + (long long)c * s.n_typed;
+    double *w0c = w0 + (long long)c * s.n_carbon;
+    for (int k = tid; k < nt * nt; k += HT) s_thr[k] = s.thr[k];
+    if (tid < nt) { s_R[tid] = s.R[tid]; s_piRRs[tid] = s.piRRs[tid]; s_P[tid] = s.P[tid]; s_S[tid] = s.S[tid]; }
+    if (tid < m) {
+        const int g = eL + tid;
+        const float *p = cbase + (long long)s.typed_atom[g] * 3;
+        ta[tid] = make_float4(p[0], p[1], p[2], __int_as_float(s.type_of[g]));     // an absent atom (1e15) is out of everyone's reach
+#pragma unroll
+        for (int b = 0; b < MAXB; ++b) tbond[tid][b] = s.bonded[g * MAXB + b];
+    }
+    if (tid == 0) ln = 0;
+    __syncthreads();
+    double tp[MAX_NEW_T];
+#pragma unroll
+    for (int n = 0; n < MAX_NEW_T; ++n) tp[n] = 1.0;
+    for (int k = tid; k < eL; k += HT) {
+        const float *p = cbase + (long long)s.typed_atom[k] * 3;
+        const float xk = p[0], yk = p[1], zk = p[2];
+        if (xk > ABSENT_X) continue;
+        int tk = -1, b0 = -1, b1 = -1, b2 = -1, b3 = -1;
+        double f = 1.0;
+#pragma unroll
+        for (int n = 0; n < MAX_NEW_T; ++n) {
+            if (n < m) {
+                const float4 q = ta[n];
+                if (dist2_fast(xk, yk, zk, q.x, q.y, q.z) < s.pre2) {
+                    const float d = __fsqrt_rn(norm2_f32(xk, yk, zk, q.x, q.y, q.z));
+                    if (tk < 0) {
+                        tk = s.type_of[k];
+                        b0 = s.bonded[k * MAXB]; b1 = s.bonded[k * MAXB + 1]; b2 = s.bonded[k * MAXB + 2]; b3 = s.bonded[k * MAXB + 3];
+                    }
+                    const int tn = __float_as_int(q.w);
+                    const double thr = s_thr[tk * nt + tn];
+                    if ((double)d < thr) {
+                        const int g = eL + n;
+                        const double pij = (g == b0 || g == b1 || g == b2 || g == b3) ? s.pij_bonded : s.pij_non_bonded;
+                        f = __dmul_rn(f, sasa_term(s_P[tk], s_S[tk], s_R[tk], s_piRRs[tn], s_R[tn], thr, d, pij));
+                        tp[n] = __dmul_rn(tp[n], sasa_term(s_P[tn], s_S[tn], s_R[tn], s_piRRs[tk], s_R[tk], thr, d, pij));
+                    }
+                }
+            }
+        }
+        if (f != 1.0) {
+            const double a = sa[k] * f;
+            sa[k] = a;
+            const int ck = carbon_ord[k];
+            if (ck >= 0) {
+                const double w = a > s.sa_threshold ? tanh(a) : 0.0;
+                const double del = w - w0c[ck];
+                if (del != 0.0) {
+                    w0c[ck] = w;
+                    const int idx = atomicAdd(&ln, 1);
+                    if (idx < EXT_LIST) {
+                        const long long o = (long long)c * EXT_LIST + idx;
+                        ext_pos[o] = make_float4(xk, yk, zk, 0.f); ext_del[o] = del; ext_ck[o] = ck;
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int n = 0; n < MAX_NEW_T; ++n) {
+        if (n < m) {
+            double v = tp[n];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v *= __shfl_xor_sync(0xffffffffu, v, off);
+            if ((tid & 31) == 0) tprod[tid >> 5][n] = v;
+        }
+    }
+    __syncthreads();
+    if (tid < m) {
+        double prod = 1.0;
+#pragma unroll
+        for (int w = 0; w < HT / 32; ++w) prod *= tprod[w][tid];
+        const float4 me = ta[tid];
+        const int ti = __float_as_int(me.w);
+        const bool absent = me.x > ABSENT_X;
+        for (int n = 0; n < m && !absent; ++n) {
+            if (n == tid) continue;
+            const float4 q = ta[n];
+            if (q.x > ABSENT_X) continue;
+            const float d = __fsqrt_rn(norm2_f32(me.x, me.y, me.z, q.x, q.y, q.z));
+            const int tn = __float_as_int(q.w);
+            const double thr = s_thr[ti * nt + tn];
+            if ((double)d < thr) {
+                const int g = eL + n;
+                const bool bonded = g == tbond[tid][0] || g == tbond[tid][1] || g == tbond[tid][2] || g == tbond[tid][3];
+                prod = __dmul_rn(prod, sasa_term(s_P[ti], s_S[ti], s_R[ti], s_piRRs[tn], s_R[tn], thr, d,
+                                                 bonded ? s.pij_bonded : s.pij_non_bonded));
+            }
+        }
+        const double a = absent ? 0.0 : __dmul_rn(s_S[ti], prod);
+        sa[eL + tid] = a;
+        const int ck = carbon_ord[eL + tid];
+        if (ck >= 0) w0c[ck] = a > s.sa_threshold ? tanh(a) : 0.0;
+    }
+    if (tid == 0) {
+        ext_n[c] = min(ln, EXT_LIST);
+        if (ln > EXT_LIST) atomicExch(overflow, 1);
+    }
+}
+
+// fields and V of the extended environment: carbons [0, cL) gain the changed weights' and the new carbons' terms,
+// the new carbons [cL, cF) get their full sums; partial[conformer][tile] = sum_i w_i F_i of the tile
+__global__ void __launch_bounds__(HT) hpmf_field_update_kernel(
+        HpmfDev s, const float *__restrict__ coords, int cL, int cF, const double *__restrict__ w0, double *__restrict__ f0,
+        const float4 *__restrict__ ext_pos, const double *__restrict__ ext_del, const int *__restrict__ ext_ck,
+        const int *__restrict__ ext_n, double *__restrict__ partial) {
+    __shared__ double red[HT];
+    const int c = blockIdx.y, tid = threadIdx.x;
+    const int i = blockIdx.x * HT + tid;
+    const float *cbase = coords + (long long)c * s.n_atoms * 3;
+    const double *w0c = w0 + (long long)c * s.n_carbon;
+    double *f0c = f0 + (long long)c * s.n_carbon;
+    const float cut2 = HPMF_CUTOFF * HPMF_CUTOFF;
+    double contrib = 0.0;
+    if (i < cF) {
+        const float *p = cbase + (long long)s.typed_atom[s.carbon[i]] * 3;
+        const float xi = p[0], yi = p[1], zi = p[2];
+        double f = 0.0;
+        if (xi <= ABSENT_X) {
+            if (i < cL) {
+                f = f0c[i];
+                const int L = ext_n[c];
+                const long long o = (long long)c * EXT_LIST;
+                for (int l = 0; l < L; ++l) {
+                    if (ext_ck[o + l] == i) continue;
+                    const float4 q = ext_pos[o + l];
+                    if (dist2_fast(xi, yi, zi, q.x, q.y, q.z) < cut2)
+                        f += ext_del[o + l] * gauss3(s, (double)__fsqrt_rn(norm2_f32(xi, yi, zi, q.x, q.y, q.z)));
+                }
+                for (int n = cL; n < cF; ++n) {
+                    const double wn = w0c[n];
+                    if (wn == 0.0) continue;
+                    const float *q = cbase + (long long)s.typed_atom[s.carbon[n]] * 3;
+                    if (dist2_fast(xi, yi, zi, q[0], q[1], q[2]) < cut2)
+                        f += wn * gauss3(s, (double)__fsqrt_rn(norm2_f32(xi, yi, zi, q[0], q[1], q[2])));
+                }
+            } else {
+                for (int j = 0; j < cF; ++j) {
+                    const double wj = w0c[j];
+                    if (wj == 0.0 || j == i) continue;
+                    const float *q = cbase + (long long)s.typed_atom[s.carbon[j]] * 3;
+                    if (dist2_fast(xi, yi, zi, q[0], q[1], q[2]) < cut2)
+                        f += wj * gauss3(s, (double)__fsqrt_rn(norm2_f32(xi, yi, zi, q[0], q[1], q[2])));
+                }
+            }
+        }
+        f0c[i] = f;
+        contrib = w0c[i] * f;
+    }
+    red[tid] = contrib;
+    __syncthreads();
+    for (int k = HT / 2; k > 0; k >>= 1) {
+        if (tid < k) red[tid] += red[tid + k];
+        __syncthreads();
+    }
+    if (tid == 0) partial[(long long)c * gridDim.x + blockIdx.x] = red[0];
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -400,6 +585,12 @@ struct mcsce_hpmf_s {
     double *d_env_state = nullptr;          // sa_env [C*n_typed] | w0 [C*n_carbon] | f0 [C*n_carbon] | v0 [C]
     size_t env_state_cap = 0;
     int *d_overflow = nullptr;
+    // carried state (mcsce_hpmf_carry): the level (first atom not yet part of the state) the buffers describe
+    bool carry = false;
+    int state_level = 0, state_nconf = 0;
+    const float *state_coords = nullptr;
+    void *d_ext = nullptr;                  // ext_pos | ext_del | ext_ck | ext_n
+    size_t ext_cap = 0;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     bool timed = false;
 };
@@ -481,6 +672,7 @@ extern "C" int mcsce_hpmf_destroy(mcsce_hpmf h) {
     for (void *p : h->owned) cudaFree(p);
     if (h->d_partial) cudaFree(h->d_partial);
     if (h->d_env_state) cudaFree(h->d_env_state);
+    if (h->d_ext) cudaFree(h->d_ext);
     for (int k = 0; k < 3; ++k) if (h->ev[k]) cudaEventDestroy(h->ev[k]);
     delete h;
     return 0;
@@ -562,6 +754,7 @@ extern "C" int mcsce_hpmf_trials(mcsce_hpmf h, int n_conf, const float *d_coords
     if (n_state > h->env_state_cap || (size_t)n_conf * tiles > h->partial_cap) {
         HCK(cudaStreamSynchronize(st));
         if (n_state > h->env_state_cap) {
+            h->state_level = 0;
             if (h->d_env_state) HCK(cudaFree(h->d_env_state));
             h->d_env_state = nullptr; h->env_state_cap = 0;
             HCK(cudaMalloc(&h->d_env_state, n_state * sizeof(double)));
@@ -579,10 +772,42 @@ extern "C" int mcsce_hpmf_trials(mcsce_hpmf h, int n_conf, const float *d_coords
     double *w0 = sa_env + (size_t)n_conf * v.n_typed;
     double *f0 = w0 + (size_t)n_conf * v.n_carbon;
     double *v0 = f0 + (size_t)n_conf * v.n_carbon;
-    // the environment alone (atoms before first_new), once per conformer
-    if (launch_sasa(h, n_conf, d_coords, sa_env, st, e1)) return -1;
-    hpmf_pair_kernel<<<dim3(tiles, n_conf), HT, 0, st>>>(v, d_coords, sa_env, h->d_partial, c1, w0, f0);
-    hpmf_finish_kernel<<<(n_conf + 127) / 128, 128, 0, st>>>(n_conf, tiles, h->d_partial, v0);
+    // the environment alone (atoms before first_new), once per conformer: extended from the previous step's state
+    // when the caller allowed it (mcsce_hpmf_carry) and the call continues that growth, else derived from scratch
+    bool extended = false;
+    if (h->carry && h->state_level > 0 && h->state_nconf == n_conf && h->state_coords == d_coords &&
+        h->state_level <= first_new) {
+        const int eL = (int)(std::lower_bound(ta.begin(), ta.end(), h->state_level) - ta.begin());
+        const int cL = (int)(std::lower_bound(h->h_carbon.begin(), h->h_carbon.end(), eL) - h->h_carbon.begin());
+        const int mL = e1 - eL;
+        if (mL == 0) extended = true;                           // only untyped atoms were added: nothing changes
+        else if (mL <= MAX_NEW_T) {
+            const size_t per = (size_t)EXT_LIST * (sizeof(float4) + sizeof(double) + sizeof(int)) + sizeof(int);
+            if ((size_t)n_conf * per > h->ext_cap) {
+                HCK(cudaStreamSynchronize(st));
+                if (h->d_ext) HCK(cudaFree(h->d_ext));
+                h->d_ext = nullptr; h->ext_cap = 0;
+                HCK(cudaMalloc(&h->d_ext, (size_t)n_conf * per));
+                h->ext_cap = (size_t)n_conf * per;
+            }
+            float4 *ext_pos = (float4 *)h->d_ext;
+            double *ext_del = (double *)(ext_pos + (size_t)n_conf * EXT_LIST);
+            int *ext_ck = (int *)(ext_del + (size_t)n_conf * EXT_LIST);
+            int *ext_n = ext_ck + (size_t)n_conf * EXT_LIST;
+            hpmf_extend_kernel<<<n_conf, HT, 0, st>>>(v, d_coords, eL, mL, h->d_carbon_ord, sa_env, w0, ext_pos, ext_del, ext_ck,
+                                                      ext_n, h->d_overflow);
+            hpmf_field_update_kernel<<<dim3(tiles, n_conf), HT, 0, st>>>(v, d_coords, cL, c1, w0, f0, ext_pos, ext_del, ext_ck,
+                                                                         ext_n, h->d_partial);
+            hpmf_finish_kernel<<<(n_conf + 127) / 128, 128, 0, st>>>(n_conf, tiles, h->d_partial, v0);
+            extended = true;
+        }
+    }
+    if (!extended) {
+        if (launch_sasa(h, n_conf, d_coords, sa_env, st, e1)) return -1;
+        hpmf_pair_kernel<<<dim3(tiles, n_conf), HT, 0, st>>>(v, d_coords, sa_env, h->d_partial, c1, w0, f0);
+        hpmf_finish_kernel<<<(n_conf + 127) / 128, 128, 0, st>>>(n_conf, tiles, h->d_partial, v0);
+    }
+    h->state_level = first_new; h->state_nconf = n_conf; h->state_coords = d_coords;
     // every trial on top of it
     {
         static int minb = -1;                 // tuning knob: resident blocks per SM the kernel is compiled for
@@ -599,8 +824,16 @@ extern "C" int mcsce_hpmf_trials(mcsce_hpmf h, int n_conf, const float *d_coords
     HCK(cudaStreamSynchronize(st));
     if (over) {
         HCK(cudaMemset(h->d_overflow, 0, sizeof(int)));
+        h->state_level = 0;
         return mcsce_fail_shared("mcsce_hpmf_trials: more than 512 environment carbons change weight under one trial");
     }
+    return 0;
+}
+
+extern "C" int mcsce_hpmf_carry(mcsce_hpmf h, int enable) {
+    if (!h) return mcsce_fail_shared("mcsce_hpmf_carry: null handle");
+    h->carry = enable != 0;
+    h->state_level = 0;                     // the next mcsce_hpmf_trials call derives the environment from scratch
     return 0;
 }
 

@@ -212,6 +212,11 @@ class HpmfCalculator:
                                          m.data_ptr() if m is not None else None, out.data_ptr(), st))
         return out
 
+    def carry(self, enable):
+        """Let consecutive ``trial_energies`` calls of one growth (same ``coords`` buffer, rising ``first_new``) extend
+        the environment's state instead of re-deriving it; every call of this method forgets the kept state."""
+        check(self.lib.mcsce_hpmf_carry(self.h, 1 if enable else 0))
+
     def last_ms(self):
         ms = (C.c_double * 2)()
         check(self.lib.mcsce_hpmf_last_ms(self.h, ms))
@@ -232,7 +237,7 @@ def calculator_for_structure(structure, device=0):
     return calculator_for_labels(structure.atom_labels, structure.res_nums, structure.res_labels, device=device)
 
 
-def growth_term(engine, calc=None, max_bytes=1 << 30, brute_force=False):
+def growth_term(engine, calc=None, max_bytes=1 << 30, brute_force=False, carry=None):
     """``extra_term`` for :meth:`GrowthEngine.grow_stepwise`: V_hpmf of every partially grown structure a trial
     would produce - the input atoms, the side chains placed so far and the trial's - which is what the reference's
     coordinate-based energy terms receive (libenergy.py:806-808 with the level's atom list, side_chain_builder.py:
@@ -240,7 +245,12 @@ def growth_term(engine, calc=None, max_bytes=1 << 30, brute_force=False):
 
     Default: ``mcsce_hpmf_trials`` - the environment once per conformer and residue, O(N^2), then every trial adds
     its own factors and pair terms, O(n_new N).  ``brute_force=True``: one whole-structure evaluation per
-    (conformer, trial), O(T N^2) per residue and conformer; same numbers, kept as the check of the first."""
+    (conformer, trial), O(T N^2) per residue and conformer; same numbers, kept as the check of the first.
+    ``carry`` (default: on unless ``MCSCE_B200_HPMF_CARRY=0``): the environment's areas, weights and fields are kept
+    from residue to residue and extended by the atoms placed since (``mcsce_hpmf_carry``) instead of re-derived."""
+    import os
+    if carry is None:
+        carry = os.environ.get("MCSCE_B200_HPMF_CARRY", "1") != "0"
     torch = engine.torch
     sysm = engine.system
     if calc is None:
@@ -252,6 +262,7 @@ def growth_term(engine, calc=None, max_bytes=1 << 30, brute_force=False):
 
     def term(st, coords, xyz, finite):
         if st is None:                                     # level 0: the input atoms alone, the same for every conformer
+            calc.carry(carry and not brute_force)          # a new growth: forget the previous one's environment
             s0 = coords[:1].clone()
             s0[:, sysm.n_input:] = parked
             return calc.energy(s0).expand(coords.shape[0])

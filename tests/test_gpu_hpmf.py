@@ -370,3 +370,41 @@ def test_per_trial_increments_equal_whole_structure_evaluation(cfg, n_conf):
         mk = mask.cpu().numpy()
         assert np.array_equal(got_m[mk], got[mk]) and (got_m[~mk] == 0).all()
     print("worst relative difference", worst)
+
+
+@pytest.mark.parametrize("cfg,n_conf", [(2, 12), (3, 6)])
+def test_carried_environment_state_equals_rederiving_it(cfg, n_conf):
+    """The hpmf growth with the environment's areas / weights / fields extended from residue to residue
+    (``mcsce_hpmf_carry``) against the same growth re-deriving them at every residue: identical selections,
+    per-trial energies to 1e-10 relative, incl. conformers that die on the way."""
+    from mcsce_b200 import synth
+    from mcsce_b200.engine import GrowthEngine
+    from mcsce_b200.hpmf import growth_term
+    from mcsce_b200.structure import Structure
+    from mcsce_b200.system import build_system
+
+    lib, ptm = library()
+    s = Structure(synth.config_backbone(cfg)).build().remove_side_chains([])
+    sysm = build_system(s, rotamer_library=lib, ptm_library=ptm)
+    eng = GrowthEngine(0).set_system(sysm).set_backbone(s.coords)
+    beta = 1.0 / (300 * 0.008314462)
+    on = growth_term(eng, carry=True)
+    off = growth_term(eng, on.calculator, carry=False)
+    ra, rb = [], []
+    a = eng.grow_stepwise(n_conf, beta, seed=13, extra_term=on, record=ra)
+    b = eng.grow_stepwise(n_conf, beta, seed=13, extra_term=off, record=rb)
+    assert np.array_equal(a["selected"].cpu().numpy(), b["selected"].cpu().numpy())
+    assert np.array_equal(a["ok"].cpu().numpy(), b["ok"].cpu().numpy())
+    worst = 0.0
+    for x, y in zip(ra, rb):
+        fin = np.isfinite(y["energies"])
+        assert np.array_equal(fin, np.isfinite(x["energies"]))
+        if fin.any():
+            worst = max(worst, float((np.abs(x["energies"][fin] - y["energies"][fin]) / np.maximum(1, np.abs(y["energies"][fin]))).max()))
+    assert worst <= 1e-10, worst
+    ok = a["ok"].cpu().numpy().astype(bool)
+    np.testing.assert_allclose(a["energy"].cpu().numpy()[ok], b["energy"].cpu().numpy()[ok], rtol=1e-11)
+    # a second growth on the same calculator starts from scratch (state forgotten)
+    a2 = eng.grow_stepwise(n_conf, beta, seed=13, extra_term=on)
+    assert np.array_equal(a2["selected"].cpu().numpy(), a["selected"].cpu().numpy())
+    print("carried vs re-derived, worst relative difference", worst)
