@@ -130,3 +130,22 @@ def test_oracle_growth_hook_is_neutral_when_the_term_is_zero():
     assert a["energy"] == b["energy"] and np.array_equal(a["coords"], b["coords"])
     assert [r["selected"] for r in ra] == [r["selected"] for r in rc]
     assert abs(c["energy"] - a["energy"] - 2.5 * (len(rc) + 1)) <= 1e-9
+
+
+def test_mirror_modules_expose_reference_constants_and_fail_without_cuda():
+    """``mcsce_b200.libs.libsasa`` / ``libhpmf`` carry the reference modules' constants; building a calculator
+    without a CUDA device raises (no CPU fallback)."""
+    import torch
+
+    from mcsce_b200.libs import libhpmf, libsasa
+
+    assert libsasa.PIJ_BONDED == 0.8875 and libsasa.PIJ_NON_BONDED == 0.3516
+    assert libsasa.R_PARAMS["CH3-SP3"] == 2.0 and libsasa.P_PARAMS["C-SP3"] == 2.149
+    assert (libhpmf.C1, libhpmf.W2, libhpmf.H3, libhpmf.AC) == (3.81679, 1.39064, -0.09055, 6.0)
+    with pytest.raises(AttributeError):
+        libsasa.NOT_THERE
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            libsasa.calc_sasa(["C-SP3"], np.zeros((1, 1)))
+        with pytest.raises(RuntimeError):
+            libhpmf.init_hpmf_calculator(["C-SP3"], np.ones(1, bool), np.zeros((1, 1)))
