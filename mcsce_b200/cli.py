@@ -21,6 +21,7 @@ parser.add_argument("-f", "--fix", default=None, help="residue ids whose side ch
 parser.add_argument("-l", "--logfile", default="log.csv", help="CSV log: file, number grown, wall time")
 parser.add_argument("-v", "--verbose", default=False, help="print the full missing-atom / HIS renaming warnings")
 parser.add_argument("--seed", type=int, default=0, help="seed of the on-device random streams (extension)")
+parser.add_argument("--hpmf", action="store_true", default=False, help="add the hydrophobic PMF term to lj + clash + coulomb (extension; the reference's CLI fixes the three terms, cli.py:149-151)")
 
 
 def parse_fix(fix):
@@ -39,7 +40,7 @@ def parse_fix(fix):
 
 
 def main(input_structure, n_conf, n_worker, output_dir, logfile, mode, fix, batch_size=4, same_structure=False,
-         verbose=False, seed=0):
+         verbose=False, seed=0, hpmf=False):
     from mcsce_b200 import sharding
     from mcsce_b200.core import side_chain_builder as scb
     from mcsce_b200.libs.libenergy import prepare_energy_function
@@ -61,7 +62,8 @@ def main(input_structure, n_conf, n_worker, output_dir, logfile, mode, fix, batc
     else:
         folder = input_structure if input_structure.endswith("/") else input_structure + "/"
         all_pdbs = sorted(folder + f for f in os.listdir(folder) if f[-3:].upper() == "PDB")
-    creator = partial(prepare_energy_function, batch_size=batch_size, forcefield=None, terms=["lj", "clash", "coulomb"])
+    terms = ["lj", "clash", "coulomb"] + (["hpmf"] if hpmf else [])
+    creator = partial(prepare_energy_function, batch_size=batch_size, forcefield=None, terms=terms)
     scb.set_seed(seed)
     fix_idxs = []
     if same_structure:

@@ -149,3 +149,13 @@ def test_mirror_modules_expose_reference_constants_and_fail_without_cuda():
             libsasa.calc_sasa(["C-SP3"], np.zeros((1, 1)))
         with pytest.raises(RuntimeError):
             libhpmf.init_hpmf_calculator(["C-SP3"], np.ones(1, bool), np.zeros((1, 1)))
+
+
+def test_cli_flag_for_the_term():
+    import inspect
+
+    from mcsce_b200 import cli
+
+    a = vars(cli.parser.parse_args(["x.pdb", "4", "--hpmf"]))
+    assert a["hpmf"] is True and vars(cli.parser.parse_args(["x.pdb", "4"]))["hpmf"] is False
+    assert set(a) == set(inspect.signature(cli.main).parameters)      # every option reaches main()
