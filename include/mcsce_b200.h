@@ -115,6 +115,10 @@ typedef struct {
     int32_t no_graph;              /* 1: never replay a cached CUDA graph (launch-bound runs do by default) */
     int32_t no_screen;             /* 1: score every trial against the whole environment; by default a short clash-only pass over
                                       the atoms near the residue runs first and trials it rejects (+inf either way) are not scored */
+    /* optional replay input, used with d_chis (parity runs): the dihedral rotate_sidechain measured before each chi
+     * rotation (libs/libscbuild.py:113,167,183,197: float32 NumPy, host dependent), rad; NaN entries and NULL = the
+     * template constant.  With the reference's recorded values K1's coordinates are bit-identical to the reference's. */
+    const double *d_ori;           /* [n_conf*n_trials_total*MAX_CHI_ROT]                        */
 } mcsce_grow_opts;
 
 const char *mcsce_last_error(void);
@@ -150,6 +154,9 @@ int mcsce_grow_host(mcsce_handle h, const mcsce_grow_opts *opts, void *d_workspa
  * (libs/libscbuild.py:56-206) + place_sidechain_template (libs/libcalc.py:419-482) for a batch.
  *   d_chis  [n_rows*MAX_CHI] degrees;  d_xyz [n_rows*n_sc*4] float32 (x,y,z,0) out            */
 int mcsce_place_trials(mcsce_handle h, int residue, int n_rows, const double *d_chis, float *d_xyz, void *stream);
+/* same with the measured dihedrals replayed: d_ori [n_rows*MAX_CHI_ROT] rad (NaN / NULL = template constant) */
+int mcsce_place_trials_replay(mcsce_handle h, int residue, int n_rows, const double *d_chis, const double *d_ori,
+                              float *d_xyz, void *stream);
 
 /* K2 - per-trial energy of residue `residue`'s side chain against an environment.  Replaces the
  * closure returned by prepare_energy_function (libs/libenergy.py:786-810) incl. the clash filter.

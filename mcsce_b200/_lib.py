@@ -48,6 +48,7 @@ class GrowOpts(C.Structure):
         ("noise_deg", C.c_double), ("d_chis", C.c_void_p), ("d_uniform", C.c_void_p),
         ("d_trial_energy", C.c_void_p), ("d_chis_out", C.c_void_p), ("d_selected", C.c_void_p),
         ("env_split", C.c_int32), ("no_dedup", C.c_int32), ("no_graph", C.c_int32), ("no_screen", C.c_int32),
+        ("d_ori", C.c_void_p),
     ]
 
 
@@ -79,6 +80,7 @@ SYMBOLS = {
     "mcsce_grow_host": (C.c_int, [C.c_void_p, C.POINTER(GrowOpts), C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p]),
     "mcsce_place_trials": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mcsce_place_trials_replay": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mcsce_score_trials": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "mcsce_score_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),

@@ -172,7 +172,10 @@ __device__ __forceinline__ void apply_chi_rotations(const TmplDev &tm, int n_rot
         const float px = __shfl_sync(0xffffffffu, x, at), py = __shfl_sync(0xffffffffu, y, at), pz = __shfl_sync(0xffffffffu, z, at);
         // unit axis in float32: (to - from)/|to - from|   (libscbuild.py:105,115,169,185,199)
         const float ux = __fsub_rn(px, fx), uy = __fsub_rn(py, fy), uz = __fsub_rn(pz, fz);
-        const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)), __fmul_rn(uz, uz)));
+        // np.linalg.norm of a float32 3-vector = sqrt(x.dot(x)) through OpenBLAS sdot's scalar tail: float32 products summed
+        // in a double, the sum rounded to float32, float32 sqrt (checked against NumPy: identical on 20000 random vectors)
+        const double acc = __dadd_rn(__dadd_rn((double)__fmul_rn(ux, ux), (double)__fmul_rn(uy, uy)), (double)__fmul_rn(uz, uz));
+        const float nrm = __fsqrt_rn(__double2float_rn(acc));
         const float ex = __fdiv_rn(ux, nrm), ey = __fdiv_rn(uy, nrm), ez = __fdiv_rn(uz, nrm);
         const double sn = sn_k[k], cs = cs_k[k];
         const double b2 = sn * (double)(-ex), b3 = sn * (double)(-ey), b4 = sn * (double)(-ez);
@@ -225,6 +228,8 @@ struct PlaceArgs {
     long long chis_set_stride;  // doubles between sets in chis_in / chis_out
     long long chis_row_off;     // offset (in rows) of this residue's first row inside a set
     double *chis_out;         // optional dump, same layout
+    const double *ori_in;     // optional replay input [set][row][MAX_ROT]: the dihedral the reference measured before each rotation (rad);
+                              // NaN or null = the template constant
     float4 *trial;            // [set][n_trials*n_sc]
     long long trial_set_stride;
     const unsigned char *alive;
@@ -274,7 +279,17 @@ __global__ void __launch_bounds__(128) place_trials_kernel(PlaceArgs a) {
             }
             if (a.chis_out) a.chis_out[at] = v;
         }
-        if (c < st.n_chi) chi_half_sincos(tm.ori[c], v, s_sn[tl][c], s_cs[tl][c]);
+        if (c < st.n_chi) {
+            // The reference re-measures the dihedral in float32 before every rotation (libscbuild.py:113,167,183,197); that
+            // value is the template constant plus float32 noise of the host's NumPy (DESIGN "K1 fidelity").  Parity runs feed
+            // the recorded values back in; otherwise the constant is used.
+            double ori = tm.ori[c];
+            if (a.ori_in) {
+                const double m = a.ori_in[((long long)set * a.chis_set_stride / MAX_CHI + row) * MAX_ROT + c];
+                if (m == m) ori = m;
+            }
+            chi_half_sincos(ori, v, s_sn[tl][c], s_cs[tl][c]);
+        }
     }
     __syncthreads();
 
@@ -1366,7 +1381,7 @@ extern "C" int mcsce_set_system(mcsce_handle h, const mcsce_system_desc *s) {
 
 static int launch_place(mcsce_handle h, int step, int n_sets, int n_rows, const double *chis_in, long long set_stride,
                         long long row_off, double *chis_out, float4 *trial, long long trial_stride,
-                        const unsigned char *alive, cudaStream_t st);
+                        const unsigned char *alive, cudaStream_t st, const double *ori_in = nullptr);
 
 __global__ void store_rigid_kernel(const float4 *src, int sc_start, int n_sc, float *rigid) {
     const int k = threadIdx.x;
@@ -1693,8 +1708,9 @@ extern "C" int mcsce_init_env(mcsce_handle h, int n_env_sets, float *d_env, void
 
 static int launch_place(mcsce_handle h, int step, int n_sets, int n_rows, const double *chis_in, long long set_stride,
                         long long row_off, double *chis_out, float4 *trial, long long trial_stride,
-                        const unsigned char *alive, cudaStream_t st) {
+                        const unsigned char *alive, cudaStream_t st, const double *ori_in) {
     PlaceArgs a{};
+    a.ori_in = ori_in;
     a.s = h->d; a.step = step; a.n_trials = n_rows; a.chis_in = chis_in; a.chis_set_stride = set_stride;
     a.chis_row_off = row_off; a.chis_out = chis_out; a.trial = trial; a.trial_set_stride = trial_stride;
     a.alive = alive; a.cp = h->cur_call;
@@ -1751,12 +1767,18 @@ static int launch_score(mcsce_handle h, int step, int n_sets, int n_trials, int 
     return launch_special(h, step, n_sets, n_trials, env, trial, trial_stride, sp_partial, alive, st);
 }
 
-extern "C" int mcsce_place_trials(mcsce_handle h, int residue, int n_rows, const double *d_chis, float *d_xyz, void *stream) {
+extern "C" int mcsce_place_trials_replay(mcsce_handle h, int residue, int n_rows, const double *d_chis, const double *d_ori,
+                                         float *d_xyz, void *stream) {
     if (!h || !h->has_bb) return fail("set_system/set_backbone first");
     if (residue < 0 || residue >= h->d.n_res) return fail("residue out of range");
     if (h->steps[residue].kind == 0) return fail("residue is retained: nothing to place");
+    if (!d_chis) return fail("mcsce_place_trials: chi rows are required");
     CK(cudaSetDevice(h->device));
-    return launch_place(h, residue, 1, n_rows, d_chis, 0, 0, nullptr, (float4 *)d_xyz, 0, nullptr, (cudaStream_t)stream);
+    return launch_place(h, residue, 1, n_rows, d_chis, 0, 0, nullptr, (float4 *)d_xyz, 0, nullptr, (cudaStream_t)stream, d_ori);
+}
+
+extern "C" int mcsce_place_trials(mcsce_handle h, int residue, int n_rows, const double *d_chis, float *d_xyz, void *stream) {
+    return mcsce_place_trials_replay(h, residue, n_rows, d_chis, nullptr, d_xyz, stream);
 }
 
 __global__ void combine_kernel(int n, int n_split, const double2 *partial, const double2 *sp_partial, double *out) {
@@ -1865,7 +1887,7 @@ static int enqueue_growth(mcsce_handle h, const mcsce_grow_opts *o, const Worksp
         // aux: K1 into the buffer last read by the residue before the previous one
         if (prev2 >= 0) CK(cudaStreamWaitEvent(aux, ln.evS[prev2], 0));
         if (launch_place(h, i, C, T, o->d_chis, chi_set_stride, sd.trial_off, o->d_chis_out, trial, trial_stride,
-                         w.alive, aux)) return -1;
+                         w.alive, aux, o->d_chis ? o->d_ori : nullptr)) return -1;
         CK(cudaEventRecord(ln.evP[i], aux));
         // st: generic pairs
         CK(cudaStreamWaitEvent(st, ln.evP[i], 0));
@@ -1984,7 +2006,8 @@ extern "C" int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *o, void *d_work
         std::vector<long long> key = {h->table_version, C, (long long)(size_t)d_workspace, (long long)workspace_bytes,
                                       (long long)(size_t)o->d_chis, (long long)(size_t)o->d_uniform,
                                       (long long)(size_t)o->d_trial_energy, (long long)(size_t)o->d_chis_out,
-                                      (long long)(size_t)o->d_selected, o->env_split, o->no_dedup, o->no_screen};
+                                      (long long)(size_t)o->d_selected, o->env_split, o->no_dedup, o->no_screen,
+                                      (long long)(size_t)o->d_ori};
         if (!h->graph_exec || key != h->graph_key) {
             if (!h->cap_stream) CK(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
             const long long before = h->launches;
@@ -2045,6 +2068,7 @@ extern "C" int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *o, void *d_work
         og.n_conf = cg; og.conf_id0 = o->conf_id0 + c0;
         if (o->d_chis) og.d_chis = o->d_chis + (long long)c0 * chi_stride;
         if (o->d_chis_out) og.d_chis_out = o->d_chis_out + (long long)c0 * chi_stride;
+        if (o->d_ori) og.d_ori = o->d_ori + (long long)c0 * (chi_stride / MAX_CHI) * MAX_ROT;
         if (o->d_uniform) og.d_uniform = o->d_uniform + (long long)c0 * d.n_res;
         if (o->d_selected) og.d_selected = o->d_selected + (long long)c0 * d.n_res;
         if (o->d_trial_energy) og.d_trial_energy = o->d_trial_energy + (long long)c0 * d.n_trials_total;

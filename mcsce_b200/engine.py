@@ -192,7 +192,7 @@ class GrowthEngine:
         return int(self.lib.mcsce_workspace_bytes(self.h, int(n_conf)))
 
     def grow(self, n_conf, beta, seed=0, conf_id0=0, noise_deg=0.5, chis=None, uniforms=None, dump=False,
-             env_split=0, host_out=False, stream=None, no_dedup=False, no_graph=False, no_screen=False):
+             env_split=0, host_out=False, stream=None, no_dedup=False, no_graph=False, no_screen=False, oris=None):
         """Grow ``n_conf`` conformers.  Returns dict(coords (C,N,3) f32 growth order, energy (C,) f64,
         ok (C,) uint8 [, trial_energy, chis, selected]); torch CUDA tensors, or NumPy arrays (pinned
         staging inside the C call) with ``host_out``."""
@@ -216,6 +216,11 @@ class GrowthEngine:
             un = torch.as_tensor(np.ascontiguousarray(uniforms, np.float64), device=self.device)
             assert un.numel() == C_ * self.system.n_res
             o.d_uniform = un.data_ptr(); keep.append(un)
+        if oris is not None:      # parity replay: the dihedrals the reference measured before each rotation (NaN = constant)
+            assert chis is not None, "oris replay the measured dihedrals of given chi rows"
+            orr = torch.as_tensor(np.ascontiguousarray(oris, np.float64), device=self.device)
+            assert orr.numel() == C_ * self.n_trials_total * MAX_CHI_ROT, "oris must be (n_conf, n_trials_total, MAX_CHI_ROT)"
+            o.d_ori = orr.data_ptr(); keep.append(orr)
         out = {}
         if dump:
             out["trial_energy"] = torch.full((C_, self.n_trials_total), float("nan"), dtype=torch.float64, device=self.device)
@@ -254,9 +259,10 @@ class GrowthEngine:
     def _stream_ptr(self):
         return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
 
-    def place_trials(self, residue, chis, keep4=False):
+    def place_trials(self, residue, chis, keep4=False, oris=None):
         """K1: chis (rows, nchi) degrees -> (rows, n_sc, 3) float32 torch tensor (``keep4``: the kernel's own
-        (rows, n_sc, 4) buffer).  ``chis`` may be a float64 device tensor of MAX_CHI columns."""
+        (rows, n_sc, 4) buffer).  ``chis`` may be a float64 device tensor of MAX_CHI columns.  ``oris`` (rows, <=5) rad:
+        the dihedrals the reference measured before each rotation (parity replay; NaN = template constant)."""
         torch = self.torch
         st = self.system.steps[residue]
         if torch.is_tensor(chis):
@@ -269,8 +275,15 @@ class GrowthEngine:
             rows[:, :chis.shape[1]] = chis[:, :MAX_CHI]
             d_ch = torch.as_tensor(rows, device=self.device)
         out = torch.empty((len(rows), st.n_sc, 4), dtype=torch.float32, device=self.device)
-        check(self.lib.mcsce_place_trials(self.h, int(residue), len(rows), C.c_void_p(d_ch.data_ptr()),
-                                          C.c_void_p(out.data_ptr()), self._stream_ptr()))
+        d_or = None
+        if oris is not None:
+            o5 = np.full((len(rows), MAX_CHI_ROT), np.nan)
+            oris = np.asarray(oris, dtype=np.float64).reshape(len(rows), -1)[:, :MAX_CHI_ROT]
+            o5[:, :oris.shape[1]] = oris
+            d_or = torch.as_tensor(o5, device=self.device)
+        check(self.lib.mcsce_place_trials_replay(self.h, int(residue), len(rows), C.c_void_p(d_ch.data_ptr()),
+                                                 C.c_void_p(d_or.data_ptr()) if d_or is not None else None,
+                                                 C.c_void_p(out.data_ptr()), self._stream_ptr()))
         return out if keep4 else out[:, :, :3]
 
     def score_trials(self, residue, trial_xyz, old_xyz, env_split=0):

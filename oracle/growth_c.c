@@ -58,6 +58,14 @@ static void cross32(const float *a, const float *b, float *o) {
 }
 static float norm32(const float *v) { return sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
 static float dot32(const float *a, const float *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+/* np.linalg.norm of a float32 3-vector as NumPy + OpenBLAS evaluate it (libscbuild.py:115,169,185,199 call it on the
+ * rotation axis): sqrt(x.dot(x)) with sdot's scalar tail - float32 products added up in a double, the sum rounded to
+ * float32, float32 sqrt.  Checked against np.linalg.norm on 20000 random vectors: identical. */
+static float norm32_blas(const float *v) {
+    const float xx = v[0] * v[0], yy = v[1] * v[1], zz = v[2] * v[2];
+    const double acc = ((double)xx + (double)yy) + (double)zz;
+    return sqrtf((float)acc);
+}
 
 static float dihedral_f32(const float *p0, const float *p1, const float *p2, const float *p3) {
     float q0[3], q1[3], q2[3], c0[3], c1[3], u3[3], u2[3];
@@ -80,19 +88,24 @@ static void rotate_q(double b1, double b2, double b3, double b4, double x, doubl
     o[2] = (c1 * n4) + (c2 * n3) - (c3 * n2) + (c4 * b1);
 }
 
-static void set_chis(const oracle_system *s, int type, int n_rot, const double *tors_deg, float xyz[MAX_TMPL][3]) {
+/* ori_in: measured dihedrals to use instead of re-measuring (the reference's recorded float32 values; NaN = measure);
+ * ori_out: the values used.  Either may be NULL. */
+static void set_chis(const oracle_system *s, int type, int n_rot, const double *tors_deg, float xyz[MAX_TMPL][3],
+                     const double *ori_in, double *ori_out) {
     const int n = s->tmpl_n_atoms[type];
     memcpy(xyz, s->tmpl_xyz + (size_t)type * MAX_TMPL * 3, sizeof(float) * MAX_TMPL * 3);
     for (int k = 0; k < n_rot; ++k) {
         const int *dih = s->tmpl_dih + ((size_t)type * MAX_ROT + k) * 4;
         const int af = s->tmpl_axis[((size_t)type * MAX_ROT + k) * 2], at = s->tmpl_axis[((size_t)type * MAX_ROT + k) * 2 + 1];
         const unsigned mv = s->tmpl_move[(size_t)type * MAX_ROT + k];
-        const float measured = dihedral_f32(xyz[dih[0]], xyz[dih[1]], xyz[dih[2]], xyz[dih[3]]);
+        double measured = (double)dihedral_f32(xyz[dih[0]], xyz[dih[1]], xyz[dih[2]], xyz[dih[3]]);
+        if (ori_in && ori_in[k] == ori_in[k]) measured = ori_in[k];
+        if (ori_out) ori_out[k] = measured;
         float piv[3], ax[3];
         for (int c = 0; c < 3; ++c) { piv[c] = xyz[at][c]; ax[c] = xyz[at][c] - xyz[af][c]; }
-        const float nrm = norm32(ax);
+        const float nrm = norm32_blas(ax);
         for (int c = 0; c < 3; ++c) ax[c] = ax[c] / nrm;
-        double rot = (double)measured - tors_deg[k] * PI / 180;
+        double rot = measured - tors_deg[k] * PI / 180;
         if (rot > PI) rot -= 2 * PI; else if (rot < -PI) rot += 2 * PI;
         const double sn = sin(rot / 2), cs = cos(rot / 2);
         const double b2 = sn * (double)(-ax[0]), b3 = sn * (double)(-ax[1]), b4 = sn * (double)(-ax[2]);
@@ -215,7 +228,8 @@ double oracle_input_energy(const oracle_system *s) {
 
 static void grow_one(const oracle_system *s, int conf, double beta, double noise_deg, uint64_t seed, const double *chis_in,
                      const double *uniforms, double e_input, const double *clsA, const double *clsB, float *coords,
-                     double *energy, unsigned char *ok, double *trial_energy_out, int *selected, float *trial_xyz_out) {
+                     double *energy, unsigned char *ok, double *trial_energy_out, int *selected, float *trial_xyz_out,
+                     const double *ori_in, double *ori_out) {
     float *xyz = coords + (size_t)conf * s->n_atoms * 3;
     memcpy(xyz, s->input_xyz, sizeof(float) * 3 * s->n_input);
     uint64_t rng = seed * 0x9E3779B97F4A7C15ull + (uint64_t)conf * 0xD1B54A32D192ED03ull + 1;
@@ -235,7 +249,7 @@ static void grow_one(const oracle_system *s, int conf, double beta, double noise
         const float *ca = s->place_ca + (size_t)i * 3;
         float tx[MAX_TMPL][3], placed[MAX_TMPL][3];
         if (kind == 1) {                       /* GLY/ALA: rigid placement, no energy (side_chain_builder.py:164-168) */
-            set_chis(s, type, 0, NULL, tx);
+            set_chis(s, type, 0, NULL, tx, NULL, NULL);
             place(q1, q2, ca, nt, tx, placed);
             for (int k = 0; k < n_sc; ++k) memcpy(xyz + (size_t)(sc0 + k) * 3, placed[s->tmpl_sc_pos[(size_t)type * MAX_SC + k]], 12);
             continue;
@@ -254,7 +268,10 @@ static void grow_one(const oracle_system *s, int conf, double beta, double noise
                     chi[k] = v + noise_deg * gauss(&rng);
                 } else chi[k] = 0.0;
             }
-            set_chis(s, type, nrot, chi, tx);
+            {
+                const size_t row = ((size_t)conf * s->n_trials_total + off + t) * MAX_ROT;
+                set_chis(s, type, nrot, chi, tx, ori_in ? ori_in + row : NULL, ori_out ? ori_out + row : NULL);
+            }
             place(q1, q2, ca, nt, tx, placed);
             float *tr = trial + (size_t)t * n_sc * 3;
             for (int k = 0; k < n_sc; ++k) memcpy(tr + (size_t)k * 3, placed[s->tmpl_sc_pos[(size_t)type * MAX_SC + k]], 12);
@@ -279,7 +296,7 @@ static void grow_one(const oracle_system *s, int conf, double beta, double noise
 
 int oracle_grow(const oracle_system *s, int n_conf, double beta, double noise_deg, uint64_t seed, const double *chis_in,
                 const double *uniforms, float *coords, double *energy, unsigned char *ok, double *trial_energy_out,
-                int *selected, float *trial_xyz_out, int n_threads) {
+                int *selected, float *trial_xyz_out, int n_threads, const double *ori_in, double *ori_out) {
     const int nc = s->n_cls;
     double *clsA = (double *)malloc(sizeof(double) * nc * nc), *clsB = (double *)malloc(sizeof(double) * nc * nc);
     for (int i = 0; i < nc * nc; ++i) {
@@ -293,7 +310,7 @@ int oracle_grow(const oracle_system *s, int n_conf, double beta, double noise_de
 #pragma omp parallel for schedule(dynamic, 1)
     for (int c = 0; c < n_conf; ++c)
         grow_one(s, c, beta, noise_deg, seed, chis_in, uniforms, e_input, clsA, clsB, coords, energy, ok,
-                 trial_energy_out, selected, trial_xyz_out);
+                 trial_energy_out, selected, trial_xyz_out, ori_in, ori_out);
     free(clsA); free(clsB);
     return 0;
 }

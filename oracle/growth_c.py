@@ -60,7 +60,8 @@ def load():
     lib = C.CDLL(str(LIB))
     lib.oracle_grow.restype = C.c_int
     lib.oracle_grow.argtypes = [C.POINTER(_System), C.c_int, C.c_double, C.c_double, C.c_uint64, C.c_void_p, C.c_void_p,
-                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                C.c_void_p, C.c_void_p]
     lib.oracle_input_energy.restype = C.c_double
     lib.oracle_input_energy.argtypes = [C.POINTER(_System)]
     lib.oracle_max_threads.restype = C.c_int
@@ -166,19 +167,23 @@ class COracle:
                                            lev.ctypes.data_as(C.c_void_p))
         return float(e), float(r.value), lev
 
-    def grow(self, n_conf, beta, seed=0, noise_deg=0.5, chis=None, uniforms=None, dump=False, n_threads=0):
+    def grow(self, n_conf, beta, seed=0, noise_deg=0.5, chis=None, uniforms=None, dump=False, n_threads=0, oris=None):
+        """``oris`` (n_conf, n_trials_total, MAX_ROT) rad: dihedrals to use instead of the float32 re-measurement (the
+        reference's recorded values; NaN = measure).  ``dump`` also returns the values used as ``ori``."""
         N = self.sysm.n_atoms
         coords = np.zeros((n_conf, N, 3), np.float32); energy = np.zeros(n_conf); ok = np.zeros(n_conf, np.uint8)
         vp = lambda x: None if x is None else x.ctypes.data_as(C.c_void_p)  # noqa: E731
         ch = None if chis is None else np.ascontiguousarray(chis, np.float64)
         un = None if uniforms is None else np.ascontiguousarray(uniforms, np.float64)
-        te = sel = txyz = None
+        te = sel = txyz = ori_out = None
+        ori_in = None if oris is None else np.ascontiguousarray(oris, np.float64)
         if dump:
+            ori_out = np.full((n_conf, self.n_trials_total, MAX_ROT), np.nan)
             te = np.full((n_conf, self.n_trials_total), np.nan); sel = np.full((n_conf, self.sysm.n_res), -2, np.int32)
             txyz = np.zeros((self.n_trials_total, MAX_SC, 3), np.float32)
         self.lib.oracle_grow(C.byref(self.desc), n_conf, float(beta), float(noise_deg), int(seed), vp(ch), vp(un),
-                             vp(coords), vp(energy), vp(ok), vp(te), vp(sel), vp(txyz), int(n_threads))
+                             vp(coords), vp(energy), vp(ok), vp(te), vp(sel), vp(txyz), int(n_threads), vp(ori_in), vp(ori_out))
         out = dict(coords=coords, energy=energy, ok=ok)
         if dump:
-            out.update(trial_energy=te, selected=sel, trial_xyz=txyz)
+            out.update(trial_energy=te, selected=sel, trial_xyz=txyz, ori=ori_out)
         return out

@@ -5,7 +5,8 @@
 The reference has no tests or known-answer vectors of its own, so these files are
 the pin for the oracle (``oracle/ref_numpy.py``) and, through it, for the CUDA path.
 Nothing in the reference is edited: its module-level callables are *wrapped* with
-recorders (``rotate_sidechain`` -> perturbed chi rows, the per-residue energy closures
+recorders (``rotate_sidechain`` -> perturbed chi rows, ``libscbuild.calc_torsion_angles`` -> the
+float32 dihedral it re-measures before every chi rotation, the per-residue energy closures
 -> trial coordinates and energies, ``choose_random`` -> Boltzmann weights and picks).
 The uniforms that ``choose_random`` consumes come from numba's own generator
 (``side_chain_builder.py:36``); they are recovered by seeding that generator from a
@@ -133,9 +134,24 @@ def run_case(name, spec, out_dir):
     orig_choose = scb.choose_random
     orig_efuncs = list(scb.energy_calculators)
 
+    import mcsce.libs.libscbuild as lsb
+    orig_torsion = lsb.calc_torsion_angles
+    measured = []
+
+    def torsion_rec(coords):
+        # the float32 dihedral rotate_sidechain re-measures before every chi rotation (libscbuild.py:113,167,183,197)
+        v = orig_torsion(coords)
+        measured.append(float(v[0]))
+        return v
+
     def rotate_rec(res_type, tors):
         rec["chis"].append(np.array(tors, dtype=np.float64))
-        return orig_rotate(res_type, tors)
+        measured.clear()
+        r = orig_rotate(res_type, tors)
+        row = np.full(5, np.nan)
+        row[:len(measured)] = measured[:5]
+        rec["ori"].append(row)
+        return r
 
     def choose_rec(weights):
         idx = orig_choose(weights)
@@ -158,6 +174,7 @@ def run_case(name, spec, out_dir):
         return g
 
     scb.rotate_sidechain = rotate_rec
+    lsb.calc_torsion_angles = torsion_rec
     scb.choose_random = choose_rec
     scb.energy_calculators[:] = [wrap_efunc(i, f) for i, f in enumerate(orig_efuncs)]
     pristine = copy.deepcopy(scb._rotamer_library._data)
@@ -173,7 +190,7 @@ def run_case(name, spec, out_dir):
             nb_seed(seed)
             np.random.seed(seed)
             rec.clear()
-            rec.update(chis=[], weights=[], selected=[], steps=[])
+            rec.update(chis=[], ori=[], weights=[], selected=[], steps=[])
             structure, ok, energy, _ = scb.create_side_chain_structure([s.coords, beta, retain, None])
             scb._rotamer_library._data = copy.deepcopy(pristine)
             # regroup the flat chi rows per growth step
@@ -181,10 +198,12 @@ def run_case(name, spec, out_dir):
             for k, st in enumerate(rec["steps"]):
                 T = st["trial"].shape[0]
                 chis = np.stack(rec["chis"][pos:pos + T])
+                ori = np.stack(rec["ori"][pos:pos + T])
                 pos += T
                 pre = "c%d_s%d_" % (c, k)
                 out[pre + "level"] = np.int64(st["level"])
                 out[pre + "chis"] = chis
+                out[pre + "ori"] = ori          # measured dihedral (rad, float32 value) before each applied rotation, nan-padded
                 out[pre + "energies"] = st["energies"]
                 out[pre + "n_env"] = np.int64(st["n_env"])
                 if spec["full"]:
@@ -206,6 +225,7 @@ def run_case(name, spec, out_dir):
             print("[%s] conformer %d ok=%s E=%s steps=%d" % (name, c, ok, energy, len(rec["steps"])))
     finally:
         scb.rotate_sidechain = orig_rotate
+        lsb.calc_torsion_angles = orig_torsion
         scb.choose_random = orig_choose
         scb.energy_calculators[:] = orig_efuncs
         scb._rotamer_library._data = pristine

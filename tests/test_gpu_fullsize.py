@@ -68,31 +68,46 @@ def test_config3_300_residues_2048_conformers():
 
 def _replay_whole_conformers(cfg, n, seed, min_selections):
     """Grow n conformers on the GPU, feed the chi rows it drew and the same uniforms to the C oracle: every selection
-    and clash decision must agree, per-trial energies within the north-star tolerance (bar the K1 float32 noise)."""
+    and clash decision must agree.  Per-trial energies are compared twice: (1) with the C oracle's measured dihedrals fed
+    back to K1 (the replay hook that pins K1: coordinates then agree bit for bit) EVERY trial must be within the north-star
+    tolerance; (2) the production K1 (template-constant dihedrals) against the oracle's float32 re-measurement: measured
+    bounds on the fraction outside and on the worst trial (DESIGN "K1 fidelity")."""
     s, sysm, eng, co = _workload(cfg)
     rng = np.random.default_rng(5)
     u = rng.random((n, sysm.n_res))
     out = eng.grow(n, BETA, seed=seed, uniforms=u, dump=True)
-    ref = co.grow(n, BETA, chis=out["chis"].cpu().numpy(), uniforms=u, dump=True)
-    sel = out["selected"].cpu().numpy()
-    assert np.array_equal(out["ok"].cpu().numpy(), ref["ok"])
+    chis = out["chis"].cpu().numpy()
+    ref = co.grow(n, BETA, chis=chis, uniforms=u, dump=True)
+    pinned = eng.grow(n, BETA, seed=seed, chis=chis, uniforms=u, oris=ref["ori"], dump=True)
     grow = [st.index for st in sysm.steps if st.kind == "grow"]
-    n_sel = 0
-    for c in range(n):
-        for i in grow:
-            assert sel[c, i] == ref["selected"][c, i], (c, i, sysm.steps[i].resname)
-            if sel[c, i] < 0:
-                break
-            n_sel += 1
-    assert n_sel > min_selections
-    te, tr = out["trial_energy"].cpu().numpy(), ref["trial_energy"]
-    both = ~np.isnan(te) & ~np.isnan(tr)
-    assert np.array_equal(np.isinf(te[both]), np.isinf(tr[both]))
-    fin = both & np.isfinite(tr)
-    bad = np.abs(te[fin] - tr[fin]) > np.maximum(1e-3, 1e-5 * np.abs(tr[fin]))
-    print("cfg%s replay: %d trials, %d selections, %d trials outside tolerance, worst %.2fx" % (
-        cfg, fin.sum(), n_sel, bad.sum(), (np.abs(te[fin] - tr[fin]) / np.maximum(1e-3, 1e-5 * np.abs(tr[fin]))).max()))
-    assert bad.mean() < 0.03
+    stats = {}
+    for tag, o in (("constant", out), ("pinned", pinned)):
+        sel = o["selected"].cpu().numpy()
+        assert np.array_equal(o["ok"].cpu().numpy(), ref["ok"])
+        n_sel = 0
+        for c in range(n):
+            for i in grow:
+                assert sel[c, i] == ref["selected"][c, i], (tag, c, i, sysm.steps[i].resname)
+                if sel[c, i] < 0:
+                    break
+                n_sel += 1
+        assert n_sel > min_selections
+        te, tr = o["trial_energy"].cpu().numpy(), ref["trial_energy"]
+        both = ~np.isnan(te) & ~np.isnan(tr)
+        assert np.array_equal(np.isinf(te[both]), np.isinf(tr[both]))
+        fin = both & np.isfinite(tr)
+        ratio = np.abs(te[fin] - tr[fin]) / np.maximum(1e-3, 1e-5 * np.abs(tr[fin]))
+        stats[tag] = (int(fin.sum()), int((ratio > 1).sum()), float(ratio.max()))
+        print("cfg%s replay (%s dihedrals): %d trials, %d selections, %d trials outside tolerance, worst %.2fx" % (
+            cfg, tag, fin.sum(), n_sel, (ratio > 1).sum(), ratio.max()))
+        if ref["ok"].any():
+            c = int(np.where(ref["ok"])[0][0])
+            dc = np.abs(o["coords"][c].cpu().numpy() - ref["coords"][c])
+            if tag == "pinned":
+                assert dc.max() == 0.0, "K1 fed the oracle's measured dihedrals must reproduce its coordinates bit for bit"
+    assert stats["pinned"][1] == 0 and stats["pinned"][2] < 0.6, stats
+    # production K1: bounds measured on B200 (round 2) - fraction outside <= 2 %, none beyond 12x
+    assert stats["constant"][1] <= 0.02 * stats["constant"][0] and stats["constant"][2] < 12.0, stats
 
 
 @pytest.mark.parametrize("cfg,n", [(3, 8), (4, 16)])

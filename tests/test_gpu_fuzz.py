@@ -14,7 +14,8 @@ def test_random_systems_shortcuts_and_oracle_replay():
     import fuzz
     from oracle.growth_c import COracle
 
-    trials = flips = 0
+    trials = flips = n_out = n_fin = 0
+    worst = 0.0
     for seed in range(500, 516):
         k = fuzz.make_case(seed)
         s, sysm, eng, C, split, u, sd = (k[x] for x in ("s", "sysm", "eng", "C", "split", "u", "sd"))
@@ -33,8 +34,19 @@ def test_random_systems_shortcuts_and_oracle_replay():
         trials += int(both.sum())
         flips += int((np.isinf(te[both]) != np.isinf(tr[both])).sum())
         fin = both & np.isfinite(te) & np.isfinite(tr)
-        bad = np.abs(te[fin] - tr[fin]) > np.maximum(1e-3, 1e-5 * np.abs(tr[fin]))
-        assert bad.mean() < 0.03, seed
-    # K1's float32 differences (~1e-6 A) flip a clash decision only for a pair within ~2e-7 of its clash distance:
-    # measured 9 flips in 2e7 trials (tools/fuzz.py, tools/fuzz_diag.py)
+        ratio = np.abs(te[fin] - tr[fin]) / np.maximum(1e-3, 1e-5 * np.abs(tr[fin]))
+        n_out += int((ratio > 1).sum()); n_fin += int(fin.sum()); worst = max(worst, float(ratio.max()) if fin.any() else 0.0)
+        # pinned: the oracle's measured dihedrals replayed through K1 -> no exceptions at all
+        p = eng.grow(C, fuzz.BETA, seed=sd, chis=a["chis"], oris=ref["ori"], uniforms=u, dump=True, no_graph=True, env_split=split)
+        tp = p["trial_energy"].cpu().numpy()
+        both = ~np.isnan(tp) & ~np.isnan(tr)
+        assert np.array_equal(np.isinf(tp[both]), np.isinf(tr[both])), seed
+        assert np.array_equal(p["selected"].cpu().numpy(), ref["selected"]), seed
+        fin = both & np.isfinite(tr)
+        assert (np.abs(tp[fin] - tr[fin]) <= np.maximum(1e-3, 1e-5 * np.abs(tr[fin]))).all(), seed
+    print("fuzz: %d trials, production K1 vs oracle: %d/%d outside tolerance, worst %.2fx, %d clash flips" % (
+        trials, n_out, n_fin, worst, flips))
+    # production K1 (template-constant dihedrals) against the oracle's float32 re-measurement: measured bounds.  Its ~1e-6 A
+    # differences flip a clash decision only for a pair within ~2e-7 of its clash distance (9 flips in 2e7 trials, tools/fuzz.py)
     assert trials > 100000 and flips <= 2, (trials, flips)
+    assert n_out <= 0.02 * n_fin and worst < 12.0, (n_out, n_fin, worst)

@@ -23,16 +23,21 @@ def _setup(pdb_text, retain=()):
     return s, sysm, eng, COracle(sysm, s.coords)
 
 
-def _replay_and_compare(sysm, eng, co, n_conf, seed, env_split=0, max_out_frac=0.03, no_graph=False):
+def _replay_and_compare(sysm, eng, co, n_conf, seed, env_split=0, no_graph=False):
+    """GPU growth -> the chi rows it drew and the uniforms go through the C oracle -> the oracle's measured dihedrals go
+    back into K1 (replay hook): coordinates bit-identical, every per-trial energy within the north-star tolerance, every
+    clash flag and selection identical.  The first (production-K1) run must already agree on flags and selections."""
     rng = np.random.default_rng(seed)
     u = rng.random((n_conf, sysm.n_res))
-    out = eng.grow(n_conf, BETA, seed=seed, uniforms=u, dump=True, env_split=env_split, no_graph=no_graph)
-    chis = out["chis"].cpu().numpy()
+    first = eng.grow(n_conf, BETA, seed=seed, uniforms=u, dump=True, env_split=env_split, no_graph=no_graph)
+    chis = first["chis"].cpu().numpy()
     ref = co.grow(n_conf, BETA, chis=chis, uniforms=u, dump=True)
+    out = eng.grow(n_conf, BETA, seed=seed, chis=chis, uniforms=u, oris=ref["ori"], dump=True, env_split=env_split,
+                   no_graph=no_graph)
+    grow = [st.index for st in sysm.steps if st.kind == "grow"]
+    assert np.array_equal(first["selected"].cpu().numpy(), out["selected"].cpu().numpy())
     sel, ok, te = out["selected"].cpu().numpy(), out["ok"].cpu().numpy(), out["trial_energy"].cpu().numpy()
     assert np.array_equal(ok, ref["ok"])
-    grow = [st.index for st in sysm.steps if st.kind == "grow"]
-    n_fin = n_out = 0
     for c in range(n_conf):
         for i in grow:
             assert sel[c, i] == ref["selected"][c, i], (c, i, sysm.steps[i].resname)
@@ -42,13 +47,12 @@ def _replay_and_compare(sysm, eng, co, n_conf, seed, env_split=0, max_out_frac=0
         both = ~np.isnan(o) & ~np.isnan(r)
         assert np.array_equal(np.isinf(o[both]), np.isinf(r[both]))
         fin = both & np.isfinite(r)
-        bad = np.abs(o[fin] - r[fin]) > np.maximum(1e-3, 1e-5 * np.abs(r[fin]))
-        n_fin += int(fin.sum()); n_out += int(bad.sum())
+        assert (np.abs(o[fin] - r[fin]) <= np.maximum(1e-3, 1e-5 * np.abs(r[fin]))).all(), (
+            c, float((np.abs(o[fin] - r[fin]) / np.maximum(1e-3, 1e-5 * np.abs(r[fin]))).max()))
         if ok[c]:
             # the total accumulates one per-residue error (each within the per-trial tolerance) per grown residue
             assert abs(float(out["energy"][c]) - ref["energy"][c]) <= 4e-4 * len(grow) + 2e-5 * abs(ref["energy"][c])
-            assert np.abs(out["coords"][c].cpu().numpy() - ref["coords"][c]).max() <= 1e-5
-    assert n_out <= max_out_frac * max(1, n_fin), (n_out, n_fin)
+            assert np.array_equal(out["coords"][c].cpu().numpy(), ref["coords"][c])
     return ok
 
 
@@ -163,4 +167,4 @@ def test_all_rigid_and_tiny_cases():
     _replay_and_compare(sysm, eng, co, 1, seed=3)
     # many conformers of a short peptide
     s, sysm, eng, co = _setup(synth.small_peptide_pdb(["LYS", "ASP", "THR", "PHE"], seed=5))
-    _replay_and_compare(sysm, eng, co, 64, seed=9, max_out_frac=0.05)
+    _replay_and_compare(sysm, eng, co, 64, seed=9)

@@ -54,6 +54,45 @@ def test_c_oracle_replays_reference(name):
             assert abs(out["energy"][0] - float(gold["energy"])) <= 2e-3 + 2e-5 * abs(float(gold["energy"]))
 
 
+@pytest.mark.parametrize("name", ["pep6", "pep6_ljclash", "pep12", "ptm14", "twochain", "std20", "helix76", "fix12", "ptm18", "bundle40"])
+def test_c_oracle_with_the_references_measured_dihedrals_is_exact(name):
+    """The only part of the path the C restatement cannot reproduce bit for bit is the float32 NumPy re-measurement of
+    each dihedral (libscbuild.py:113,167,183,197).  Fed the values the reference recorded (fixture key ``ori``), its
+    trial coordinates are bit-identical to the reference's and its energies agree to summation order."""
+    from mcsce_b200._lib import MAX_CHI, MAX_CHI_ROT
+
+    case, s, sysm, co = _setup(name)
+    n_rows = n_exact = 0
+    for c in range(case.n_conf):
+        steps = case.steps_by_level(c)
+        chis = np.zeros((1, co.n_trials_total, MAX_CHI)); u = np.zeros((1, sysm.n_res))
+        oris = np.full((1, co.n_trials_total, MAX_CHI_ROT), np.nan)
+        for i, g in steps.items():
+            o = co.trial_off[i]
+            chis[0, o:o + len(g["chis"]), :g["chis"].shape[1]] = g["chis"]
+            oris[0, o:o + len(g["ori"])] = g["ori"]
+            if "u" in g:
+                u[0, i] = float(g["u"])
+        out = co.grow(1, case.beta, chis=chis, uniforms=u, dump=True, oris=oris)
+        gold = case.conf(c)
+        assert bool(out["ok"][0]) == bool(gold["ok"])
+        for i, g in steps.items():
+            o = co.trial_off[i]
+            got, ref = out["trial_energy"][0, o:o + len(g["energies"])], g["energies"]
+            assert np.array_equal(np.isinf(got), np.isinf(ref)), (name, c, i)
+            fin = ~np.isinf(ref)
+            np.testing.assert_allclose(got[fin], ref[fin], rtol=1e-10, atol=1e-8)
+            if "selected" in g:
+                assert out["selected"][0, i] == int(g["selected"])
+            if case.full and c == 0:
+                xyz = out["trial_xyz"][o:o + len(g["trial"]), :sysm.steps[i].n_sc]
+                n_rows += xyz.size; n_exact += int((xyz == g["trial"]).sum())
+        if gold["ok"]:
+            np.testing.assert_allclose(out["energy"][0], float(gold["energy"]), rtol=1e-10)
+    if case.full:
+        assert n_exact == n_rows, (n_exact, n_rows)
+
+
 def test_c_oracle_threads_and_rng():
     case, s, sysm, co = _setup("pep12")
     a = co.grow(8, case.beta, seed=3, n_threads=1)
