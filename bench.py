@@ -48,7 +48,7 @@ def build_workload(name):
 
     cfg, n_conf, desc = WORKLOADS[name]
     s = Structure(synth.config_backbone(cfg)).build().remove_side_chains([])
-    lib, ptm = DunbrakRotamerLibrary(), ptmRotamerLib()
+    lib, ptm = DunbrakRotamerLibrary(path=synth.synthetic_library_path(0)), ptmRotamerLib()     # synthetic inputs, stated in "data"
     sysm = build_system(s, rotamer_library=lib, ptm_library=ptm)
     return s, sysm, n_conf, desc
 

@@ -212,6 +212,16 @@ int mcsce_write_pdbs(int n_conf, int n_atoms, const float *h_coords, const uint8
                      const char *line_template, int line_len, int coord_off, const char *dir, int n_threads,
                      int32_t *n_written);
 
+/* Peer-memory result buffer (multi-GPU, one process per GPU): rank 0 allocates the ensemble's result buffer and publishes
+ * its 64-byte CUDA IPC handle; the other ranks map it and hand their slice to mcsce_grow as d_coords/d_energy/d_ok, so the
+ * result kernels store straight into rank 0's memory over NVLink - no collective, no staging copy.  Replaces the result
+ * hand-back of multiprocessing.Pool.imap_unordered (core/side_chain_builder.py:328-347).
+ *   alloc: cudaMalloc + cudaIpcGetMemHandle on the owning rank;  open/close: map/unmap on a peer;  free: owner. */
+int mcsce_peer_alloc(int device, size_t bytes, void **d_ptr, unsigned char *handle64);
+int mcsce_peer_open(int device, const unsigned char *handle64, void **d_ptr);
+int mcsce_peer_close(int device, void *d_ptr);
+int mcsce_peer_free(int device, void *d_ptr);
+
 /* per-kernel-class device timing for the benchmark's roofline: enable=1 starts recording CUDA-event
  * pairs around every launch (on the launch stream); enable=0 synchronises and returns summed
  * milliseconds / launch counts for [place, score_generic, score_special, select]. */

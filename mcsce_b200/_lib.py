@@ -80,6 +80,10 @@ SYMBOLS = {
     "mcsce_grow_host": (C.c_int, [C.c_void_p, C.POINTER(GrowOpts), C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p]),
     "mcsce_place_trials": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mcsce_peer_alloc": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]),
+    "mcsce_peer_open": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "mcsce_peer_close": (C.c_int, [C.c_int, C.c_void_p]),
+    "mcsce_peer_free": (C.c_int, [C.c_int, C.c_void_p]),
     "mcsce_place_trials_replay": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mcsce_score_trials": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),

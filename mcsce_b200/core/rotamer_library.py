@@ -28,15 +28,38 @@ _TWO_CHI = ("ASN", "ASP", "HIS", "ILE", "LEU", "PHE", "PRO", "TRP", "TYR")
 _THREE_CHI = ("GLN", "GLU", "MET")
 
 
+ALLOW_SYNTHETIC_ENV = "MCSCE_B200_ALLOW_SYNTHETIC"
+_REAL_LIBRARY_NAMES = ("ALL.bbdep.rotamers.lib", "ALL.bbdep.rotamers.lib.gz")
+
+
 def default_library_path():
-    """bbdep library location: ``$MCSCE_ROTAMER_LIB`` or the seeded synthetic stand-in
-    (the real archive is absent from the reference checkout)."""
+    """bbdep library location, in this order: ``$MCSCE_ROTAMER_LIB``; the Dunbrack archive beside the package data
+    (``mcsce_b200/data/SimpleOpt1-5/ALL.bbdep.rotamers.lib``, where the reference keeps it: ``core/rotamer_library.py:16``).
+    The archive is absent from the reference checkout, so tests and the benchmark run on a *seeded synthetic* stand-in
+    (random priors: scientifically meaningless ensembles) - that one is only served when the caller opts in with
+    ``MCSCE_B200_ALLOW_SYNTHETIC=1`` (or passes ``synth.synthetic_library_path()`` explicitly); otherwise this raises."""
     env = os.environ.get("MCSCE_ROTAMER_LIB")
     if env:
+        if not Path(env).exists():
+            raise FileNotFoundError("MCSCE_ROTAMER_LIB=%s does not exist" % env)
         return Path(env)
-    from mcsce_b200 import synth
+    data = Path(__file__).resolve().parents[1] / "data"
+    for sub in ("SimpleOpt1-5", ""):
+        for name in _REAL_LIBRARY_NAMES:
+            if (data / sub / name).exists():
+                return data / sub / name
+    if os.environ.get(ALLOW_SYNTHETIC_ENV, "") not in ("", "0"):
+        import warnings
 
-    return synth.synthetic_library_path(0)
+        from mcsce_b200 import synth
+
+        warnings.warn("mcsce_b200: using the SYNTHETIC backbone-dependent rotamer library (seeded random priors); "
+                      "ensembles grown from it are for testing/benchmarking only", stacklevel=2)
+        return synth.synthetic_library_path(0)
+    raise FileNotFoundError(
+        "no backbone-dependent rotamer library: set MCSCE_ROTAMER_LIB to the Dunbrack bbdep file (the reference's "
+        "data/SimpleOpt1-5/ALL.bbdep.rotamers.lib) or place it under %s; set %s=1 to run on the synthetic stand-in "
+        "(tests and benchmarks only)" % (data / "SimpleOpt1-5", ALLOW_SYNTHETIC_ENV))
 
 
 def wrap_angles(a):

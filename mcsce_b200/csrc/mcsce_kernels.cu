@@ -1147,6 +1147,7 @@ struct mcsce_handle_s {
     size_t bb_cap = 0;
     SysDev d{};
     bool has_sys = false, has_bb = false;
+    bool warned_screen_limit = false;
     // host mirrors needed for launch geometry
     std::vector<StepDev> steps;
     std::vector<TmplDev> tmpl_host;
@@ -1214,6 +1215,20 @@ static float exact_thr2(double thr) {
     while (pred(x)) x = nextafterf(x, INFINITY);
     while (x > 0.f && !pred(nextafterf(x, 0.f))) x = nextafterf(x, 0.f);
     return x;
+}
+
+// Dynamic shared memory of the selection kernels: 2 (select_kernel) or 1 (select_plain_kernel) doubles per trial.  Above the
+// 48 KB default the kernel needs an explicit opt-in; above the 227 KB a CTA can have the trial set is refused with a message
+// (the reference's largest sets: 81 x 9 = 729 rows for ARG/LYS, 288 for M3L/KCX - far below either limit).
+#define MAX_DYN_SMEM (227 * 1024 - 2048)
+template <typename K>
+static int ensure_dyn_smem(K kernel, size_t bytes, const char *what) {
+    if (bytes <= 48 * 1024) return 0;
+    if (bytes > MAX_DYN_SMEM)
+        return fail(std::string(what) + ": trial set too large for the selection kernel's shared memory (" +
+                    std::to_string(bytes / 1024) + " KB needed, " + std::to_string(MAX_DYN_SMEM / 1024) + " KB available)");
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return 0;
 }
 
 extern "C" const char *mcsce_last_error(void) { return g_err.c_str(); }
@@ -1445,7 +1460,14 @@ static int build_screen_lists(mcsce_handle h, const mcsce_backbone_desc *b, std:
     for (int i = 0; i < n_res && scale > 0.0; ++i) {
         off[i] = (int)slots.size();
         const StepDev &si = h->steps[i];
-        if (si.kind != 2 || si.n_trials < 8 || si.n_trials > SCREEN_WORDS * 32) continue;
+        if (si.kind == 2 && si.n_trials > SCREEN_WORDS * 32) {      // the screen's survivor mask holds SCREEN_WORDS x 32 trials
+            if (!h->warned_screen_limit)
+                fprintf(stderr, "[mcsce_b200] note: residue %d has %d trials (> %d): the neighbour screen is off for it, every trial "
+                                "is scored against the whole environment (same results, more work)\n", i, si.n_trials, SCREEN_WORDS * 32);
+            h->warned_screen_limit = true;
+            continue;
+        }
+        if (si.kind != 2 || si.n_trials < 8) continue;
         int n_active = 0;
         for (int c = 0; c < n_cls; ++c) n_active += h->cls_active[(size_t)i * n_cls + c];
         if (n_active < 256) continue;
@@ -1536,6 +1558,7 @@ extern "C" int mcsce_set_backbone(mcsce_handle h, const mcsce_backbone_desc *b) 
             h->max_trial_atoms = std::max(h->max_trial_atoms, o.n_trials * o.n_sc);
         }
     }
+    if (ensure_dyn_smem(select_kernel, sizeof(double) * 2 * (size_t)h->max_trials, "mcsce_set_backbone")) return -1;
     CK(cudaMemcpy(h->d_steps, h->steps.data(), sizeof(StepDev) * d.n_res, cudaMemcpyHostToDevice));
     std::vector<int> scr_off, scr_slots, scr_prefix;
     if (build_screen_lists(h, b, scr_off, scr_slots, scr_prefix)) return -1;
@@ -1843,7 +1866,9 @@ extern "C" int mcsce_pack_env(mcsce_handle h, int n_env_sets, int n_old, const f
 extern "C" int mcsce_select(mcsce_handle h, int n_sets, int n_trials, const double *d_energy, const double *d_prob,
                             double beta, const double *d_uniform, int32_t *d_selected, double *d_e_selected, void *stream) {
     if (!h) return fail("null handle");
+    if (n_sets <= 0 || n_trials <= 0) return fail("mcsce_select: n_sets and n_trials must be positive");
     CK(cudaSetDevice(h->device));
+    if (ensure_dyn_smem(select_plain_kernel, sizeof(double) * (size_t)n_trials, "mcsce_select")) return -1;
     select_plain_kernel<<<n_sets, 128, sizeof(double) * n_trials, (cudaStream_t)stream>>>(n_trials, d_energy, d_prob, beta,
                                                                                          d_uniform, d_selected, d_e_selected);
     h->launches += 1;
@@ -2137,6 +2162,50 @@ extern "C" int mcsce_place_template(int device, int n_atoms, const float *h_xyz,
     cudaError_t e = cudaMemcpy(h_out, d_out, sizeof(double) * (size_t)n_atoms * 3, cudaMemcpyDeviceToHost);
     cudaFree(d_in); cudaFree(d_out);
     if (e != cudaSuccess) return fail(std::string("place_template: ") + cudaGetErrorString(e));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Peer-memory result buffer: the multi-GPU "gather" without a collective.  Rank 0 owns one buffer for the whole ensemble;
+// every other rank maps it (CUDA IPC over NVLink/NVSwitch) and passes its slice as d_coords / d_energy / d_ok of mcsce_grow,
+// so the result kernels (gather_kernel, finish_kernel) store straight into rank 0's HBM - the transfer is the kernel's own
+// store stream, there is no staging copy and no second pass.  Replaces what multiprocessing.Pool.imap_unordered ships back to
+// the parent in the reference (core/side_chain_builder.py:328-347).
+// ------------------------------------------------------------------------------------------------
+extern "C" int mcsce_peer_alloc(int device, size_t bytes, void **d_ptr, unsigned char *handle64) {
+    if (!d_ptr || !handle64 || bytes == 0) return fail("mcsce_peer_alloc: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CK(cudaSetDevice(device));
+    void *p = nullptr;
+    CK(cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t hd;
+    cudaError_t e = cudaIpcGetMemHandle(&hd, p);
+    if (e != cudaSuccess) { cudaFree(p); return fail(std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); }
+    memcpy(handle64, &hd, 64);
+    *d_ptr = p;
+    return 0;
+}
+
+extern "C" int mcsce_peer_open(int device, const unsigned char *handle64, void **d_ptr) {
+    if (!d_ptr || !handle64) return fail("mcsce_peer_open: bad arguments");
+    CK(cudaSetDevice(device));
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handle64, 64);
+    void *p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+    *d_ptr = p;
+    return 0;
+}
+
+extern "C" int mcsce_peer_close(int device, void *d_ptr) {
+    CK(cudaSetDevice(device));
+    CK(cudaIpcCloseMemHandle(d_ptr));
+    return 0;
+}
+
+extern "C" int mcsce_peer_free(int device, void *d_ptr) {
+    CK(cudaSetDevice(device));
+    CK(cudaFree(d_ptr));
     return 0;
 }
 

@@ -192,10 +192,12 @@ class GrowthEngine:
         return int(self.lib.mcsce_workspace_bytes(self.h, int(n_conf)))
 
     def grow(self, n_conf, beta, seed=0, conf_id0=0, noise_deg=0.5, chis=None, uniforms=None, dump=False,
-             env_split=0, host_out=False, stream=None, no_dedup=False, no_graph=False, no_screen=False, oris=None):
+             env_split=0, host_out=False, stream=None, no_dedup=False, no_graph=False, no_screen=False, oris=None,
+             out_ptrs=None):
         """Grow ``n_conf`` conformers.  Returns dict(coords (C,N,3) f32 growth order, energy (C,) f64,
         ok (C,) uint8 [, trial_energy, chis, selected]); torch CUDA tensors, or NumPy arrays (pinned
-        staging inside the C call) with ``host_out``."""
+        staging inside the C call) with ``host_out``.  ``out_ptrs`` = (coords, energy, ok) raw device addresses: the
+        results are stored there instead (e.g. this rank's slice of rank 0's peer-mapped buffer, ``sharding.PeerResults``)."""
         torch = self.torch
         assert self._has_backbone, "set_backbone first"
         if any(st.kind == "grow" and st.chi_mean is None for st in self.system.steps):
@@ -243,6 +245,11 @@ class GrowthEngine:
                                            C.c_void_p(coords.data_ptr()), C.c_void_p(energy.data_ptr()),
                                            C.c_void_p(ok.data_ptr()), s_ptr))
             out.update(coords=coords.numpy(), energy=energy.numpy(), ok=ok.numpy())   # views of the pinned staging: copy to keep
+        elif out_ptrs is not None:
+            ws = self._ws(base)
+            check(self.lib.mcsce_grow(self.h, C.byref(o), C.c_void_p(ws.data_ptr()), ws.numel(),
+                                      C.c_void_p(int(out_ptrs[0])), C.c_void_p(int(out_ptrs[1])),
+                                      C.c_void_p(int(out_ptrs[2])), s_ptr))
         else:
             ws = self._ws(base)
             coords = torch.empty((C_, N, 3), dtype=torch.float32, device=self.device)

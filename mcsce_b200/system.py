@@ -183,12 +183,25 @@ def build_system(structure, retain_idxs=(), terms=("lj", "clash", "coulomb"), ro
     res_index = [ordinal_of_num.get(n, -1) for n in resnums]
     if min(res_index) < 0:
         raise ValueError("residue numbers must be contiguous and unique across chains")
+    # every (chain, number) of the input must be one residue of the ordered list: chains that restart their numbering
+    # (A:1-10, B:1-10) would pass the test above and silently alias two residues onto one ordinal
+    seen = []
+    for key in zip(chains, resnums):
+        if not seen or seen[-1] != key:
+            seen.append(key)
+    if len(set(seen)) != len(res_types) or [n for _, n in sorted(set(seen), key=lambda k: k[1])] != list(
+            range(first_num, first_num + len(res_types))):
+        raise ValueError("residue numbers must be contiguous and unique across chains (found %d distinct (chain, number) "
+                         "pairs for %d residues; renumber chains consecutively)" % (len(set(seen)), len(res_types)))
     appear = [-1] * n_input
 
     ncac = structure.get_sorted_minimal_backbone_coords()
     phi, psi = backbone_torsions_deg(ncac)
     name_arr = np.array(names)
     n_rows, ca_rows, c_rows = (np.where(name_arr == a)[0] for a in ("N", "CA", "C"))
+    if not (len(n_rows) == len(ca_rows) == len(c_rows) == len(res_types)):
+        raise ValueError("every residue needs exactly one N, CA and C atom (found %d/%d/%d for %d residues)"
+                         % (len(n_rows), len(ca_rows), len(c_rows), len(res_types)))
 
     steps = []
     for i, (res, chain) in enumerate(zip(res_types, res_chains)):

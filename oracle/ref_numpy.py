@@ -20,9 +20,7 @@ results agree with the running reference to the last bit or close to it):
 PARITY PIN: the reference ships no tests or golden vectors (tests/test_1.py is
 empty), so this oracle is pinned against outputs of the *running* reference,
 generated in the build container by ``tests/golden/make_golden.py`` and committed
-under ``tests/golden/*.npz`` (``tests/test_oracle_golden.py``), and - when
-``/root/reference`` is present - against the live reference functions
-(``tests/test_oracle_vs_reference.py``).
+under ``tests/golden/*.npz`` (``tests/test_oracle_golden.py``).
 
 The chemistry tables (force-field parameters, templates, topology) and the
 rotamer-library lookup come from ``mcsce_b200.chem`` / ``mcsce_b200.core`` (host

@@ -52,6 +52,10 @@ CASES = {
                        "MGN", "CGU", "LYZ", "GLU"], n_conf=2, seed=19, full=True),
     # two 20-residue helices 11 A apart in one chain: trials meet atoms of the other helix (clashes that are not local in sequence)
     "bundle40": dict(seq=None, n_conf=1, seed=20, full=False),
+    # BASELINE configs 4 and 3 at full size, one conformer each, light records (no trial coordinates): the stock reference's
+    # per-trial energies / selections at 150 residues with PTMs and at 300 residues (init: minutes to an hour on one core)
+    "cfg4_150": dict(cfg=4, n_conf=1, seed=21, full=False, skip_failed=True),
+    "cfg3_300": dict(cfg=3, n_conf=1, seed=22, full=False, skip_failed=True),
     # --fix mode (cli.py:118-147): residues 3, 4 and 9 keep the side chains of an earlier growth of pep12
     "fix12": dict(base="pep12", retain=[3, 4, 9], n_conf=2, seed=18, full=True),
 }
@@ -183,8 +187,12 @@ def run_case(name, spec, out_dir):
                n_conf=np.int64(spec["n_conf"]), full=np.bool_(spec["full"]), retain=np.array(retain, dtype=np.int64))
     n_grow = sum(1 for f in orig_efuncs[1:] if f is not None)
     try:
-        for c in range(spec["n_conf"]):
-            seed = spec["seed"] * 100 + c
+        c = -1
+        for attempt in range(spec["n_conf"] if not spec.get("skip_failed") else 12 * spec["n_conf"]):
+            if c + 1 >= spec["n_conf"]:
+                break
+            c += 1
+            seed = spec["seed"] * 100 + attempt
             nb_seed(seed)
             uniforms = nb_draw(n_grow)
             nb_seed(seed)
@@ -193,6 +201,11 @@ def run_case(name, spec, out_dir):
             rec.update(chis=[], ori=[], weights=[], selected=[], steps=[])
             structure, ok, energy, _ = scb.create_side_chain_structure([s.coords, beta, retain, None])
             scb._rotamer_library._data = copy.deepcopy(pristine)
+            if spec.get("skip_failed") and not ok:          # full-size cases keep conformers that grew to the end
+                print("[%s] seed %d died after %d steps: skipped" % (name, seed, len(rec["steps"])))
+                c -= 1
+                continue
+            out["c%d_seed" % c] = np.int64(seed)
             # regroup the flat chi rows per growth step
             pos = 0
             for k, st in enumerate(rec["steps"]):

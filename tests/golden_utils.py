@@ -49,5 +49,8 @@ def library():
     try:
         return _LIB
     except NameError:
-        _LIB = (DunbrakRotamerLibrary(), ptmRotamerLib())
+        from mcsce_b200 import synth
+
+        # the fixtures were generated on the seeded synthetic library (the Dunbrack archive is not in the reference checkout)
+        _LIB = (DunbrakRotamerLibrary(path=synth.synthetic_library_path(0)), ptmRotamerLib())
         return _LIB

@@ -15,7 +15,8 @@ from golden_utils import GoldenCase, library
 pytestmark = pytest.mark.gpu
 
 FULL_CASES = ["pep6", "pep6_ljclash", "pep12", "ptm14", "twochain", "fix12", "ptm18"]
-ALL_CASES = FULL_CASES + ["std20", "helix76", "bundle40"]
+# cfg4_150 / cfg3_300: the stock reference at BASELINE sizes (150 residues with PTMs, 300 residues), one conformer each
+ALL_CASES = FULL_CASES + ["std20", "helix76", "bundle40", "cfg4_150", "cfg3_300"]
 _ENG = {}
 
 

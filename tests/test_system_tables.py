@@ -196,3 +196,20 @@ def test_batched_placement_quaternions_are_bit_identical_to_the_per_residue_rout
         for i in range(L):
             r1, r2, rc = placement_quaternions(bb[i], TN[i], TC[i])
             assert np.array_equal(r1, q1[i]) and np.array_equal(r2, q2[i]) and np.array_equal(rc, ca[i]), (L, i)
+
+
+def test_chains_that_restart_their_numbering_are_rejected():
+    """Two chains numbered 1..6 each would alias onto the same residue ordinals (the reference maps ordinal <-> number as
+    ordinal + res_nums[0], side_chain_builder.py:88-90); build_system must refuse instead of mis-assigning bonded pairs."""
+    from mcsce_b200 import synth
+    from mcsce_b200.structure import Structure
+    from mcsce_b200.system import build_system
+
+    a = ["LYS", "GLU", "PHE", "SER", "TRP", "ASN"]
+    s = Structure(synth.helix_bundle_pdb([a, a], seed=15, one_chain=False, spacing=12.0)).build().remove_side_chains([])
+    build_system(s)                                           # consecutive numbering across chains: accepted
+    num = s.cols["resseq"].copy()
+    num[s.cols["chain"] != s.cols["chain"][0]] -= 6           # chain B restarts at the first number
+    s.cols["resseq"] = num
+    with pytest.raises(ValueError):
+        build_system(s)
