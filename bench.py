@@ -4,13 +4,17 @@ trial atom-pair energies/s vs the FP32 peak).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3]
 
-One "step" = growing C conformers of the workload backbone end to end on the device (chi -> xyz,
-all-pairs scoring, Boltzmann selection for every residue) with on-device RNG.  Under torchrun every
-rank grows its own C conformers (conformer ids offset by rank: independent units, no collective on
-the data path; scaling = weak).  Rank 0 prints ONE JSON line.
+One "step" = growing the workload's conformers end to end on the device (chi -> xyz, all-pairs scoring,
+Boltzmann selection for every residue) with on-device RNG, results delivered to rank 0's HBM.  The headline
+workload is BASELINE config 3 as written: 2048 conformers IN TOTAL, sharded over the ranks under torchrun
+(strong scaling; conformer ids are global, so the ensemble does not depend on the number of ranks); every
+rank's result kernels store straight into rank 0's peer-mapped buffer (mcsce_b200.sharding.PeerResults), the
+NCCL gather being the cross-check.  Rank 0 prints ONE JSON line; the other BASELINE configs are timed after
+the headline and reported under "other_workloads".
 
---impl reference times the CPU restatement of the reference (oracle/, a port: the reference itself
-is pure Python and cannot travel to the GPU box) on all host cores on a bounded sample.
+--impl reference times the reference's CPU path on all host cores on a bounded sample: the C port of the
+loop (oracle/growth_c.c, 2 conformers per core) and - with --stock, or from the committed record - the
+unmodified reference itself (baseline/_ref, create_side_chain_ensemble on a multiprocessing.Pool).
 """
 from __future__ import annotations
 
@@ -18,6 +22,7 @@ import argparse
 import json
 import os
 import subprocess
+import tempfile
 import sys
 import threading
 import time
@@ -31,11 +36,12 @@ import numpy as np  # noqa: E402
 
 FLOPS_PER_PAIR = 22          # algorithmic FP32 flops of one pair evaluation
 WORKLOADS = {
-    # name: (synth config, conformers per GPU, description)
-    "cfg2": (2, 128, "76-residue helix backbone, 128 conformers per GPU"),
-    "cfg3": (3, 2048, "300-residue 6-helix bundle backbone, 2048 conformers per GPU"),
-    "cfg4": (4, 512, "150-residue backbone with PTM residues, 512 conformers per GPU"),
-    "cfg5": (5, 32, "2000-residue 8-chain complex, 32 conformers per GPU"),
+    # name: (synth config, conformers, "total" = sharded over the ranks | "per_gpu", description)
+    "cfg1": (1, 1, "total", "76-residue helix backbone, 1 conformer (BASELINE config 1)"),
+    "cfg2": (2, 128, "total", "76-residue helix backbone, 128 conformers (BASELINE config 2)"),
+    "cfg3": (3, 2048, "total", "300-residue 6-helix bundle backbone, 2048 conformers in total (BASELINE config 3)"),
+    "cfg4": (4, 512, "total", "150-residue backbone with PTM residues, 512 conformers (BASELINE config 4)"),
+    "cfg5": (5, 32, "per_gpu", "2000-residue 8-chain complex, 32 conformers per GPU = 256 on 8 GPUs (BASELINE config 5)"),
 }
 BETA = 1.0 / (300 * 0.008314462)
 
@@ -46,11 +52,11 @@ def build_workload(name):
     from mcsce_b200.structure import Structure
     from mcsce_b200.system import build_system
 
-    cfg, n_conf, desc = WORKLOADS[name]
+    cfg, n_conf, mode, desc = WORKLOADS[name]
     s = Structure(synth.config_backbone(cfg)).build().remove_side_chains([])
     lib, ptm = DunbrakRotamerLibrary(path=synth.synthetic_library_path(0)), ptmRotamerLib()     # synthetic inputs, stated in "data"
     sysm = build_system(s, rotamer_library=lib, ptm_library=ptm)
-    return s, sysm, n_conf, desc
+    return s, sysm, n_conf, mode, desc
 
 
 class ClockSampler(threading.Thread):
@@ -84,14 +90,13 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------------------------------------
-# CPU baseline: the oracle's C restatement of the reference on all host cores
+# CPU baselines: the oracle's C restatement of the reference on all host cores, and the stock reference
 # ----------------------------------------------------------------------------------------------
-def cpu_baseline(s, sysm, n_steps=1, warmup=0, conformers_per_core=1):
-    """conformers/s of the C port of the reference's growth loop (oracle/growth_c.c), one conformer per
-    OpenMP thread on every host core - the reference's own parallelism is one conformer per
-    multiprocessing worker (side_chain_builder.py:328-347).  The reference itself is pure Python/numba
-    and lives in /root/reference, which does not exist on the GPU box; its setup (initialize_func_calc,
-    63 s at 76 residues) is not part of the hot path and is not timed, like here."""
+def cpu_baseline(s, sysm, n_steps=1, warmup=0, conformers_per_core=2):
+    """conformers/s of the C port of the reference's growth loop (oracle/growth_c.c), OpenMP over conformers on every host
+    core, 2 conformers per core as BASELINE.md plans - the reference's own parallelism is one conformer per
+    multiprocessing worker (side_chain_builder.py:328-347).  Its setup (initialize_func_calc, minutes) is not part of the
+    hot path and is not timed, like here."""
     from oracle.growth_c import COracle
 
     cores = os.cpu_count() or 1
@@ -108,6 +113,70 @@ def cpu_baseline(s, sysm, n_steps=1, warmup=0, conformers_per_core=1):
             times.append(dt); ok.append(float(out["ok"].mean()))
     return {"conformers_per_step": n, "cores": cores, "step_seconds": times, "setup_seconds": setup_s,
             "succeeded_fraction": float(np.mean(ok))}
+
+
+def stock_reference_records():
+    """The unmodified reference timed on a GPU box's host cores (baseline/stock_reference.py through gpurun), committed
+    under profiles/: {workload: record}."""
+    out = {}
+    for p in sorted((ROOT / "profiles").glob("r2_stock_reference_*.json")):
+        try:
+            rec = json.loads(p.read_text())
+            rec["record"] = "profiles/" + p.name
+            out[rec.get("workload", p.stem)] = rec
+        except Exception:
+            pass
+    return out
+
+
+def stock_reference_live(workload, timeout_s=600):
+    """Run the unmodified reference (baseline/_ref) on this host now; None when it is not installed."""
+    if not (ROOT / "baseline" / "_ref" / "mcsce").exists():
+        return None
+    try:
+        r = subprocess.run([sys.executable, str(ROOT / "baseline" / "stock_reference.py"), "--workload", workload],
+                           capture_output=True, text=True, timeout=timeout_s, cwd=tempfile.gettempdir())
+        rec = json.loads(r.stdout.strip().splitlines()[-1])
+        rec["record"] = "live, this run"
+        return None if "unavailable" in rec else rec
+    except Exception as e:                                    # a baseline leg must never break the bench line
+        return {"error": "%s: %s" % (type(e).__name__, e)}
+
+
+def parity_block(eng, s, sysm, n=4, seed=77):
+    """Replay of n whole conformers of the bench workload through the C oracle (the checker), in the CPU leg: the GPU's chi
+    rows and uniforms go to the oracle; 'pinned' feeds the oracle's measured dihedrals back into K1 (the replay hook),
+    'production' is the GPU run as shipped (template-constant dihedrals)."""
+    from oracle.growth_c import COracle
+
+    co = COracle(sysm, s.coords)
+    u = np.random.default_rng(seed).random((n, sysm.n_res))
+    out = eng.grow(n, BETA, seed=seed, uniforms=u, dump=True)
+    chis = out["chis"].cpu().numpy()
+    ref = co.grow(n, BETA, chis=chis, uniforms=u, dump=True)
+    pinned = eng.grow(n, BETA, seed=seed, chis=chis, uniforms=u, oris=ref["ori"], dump=True)
+    grow = [st.index for st in sysm.steps if st.kind == "grow"]
+    res = {"conformers": n, "checker": "oracle/growth_c.c fed the GPU's chi rows and uniforms",
+           "tolerance": "max(1e-3 kJ/mol, 1e-5 |E|) per trial; flags and selections exact"}
+    for tag, o in (("production", out), ("pinned", pinned)):
+        te, tr = o["trial_energy"].cpu().numpy(), ref["trial_energy"]
+        both = ~np.isnan(te) & ~np.isnan(tr)
+        flips = int((np.isinf(te[both]) != np.isinf(tr[both])).sum())
+        fin = both & np.isfinite(te) & np.isfinite(tr)
+        ratio = np.abs(te[fin] - tr[fin]) / np.maximum(1e-3, 1e-5 * np.abs(tr[fin]))
+        sel = o["selected"].cpu().numpy()
+        mism = 0
+        for c in range(n):
+            for i in grow:
+                mism += int(sel[c, i] != ref["selected"][c, i])
+                if sel[c, i] < 0 or ref["selected"][c, i] < 0:
+                    break
+        res[tag] = {"trials": int(both.sum()), "finite_trials": int(fin.sum()), "outside": int((ratio > 1).sum()),
+                    "worst_over_tolerance": float(ratio.max()) if fin.any() else 0.0, "clash_flag_flips": flips,
+                    "selection_mismatches": mism}
+    res["pinned"]["coordinates_bit_identical"] = bool(np.array_equal(pinned["coords"].cpu().numpy()[ref["ok"] == 1],
+                                                                     ref["coords"][ref["ok"] == 1]))
+    return res
 
 
 _RESULT_FD = None
@@ -136,29 +205,191 @@ def pairs_per_conformer(sysm):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    s, sysm, n_conf, desc = build_workload(args.workload)
-    res = cpu_baseline(s, sysm, n_steps=args.steps, warmup=args.warmup, conformers_per_core=1)
+    s, sysm, n_conf, mode, desc = build_workload(args.workload)
+    res = cpu_baseline(s, sysm, n_steps=args.steps, warmup=args.warmup, conformers_per_core=2)
     sec = float(np.mean(res["step_seconds"]))
     value = res["conformers_per_step"] / sec
-    sample = "%d conformers per step (1 per host core, OpenMP) of %s; C port of the reference loop (oracle/growth_c.c)" % (
+    sample = "%d conformers per step (2 per host core, OpenMP) of %s; C port of the reference loop (oracle/growth_c.c)" % (
         res["conformers_per_step"], desc)
+    stock = stock_reference_records()
+    if args.stock:
+        live = stock_reference_live(args.workload)
+        if live:
+            stock[args.workload] = live
     line = {
         "impl": "reference", "metric": "conformers_per_second", "value": value, "unit": "conformers/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "%s: %s" % (args.workload, desc), "sample": sample},
         "cpu_baseline": {"value": value, "unit": "conformers/s", "cores": res["cores"], "kind": "port", "sample": sample,
-                         "pairs_per_second": value * pairs_per_conformer(sysm), "setup_seconds": res["setup_seconds"]},
+                         "pairs_per_second": value * pairs_per_conformer(sysm), "setup_seconds": res["setup_seconds"],
+                         "stock_reference": stock or None,
+                         "note": "value is the C port (faster than the stock Python/numba reference, whose timing on a GPU "
+                                 "box's host cores is under stock_reference)"},
         "e2e": {"value": value, "unit": "conformers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
 
 
+class Harness:
+    """One workload on this rank: engine, shard, result delivery to rank 0, timing helpers."""
+
+    def __init__(self, name, rank, world, local_rank, n_override=0):
+        import torch
+
+        from mcsce_b200 import sharding
+        from mcsce_b200.engine import GrowthEngine
+
+        self.torch, self.sharding = torch, sharding
+        self.name, self.rank, self.world, self.local_rank = name, rank, world, local_rank
+        self.s, self.sysm, n_conf, self.mode, self.desc = build_workload(name)
+        if n_override:
+            n_conf = n_override
+        if self.mode == "total":
+            self.n_total = n_conf
+            self.lo, self.hi = sharding.shard_range(n_conf, rank, world)
+        else:
+            self.n_total = n_conf * world
+            self.lo, self.hi = rank * n_conf, (rank + 1) * n_conf
+        self.n_local = self.hi - self.lo
+        self.eng = GrowthEngine(local_rank).set_system(self.sysm).set_backbone(self.s.coords)
+        self.peer = sharding.PeerResults(self.n_total, self.sysm.n_atoms, local_rank) if world > 1 else None
+        self.host = None
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def step(self, k, host=False):
+        """Grow this rank's conformers of ensemble k; results land in rank 0's buffer (peer stores) when world > 1."""
+        if self.n_local == 0:
+            return None
+        kw = dict(seed=1234 + k, conf_id0=self.lo)
+        if self.peer is not None:
+            return self.eng.grow(self.n_local, BETA, out_ptrs=self.peer.slice_ptrs(self.lo, self.hi), **kw)
+        return self.eng.grow(self.n_local, BETA, host_out=host, **kw)
+
+    def timed(self, first, steps, fn=None):
+        """max-over-ranks device milliseconds of `steps` calls of fn (default: self.step), barrier + sync on both sides."""
+        torch = self.torch
+        fn = fn or self.step
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        last = None
+        for k in range(steps):
+            last = fn(first + k)
+        e1.record()
+        self.barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        ms = e0.elapsed_time(e1)
+        return ms, wall, last
+
+    def reduce_max(self, *vals):
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    def reduce_sum(self, *vals):
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(x) for x in t]
+
+    def e2e_step(self, k):
+        """The public call with HOST buffers: backbone tables host -> device, growth, results device -> pinned host
+        (on rank 0, for the whole ensemble)."""
+        torch = self.torch
+        self.eng.set_backbone(self.s.coords)
+        if self.peer is None:
+            return self.step(k, host=True)
+        self.step(k)
+        self.peer.fence()
+        if self.rank == 0:
+            c, e, ok = self.peer.tensors()
+            if self.host is None:
+                self.host = tuple(torch.empty(x.shape, dtype=x.dtype).pin_memory() for x in (c, e, ok))
+            for dst, src in zip(self.host, (c, e, ok)):
+                dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+        return None
+
+    def succeeded_fraction(self, k):
+        """Fraction of the ensemble that grew to the end, from one more (untimed) ensemble."""
+        out = self.step(k)
+        if self.peer is not None:
+            self.peer.fence()
+            ok = float(self.peer.tensors()[2].sum().item()) if self.rank == 0 else 0.0
+            return ok / self.n_total
+        return float(out["ok"].sum().item()) / self.n_total
+
+    def measure(self, steps, warmup):
+        """{value, e2e, ...} of this workload (conformers/s over all ranks)."""
+        for k in range(warmup):
+            self.step(k)
+        self.eng.counters(reset=True)
+        ms, wall, _ = self.timed(warmup, steps)
+        launches, pairs = self.eng.counters(reset=True)
+        ms, = self.reduce_max(ms)
+        pairs, launches = self.reduce_sum(float(pairs), float(launches))
+        e2e_steps = max(1, min(steps, 3))
+        self.e2e_step(9_999)              # untimed: first use of the host-buffer path allocates its pinned staging
+        e_ms, e_wall, _ = self.timed(10_000, e2e_steps, fn=self.e2e_step)
+        e_ms, = self.reduce_max(max(e_ms, e_wall))
+        ok_frac = self.succeeded_fraction(20_000)
+        sysm = self.sysm
+        h2d = int(sysm.n_input * 12 + self.eng.n_trials_total * (6 * 8 * 2 + 8) + sysm.n_res * (4 * 4 + 8 * 8 + 12))
+        d2h = int(self.n_total * (sysm.n_atoms * 12 + 9))
+        return {"value": self.n_total * steps / (ms * 1e-3), "ms_per_step": ms / steps, "pairs_per_second": pairs / (ms * 1e-3),
+                "gpu_launches": int(launches), "succeeded_fraction": ok_frac,
+                "e2e": {"value": self.n_total * e2e_steps / (e_ms * 1e-3), "unit": "conformers/s",
+                        "h2d_bytes_per_step": h2d * self.world, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                        "call": "GrowthEngine.set_backbone + grow(host_out=True) -> mcsce_grow_host" if self.peer is None else
+                                "per rank: GrowthEngine.set_backbone + grow into rank 0's peer-mapped buffer; rank 0: device -> "
+                                "pinned host copy of the whole ensemble"}}
+
+    def kernel_profile(self, k=30_000):
+        """CUDA events around every kernel launch of one ensemble, all on one stream (rank-local)."""
+        torch = self.torch
+        self.eng.counters(reset=True)
+        torch.cuda.synchronize()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.eng.profile_begin()
+        p0.record()
+        self.eng.grow(self.n_local, BETA, seed=1234 + k, conf_id0=self.lo)
+        p1.record()
+        prof = self.eng.profile_end()
+        step_ms = p0.elapsed_time(p1)
+        _, pairs, computed = self.eng.counters(reset=True, computed=True)
+        return prof, step_ms, pairs, computed
+
+    def close(self):
+        if self.peer is not None:
+            self.peer.close()
+        self.eng.close()
+
+
+def fp32_peak_tflops(local_rank, clocks):
+    import torch
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    sm_max = float(peaks.get("sm_max_mhz") or clocks.get("sm_max_mhz") or 1965.0)
+    sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    return sm_count * 128 * 2 * sm_max * 1e6 / 1e12, sm_count, sm_max
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
-
-    from mcsce_b200.engine import GrowthEngine
 
     torch.cuda.set_device(local_rank)
     dist = None
@@ -167,102 +398,103 @@ def run_ours(args, rank, world, local_rank):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's version/debug lines must not land on stdout (one JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    s, sysm, n_conf, desc = build_workload(args.workload)
-    if args.conformers:
-        n_conf = args.conformers
-    eng = GrowthEngine(local_rank).set_system(sysm).set_backbone(s.coords)
-    conf0 = rank * n_conf
-
-    def step(k, host=False):
-        return eng.grow(n_conf, BETA, seed=1234 + k, conf_id0=conf0 + k * world * n_conf, host_out=host)
-
+    H = Harness(args.workload, rank, world, local_rank, n_override=args.conformers)
+    s, sysm, eng = H.s, H.sysm, H.eng
     for k in range(args.warmup):
-        step(k)
+        H.step(k)
     eng.counters(reset=True)
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    barrier()
     if sampler:
         sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    ok_total = 0
-    outs = []
-    for k in range(args.steps):
-        outs.append(step(args.warmup + k)["ok"])
-    ev1.record()
-    barrier()
+    ms, _, _ = H.timed(args.warmup, args.steps)
     if sampler:
         sampler.stop_flag = True
-    ms = ev0.elapsed_time(ev1)
     launches, pairs = eng.counters(reset=True)
-    ok_total = int(sum(int(o.sum().item()) for o in outs))
-    t = torch.tensor([ms, float(pairs), float(ok_total), float(launches)], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms, pairs, ok_total, launches = float(tmax[0]), float(tsum[1]), float(tsum[2]), float(tsum[3])
-    total_conf = n_conf * world * args.steps
+    ms, = H.reduce_max(ms)
+    pairs, launches = H.reduce_sum(float(pairs), float(launches))
+    total_conf = H.n_total * args.steps
     value = total_conf / (ms * 1e-3)
 
-    # ---- end-to-end through the public call with host buffers: set_backbone (H2D of the step's inputs)
-    #      + grow_host (D2H of coordinates, energies, flags), every step ----
+    # ---- end to end through the public call with host buffers ----
     e2e_steps = max(1, min(args.steps, 3))
-    eng.set_backbone(s.coords)
-    step(9_999, host=True)               # untimed: first use of the host-buffer path allocates its pinned staging
-    barrier()
-    t0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for k in range(e2e_steps):
-        eng.set_backbone(s.coords)
-        o = step(10_000 + k, host=True)
-    e1.record()
-    barrier()
-    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
-    e2e_t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_value = n_conf * world * e2e_steps / (float(e2e_t[0]) * 1e-3)
-    h2d = int(sysm.n_input * 12 + eng.n_trials_total * (6 * 8 * 2 + 8) + sysm.n_res * (4 * 4 + 8 * 8 + 12))
-    d2h = int(n_conf * (sysm.n_atoms * 12 + 9))
+    H.e2e_step(9_999)
+    e_ms, e_wall, _ = H.timed(10_000, e2e_steps, fn=H.e2e_step)
+    e_ms, = H.reduce_max(max(e_ms, e_wall))
+    e2e_value = H.n_total * e2e_steps / (e_ms * 1e-3)
+    h2d = int(sysm.n_input * 12 + eng.n_trials_total * (6 * 8 * 2 + 8) + sysm.n_res * (4 * 4 + 8 * 8 + 12)) * world
+    d2h = int(H.n_total * (sysm.n_atoms * 12 + 9))
+    ok_frac = H.succeeded_fraction(20_000)
+
+    # ---- multi-GPU extras: the NCCL gather as cross-check of the peer stores, and the weak-scaling figure ----
+    multi = None
+    if world > 1:
+        from mcsce_b200 import sharding
+
+        def nccl_step(k):
+            o = eng.grow(H.n_local, BETA, seed=1234 + k, conf_id0=H.lo)
+            return sharding.gather_results(o["coords"], o["energy"], o["ok"], H.n_total, to_host=False)
+
+        nccl_step(0)
+        g_ms, _, got = H.timed(args.warmup, args.steps, fn=nccl_step)
+        g_ms, = H.reduce_max(g_ms)
+        H.step(args.warmup + args.steps - 1)                 # the same ensemble through the peer buffer
+        H.peer.fence()
+        same = None
+        if rank == 0:
+            c, e, k_ = H.peer.tensors()
+            same = bool(torch.equal(c, got[0]) and torch.equal(k_, got[2])
+                        and torch.equal(torch.nan_to_num(e, nan=0.0), torch.nan_to_num(got[1], nan=0.0)))
+        del got
+        n_weak = 2048 if args.workload == "cfg3" else H.n_total
+        for k in range(2):
+            eng.grow(n_weak, BETA, seed=99 + k, conf_id0=rank * n_weak)
+        w_ms, _, _ = H.timed(0, 2, fn=lambda k: eng.grow(n_weak, BETA, seed=199 + k, conf_id0=rank * n_weak))
+        w_ms, = H.reduce_max(w_ms)
+        multi = {"delivery": "every rank's result kernels store into rank 0's buffer over NVLink (CUDA IPC peer mapping); no collective",
+                 "nccl_gather_ms_per_step": g_ms / args.steps, "peer_store_ms_per_step": ms / args.steps,
+                 "peer_equals_nccl_gather": same,
+                 "weak": {"value": n_weak * world * 2 / (w_ms * 1e-3), "unit": "conformers/s", "conformers_per_gpu": n_weak,
+                          "ms_per_step": w_ms / 2, "note": "fixed work per GPU, no result delivery (round-1 definition)"}}
+
+    # ---- the other BASELINE configs (all ranks take part: sharded conformers, peer delivery) ----
+    others = {}
+    if not args.no_others:
+        for name in ("cfg1", "cfg2", "cfg4", "cfg5"):
+            if name == args.workload or (name == "cfg1" and world > 1):
+                continue
+            Ho = Harness(name, rank, world, local_rank)
+            r = Ho.measure(args.steps, args.warmup)
+            if rank == 0 and Ho.n_local > 0:
+                prof, step_ms, p_alg, p_exec = Ho.kernel_profile()
+                k2_ms = prof["score_generic"][0]
+                peak, _, _ = fp32_peak_tflops(local_rank, {})
+                r["frac_executed"] = FLOPS_PER_PAIR * p_exec / (k2_ms * 1e-3) / 1e12 / peak if k2_ms > 0 else None
+                r["k2_share_of_step"] = k2_ms / step_ms if step_ms else None
+            r["config"] = {"workload": "%s: %s" % (name, Ho.desc), "conformers_total": Ho.n_total, "residues": Ho.sysm.n_res,
+                           "atoms": Ho.sysm.n_atoms}
+            others[name] = r
+            H.barrier()
+            Ho.close()
 
     if rank != 0:
+        H.close()
         if dist is not None:
             dist.destroy_process_group()
         return
 
     # ---- roofline of the dominant kernel (score_generic), CUDA events around every launch, separate pass ----
-    eng.counters(reset=True)
-    torch.cuda.synchronize()
-    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    eng.profile_begin()
-    p0.record()
-    step(20_000)
-    p1.record()
-    prof = eng.profile_end()
-    prof_step_ms = p0.elapsed_time(p1)
-    _, prof_pairs, prof_computed = eng.counters(reset=True, computed=True)
+    prof, prof_step_ms, prof_pairs, prof_computed = H.kernel_profile()
     k2_ms, k2_n = prof["score_generic"]
     clocks = sampler.summary() if sampler else {}
-    peaks = {}
-    try:
-        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
-    except Exception:
-        pass
-    sm_max = float(peaks.get("sm_max_mhz") or clocks.get("sm_max_mhz") or 1965.0)
-    sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
-    peak_tflops = sm_count * 128 * 2 * sm_max * 1e6 / 1e12
+    peak_tflops, sm_count, sm_max = fp32_peak_tflops(local_rank, clocks)
     achieved = FLOPS_PER_PAIR * prof_pairs / (k2_ms * 1e-3) / 1e12 if k2_ms > 0 else 0.0
     traffic = None
-    try:          # dram__bytes_read+write of one ncu --set full capture of this kernel (profiles/, per launch of THAT capture)
-        traffic = json.loads((ROOT / "profiles" / "r1_traffic.json").read_text())
-    except Exception:
-        pass
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:          # dram__bytes_read+write of one ncu --set full capture of this kernel (profiles/, per launch of THAT capture)
+            traffic = json.loads((ROOT / "profiles" / name).read_text())
+            break
+        except Exception:
+            pass
     executed = FLOPS_PER_PAIR * prof_computed / (k2_ms * 1e-3) / 1e12 if k2_ms > 0 else 0.0
     roofline = {
         "bound": "fp32", "kernel": "score_generic_kernel", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
@@ -272,6 +504,7 @@ def run_ours(args, rank, world, local_rank):
         "flops_per_pair": FLOPS_PER_PAIR, "pairs_per_launch_avg": prof_pairs / max(1, k2_n),
         "launch_ms_avg": k2_ms / max(1, k2_n), "launches": k2_n, "share_of_step": k2_ms / prof_step_ms if prof_step_ms else None,
         "kernel_ms": {k: v[0] for k, v in prof.items()}, "step_ms_in_this_pass": prof_step_ms,
+        "conformers_in_this_pass": H.n_local,
         "note": "achieved counts ALGORITHMIC pairs (the reference's P, libcalc.py:56) over the K2 launches (neighbour screen + "
                 "scoring pass of a residue, one event pair). The kernel executes fewer: chi-independent atoms (HA, CB) are scored "
                 "once per residue and trials that the clash-only screen rejects (+inf either way) are not scored - "
@@ -282,34 +515,54 @@ def run_ours(args, rank, world, local_rank):
         "frac_at_observed_clock": (achieved / (sm_count * 128 * 2 * clocks["sm_mhz"] * 1e6 / 1e12)) if clocks.get("sm_mhz") else None,
     }
 
-    cpu = None
+    cpu = parity = None
     if world == 1 and not args.no_cpu:
-        res = cpu_baseline(s, sysm, n_steps=1, warmup=0, conformers_per_core=1)
+        parity = parity_block(eng, s, sysm)
+        res = cpu_baseline(s, sysm, n_steps=1, warmup=0, conformers_per_core=2)
         sec = float(np.mean(res["step_seconds"]))
         v = res["conformers_per_step"] / sec
+        stock = stock_reference_records()
+        if args.stock:
+            live = stock_reference_live(args.workload)
+            if live:
+                stock[args.workload] = live
         cpu = {"value": v, "unit": "conformers/s", "cores": res["cores"], "kind": "port",
-               "sample": "%d conformers (1 per host core, OpenMP) of the same backbone, C port of the reference loop "
+               "sample": "%d conformers (2 per host core, OpenMP) of the same backbone, C port of the reference loop "
                          "(oracle/growth_c.c), %.1f s" % (res["conformers_per_step"], sec),
-               "pairs_per_second": v * pairs_per_conformer(sysm), "setup_seconds": res["setup_seconds"]}
+               "pairs_per_second": v * pairs_per_conformer(sysm), "setup_seconds": res["setup_seconds"],
+               "stock_reference": stock or None,
+               "note": "value is the C port; the unmodified Python/numba reference (create_side_chain_ensemble on a "
+                       "multiprocessing.Pool, baseline/_ref) timed on a GPU box's host cores is under stock_reference"}
 
     line = {
         "metric": "conformers_per_second", "value": value, "unit": "conformers/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong" if H.mode == "total" else "weak",
         "vs_baseline": None, "dtype": "f32 pair terms, f64 accumulation/selection", "data": "synthetic",
-        "config": {"workload": "%s: %s" % (args.workload, desc), "conformers_per_gpu": n_conf,
-                   "conformers_total_per_step": n_conf * world, "residues": sysm.n_res, "atoms": sysm.n_atoms,
+        "config": {"workload": "%s: %s" % (args.workload, H.desc), "conformers_total_per_step": H.n_total,
+                   "conformers_per_gpu": H.n_local, "residues": sysm.n_res, "atoms": sysm.n_atoms,
                    "trials_per_conformer": int(eng.n_trials_total), "pairs_per_conformer": pairs_per_conformer(sysm),
                    "terms": list(sysm.terms), "rng": "on-device Philox4x32-10",
-                   "l2_note": "per-step working set (environment + trial buffers, %.0f MB) exceeds the 126 MB L2"
-                              % (n_conf * (sysm.n_atoms + 4000) * 16 / 1e6)},
-        "pairs_per_second": pairs / (ms * 1e-3), "succeeded_fraction": ok_total / total_conf,
+                   "result_delivery": "none (one GPU)" if world == 1 else "peer stores into rank 0's HBM inside the timed step",
+                   "l2_note": "per-step working set (environment + trial buffers, %.0f MB per GPU) exceeds the 126 MB L2"
+                              % (H.n_local * (sysm.n_atoms + 4000) * 16 / 1e6)},
+        "pairs_per_second": pairs / (ms * 1e-3), "succeeded_fraction": ok_frac,
         "e2e": {"value": e2e_value, "unit": "conformers/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "call": "GrowthEngine.set_backbone + grow(host_out=True) -> mcsce_grow_host"},
+                "steps": e2e_steps,
+                "call": "GrowthEngine.set_backbone + grow(host_out=True) -> mcsce_grow_host" if world == 1 else
+                        "per rank: set_backbone + grow into rank 0's peer-mapped buffer; rank 0: device -> pinned host copy"},
         "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
     }
+    if multi:
+        line["multi_gpu"] = multi
+    if others:
+        line["other_workloads"] = others
+    if parity:
+        line["parity"] = parity
     if cpu:
         line["cpu_baseline"] = cpu
     emit(line)
+    H.close()
     if dist is not None:
         dist.destroy_process_group()
 
@@ -321,8 +574,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
-    ap.add_argument("--conformers", type=int, default=0, help="conformers per GPU per step (default: the workload's)")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--conformers", type=int, default=0, help="conformers of the workload (default: BASELINE's)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline and parity legs")
+    ap.add_argument("--no-others", action="store_true", help="skip the other BASELINE configs")
+    ap.add_argument("--stock", action="store_true", help="also time the unmodified reference (baseline/_ref) live: minutes")
     args = ap.parse_args()
     # stdout carries exactly one JSON line: anything libraries print there (NCCL's version banner, ...) is sent to stderr
     # by pointing fd 1 at fd 2 for the whole run; the line itself goes to the saved descriptor

@@ -106,8 +106,8 @@ def _replay_whole_conformers(cfg, n, seed, min_selections):
             if tag == "pinned":
                 assert dc.max() == 0.0, "K1 fed the oracle's measured dihedrals must reproduce its coordinates bit for bit"
     assert stats["pinned"][1] == 0 and stats["pinned"][2] <= 1.0, stats      # measured worst: 0.60x (config 3), 0.78x (config 4)
-    # production K1: bounds measured on B200 (round 2) - fraction outside <= 2 %, none beyond 12x
-    assert stats["constant"][1] <= 0.02 * stats["constant"][0] and stats["constant"][2] < 12.0, stats
+    # production K1: bounds measured on B200 (round 2) - fraction outside <= 2 %, none beyond 20x (measured worst 9.4x-11.1x, an ARG rotamer with a steep contact inside the side chain)
+    assert stats["constant"][1] <= 0.02 * stats["constant"][0] and stats["constant"][2] < 20.0, stats
 
 
 @pytest.mark.parametrize("cfg,n", [(3, 8), (4, 16)])

@@ -55,4 +55,4 @@ def test_random_systems_shortcuts_and_oracle_replay():
     # production K1 (template-constant dihedrals) against the oracle's float32 re-measurement: measured bounds.  Its ~1e-6 A
     # differences flip a clash decision only for a pair within ~2e-7 of its clash distance (9 flips in 2e7 trials, tools/fuzz.py)
     assert trials > 100000 and flips <= 2, (trials, flips)
-    assert n_out <= 0.02 * n_fin and worst < 12.0, (n_out, n_fin, worst)
+    assert n_out <= 0.02 * n_fin and worst < 20.0, (n_out, n_fin, worst)
