@@ -329,12 +329,13 @@ __global__ void __launch_bounds__(128) place_trials_kernel(PlaceArgs a) {
 #define SCORE_THREADS 128               // 128 x 2 measured best on B200 (tools/time_variants.py): finer CTA granularity per launch
 #endif
 #ifndef SCORE_R
-#define SCORE_R 2                       // trial atoms per thread
+#define SCORE_R 3                       // trial atoms per thread at most: a tile holds 1, 2 or 3 rows of 128 atoms (see tile_layout)
 #endif
 #ifndef SCORE_MINB
 #define SCORE_MINB 4                    // min resident blocks per SM asked of the compiler (keeps the kernel at <= 128 registers: 4 CTAs/SM)
 #endif
 #define TILE_A (SCORE_THREADS * SCORE_R)
+#define SCREEN_TILE_A (SCORE_THREADS * 2)   // the clash-only screen pass keeps 256-atom tiles (it is overhead bound, not pair bound)
 #ifndef TILE_E
 #define TILE_E 1024                     // environment atoms staged per smem tile
 #endif
@@ -353,6 +354,37 @@ constexpr int kPairUnroll = PAIR_UNROLL;
 #define FLUSH 32                        // pairs accumulated in float32 before a float64 flush
 #endif
 
+// Tile layout of the scoring pass for one conformer: nk trials of n_per atoms each (+ n_fix chi-independent atoms riding in the
+// last tile) are cut into n_tiles tiles of tpt whole trials.  A tile runs on one CTA with 1, 2 or 3 atoms per thread (rows of
+// SCORE_THREADS atoms); its time follows its number of rows, full or not.  Before this, tiles were always filled to 256 atoms
+// and the last one of a conformer was on average 40 % full - 30 % of the kernel's lane-time idle (config 3: ~350 atoms per
+// conformer and residue = 1.4 tiles).  Here the number of tiles is chosen to minimise  tiles x (rows + 0.4)  (0.4 rows = a CTA's
+// staging/prologue/epilogue share), so 355 atoms run as one 3-row tile instead of 256 + 99.
+struct TileRule { int max_rows, packed; float overhead; };
+__host__ __device__ __forceinline__ void tile_layout(TileRule rule, int nk, int n_per, int n_fix, int &n_tiles, int &tpt) {
+    n_tiles = 1; tpt = nk > 0 ? nk : 1;
+    if (nk <= 0) return;
+    const int cap = SCORE_THREADS * rule.max_rows;
+    const int atoms = nk * n_per + n_fix;
+    if (rule.packed) {       // fill tiles to the cap, the remainder (and the chi-independent atoms) in the last one
+        tpt = cap / n_per; if (tpt < 1) tpt = 1;
+        n_tiles = (nk + tpt - 1) / tpt;
+        if ((nk - (n_tiles - 1) * tpt) * n_per + n_fix > cap) ++n_tiles;    // (an extra tile for the chi-independent atoms)
+        return;
+    }
+    const int n_min = (atoms + cap - 1) / cap;
+    float best = 1.0e30f;
+    for (int n = (n_min > 0 ? n_min : 1); n <= n_min + 5; ++n) {
+        const int t = (nk + n - 1) / n;
+        const int tile_atoms = t * n_per + n_fix;                 // the last tile carries the chi-independent atoms: bound every tile by it
+        if (tile_atoms > cap) { if (t <= 1) break; continue; }
+        const int used = (nk + t - 1) / t;                        // tiles that actually hold trials
+        const float cost = (float)used * ((float)((tile_atoms + SCORE_THREADS - 1) / SCORE_THREADS) + rule.overhead);
+        if (cost < best) { best = cost; n_tiles = used; tpt = t; }
+        if (t <= 1) break;
+    }
+}
+
 struct ScoreArgs {
     SysDev s;
     int step;
@@ -364,8 +396,8 @@ struct ScoreArgs {
     long long trial_set_stride;
     double2 *partial;                  // [set][n_trials + dedup][n_split] (energy, clash); slot n_trials = chi-independent atoms
     const unsigned char *alive;
-    int dedup;                         // 1: score chi-independent atoms once per residue (trial 0's copy)
-    int fixed_extra_tile;              // 1: they get a tile of their own (the last one); 0: they ride in the last tile
+    int dedup;                         // 1: score chi-independent atoms once per residue (trial 0's copy); they ride in the last tile
+    TileRule rule;                     // how the scoring pass cuts a conformer's trials into tiles
     unsigned char *screen;             // [set][n_trials] neighbour screen: 1 = the trial clashes with a nearby atom.  Written by
                                        // the screen pass; the main pass (null = no screen) scores only the trials left
     const double2 *sp_partial;         // screen pass: the special-pair kernel's results [set][n_trials]; its clash flags are merged in
@@ -559,15 +591,13 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MINB) score_generic_kerne
     const StepDev &st = a.s.steps[a.step];
     const int n_cls = a.s.n_cls;
     const int n_sc = st.n_sc;
-    // The chi-independent atoms ride in the last tile that has trials (the next one if that tile is full): without a screen
-    // that is the last tile of the grid, with a screen it follows from the number of trials the screen left - and the
-    // tiles beyond have nothing to do.
-    int fix_tile = gridDim.x - 1;
-    if (compact) {
-        const int nk = a.n_keep[set], tpt = a.trials_per_tile, n_per0 = a.dedup ? st.n_var : n_sc;
-        const int lt = nk > 0 ? (nk - 1) / tpt : 0;
-        fix_tile = ((nk - lt * tpt) * n_per0 + st.n_fix <= TILE_A) ? lt : lt + 1;
-        if (blockIdx.x * tpt >= nk && !(a.dedup && (int)blockIdx.x == fix_tile)) return;
+    // Tiles of the scoring pass: chosen per conformer from the number of trials the screen left (tile_layout); the
+    // chi-independent atoms ride in the last tile, tiles beyond have nothing to do.
+    const int n_per = a.dedup ? st.n_var : n_sc;                 // atoms per trial in a tile
+    int lay_tiles = gridDim.x, lay_tpt = a.trials_per_tile;
+    if (!SCREEN) {
+        tile_layout(a.rule, compact ? a.n_keep[set] : a.n_trials, n_per, a.dedup ? st.n_fix : 0, lay_tiles, lay_tpt);
+        if ((int)blockIdx.x >= lay_tiles) return;
     }
 
     const int warp = tid >> 5, lane = tid & 31;
@@ -618,13 +648,10 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MINB) score_generic_kerne
     };
 
     // this block's trial atoms: atom la = r*SCORE_THREADS + tid of the tile.  With dedup the tiles hold only the
-    // chi-dependent atoms of whole trials; the chi-independent atoms (trial 0's copy) ride in the free lanes of
-    // the last tile, or in one extra tile when that one is full.
-    const int n_per = a.dedup ? st.n_var : n_sc;                 // atoms per trial in a tile
-    const bool last = (int)blockIdx.x == fix_tile;
-    const bool extra = !SCREEN && !compact && a.dedup && a.fixed_extra_tile && last;    // tile of chi-independent atoms only
-    const int t0 = extra ? 0 : blockIdx.x * a.trials_per_tile;
-    const int nt = extra ? 0 : max(0, min(a.trials_per_tile, n_keep - t0));
+    // chi-dependent atoms of whole trials; the chi-independent atoms (trial 0's copy) ride in the free lanes of the last tile.
+    const bool last = !SCREEN && (int)blockIdx.x == lay_tiles - 1;
+    const int t0 = blockIdx.x * lay_tpt;
+    const int nt = max(0, min(lay_tpt, n_keep - t0));
     const int n_varatoms = nt * n_per;
     const int n_fixatoms = (!SCREEN && a.dedup && last) ? st.n_fix : 0;
     const int n_local = n_varatoms + n_fixatoms;
@@ -1148,6 +1175,7 @@ struct mcsce_handle_s {
     SysDev d{};
     bool has_sys = false, has_bb = false;
     bool warned_screen_limit = false;
+    TileRule rule{SCORE_R, 0, 0.4f};       // tuning knobs: MCSCE_B200_TILE_ROWS / _TILE_PACKED / _TILE_OVERHEAD
     // host mirrors needed for launch geometry
     std::vector<StepDev> steps;
     std::vector<TmplDev> tmpl_host;
@@ -1253,8 +1281,11 @@ extern "C" int mcsce_create(mcsce_handle *out, int device) {
         CK(cudaMemset(ln.d_call, 0, sizeof(CallParams)));
     }
     h->cur_call = h->lane[0].d_call;
+    if (const char *e = getenv("MCSCE_B200_TILE_ROWS")) h->rule.max_rows = std::max(1, std::min(SCORE_R, atoi(e)));
+    if (const char *e = getenv("MCSCE_B200_TILE_PACKED")) h->rule.packed = atoi(e) ? 1 : 0;
+    if (const char *e = getenv("MCSCE_B200_TILE_OVERHEAD")) h->rule.overhead = (float)atof(e);
     CK(cudaMalloc((void **)&h->d_input_energy, sizeof(double)));
-    CK(cudaMallocHost((void **)&h->h_n_dead, sizeof(int)));
+    CK(cudaMallocHost((void **)&h->h_n_dead, sizeof(int) * MAX_LANES));
     *out = h;
     return 0;
 }
@@ -1628,7 +1659,17 @@ extern "C" int mcsce_set_backbone(mcsce_handle h, const mcsce_backbone_desc *b) 
 
 static inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
-static int trials_per_tile_for(int n_per) { return std::max(1, TILE_A / std::max(1, n_per)); }
+static int trials_per_tile_for(int n_per) { return std::max(1, SCREEN_TILE_A / std::max(1, n_per)); }   // screen pass
+// tiles the scoring pass can need for up to n_trials surviving trials (the device picks the layout per conformer)
+static int max_tiles_for(TileRule rule, int n_trials, int n_per, int n_fix, bool any_count) {
+    int best = 1;
+    for (int nk = any_count ? 1 : std::max(1, n_trials); nk <= n_trials; ++nk) {
+        int n, t;
+        tile_layout(rule, nk, n_per, n_fix, n, t);
+        best = std::max(best, n);
+    }
+    return best;
+}
 
 // Environment split of the scoring pass: 1 when the conformers (x trial tiles) fill the GPU, otherwise enough shares of the
 // environment to reach about one resident round of CTAs.  (A rule that also balanced the last round of big launches
@@ -1638,19 +1679,22 @@ static int choose_split(const mcsce_handle h, int step, int n_sets, int n_trials
     int n_active = 0;
     for (int c = 0; c < h->d.n_cls; ++c) n_active += h->cls_active[(size_t)step * h->d.n_cls + c];
     if (screened) n_trials = std::max(1, (n_trials * 5 + 7) / 8);      // the screen leaves about 5 trials in 8 (measured, cfg3/cfg5)
-    const int tiles = (n_trials + trials_per_tile_for(st.n_sc) - 1) / trials_per_tile_for(st.n_sc);   // (upper bound with dedup)
+    int tiles, tpt_;
+    tile_layout(h->rule, n_trials, st.n_var > 0 && st.n_fix > 0 ? st.n_var : st.n_sc, st.n_var > 0 ? st.n_fix : 0, tiles, tpt_);
     const long long ctas = (long long)tiles * n_sets;
     int max_split = std::max(1, std::min(32, (n_active + 255) / 256));
     if (forced > 0) return std::min(forced, max_split);
-    const long long want = 4LL * h->sm_count;
-    int split = (int)std::min<long long>(max_split, std::max<long long>(1, (want + ctas - 1) / ctas));
+    // about two resident rounds of CTAs: a launch ends with a tail of one CTA's duration in which the SMs run dry, and smaller
+    // CTAs shorten it (measured, config 3 at 256 / 512 conformers: 87.9 -> 84.2 ms / 155.1 -> 152.0 ms against one round)
+    const long long want = 8LL * h->sm_count;
+    int split = (int)std::min<long long>(max_split, std::max<long long>(1, (want + ctas / 2) / ctas));
     return split;
 }
 static int max_split_for(int n_sets, int sm_count) {
     // split factors the workspace is sized for: 1 when the conformers alone fill the GPU, else the maximum (32),
     // because the factor is raised while conformers die (see mcsce_grow)
-    long long want = 4LL * sm_count;
-    return (want + n_sets - 1) / n_sets > 1 ? 32 : 1;
+    long long want = 8LL * sm_count;
+    return (want + n_sets / 2) / n_sets > 1 ? 32 : 1;
 }
 
 struct Workspace {
@@ -1754,10 +1798,10 @@ static int launch_generic(mcsce_handle h, int step, int n_sets, int n_trials, in
     a.s = h->d; a.step = step; a.n_trials = n_trials; a.trials_per_tile = trials_per_tile_for(dedup ? sd.n_var : sd.n_sc);
     a.n_split = n_split; a.env = env; a.trial = trial; a.trial_set_stride = trial_stride; a.partial = partial; a.alive = alive;
     a.dedup = dedup; a.screen = screen; a.sp_partial = sp_partial; a.n_keep = n_keep;
-    const int tiles = (n_trials + a.trials_per_tile - 1) / a.trials_per_tile;
-    const int last_atoms = (n_trials - (tiles - 1) * a.trials_per_tile) * (dedup ? sd.n_var : sd.n_sc);
-    a.fixed_extra_tile = (dedup && last_atoms + sd.n_fix > TILE_A) ? 1 : 0;
-    dim3 grid(tiles + a.fixed_extra_tile, n_sets, n_split);
+    const int tiles = (n_trials + a.trials_per_tile - 1) / a.trials_per_tile;        // screen pass: fixed 256-atom tiles
+    const int n_per = dedup ? sd.n_var : sd.n_sc;
+    a.rule = h->rule;
+    dim3 grid(max_tiles_for(h->rule, n_trials, n_per, dedup ? sd.n_fix : 0, screen != nullptr), n_sets, n_split);
     {
         ProfScope ps(h, 1, st);
         if (screen) {      // neighbour screen first: flags the trials the scoring pass can skip
@@ -1876,77 +1920,88 @@ extern "C" int mcsce_select(mcsce_handle h, int n_sets, int n_trials, const doub
     return 0;
 }
 
-// Enqueue the whole growth (environment init, input-atom energy, then K1/K2/K2s/K3 for every grown residue) on
-// `st` + `aux`.  `resync` allows the occasional read-back of the number of dead conformers (never while capturing).
-static int enqueue_growth(mcsce_handle h, const mcsce_grow_opts *o, const Workspace &w, mcsce_handle_s::Lane &ln,
-                          cudaStream_t st, cudaStream_t aux, bool resync) {
-    const SysDev &d = h->d;
-    h->cur_call = ln.d_call;
-    // per-call scalars -> device parameter block (by-value kernel argument: no host buffer to keep alive)
-    // (not while capturing: a replayed graph must read the values of the call that replays it, written by mcsce_grow)
-    if (!h->capturing) {
-        CallParams cp{o->seed, o->conf_id0, o->beta, o->noise_deg};
-        set_call_params_kernel<<<1, 1, 0, st>>>(ln.d_call, cp);
+// Enqueue of one growth (environment init, then K1 / K2s / screen / K2 / K3 for every grown residue) on `st` + `aux`, as a
+// stepper: begin(), residue(i) for every residue in order, so that several conformer groups (lanes) can be enqueued
+// interleaved residue by residue - the occasional read-back of the number of dead conformers (`resync`, never while
+// capturing) then stalls the host at the same point of every group's progress instead of serialising the groups.
+struct GrowthEnqueue {
+    mcsce_handle h; mcsce_grow_opts o; Workspace w; mcsce_handle_s::Lane *ln; cudaStream_t st, aux; bool resync;
+    int groups;                 // conformer groups in flight: the environment split is chosen for all of them together
+    int prev = -1, prev2 = -1, count = 0, ms_alloc = 1, n_alive = 0;
+    long long trial_stride = 1, chi_set_stride = 0;
+
+    int begin() {
+        const SysDev &d = h->d;
+        h->cur_call = ln->d_call;
+        // per-call scalars -> device parameter block (by-value kernel argument: no host buffer to keep alive)
+        // (not while capturing: a replayed graph must read the values of the call that replays it, written by mcsce_grow)
+        if (!h->capturing) {
+            CallParams cp{o.seed, o.conf_id0, o.beta, o.noise_deg};
+            set_call_params_kernel<<<1, 1, 0, st>>>(ln->d_call, cp);
+            h->launches += 1;
+        }
+        const int C = o.n_conf;
+        trial_stride = std::max(1, h->max_trial_atoms);
+        chi_set_stride = (long long)d.n_trials_total * MAX_CHI;
+        if (mcsce_init_env(h, C, (float *)w.env, (void *)st)) return -1;
+        init_state_kernel<<<(C + 255) / 256, 256, 0, st>>>(C, w.alive, w.e_acc, h->d_input_energy);   // starts from the input atoms' energy (:149)
         h->launches += 1;
+        // Two streams: `st` runs the generic-pair kernel and the selection of every residue in order; `aux` runs the
+        // placement of the next residue (independent of the pending selection) and the special-pair kernel.
+        CK(cudaEventRecord(ln->ev0, st));
+        CK(cudaStreamWaitEvent(aux, ln->ev0, 0));
+        ms_alloc = max_split_for(C, h->sm_count);
+        n_alive = C;
+        CK(cudaMemsetAsync(ln->d_n_dead, 0, sizeof(int), st));
+        CK(cudaMemsetAsync(w.n_keep, 0, sizeof(int) * (size_t)C, st));
+        return 0;
     }
-    const int C = o->n_conf;
-    const long long trial_stride = std::max(1, h->max_trial_atoms);
-    const long long chi_set_stride = (long long)d.n_trials_total * MAX_CHI;
-    if (mcsce_init_env(h, C, (float *)w.env, (void *)st)) return -1;
-    init_state_kernel<<<(C + 255) / 256, 256, 0, st>>>(C, w.alive, w.e_acc, h->d_input_energy);   // starts from the input atoms' energy (:149)
-    h->launches += 1;
-    // Two streams: `st` runs the generic-pair kernel and the selection of every residue in order; `aux` runs the
-    // placement of the next residue (independent of the pending selection) and the special-pair kernel.
-    CK(cudaEventRecord(ln.ev0, st));
-    CK(cudaStreamWaitEvent(aux, ln.ev0, 0));
-    int prev = -1, prev2 = -1, count = 0;
-    const int ms_alloc = max_split_for(C, h->sm_count);
-    int n_alive = C;
-    CK(cudaMemsetAsync(ln.d_n_dead, 0, sizeof(int), st));
-    CK(cudaMemsetAsync(w.n_keep, 0, sizeof(int) * (size_t)C, st));
-    for (int i = 0; i < d.n_res; ++i) {
+
+    int residue(int i) {
+        const SysDev &d = h->d;
         const StepDev &sd = h->steps[i];
-        if (sd.kind != 2 || sd.n_trials <= 0) continue;
-        const int T = sd.n_trials;
+        if (sd.kind != 2 || sd.n_trials <= 0) return 0;
+        h->cur_call = ln->d_call;
+        const int C = o.n_conf, T = sd.n_trials;
         float4 *trial = (count & 1) ? w.trial2 : w.trial;
         // aux: K1 into the buffer last read by the residue before the previous one
-        if (prev2 >= 0) CK(cudaStreamWaitEvent(aux, ln.evS[prev2], 0));
-        if (launch_place(h, i, C, T, o->d_chis, chi_set_stride, sd.trial_off, o->d_chis_out, trial, trial_stride,
-                         w.alive, aux, o->d_chis ? o->d_ori : nullptr)) return -1;
-        CK(cudaEventRecord(ln.evP[i], aux));
+        if (prev2 >= 0) CK(cudaStreamWaitEvent(aux, ln->evS[prev2], 0));
+        if (launch_place(h, i, C, T, o.d_chis, chi_set_stride, sd.trial_off, o.d_chis_out, trial, trial_stride,
+                         w.alive, aux, o.d_chis ? o.d_ori : nullptr)) return -1;
+        CK(cudaEventRecord(ln->evP[i], aux));
         // st: generic pairs
-        CK(cudaStreamWaitEvent(st, ln.evP[i], 0));
+        CK(cudaStreamWaitEvent(st, ln->evP[i], 0));
         // few conformers: the environment is split over blockIdx.z to fill the GPU; conformers that died leave empty
         // CTAs, so the number still alive is read back every 32 residues and the split re-derived from it
-        if (resync && ms_alloc > 1 && o->env_split <= 0 && count > 0 && (count & 31) == 0) {
-            CK(cudaMemcpyAsync(h->h_n_dead, ln.d_n_dead, sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (resync && ms_alloc > 1 && o.env_split <= 0 && count > 0 && (count & 31) == 0) {
+            CK(cudaMemcpyAsync(h->h_n_dead + (ln - h->lane), ln->d_n_dead, sizeof(int), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
-            n_alive = std::max(1, C - *h->h_n_dead);
+            n_alive = std::max(1, C - h->h_n_dead[ln - h->lane]);
         }
         // neighbour screen: not in the launch-bound (graph) regime, where one more kernel per residue costs more than it saves
-        unsigned char *screen = (!o->no_screen && resync && h->scr_len[i] > 0) ? w.screen : nullptr;
-        const int dedup = (sd.n_fix > 0 && sd.n_var > 0 && !o->no_dedup) ? 1 : 0;
-        const int split = std::min(ms_alloc, choose_split(h, i, n_alive, T, o->env_split, screen != nullptr));
+        unsigned char *screen = (!o.no_screen && resync && h->scr_len[i] > 0) ? w.screen : nullptr;
+        const int dedup = (sd.n_fix > 0 && sd.n_var > 0 && !o.no_dedup) ? 1 : 0;
+        const int split = std::min(ms_alloc, choose_split(h, i, n_alive * groups, T, o.env_split, screen != nullptr));
         if (!screen && launch_generic(h, i, C, T, split, w.env, trial, trial_stride, w.partial, w.alive, st, dedup)) return -1;
         // aux: special pairs (need the environment as updated by the previous selection)
-        if (prev >= 0) CK(cudaStreamWaitEvent(aux, ln.evS[prev], 0));
+        if (prev >= 0) CK(cudaStreamWaitEvent(aux, ln->evS[prev], 0));
         if (launch_special(h, i, C, T, w.env, trial, trial_stride, w.sp_partial, w.alive, aux)) return -1;
-        CK(cudaEventRecord(ln.evQ[i], aux));
+        CK(cudaEventRecord(ln->evQ[i], aux));
         // screened residue: the special pairs go first, their clash flags join the screen's, then the scoring pass
         if (screen) {
-            CK(cudaStreamWaitEvent(st, ln.evQ[i], 0));
+            CK(cudaStreamWaitEvent(st, ln->evQ[i], 0));
             if (launch_generic(h, i, C, T, split, w.env, trial, trial_stride, w.partial, w.alive, st, dedup, screen, w.sp_partial,
                                w.n_keep)) return -1;
         }
         // st: selection
-        CK(cudaStreamWaitEvent(st, ln.evQ[i], 0));
+        CK(cudaStreamWaitEvent(st, ln->evQ[i], 0));
         SelectArgs a{};
         a.s = d; a.step = i; a.n_trials = T; a.n_split = split; a.partial = w.partial; a.sp_partial = w.sp_partial;
         a.dedup = dedup;
-        a.prob = d.prob + sd.trial_off; a.cp = ln.d_call; a.uniform = o->d_uniform; a.u_stride = d.n_res;
+        a.prob = d.prob + sd.trial_off; a.cp = ln->d_call; a.uniform = o.d_uniform; a.u_stride = d.n_res;
         a.env = w.env; a.trial = trial; a.trial_set_stride = trial_stride;
-        a.alive = w.alive; a.e_acc = w.e_acc; a.selected = o->d_selected; a.trial_energy = o->d_trial_energy;
-        a.pair_counter = h->d_pairs; a.n_dead = ln.d_n_dead;
+        a.alive = w.alive; a.e_acc = w.e_acc; a.selected = o.d_selected; a.trial_energy = o.d_trial_energy;
+        a.pair_counter = h->d_pairs; a.n_dead = ln->d_n_dead;
         long long n_active = 0;
         for (int c = 0; c < d.n_cls; ++c) n_active += h->cls_active[(size_t)i * d.n_cls + c];
         a.pairs_per_set = (long long)T * ((long long)sd.n_sc * (sd.n_sc - 1) / 2 + (long long)sd.n_sc * n_active);
@@ -1959,20 +2014,30 @@ static int enqueue_growth(mcsce_handle h, const mcsce_grow_opts *o, const Worksp
                                    + (screen ? (long long)T * n_per * h->scr_len[i] / 2 : 0);
         { ProfScope ps(h, 3, st); select_kernel<<<C, 128, sizeof(double) * 2 * T, st>>>(a); }
         h->launches += 1;
-        CK(cudaEventRecord(ln.evS[i], st));
+        CK(cudaEventRecord(ln->evS[i], st));
         prev2 = prev; prev = i; ++count;
+        return 0;
     }
+};
+
+static int enqueue_growth(mcsce_handle h, const mcsce_grow_opts *o, const Workspace &w, mcsce_handle_s::Lane &ln,
+                          cudaStream_t st, cudaStream_t aux, bool resync) {
+    GrowthEnqueue g{h, *o, w, &ln, st, aux, resync, 1};
+    if (g.begin()) return -1;
+    for (int i = 0; i < h->d.n_res; ++i) if (g.residue(i)) return -1;
     CK(cudaGetLastError());
     return 0;
 }
 
-// conformer groups in flight for one call: two when each half alone still fills the GPU (>= 4 CTAs per SM with one tile
-// per conformer, so that both halves keep the environment split of the whole: results do not depend on the grouping)
+// conformer groups in flight for one call: two when each holds at least 96 conformers.  The groups share the environment
+// split of the whole call (GrowthEnqueue::groups), so a call's result does not depend on the grouping.
 static int lane_count(const mcsce_handle h, int n_conf) {
     int g = 1;
     if (const char *e = getenv("MCSCE_B200_LANES")) { g = atoi(e); g = std::max(1, std::min(g, MAX_LANES)); }   // tuning knob
     else g = LANE_LIMIT;
-    while (g > 1 && n_conf / g < 4 * h->sm_count) --g;
+    int per_lane = 96;
+    if (const char *e = getenv("MCSCE_B200_LANE_MIN")) per_lane = std::max(1, atoi(e));          // tuning knob
+    while (g > 1 && n_conf / g < per_lane) --g;
     return g;
 }
 
@@ -2074,16 +2139,18 @@ extern "C" int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *o, void *d_work
         if (enqueue_growth(h, o, w, h->lane[0], st, h->profiling ? st : h->lane[0].aux, true)) return -1;
         return finish_growth(h, C, w, d_coords, d_energy, d_ok, st);
     }
-    // G groups of conformers, each a complete growth on its own pair of streams; group 0 on the caller's stream
+    // G groups of conformers, each a complete growth on its own pair of streams; group 0 on the caller's stream.  The groups
+    // are enqueued interleaved, residue by residue, and share one environment-split rule (that of the whole call).
     const long long chi_stride = (long long)d.n_trials_total * MAX_CHI;
     size_t ws_off = 0;
-    Workspace w0{};
     for (int g = 1; g < G; ++g) {                               // fork: the other groups start after whatever precedes the call on `st`
         auto &ln = h->lane[g];
         if (prepare_lane(h, ln, true)) return -1;
         CK(cudaEventRecord(ln.ev0, st));
         CK(cudaStreamWaitEvent(ln.main, ln.ev0, 0));
     }
+    std::vector<GrowthEnqueue> ge;
+    std::vector<int> c0s, cgs;
     for (int g = 0; g < G; ++g) {
         auto &ln = h->lane[g];
         const int c0 = (int)((long long)C * g / G), cg = (int)((long long)C * (g + 1) / G) - c0;
@@ -2097,14 +2164,17 @@ extern "C" int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *o, void *d_work
         if (o->d_uniform) og.d_uniform = o->d_uniform + (long long)c0 * d.n_res;
         if (o->d_selected) og.d_selected = o->d_selected + (long long)c0 * d.n_res;
         if (o->d_trial_energy) og.d_trial_energy = o->d_trial_energy + (long long)c0 * d.n_trials_total;
-        cudaStream_t sg = g == 0 ? st : ln.main;
-        if (enqueue_growth(h, &og, w, ln, sg, ln.aux, true)) return -1;
-        if (g == 0) { w0 = w; continue; }
-        if (finish_growth(h, cg, w, d_coords + (size_t)c0 * d.n_atoms * 3, d_energy + c0, d_ok + c0, sg)) return -1;
-        CK(cudaEventRecord(ln.done, sg));
+        ge.push_back(GrowthEnqueue{h, og, w, &ln, g == 0 ? st : ln.main, ln.aux, true, G});
+        c0s.push_back(c0); cgs.push_back(cg);
     }
-    if (finish_growth(h, (int)((long long)C / G), w0, d_coords, d_energy, d_ok, st)) return -1;
-    for (int g = 1; g < G; ++g) CK(cudaStreamWaitEvent(st, h->lane[g].done, 0));
+    for (auto &g : ge) if (g.begin()) return -1;
+    for (int i = 0; i < d.n_res; ++i)
+        for (auto &g : ge) if (g.residue(i)) return -1;
+    CK(cudaGetLastError());
+    for (int g = G - 1; g >= 0; --g) {
+        if (finish_growth(h, cgs[g], ge[g].w, d_coords + (size_t)c0s[g] * d.n_atoms * 3, d_energy + c0s[g], d_ok + c0s[g], ge[g].st)) return -1;
+        if (g > 0) { CK(cudaEventRecord(h->lane[g].done, ge[g].st)); CK(cudaStreamWaitEvent(st, h->lane[g].done, 0)); }
+    }
     return 0;
 }
 

@@ -208,17 +208,18 @@ def test_per_trial_energies_against_the_table_independent_numpy_oracle(cfg, n, n
 
 
 def test_conformer_groups_in_flight_keep_per_conformer_buffers_apart():
-    """Calls of >= 1184 conformers grow two groups side by side on separate streams; dumps and replay inputs are
-    per-conformer arrays that each group must address with its own offset."""
+    """Calls of >= 192 conformers grow two groups side by side on separate streams; dumps and replay inputs are
+    per-conformer arrays that each group must address with its own offset.  (The environment split is pinned to 1: the
+    automatic rule depends on the number of conformers in the call, and a different split regroups float32 partial sums.)"""
     s, sysm, eng, co = _workload(3)
     n, half = 1280, 640
     u = np.random.default_rng(3).random((n, sysm.n_res))
-    whole = eng.grow(n, BETA, seed=17, uniforms=u, dump=True)
+    whole = eng.grow(n, BETA, seed=17, uniforms=u, dump=True, env_split=1)
     sel, te, ch = (whole[k].cpu().numpy().copy() for k in ("selected", "trial_energy", "chis"))
     en, ok = whole["energy"].cpu().numpy().copy(), whole["ok"].cpu().numpy().copy()
     del whole
     for lo in (0, half):
-        part = eng.grow(half, BETA, seed=17, conf_id0=lo, uniforms=u[lo:lo + half], dump=True)
+        part = eng.grow(half, BETA, seed=17, conf_id0=lo, uniforms=u[lo:lo + half], dump=True, env_split=1)
         assert np.array_equal(part["selected"].cpu().numpy(), sel[lo:lo + half])
         assert np.array_equal(part["trial_energy"].cpu().numpy(), te[lo:lo + half], equal_nan=True)
         assert np.array_equal(part["chis"].cpu().numpy(), ch[lo:lo + half])
@@ -226,7 +227,7 @@ def test_conformer_groups_in_flight_keep_per_conformer_buffers_apart():
         assert np.array_equal(part["ok"].cpu().numpy(), ok[lo:lo + half])
         del part
     # replaying the recorded chi rows through the explicit-input path gives the same growth
-    again = eng.grow(n, BETA, seed=99, uniforms=u, chis=ch, dump=True)
+    again = eng.grow(n, BETA, seed=99, uniforms=u, chis=ch, dump=True, env_split=1)
     assert np.array_equal(again["selected"].cpu().numpy(), sel)
 
 
