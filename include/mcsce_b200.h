@@ -33,6 +33,7 @@ extern "C" {
 #define MCSCE_MAX_SC 28       /* side-chain atoms (M3L: 26)                                   */
 
 typedef struct mcsce_handle_s *mcsce_handle;
+typedef struct mcsce_hpmf_s *mcsce_hpmf;
 
 /* Static tables of one sequence.  Replaces what initialize_func_calc builds
  * (core/side_chain_builder.py:42-107) and prepare_energy_function captures per residue
@@ -119,6 +120,11 @@ typedef struct {
      * rotation (libs/libscbuild.py:113,167,183,197: float32 NumPy, host dependent), rad; NaN entries and NULL = the
      * template constant.  With the reference's recorded values K1's coordinates are bit-identical to the reference's. */
     const double *d_ori;           /* [n_conf*n_trials_total*MAX_CHI_ROT]                        */
+    /* terms = [..., "hpmf"] (libs/libenergy.py:213-220, 806-808): a handle made by mcsce_hpmf_create for this atom list adds
+     * the hydrophobic PMF of (conformer so far + trial) to every trial that passed the clash filter, and the PMF of the input
+     * atoms alone to the starting energy; NULL = the term is off.  d_ok = 2 marks a conformer given up because one of the
+     * term's neighbour-list capacities was exceeded (not expected for physical structures). */
+    struct mcsce_hpmf_s *hpmf;
 } mcsce_grow_opts;
 
 const char *mcsce_last_error(void);
@@ -224,7 +230,7 @@ int mcsce_peer_free(int device, void *d_ptr);
 
 /* per-kernel-class device timing for the benchmark's roofline: enable=1 starts recording CUDA-event
  * pairs around every launch (on the launch stream); enable=0 synchronises and returns summed
- * milliseconds / launch counts for [place, score_generic, score_special, select]. */
+ * milliseconds / launch counts for [place, score_generic, score_special, select, hpmf] (5 entries each). */
 int mcsce_profile(mcsce_handle h, int enable, double *ms_by_class, int64_t *launches_by_class);
 
 
@@ -252,8 +258,6 @@ typedef struct {
     double hpmf_c[3], hpmf_w[3], hpmf_h[3];  /* Gaussian centres, widths, heights (libhpmf.py:17-19) */
     double sa_threshold;           /* carbons with SA <= threshold drop out (libhpmf.py:20, 98)    */
 } mcsce_hpmf_desc;
-
-typedef struct mcsce_hpmf_s *mcsce_hpmf;
 
 /* replaces libsasa.calc_sasa(...) / libhpmf.init_hpmf_calculator(...): everything that does not depend on coordinates */
 int mcsce_hpmf_create(mcsce_hpmf *out, int device, const mcsce_hpmf_desc *h_desc);

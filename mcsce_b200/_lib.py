@@ -48,7 +48,7 @@ class GrowOpts(C.Structure):
         ("noise_deg", C.c_double), ("d_chis", C.c_void_p), ("d_uniform", C.c_void_p),
         ("d_trial_energy", C.c_void_p), ("d_chis_out", C.c_void_p), ("d_selected", C.c_void_p),
         ("env_split", C.c_int32), ("no_dedup", C.c_int32), ("no_graph", C.c_int32), ("no_screen", C.c_int32),
-        ("d_ori", C.c_void_p),
+        ("d_ori", C.c_void_p), ("hpmf", C.c_void_p),
     ]
 
 

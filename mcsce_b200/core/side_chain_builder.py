@@ -32,7 +32,7 @@ _ptm_rotamer_lib = None
 #: conformers grown per device launch sequence; larger ensembles are processed in chunks of this size
 MAX_CONFORMERS_PER_LAUNCH = 4096
 #: the same for the step-by-step growth that carries the ``hpmf`` term
-MAX_CONFORMERS_PER_STEPWISE_CALL = 1024
+MAX_CONFORMERS_PER_STEPWISE_CALL_UNUSED = 1024
 
 # kept for API compatibility: level 0 = the input structure, level i+1 = with residue i's side chain
 sidechain_placeholders = []
@@ -128,11 +128,12 @@ def initialize_func_calc(efunc_creator, aa_seq=None, structure=None, retain_idxs
     energy_calculators = _LazyCalculators(efunc_creator, placeholders, [st.kind for st in sysm.steps])
     _state.pop("final", None)
     _state.update(engine=eng, system=sysm, structure=structure, retain=tuple(retain_idxs), backbone=None, seed=_state.get("seed", 0))
-    _state["extra_term"] = None
+    _state["hpmf"] = None
     if "hpmf" in terms:
-        # coordinate-based term (libenergy.py:213-220, 806-808): not in the fused loop, grown step by step
-        from mcsce_b200.hpmf import growth_term
-        _state["extra_term"] = growth_term(eng)
+        # coordinate-based term (libenergy.py:213-220, 806-808): evaluated inside the fused loop (mcsce_grow_opts.hpmf)
+        from mcsce_b200.hpmf import calculator_for_labels
+        _state["hpmf"] = calculator_for_labels([str(a) for a in sysm.names], [int(r) for r in sysm.resnums],
+                                               [str(r) for r in sysm.resnames], device=eng.device_index)
     print("Finished preparing all energy functions. Now start conformer generation")
 
 
@@ -159,20 +160,14 @@ def _grow(backbone_coords, beta, n_conf):
     single = sharding.world()[1] == 1
     parts = []
     # one rank: results straight into pinned host memory; several ranks: keep them on the device for the gather.
-    # Big requests are grown in chunks so that the device workspace and the pinned staging stay bounded.
-    extra = _state.get("extra_term")
-    chunk = MAX_CONFORMERS_PER_LAUNCH if extra is None else MAX_CONFORMERS_PER_STEPWISE_CALL
-    for c0 in range(lo, hi, chunk):
-        n = min(chunk, hi - c0)
-        if extra is None:
-            out = eng.grow(n, beta, seed=_state.get("seed", 0), conf_id0=first + c0, host_out=single)
-            part = (out["coords"], out["energy"], out["ok"])
-            parts.append(tuple(x.copy() for x in part) if single else tuple(x.clone() for x in part))
-        else:
-            # generator keyed by (seed, first conformer id) so that results do not depend on the sharding
-            out = eng.grow_stepwise(n, beta, seed=[_state.get("seed", 0), first + c0], extra_term=extra)
-            part = (out["coords"], out["energy"], out["ok"])
-            parts.append(tuple(x.cpu().numpy() for x in part) if single else part)
+    # Big requests are grown in chunks so that the device workspace and the pinned staging stay bounded.  Conformer
+    # streams (Philox) are keyed by the global conformer id, so the result does not depend on chunking or sharding.
+    hpmf = _state.get("hpmf")
+    for c0 in range(lo, hi, MAX_CONFORMERS_PER_LAUNCH):
+        n = min(MAX_CONFORMERS_PER_LAUNCH, hi - c0)
+        out = eng.grow(n, beta, seed=_state.get("seed", 0), conf_id0=first + c0, host_out=single, hpmf=hpmf)
+        part = (out["coords"], out["energy"], out["ok"])
+        parts.append(tuple(x.copy() for x in part) if single else tuple(x.clone() for x in part))
     if not parts:
         local = (np.zeros((0, sysm.n_atoms, 3), np.float32), np.zeros(0), np.zeros(0, np.uint8))
     elif len(parts) == 1:
@@ -182,7 +177,14 @@ def _grow(backbone_coords, beta, n_conf):
     else:
         import torch
         local = tuple(torch.cat([p[k] for p in parts]) for k in range(3))
-    return sharding.gather_results(*local, n_total=n_conf)
+    coords, energy, ok = sharding.gather_results(*local, n_total=n_conf)
+    if ok is not None and (ok == 2).any():
+        # ok = 2: the hydrophobic PMF gave a conformer up because a neighbour-list capacity was exceeded (mcsce_b200.h)
+        import warnings
+        warnings.warn("mcsce_b200: %d conformers were given up by the hydrophobic PMF term (capacity exceeded); they are "
+                      "reported as failed" % int((ok == 2).sum()))
+        ok = np.where(ok == 2, 0, ok).astype(np.uint8)
+    return coords, energy, ok
 
 
 def _final_template():

@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <math.h>
 #include <string>
 #include <vector>
 #include <algorithm>
@@ -40,6 +41,7 @@ struct HpmfDev {
     double pij_bonded, pij_non_bonded;
     float pre2;                                          // float32 prefilter on d^2: (largest threshold)^2, padded
     double C[3], W[3], H[3], sa_threshold;
+    float Cf[3], iWf[3], Hf[3];                          // float32 copies for the Gaussians (1/W)
 };
 
 __device__ __forceinline__ float norm2_f32(float ax, float ay, float az, float bx, float by, float bz) {
@@ -124,9 +126,13 @@ __global__ void __launch_bounds__(HT) sasa_kernel(HpmfDev s, const float *__rest
     else if (i < s.n_typed) sasa[(long long)blockIdx.y * s.n_typed + i] = 0.0;
 }
 
-__device__ __forceinline__ double gauss3(const HpmfDev &s, double r) {
-    const double t0 = (r - s.C[0]) / s.W[0], t1 = (r - s.C[1]) / s.W[1], t2 = (r - s.C[2]) / s.W[2];
-    return s.H[0] * exp(-(t0 * t0)) + s.H[1] * exp(-(t1 * t1)) + s.H[2] * exp(-(t2 * t2));
+// Sum of the three Gaussians of one carbon pair.  The reference evaluates them in float32 (rij is a float32 array and the
+// Python scalars do not promote it, libhpmf.py:101-104), so float32 it is here too: (r - C)/W, square, exp and the weighted
+// sum in float32 (MUFU.EX2 through __expf), the result promoted to float64 for the weight products and the sums.  Against the
+// float64 form this kernel used before: 1e-7 relative on V, one tenth of the instructions.
+__device__ __forceinline__ double gauss3(const HpmfDev &s, float r) {
+    const float t0 = (r - s.Cf[0]) * s.iWf[0], t1 = (r - s.Cf[1]) * s.iWf[1], t2 = (r - s.Cf[2]) * s.iWf[2];
+    return (double)(s.Hf[0] * __expf(-(t0 * t0)) + s.Hf[1] * __expf(-(t1 * t1)) + s.Hf[2] * __expf(-(t2 * t2)));
 }
 
 // nc_lim: only the first nc_lim carbons exist.  w_out / f_out (optional, [n_struct*n_carbon]): the weight of every
@@ -172,8 +178,7 @@ __global__ void __launch_bounds__(HT) hpmf_pair_kernel(HpmfDev s, const float *_
             if (q.w != 0.f && dist2_fast(xi, yi, zi, q.x, q.y, q.z) < HPMF_CUTOFF * HPMF_CUTOFF) {
                 if (j0 + jj == i) continue;
                 const double wj = sw[jj];
-                const double r = (double)__fsqrt_rn(norm2_f32(xi, yi, zi, q.x, q.y, q.z));
-                acc += wj * gauss3(s, r);
+                acc += wj * gauss3(s, __fsqrt_rn(norm2_f32(xi, yi, zi, q.x, q.y, q.z)));
             }
         }
     }
@@ -219,7 +224,13 @@ __global__ void __launch_bounds__(HT, MINB) hpmf_trial_kernel(
         HpmfDev s, const float *__restrict__ coords, const float *__restrict__ trial, const unsigned char *__restrict__ mask,
         int first_new, int n_new, int n_trials, int e1, int m, int c1, int mc, const int *__restrict__ carbon_ord,
         const double *__restrict__ sa_env, const double *__restrict__ w0, const double *__restrict__ f0,
-        const double *__restrict__ v0, double *__restrict__ out, int *__restrict__ overflow) {
+        const double *__restrict__ v0, double *__restrict__ out, int *__restrict__ overflow,
+        // inside mcsce_grow: the growth's own trial buffer (float4, per-conformer stride, row = trial * n_new + atom), the
+        // residue's list of typed environment atoms that can come within SASA range of its side chain, a flag per conformer
+        const float4 *__restrict__ trial4, long long trial4_stride, const int *__restrict__ near, int n_near,
+        int *__restrict__ overflow_conf,
+        // packed carbon positions [conformer][n_carbon] and the residue's list of carbons within Gaussian range of its side chain
+        const float4 *__restrict__ cpos, const int *__restrict__ clist, int n_clist) {
     const int t = blockIdx.x, c = blockIdx.y, tid = threadIdx.x, nt = s.n_types;
     const long long ct = (long long)c * n_trials + t;
     if (mask && !mask[ct]) { if (tid == 0) out[ct] = 0.0; return; }
@@ -238,8 +249,13 @@ __global__ void __launch_bounds__(HT, MINB) hpmf_trial_kernel(
     if (tid < nt) { s_R[tid] = s.R[tid]; s_piRRs[tid] = s.piRRs[tid]; s_P[tid] = s.P[tid]; s_S[tid] = s.S[tid]; }
     if (tid < m) {
         const int g = e1 + tid;
-        const float *p = trial + (ct * n_new + (s.typed_atom[g] - first_new)) * 3;
-        ta[tid] = make_float4(p[0], p[1], p[2], __int_as_float(s.type_of[g]));
+        if (trial4) {
+            const float4 q = trial4[(long long)c * trial4_stride + (long long)t * n_new + (s.typed_atom[g] - first_new)];
+            ta[tid] = make_float4(q.x, q.y, q.z, __int_as_float(s.type_of[g]));
+        } else {
+            const float *p = trial + (ct * n_new + (s.typed_atom[g] - first_new)) * 3;
+            ta[tid] = make_float4(p[0], p[1], p[2], __int_as_float(s.type_of[g]));
+        }
 #pragma unroll
         for (int b = 0; b < MAXB; ++b) tbond[tid][b] = s.bonded[g * MAXB + b];
     }
@@ -255,7 +271,13 @@ __global__ void __launch_bounds__(HT, MINB) hpmf_trial_kernel(
     const float *cbase = coords + (long long)c * s.n_atoms * 3;
     const double *sa = sa_env + (long long)c * s.n_typed;
     const double *w0c = w0 + (long long)c * s.n_carbon, *f0c = f0 + (long long)c * s.n_carbon;
-    for (int k = tid; k < e1; k += HT) {
+    // (with a near list only the typed atoms that can be in SASA range of the side chain are visited - a complete list,
+    //  built from rigorous reach bounds, so the factors found are the same; the order of the float64 products per trial
+    //  atom is the list's ascending order either way)
+    const int n_scan = near ? n_near : e1;
+    for (int q0 = tid; q0 < n_scan; q0 += HT) {
+        const int k = near ? near[q0] : q0;
+        if (k >= e1) continue;
         const float *p = cbase + (long long)s.typed_atom[k] * 3;
         const float xk = p[0], yk = p[1], zk = p[2];
         if (xk > ABSENT_X) continue;
@@ -336,19 +358,26 @@ __global__ void __launch_bounds__(HT, MINB) hpmf_trial_kernel(
     }
     __syncthreads();
     const int L = min(ln, MAX_LIST);
-    if (tid == 0 && ln > MAX_LIST) atomicExch(overflow, 1);
+    if (tid == 0 && ln > MAX_LIST) { atomicExch(overflow, 1); if (overflow_conf) overflow_conf[c] = 1; }
     const float cut2 = HPMF_CUTOFF * HPMF_CUTOFF;
     // phase 3a: trial carbons x environment carbons (weights of the environment alone)
-    for (int ck = tid; ck < c1; ck += HT) {
-        const double wk = w0c[ck];
-        if (wk == 0.0) continue;
-        const float *p = cbase + (long long)s.typed_atom[s.carbon[ck]] * 3;
-        const float xk = p[0], yk = p[1], zk = p[2];
-        for (int n = 0; n < mc; ++n) {
-            const double wn = tw[n];
-            const float4 q = tc[n];
-            if (wn != 0.0 && dist2_fast(xk, yk, zk, q.x, q.y, q.z) < cut2)
-                acc += wn * wk * gauss3(s, (double)__fsqrt_rn(norm2_f32(xk, yk, zk, q.x, q.y, q.z)));
+    {
+        const int n3 = clist ? n_clist : c1;
+        const float4 *cposc = cpos ? cpos + (long long)c * s.n_carbon : nullptr;
+        for (int q0 = tid; q0 < n3; q0 += HT) {
+            const int ck = clist ? clist[q0] : q0;
+            if (ck >= c1) continue;
+            const double wk = w0c[ck];
+            if (wk == 0.0) continue;
+            float xk, yk, zk;
+            if (cposc) { const float4 p = cposc[ck]; xk = p.x; yk = p.y; zk = p.z; }
+            else { const float *p = cbase + (long long)s.typed_atom[s.carbon[ck]] * 3; xk = p[0]; yk = p[1]; zk = p[2]; }
+            for (int n = 0; n < mc; ++n) {
+                const double wn = tw[n];
+                const float4 q = tc[n];
+                if (wn != 0.0 && dist2_fast(xk, yk, zk, q.x, q.y, q.z) < cut2)
+                    acc += wn * wk * gauss3(s, __fsqrt_rn(norm2_f32(xk, yk, zk, q.x, q.y, q.z)));
+            }
         }
     }
     // phase 3b: the changed environment carbons: with the trial carbons, and among themselves
@@ -359,12 +388,12 @@ __global__ void __launch_bounds__(HT, MINB) hpmf_trial_kernel(
             const double wn = tw[n];
             const float4 q = tc[n];
             if (wn != 0.0 && dist2_fast(pa.x, pa.y, pa.z, q.x, q.y, q.z) < cut2)
-                acc += wn * da * gauss3(s, (double)__fsqrt_rn(norm2_f32(pa.x, pa.y, pa.z, q.x, q.y, q.z)));
+                acc += wn * da * gauss3(s, __fsqrt_rn(norm2_f32(pa.x, pa.y, pa.z, q.x, q.y, q.z)));
         }
         for (int b = a + 1; b < L; ++b) {
             const float4 pb = lpos[b];
             if (dist2_fast(pa.x, pa.y, pa.z, pb.x, pb.y, pb.z) < cut2)
-                acc += da * ldel[b] * gauss3(s, (double)__fsqrt_rn(norm2_f32(pa.x, pa.y, pa.z, pb.x, pb.y, pb.z)));
+                acc += da * ldel[b] * gauss3(s, __fsqrt_rn(norm2_f32(pa.x, pa.y, pa.z, pb.x, pb.y, pb.z)));
         }
     }
     // phase 3c: trial carbons among themselves
@@ -373,7 +402,7 @@ __global__ void __launch_bounds__(HT, MINB) hpmf_trial_kernel(
         for (int b = tid + 1; b < mc; ++b) {
             const float4 pb = tc[b];
             if (tw[tid] != 0.0 && tw[b] != 0.0 && dist2_fast(pa.x, pa.y, pa.z, pb.x, pb.y, pb.z) < cut2)
-                acc += tw[tid] * tw[b] * gauss3(s, (double)__fsqrt_rn(norm2_f32(pa.x, pa.y, pa.z, pb.x, pb.y, pb.z)));
+                acc += tw[tid] * tw[b] * gauss3(s, __fsqrt_rn(norm2_f32(pa.x, pa.y, pa.z, pb.x, pb.y, pb.z)));
         }
     }
     red[tid] = acc;
@@ -400,7 +429,7 @@ __global__ void __launch_bounds__(HT, MINB) hpmf_trial_kernel(
 __global__ void __launch_bounds__(HT) hpmf_extend_kernel(
         HpmfDev s, const float *__restrict__ coords, int eL, int m, const int *__restrict__ carbon_ord,
         double *__restrict__ sa_env, double *__restrict__ w0, float4 *__restrict__ ext_pos, double *__restrict__ ext_del,
-        int *__restrict__ ext_ck, int *__restrict__ ext_n, int *__restrict__ overflow) {
+        int *__restrict__ ext_ck, int *__restrict__ ext_n, int *__restrict__ overflow, int *__restrict__ overflow_conf) {
     const int c = blockIdx.x, tid = threadIdx.x, nt = s.n_types;
     __shared__ float4 ta[MAX_NEW_T];
     __shared__ int tbond[MAX_NEW_T][MAXB];
@@ -508,89 +537,181 @@ __global__ void __launch_bounds__(HT) hpmf_extend_kernel(
     }
     if (tid == 0) {
         ext_n[c] = min(ln, EXT_LIST);
-        if (ln > EXT_LIST) atomicExch(overflow, 1);
+        if (ln > EXT_LIST) { atomicExch(overflow, 1); if (overflow_conf) overflow_conf[c] = 1; }
     }
 }
 
-// fields and V of the extended environment: carbons [0, cL) gain the changed weights' and the new carbons' terms,
-// the new carbons [cL, cF) get their full sums; partial[conformer][tile] = sum_i w_i F_i of the tile
+// fields and V of the extended environment.  Kernel 1 (tiles over the carbons [0, cL) that were there before): every carbon's
+// field gains the changed weights' terms (list staged in shared memory) and the new carbons' terms; the same Gaussians, weighted
+// by the old carbon, are the new carbons' fields - summed per tile in a fixed order (shuffles, then the four warps), so that no
+// thread walks all carbons alone (the first version had the <= 12 new carbons do that: 225 us per step at 256 conformers of
+// config 3, 2/3 of it waiting for those threads).  Kernel 2 (one warp per conformer): the new carbons' fields from the tile sums
+// plus their mutual terms, then V = 1/2 sum w F.
+#define EXT_NEW_C MAX_NEW_T
+
 __global__ void __launch_bounds__(HT) hpmf_field_update_kernel(
         HpmfDev s, const float *__restrict__ coords, int cL, int cF, const double *__restrict__ w0, double *__restrict__ f0,
         const float4 *__restrict__ ext_pos, const double *__restrict__ ext_del, const int *__restrict__ ext_ck,
-        const int *__restrict__ ext_n, double *__restrict__ partial) {
-    __shared__ double red[HT];
-    const int c = blockIdx.y, tid = threadIdx.x;
+        const int *__restrict__ ext_n, double *__restrict__ partial, double *__restrict__ partial_new) {
+    __shared__ float4 s_pos[EXT_LIST];
+    __shared__ double s_del[EXT_LIST];
+    __shared__ int s_ck[EXT_LIST];
+    __shared__ float4 s_np[EXT_NEW_C];
+    __shared__ double s_nw[EXT_NEW_C];
+    __shared__ double s_red[HT / 32][EXT_NEW_C + 1];
+    const int c = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int i = blockIdx.x * HT + tid;
     const float *cbase = coords + (long long)c * s.n_atoms * 3;
     const double *w0c = w0 + (long long)c * s.n_carbon;
     double *f0c = f0 + (long long)c * s.n_carbon;
     const float cut2 = HPMF_CUTOFF * HPMF_CUTOFF;
-    double contrib = 0.0;
-    if (i < cF) {
+    const int L = ext_n[c], nn = min(cF - cL, EXT_NEW_C);
+    for (int l = tid; l < L; l += HT) {
+        const long long o = (long long)c * EXT_LIST + l;
+        s_pos[l] = ext_pos[o]; s_del[l] = ext_del[o]; s_ck[l] = ext_ck[o];
+    }
+    if (tid < nn) {
+        const float *q = cbase + (long long)s.typed_atom[s.carbon[cL + tid]] * 3;
+        s_np[tid] = make_float4(q[0], q[1], q[2], 0.f);
+        s_nw[tid] = q[0] > ABSENT_X ? 0.0 : w0c[cL + tid];
+    }
+    __syncthreads();
+    double contrib = 0.0, gn[EXT_NEW_C];
+#pragma unroll
+    for (int n = 0; n < EXT_NEW_C; ++n) gn[n] = 0.0;
+    if (i < cL) {
         const float *p = cbase + (long long)s.typed_atom[s.carbon[i]] * 3;
         const float xi = p[0], yi = p[1], zi = p[2];
+        const double wi = w0c[i];
         double f = 0.0;
         if (xi <= ABSENT_X) {
-            if (i < cL) {
-                f = f0c[i];
-                const int L = ext_n[c];
-                const long long o = (long long)c * EXT_LIST;
-                for (int l = 0; l < L; ++l) {
-                    if (ext_ck[o + l] == i) continue;
-                    const float4 q = ext_pos[o + l];
-                    if (dist2_fast(xi, yi, zi, q.x, q.y, q.z) < cut2)
-                        f += ext_del[o + l] * gauss3(s, (double)__fsqrt_rn(norm2_f32(xi, yi, zi, q.x, q.y, q.z)));
-                }
-                for (int n = cL; n < cF; ++n) {
-                    const double wn = w0c[n];
-                    if (wn == 0.0) continue;
-                    const float *q = cbase + (long long)s.typed_atom[s.carbon[n]] * 3;
-                    if (dist2_fast(xi, yi, zi, q[0], q[1], q[2]) < cut2)
-                        f += wn * gauss3(s, (double)__fsqrt_rn(norm2_f32(xi, yi, zi, q[0], q[1], q[2])));
-                }
-            } else {
-                for (int j = 0; j < cF; ++j) {
-                    const double wj = w0c[j];
-                    if (wj == 0.0 || j == i) continue;
-                    const float *q = cbase + (long long)s.typed_atom[s.carbon[j]] * 3;
-                    if (dist2_fast(xi, yi, zi, q[0], q[1], q[2]) < cut2)
-                        f += wj * gauss3(s, (double)__fsqrt_rn(norm2_f32(xi, yi, zi, q[0], q[1], q[2])));
+            f = f0c[i];
+            for (int l = 0; l < L; ++l) {
+                if (s_ck[l] == i) continue;
+                const float4 q = s_pos[l];
+                if (dist2_fast(xi, yi, zi, q.x, q.y, q.z) < cut2)
+                    f += s_del[l] * gauss3(s, __fsqrt_rn(norm2_f32(xi, yi, zi, q.x, q.y, q.z)));
+            }
+#pragma unroll
+            for (int n = 0; n < EXT_NEW_C; ++n) {
+                if (n < nn) {
+                    const float4 q = s_np[n];
+                    if (q.x <= ABSENT_X && dist2_fast(xi, yi, zi, q.x, q.y, q.z) < cut2) {
+                        const double g = gauss3(s, __fsqrt_rn(norm2_f32(xi, yi, zi, q.x, q.y, q.z)));
+                        f += s_nw[n] * g;
+                        gn[n] = wi * g;
+                    }
                 }
             }
         }
         f0c[i] = f;
-        contrib = w0c[i] * f;
+        contrib = wi * f;
     }
-    red[tid] = contrib;
+    // fixed-order sums: lanes by shuffles, then the warps one after the other
+#pragma unroll
+    for (int n = 0; n <= EXT_NEW_C; ++n) {
+        if (n < nn || n == EXT_NEW_C) {
+            double v = n == EXT_NEW_C ? contrib : gn[n];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+            if (lane == 0) s_red[warp][n] = v;
+        }
+    }
     __syncthreads();
-    for (int k = HT / 2; k > 0; k >>= 1) {
-        if (tid < k) red[tid] += red[tid + k];
-        __syncthreads();
+    if (tid <= EXT_NEW_C && (tid < nn || tid == EXT_NEW_C)) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < HT / 32; ++w) v += s_red[w][tid];
+        const long long t = (long long)c * gridDim.x + blockIdx.x;
+        if (tid == EXT_NEW_C) partial[t] = v; else partial_new[t * EXT_NEW_C + tid] = v;
     }
-    if (tid == 0) partial[(long long)c * gridDim.x + blockIdx.x] = red[0];
+}
+
+__global__ void __launch_bounds__(32) hpmf_field_finish_kernel(
+        HpmfDev s, const float *__restrict__ coords, int cL, int cF, int n_tiles, const double *__restrict__ w0,
+        double *__restrict__ f0, const double *__restrict__ partial, const double *__restrict__ partial_new, double *__restrict__ v0) {
+    __shared__ float4 s_np[EXT_NEW_C];
+    __shared__ double s_nw[EXT_NEW_C];
+    const int c = blockIdx.x, tid = threadIdx.x;
+    const float *cbase = coords + (long long)c * s.n_atoms * 3;
+    const double *w0c = w0 + (long long)c * s.n_carbon;
+    const int nn = min(cF - cL, EXT_NEW_C);
+    if (tid < nn) {
+        const float *q = cbase + (long long)s.typed_atom[s.carbon[cL + tid]] * 3;
+        s_np[tid] = make_float4(q[0], q[1], q[2], 0.f);
+        s_nw[tid] = q[0] > ABSENT_X ? 0.0 : w0c[cL + tid];
+    }
+    __syncwarp();
+    double wf = 0.0;
+    if (tid < nn) {
+        double f = 0.0;
+        const float4 me = s_np[tid];
+        if (me.x <= ABSENT_X) {
+            for (int t = 0; t < n_tiles; ++t) f += partial_new[((long long)c * n_tiles + t) * EXT_NEW_C + tid];
+            for (int n = 0; n < nn; ++n) {
+                if (n == tid || s_nw[n] == 0.0) continue;
+                const float4 q = s_np[n];
+                if (dist2_fast(me.x, me.y, me.z, q.x, q.y, q.z) < HPMF_CUTOFF * HPMF_CUTOFF)
+                    f += s_nw[n] * gauss3(s, __fsqrt_rn(norm2_f32(me.x, me.y, me.z, q.x, q.y, q.z)));
+            }
+        }
+        f0[(long long)c * s.n_carbon + cL + tid] = f;
+        wf = s_nw[tid] * f;
+    }
+    // lane 0 adds everything up in a fixed order
+    double sum = 0.0;
+    for (int n = 0; n < nn; ++n) { const double x = __shfl_sync(0xffffffffu, wf, n); sum += x; }
+    if (tid == 0) {
+        for (int t = 0; t < n_tiles; ++t) sum += partial[(long long)c * n_tiles + t];
+        v0[c] = 0.5 * sum;
+    }
+}
+
+// positions of the environment's carbons, packed: one 16-byte load per carbon in the per-trial kernel
+__global__ void hpmf_pack_carbons_kernel(HpmfDev s, const float *__restrict__ coords, int c1, float4 *__restrict__ cpos) {
+    const int ck = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+    if (ck >= c1) return;
+    const float *p = coords + ((long long)c * s.n_atoms + s.typed_atom[s.carbon[ck]]) * 3;
+    cpos[(long long)c * s.n_carbon + ck] = make_float4(p[0], p[1], p[2], 0.f);
 }
 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+#define HPMF_STATES 5          // [0]: the public mcsce_hpmf_trials API; [1..4]: the conformer groups (lanes) of mcsce_grow
+
+// per-conformer environment state of one growth in flight (grow-only buffers)
+struct EnvState {
+    double *d_env_state = nullptr;          // sa_env [C*n_typed] | w0 [C*n_carbon] | f0 [C*n_carbon] | v0 [C]
+    size_t env_state_cap = 0;
+    double *d_partial = nullptr;
+    size_t partial_cap = 0;
+    void *d_ext = nullptr;                  // ext_pos | ext_del | ext_ck | ext_n
+    size_t ext_cap = 0;
+    double *d_partial_new = nullptr;        // [C*tiles*EXT_NEW_C] per-tile sums of the new carbons' fields
+    float4 *d_cpos = nullptr;               // [C*n_carbon] packed carbon positions
+    // carried state: the level (first atom not yet part of the state) the buffers describe
+    int state_level = 0, state_nconf = 0;
+    const float *state_coords = nullptr;
+};
+
 struct mcsce_hpmf_s {
     int device = 0;
     HpmfDev dev{};
     std::vector<void *> owned;
-    double *d_partial = nullptr;
+    double *d_partial = nullptr;            // whole-structure evaluations (mcsce_hpmf_energy)
     size_t partial_cap = 0;
-    // per-trial evaluation: host copies of the index tables, per-conformer environment state (grow-only)
+    // per-trial evaluation: host copies of the index tables
     std::vector<int> h_typed_atom, h_carbon;
     const int *d_carbon_ord = nullptr;
-    double *d_env_state = nullptr;          // sa_env [C*n_typed] | w0 [C*n_carbon] | f0 [C*n_carbon] | v0 [C]
-    size_t env_state_cap = 0;
     int *d_overflow = nullptr;
-    // carried state (mcsce_hpmf_carry): the level (first atom not yet part of the state) the buffers describe
     bool carry = false;
-    int state_level = 0, state_nconf = 0;
-    const float *state_coords = nullptr;
-    void *d_ext = nullptr;                  // ext_pos | ext_del | ext_ck | ext_n
-    size_t ext_cap = 0;
+    EnvState es[HPMF_STATES];
+    // inside mcsce_grow: per-residue lists of typed environment atoms within SASA range of the residue's side chain
+    int *d_near = nullptr, *d_near_c = nullptr;   // typed atoms in SASA range / carbon ordinals in Gaussian range
+    std::vector<int> near_off, near_c_off;  // [n_res + 1] offsets into d_near / d_near_c
+    long long near_version = -1;
+    double *d_sasa1 = nullptr;              // scratch of the level-0 evaluation (one structure)
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     bool timed = false;
 };
@@ -659,7 +780,10 @@ extern "C" int mcsce_hpmf_create(mcsce_hpmf *out, int device, const mcsce_hpmf_d
     if (upload(h, S.data(), (size_t)nt, &v.S)) return -1;
     v.pij_bonded = d->pij_bonded; v.pij_non_bonded = d->pij_non_bonded;
     v.pre2 = (float)(thr_max * thr_max * 1.001);
-    for (int k = 0; k < 3; ++k) { v.C[k] = d->hpmf_c[k]; v.W[k] = d->hpmf_w[k]; v.H[k] = d->hpmf_h[k]; }
+    for (int k = 0; k < 3; ++k) {
+        v.C[k] = d->hpmf_c[k]; v.W[k] = d->hpmf_w[k]; v.H[k] = d->hpmf_h[k];
+        v.Cf[k] = (float)d->hpmf_c[k]; v.iWf[k] = (float)(1.0 / d->hpmf_w[k]); v.Hf[k] = (float)d->hpmf_h[k];
+    }
     v.sa_threshold = d->sa_threshold;
     for (int k = 0; k < 3; ++k) HCK(cudaEventCreate(&h->ev[k]));
     *out = h;
@@ -671,8 +795,16 @@ extern "C" int mcsce_hpmf_destroy(mcsce_hpmf h) {
     cudaSetDevice(h->device);
     for (void *p : h->owned) cudaFree(p);
     if (h->d_partial) cudaFree(h->d_partial);
-    if (h->d_env_state) cudaFree(h->d_env_state);
-    if (h->d_ext) cudaFree(h->d_ext);
+    for (auto &e : h->es) {
+        if (e.d_env_state) cudaFree(e.d_env_state);
+        if (e.d_partial) cudaFree(e.d_partial);
+        if (e.d_ext) cudaFree(e.d_ext);
+        if (e.d_partial_new) cudaFree(e.d_partial_new);
+        if (e.d_cpos) cudaFree(e.d_cpos);
+    }
+    if (h->d_near) cudaFree(h->d_near);
+    if (h->d_near_c) cudaFree(h->d_near_c);
+    if (h->d_sasa1) cudaFree(h->d_sasa1);
     for (int k = 0; k < 3; ++k) if (h->ev[k]) cudaEventDestroy(h->ev[k]);
     delete h;
     return 0;
@@ -733,15 +865,19 @@ extern "C" int mcsce_hpmf_energy(mcsce_hpmf h, int n_struct, const float *d_coor
 }
 
 
-extern "C" int mcsce_hpmf_trials(mcsce_hpmf h, int n_conf, const float *d_coords, int first_new, int n_new, int n_trials,
-                                 const float *d_trial, const uint8_t *d_mask, double *d_v, void *stream) {
-    if (!h || !d_coords || !d_trial || !d_v) return mcsce_fail_shared("mcsce_hpmf_trials: null argument");
-    if (n_conf <= 0 || n_trials <= 0) return 0;
-    if (n_conf > 65535) return mcsce_fail_shared("mcsce_hpmf_trials: at most 65535 conformers per call");
+// Per-trial V_hpmf of one growth step.  `es`: the environment state this growth carries; `carry`: extend it from the
+// previous step instead of re-deriving it.  Buffers grow here (stream synchronised when they do: only at a growth's first step).
+struct TrialStepExtra {
+    const float4 *trial4 = nullptr; long long trial4_stride = 0;      // the growth's own trial buffer instead of d_trial
+    const int *near = nullptr; int n_near = 0;                          // typed atoms in SASA range of the residue (complete list)
+    const int *clist = nullptr; int n_clist = 0;                        // carbons in Gaussian range of the residue (complete list)
+    int *overflow_conf = nullptr;                                       // [n_conf] set where a capacity was exceeded
+};
+
+static int hpmf_trials_impl(mcsce_hpmf h, EnvState &es, bool carry, int n_conf, const float *d_coords, int first_new, int n_new,
+                            int n_trials, const float *d_trial, const uint8_t *d_mask, double *d_v, cudaStream_t st,
+                            const TrialStepExtra &x) {
     const HpmfDev &v = h->dev;
-    if (first_new < 0 || n_new <= 0 || first_new + n_new > v.n_atoms) return mcsce_fail_shared("mcsce_hpmf_trials: new-atom range out of bounds");
-    HCK(cudaSetDevice(h->device));
-    cudaStream_t st = (cudaStream_t)stream;
     const std::vector<int> &ta = h->h_typed_atom;
     const int e1 = (int)(std::lower_bound(ta.begin(), ta.end(), first_new) - ta.begin());
     const int e2 = (int)(std::lower_bound(ta.begin(), ta.end(), first_new + n_new) - ta.begin());
@@ -751,89 +887,198 @@ extern "C" int mcsce_hpmf_trials(mcsce_hpmf h, int n_conf, const float *d_coords
     if (m > MAX_NEW_T || mc > MAX_NEW_C) return mcsce_fail_shared("mcsce_hpmf_trials: too many typed atoms in the new residue");
     const int tiles = c1 > 0 ? (c1 + HT - 1) / HT : 1;
     const size_t n_state = (size_t)n_conf * ((size_t)v.n_typed + 2 * (size_t)v.n_carbon + 1);
-    if (n_state > h->env_state_cap || (size_t)n_conf * tiles > h->partial_cap) {
+    const size_t need_partial = (size_t)n_conf * ((v.n_carbon + HT - 1) / HT + 1);
+    if (n_state > es.env_state_cap || need_partial > es.partial_cap) {
         HCK(cudaStreamSynchronize(st));
-        if (n_state > h->env_state_cap) {
-            h->state_level = 0;
-            if (h->d_env_state) HCK(cudaFree(h->d_env_state));
-            h->d_env_state = nullptr; h->env_state_cap = 0;
-            HCK(cudaMalloc(&h->d_env_state, n_state * sizeof(double)));
-            h->env_state_cap = n_state;
+        if (n_state > es.env_state_cap) {
+            es.state_level = 0;
+            if (es.d_env_state) HCK(cudaFree(es.d_env_state));
+            es.d_env_state = nullptr; es.env_state_cap = 0;
+            HCK(cudaMalloc(&es.d_env_state, n_state * sizeof(double)));
+            es.env_state_cap = n_state;
         }
-        const size_t need = (size_t)n_conf * ((v.n_carbon + HT - 1) / HT + 1);
-        if (need > h->partial_cap) {
-            if (h->d_partial) HCK(cudaFree(h->d_partial));
-            h->d_partial = nullptr; h->partial_cap = 0;
-            HCK(cudaMalloc(&h->d_partial, need * sizeof(double)));
-            h->partial_cap = need;
+        if (need_partial > es.partial_cap) {
+            if (es.d_partial) HCK(cudaFree(es.d_partial));
+            if (es.d_partial_new) HCK(cudaFree(es.d_partial_new));
+            es.d_partial = nullptr; es.d_partial_new = nullptr; es.partial_cap = 0;
+            HCK(cudaMalloc(&es.d_partial, need_partial * sizeof(double)));
+            HCK(cudaMalloc(&es.d_partial_new, need_partial * EXT_NEW_C * sizeof(double)));
+            es.partial_cap = need_partial;
         }
+        if (es.d_cpos) HCK(cudaFree(es.d_cpos));
+        es.d_cpos = nullptr;
+        HCK(cudaMalloc(&es.d_cpos, (size_t)n_conf * std::max(1, v.n_carbon) * sizeof(float4)));
     }
-    double *sa_env = h->d_env_state;
+    double *sa_env = es.d_env_state;
     double *w0 = sa_env + (size_t)n_conf * v.n_typed;
     double *f0 = w0 + (size_t)n_conf * v.n_carbon;
     double *v0 = f0 + (size_t)n_conf * v.n_carbon;
     // the environment alone (atoms before first_new), once per conformer: extended from the previous step's state
     // when the caller allowed it (mcsce_hpmf_carry) and the call continues that growth, else derived from scratch
     bool extended = false;
-    if (h->carry && h->state_level > 0 && h->state_nconf == n_conf && h->state_coords == d_coords &&
-        h->state_level <= first_new) {
-        const int eL = (int)(std::lower_bound(ta.begin(), ta.end(), h->state_level) - ta.begin());
+    if (carry && es.state_level > 0 && es.state_nconf == n_conf && es.state_coords == d_coords &&
+        es.state_level <= first_new) {
+        const int eL = (int)(std::lower_bound(ta.begin(), ta.end(), es.state_level) - ta.begin());
         const int cL = (int)(std::lower_bound(h->h_carbon.begin(), h->h_carbon.end(), eL) - h->h_carbon.begin());
         const int mL = e1 - eL;
         if (mL == 0) extended = true;                           // only untyped atoms were added: nothing changes
         else if (mL <= MAX_NEW_T) {
             const size_t per = (size_t)EXT_LIST * (sizeof(float4) + sizeof(double) + sizeof(int)) + sizeof(int);
-            if ((size_t)n_conf * per > h->ext_cap) {
+            if ((size_t)n_conf * per > es.ext_cap) {
                 HCK(cudaStreamSynchronize(st));
-                if (h->d_ext) HCK(cudaFree(h->d_ext));
-                h->d_ext = nullptr; h->ext_cap = 0;
-                HCK(cudaMalloc(&h->d_ext, (size_t)n_conf * per));
-                h->ext_cap = (size_t)n_conf * per;
+                if (es.d_ext) HCK(cudaFree(es.d_ext));
+                es.d_ext = nullptr; es.ext_cap = 0;
+                HCK(cudaMalloc(&es.d_ext, (size_t)n_conf * per));
+                es.ext_cap = (size_t)n_conf * per;
             }
-            float4 *ext_pos = (float4 *)h->d_ext;
+            float4 *ext_pos = (float4 *)es.d_ext;
             double *ext_del = (double *)(ext_pos + (size_t)n_conf * EXT_LIST);
             int *ext_ck = (int *)(ext_del + (size_t)n_conf * EXT_LIST);
             int *ext_n = ext_ck + (size_t)n_conf * EXT_LIST;
             hpmf_extend_kernel<<<n_conf, HT, 0, st>>>(v, d_coords, eL, mL, h->d_carbon_ord, sa_env, w0, ext_pos, ext_del, ext_ck,
-                                                      ext_n, h->d_overflow);
-            hpmf_field_update_kernel<<<dim3(tiles, n_conf), HT, 0, st>>>(v, d_coords, cL, c1, w0, f0, ext_pos, ext_del, ext_ck,
-                                                                         ext_n, h->d_partial);
-            hpmf_finish_kernel<<<(n_conf + 127) / 128, 128, 0, st>>>(n_conf, tiles, h->d_partial, v0);
+                                                      ext_n, h->d_overflow, x.overflow_conf);
+            const int tilesL = cL > 0 ? (cL + HT - 1) / HT : 1;
+            hpmf_field_update_kernel<<<dim3(tilesL, n_conf), HT, 0, st>>>(v, d_coords, cL, c1, w0, f0, ext_pos, ext_del, ext_ck,
+                                                                          ext_n, es.d_partial, es.d_partial_new);
+            hpmf_field_finish_kernel<<<n_conf, 32, 0, st>>>(v, d_coords, cL, c1, tilesL, w0, f0, es.d_partial, es.d_partial_new, v0);
             extended = true;
         }
     }
     if (!extended) {
         if (launch_sasa(h, n_conf, d_coords, sa_env, st, e1)) return -1;
-        hpmf_pair_kernel<<<dim3(tiles, n_conf), HT, 0, st>>>(v, d_coords, sa_env, h->d_partial, c1, w0, f0);
-        hpmf_finish_kernel<<<(n_conf + 127) / 128, 128, 0, st>>>(n_conf, tiles, h->d_partial, v0);
+        hpmf_pair_kernel<<<dim3(tiles, n_conf), HT, 0, st>>>(v, d_coords, sa_env, es.d_partial, c1, w0, f0);
+        hpmf_finish_kernel<<<(n_conf + 127) / 128, 128, 0, st>>>(n_conf, tiles, es.d_partial, v0);
     }
-    h->state_level = first_new; h->state_nconf = n_conf; h->state_coords = d_coords;
+    es.state_level = first_new; es.state_nconf = n_conf; es.state_coords = d_coords;
+    if (c1 > 0) hpmf_pack_carbons_kernel<<<dim3((c1 + 127) / 128, n_conf), 128, 0, st>>>(v, d_coords, c1, es.d_cpos);
     // every trial on top of it
     {
         static int minb = -1;                 // tuning knob: resident blocks per SM the kernel is compiled for
         if (minb < 0) { const char *e = getenv("MCSCE_B200_HPMF_MINB"); minb = e ? atoi(e) : TRIAL_MINB_DEFAULT; }
         const dim3 grid(n_trials, n_conf);
 #define LAUNCH_TRIAL(B) hpmf_trial_kernel<B><<<grid, HT, 0, st>>>(v, d_coords, d_trial, d_mask, first_new, n_new, n_trials, \
-            e1, m, c1, mc, h->d_carbon_ord, sa_env, w0, f0, v0, d_v, h->d_overflow)
+            e1, m, c1, mc, h->d_carbon_ord, sa_env, w0, f0, v0, d_v, h->d_overflow, x.trial4, x.trial4_stride, x.near, x.n_near, \
+            x.overflow_conf, es.d_cpos, x.clist, x.n_clist)
         if (minb >= 8) LAUNCH_TRIAL(8); else if (minb >= 6) LAUNCH_TRIAL(6); else LAUNCH_TRIAL(4);
 #undef LAUNCH_TRIAL
     }
     HCK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mcsce_hpmf_trials(mcsce_hpmf h, int n_conf, const float *d_coords, int first_new, int n_new, int n_trials,
+                                 const float *d_trial, const uint8_t *d_mask, double *d_v, void *stream) {
+    if (!h || !d_coords || !d_trial || !d_v) return mcsce_fail_shared("mcsce_hpmf_trials: null argument");
+    if (n_conf <= 0 || n_trials <= 0) return 0;
+    if (n_conf > 65535) return mcsce_fail_shared("mcsce_hpmf_trials: at most 65535 conformers per call");
+    const HpmfDev &v = h->dev;
+    if (first_new < 0 || n_new <= 0 || first_new + n_new > v.n_atoms) return mcsce_fail_shared("mcsce_hpmf_trials: new-atom range out of bounds");
+    HCK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (hpmf_trials_impl(h, h->es[0], h->carry, n_conf, d_coords, first_new, n_new, n_trials, d_trial, d_mask, d_v, st,
+                         TrialStepExtra{})) return -1;
     int over = 0;
     HCK(cudaMemcpyAsync(&over, h->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
     HCK(cudaStreamSynchronize(st));
     if (over) {
         HCK(cudaMemset(h->d_overflow, 0, sizeof(int)));
-        h->state_level = 0;
+        h->es[0].state_level = 0;
         return mcsce_fail_shared("mcsce_hpmf_trials: more than 512 environment carbons change weight under one trial");
     }
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// the term inside mcsce_grow (called from mcsce_kernels.cu; not part of the C ABI)
+// ------------------------------------------------------------------------------------------------
+// Lists of typed environment atoms per grown residue, from growth-order atom lists (mcsce_kernels.cu builds those from
+// rigorous reach bounds): untyped atoms (carbon-bound hydrogens) are dropped, indices become typed indices.
+int mcsce_hpmf_set_near_lists(mcsce_hpmf h, long long version, int n_res, const int *off, const int *atoms, const int *off2,
+                              const int *atoms2) {
+    if (!h) return mcsce_fail_shared("null hpmf handle");
+    HCK(cudaSetDevice(h->device));
+    const std::vector<int> &ta = h->h_typed_atom;
+    std::vector<int> ord((size_t)h->dev.n_typed, -1);
+    for (size_t k = 0; k < h->h_carbon.size(); ++k) ord[h->h_carbon[k]] = (int)k;
+    auto convert = [&](const int *o, const int *at, bool carbons, std::vector<int> &offs, std::vector<int> &out) {
+        out.clear(); out.reserve(o[n_res]);
+        offs.assign(n_res + 1, 0);
+        for (int i = 0; i < n_res; ++i) {
+            offs[i] = (int)out.size();
+            for (int q = o[i]; q < o[i + 1]; ++q) {
+                auto it = std::lower_bound(ta.begin(), ta.end(), at[q]);
+                if (it == ta.end() || *it != at[q]) continue;
+                const int k = (int)(it - ta.begin());
+                if (!carbons) out.push_back(k);
+                else if (ord[k] >= 0) out.push_back(ord[k]);
+            }
+            std::sort(out.begin() + offs[i], out.end());
+        }
+        offs[n_res] = (int)out.size();
+    };
+    std::vector<int> l1, l2;
+    convert(off, atoms, false, h->near_off, l1);
+    convert(off2, atoms2, true, h->near_c_off, l2);
+    HCK(cudaDeviceSynchronize());
+    if (h->d_near) HCK(cudaFree(h->d_near));
+    if (h->d_near_c) HCK(cudaFree(h->d_near_c));
+    h->d_near = nullptr; h->d_near_c = nullptr;
+    HCK(cudaMalloc(&h->d_near, sizeof(int) * std::max<size_t>(1, l1.size())));
+    HCK(cudaMalloc(&h->d_near_c, sizeof(int) * std::max<size_t>(1, l2.size())));
+    if (!l1.empty()) HCK(cudaMemcpy(h->d_near, l1.data(), sizeof(int) * l1.size(), cudaMemcpyHostToDevice));
+    if (!l2.empty()) HCK(cudaMemcpy(h->d_near_c, l2.data(), sizeof(int) * l2.size(), cudaMemcpyHostToDevice));
+    h->near_version = version;
+    return 0;
+}
+
+long long mcsce_hpmf_near_version(mcsce_hpmf h) { return h ? h->near_version : -1; }
+// largest distance at which two typed atoms shadow each other: max (R_i + R_j + 2 R_s), as padded for the float32 prefilter
+double mcsce_hpmf_sasa_range(mcsce_hpmf h) { return h ? sqrt((double)h->dev.pre2) : 0.0; }
+double mcsce_hpmf_pair_range(mcsce_hpmf) { return (double)HPMF_CUTOFF; }
+int mcsce_hpmf_n_atoms(mcsce_hpmf h) { return h ? h->dev.n_atoms : -1; }
+
+// Start of a growth on lane `lane`: forget the carried state; d_v_init[0] = V_hpmf of the first n_input atoms alone (the level-0
+// energy every conformer starts from, side_chain_builder.py:149), evaluated on one structure of d_coords.
+int mcsce_hpmf_growth_begin(mcsce_hpmf h, int lane, const float *d_coords, int n_input, double *d_v_init, cudaStream_t st) {
+    if (!h || lane < 0 || lane + 1 >= HPMF_STATES) return mcsce_fail_shared("mcsce_hpmf_growth_begin: bad arguments");
+    HCK(cudaSetDevice(h->device));
+    h->es[lane + 1].state_level = 0;
+    if (!d_v_init) return 0;
+    const HpmfDev &v = h->dev;
+    const std::vector<int> &ta = h->h_typed_atom;
+    const int e0 = (int)(std::lower_bound(ta.begin(), ta.end(), n_input) - ta.begin());
+    const int c0 = (int)(std::lower_bound(h->h_carbon.begin(), h->h_carbon.end(), e0) - h->h_carbon.begin());
+    const int tiles = c0 > 0 ? (c0 + HT - 1) / HT : 1;
+    if (!h->d_sasa1) HCK(cudaMalloc(&h->d_sasa1, sizeof(double) * (std::max(1, v.n_typed) + (v.n_carbon + HT - 1) / HT + 2)));
+    double *partial = h->d_sasa1 + std::max(1, v.n_typed);
+    if (launch_sasa(h, 1, d_coords, h->d_sasa1, st, e0)) return -1;
+    hpmf_pair_kernel<<<dim3(tiles, 1), HT, 0, st>>>(v, d_coords, h->d_sasa1, partial, c0, nullptr, nullptr);
+    hpmf_finish_kernel<<<1, 128, 0, st>>>(1, tiles, partial, d_v_init);
+    HCK(cudaGetLastError());
+    return 0;
+}
+
+// One residue of a growth: V_hpmf(environment + trial) for the masked (conformer, trial) pairs, into d_v [n_conf*n_trials].
+int mcsce_hpmf_growth_step(mcsce_hpmf h, int lane, int residue, int n_conf, const float *d_coords, int first_new, int n_new,
+                           int n_trials, const float4 *d_trial4, long long trial4_stride, const uint8_t *d_mask, double *d_v,
+                           int *d_overflow_conf, cudaStream_t st) {
+    if (!h || lane < 0 || lane + 1 >= HPMF_STATES) return mcsce_fail_shared("mcsce_hpmf_growth_step: bad arguments");
+    HCK(cudaSetDevice(h->device));
+    TrialStepExtra x;
+    x.trial4 = d_trial4; x.trial4_stride = trial4_stride; x.overflow_conf = d_overflow_conf;
+    static int no_lists = -1;                 // diagnostic knob: visit every environment atom instead of the residue's lists
+    if (no_lists < 0) { const char *e = getenv("MCSCE_B200_HPMF_NO_LISTS"); no_lists = e ? atoi(e) : 0; }
+    if (h->d_near && !no_lists && residue + 1 < (int)h->near_off.size()) {
+        x.near = h->d_near + h->near_off[residue]; x.n_near = h->near_off[residue + 1] - h->near_off[residue];
+        x.clist = h->d_near_c + h->near_c_off[residue]; x.n_clist = h->near_c_off[residue + 1] - h->near_c_off[residue];
+    }
+    return hpmf_trials_impl(h, h->es[lane + 1], true, n_conf, d_coords, first_new, n_new, n_trials, nullptr, d_mask, d_v, st, x);
+}
+
 extern "C" int mcsce_hpmf_carry(mcsce_hpmf h, int enable) {
     if (!h) return mcsce_fail_shared("mcsce_hpmf_carry: null handle");
     h->carry = enable != 0;
-    h->state_level = 0;                     // the next mcsce_hpmf_trials call derives the environment from scratch
+    h->es[0].state_level = 0;               // the next mcsce_hpmf_trials call derives the environment from scratch
     return 0;
 }
 

@@ -26,8 +26,21 @@
 #include <vector>
 #include <algorithm>
 #include <chrono>
+#include <functional>
 
 #include "../../include/mcsce_b200.h"
+
+// the hydrophobic PMF inside the growth (hpmf_kernels.cu)
+int mcsce_hpmf_set_near_lists(mcsce_hpmf h, long long version, int n_res, const int *off, const int *atoms, const int *off2,
+                              const int *atoms2);
+double mcsce_hpmf_pair_range(mcsce_hpmf h);
+long long mcsce_hpmf_near_version(mcsce_hpmf h);
+int mcsce_hpmf_n_atoms(mcsce_hpmf h);
+double mcsce_hpmf_sasa_range(mcsce_hpmf h);
+int mcsce_hpmf_growth_begin(mcsce_hpmf h, int lane, const float *d_coords, int n_input, double *d_v_init, cudaStream_t st);
+int mcsce_hpmf_growth_step(mcsce_hpmf h, int lane, int residue, int n_conf, const float *d_coords, int first_new, int n_new,
+                           int n_trials, const float4 *d_trial4, long long trial4_stride, const uint8_t *d_mask, double *d_v,
+                           int *d_overflow_conf, cudaStream_t st);
 
 #define MAX_CLS MCSCE_MAX_CLS
 #define MAX_SP_ENV MCSCE_MAX_SP_ENV
@@ -329,7 +342,8 @@ __global__ void __launch_bounds__(128) place_trials_kernel(PlaceArgs a) {
 #define SCORE_THREADS 128               // 128 x 2 measured best on B200 (tools/time_variants.py): finer CTA granularity per launch
 #endif
 #ifndef SCORE_R
-#define SCORE_R 3                       // trial atoms per thread at most: a tile holds 1, 2 or 3 rows of 128 atoms (see tile_layout)
+#define SCORE_R 2                       // trial atoms per thread at most: a tile holds up to SCORE_R rows of 128 atoms (see tile_layout;
+                                        // 3 compiles to 127 registers without spills and was measured: no gain)
 #endif
 #ifndef SCORE_MINB
 #define SCORE_MINB 4                    // min resident blocks per SM asked of the compiler (keeps the kernel at <= 128 registers: 4 CTAs/SM)
@@ -355,11 +369,11 @@ constexpr int kPairUnroll = PAIR_UNROLL;
 #endif
 
 // Tile layout of the scoring pass for one conformer: nk trials of n_per atoms each (+ n_fix chi-independent atoms riding in the
-// last tile) are cut into n_tiles tiles of tpt whole trials.  A tile runs on one CTA with 1, 2 or 3 atoms per thread (rows of
-// SCORE_THREADS atoms); its time follows its number of rows, full or not.  Before this, tiles were always filled to 256 atoms
-// and the last one of a conformer was on average 40 % full - 30 % of the kernel's lane-time idle (config 3: ~350 atoms per
-// conformer and residue = 1.4 tiles).  Here the number of tiles is chosen to minimise  tiles x (rows + 0.4)  (0.4 rows = a CTA's
-// staging/prologue/epilogue share), so 355 atoms run as one 3-row tile instead of 256 + 99.
+// last tile) are cut into n_tiles tiles of tpt whole trials; a tile runs on one CTA with up to max_rows atoms per thread (rows of
+// SCORE_THREADS atoms).  Two rules: packed - fill every tile to the cap, remainder last (the shipped one, 2 rows); balanced -
+// the number of tiles that minimises  tiles x (rows + overhead).  Measured on config 3 x 2048 (round 2, tools/strong_curve.py):
+// packed/2 rows 543 ms, packed/3 rows 550, balanced/3 rows 570, balanced/2 rows 578, packed/1 row 602 - a half-empty last tile
+// costs far less than its idle lanes suggest, because the other CTAs resident on the SM take the issue slots it leaves free.
 struct TileRule { int max_rows, packed; float overhead; };
 __host__ __device__ __forceinline__ void tile_layout(TileRule rule, int nk, int n_per, int n_fix, int &n_tiles, int &tpt) {
     n_tiles = 1; tpt = nk > 0 ? nk : 1;
@@ -945,7 +959,29 @@ struct SelectArgs {
     const unsigned char *screen;        // [set][n_trials] neighbour-screen flags (null = no screen): flagged trials are +inf and were not scored
     long long pairs_computed_per_kept;  // executed pairs of one trial the screen left (pairs_computed_per_set then holds the rest)
     int *n_keep;                        // [set] the screen's survivor counter, reset here for the next residue
+    // coordinate-based term (hydrophobic PMF, libenergy.py:806-808): added to every trial that passed the clash filter
+    const double *extra;                // [set][n_trials] or null
+    float *gcoords;                     // [set][n_atoms][3] growth-order copy of the conformers (the term's kernels read it) or null
+    const int *term_overflow;           // [set] the term exceeded a capacity for this conformer: it is given up (ok = 2)
 };
+
+// which (conformer, trial) pairs passed the clash filter: what the coordinate-based term is evaluated for
+__global__ void __launch_bounds__(128) finite_mask_kernel(SelectArgs a, unsigned char *mask) {
+    const int set = blockIdx.y;
+    const int t = blockIdx.x * 128 + threadIdx.x;
+    if (t >= a.n_trials) return;
+    unsigned char ok = 0;
+    if (!(a.alive && !a.alive[set]) && !(a.screen && a.screen[(long long)set * a.n_trials + t])) {
+        const int stride = a.n_trials + (a.dedup ? 1 : 0);
+        bool cl = a.sp_partial[(long long)set * a.n_trials + t].y != 0.0;
+        for (int zz = 0; zz < a.n_split && !cl; ++zz) {
+            cl |= a.partial[((long long)set * stride + t) * a.n_split + zz].y != 0.0;
+            if (a.dedup) cl |= a.partial[((long long)set * stride + a.n_trials) * a.n_split + zz].y != 0.0;
+        }
+        ok = cl ? 0 : 1;
+    }
+    mask[(long long)set * a.n_trials + t] = ok;
+}
 
 __global__ void __launch_bounds__(128) select_kernel(SelectArgs a) {
     extern __shared__ double s_dyn[];
@@ -980,6 +1016,7 @@ __global__ void __launch_bounds__(128) select_kernel(SelectArgs a) {
             }
             e += e_fix;
             if (cl) e = CUDART_INF;                           // energies[clash] = inf (libenergy.py:801)
+            else if (a.extra) e += a.extra[(long long)set * a.n_trials + t];    // efuncs_coords (libenergy.py:806-808)
             ++kept;
         }
         s_E[t] = e;
@@ -999,7 +1036,7 @@ __global__ void __launch_bounds__(128) select_kernel(SelectArgs a) {
         atomicAdd(a.pair_counter, (unsigned long long)a.pairs_per_set);
         atomicAdd(a.pair_counter + 1, (unsigned long long)(a.pairs_computed_per_set + kept * a.pairs_computed_per_kept));
     }
-    if (isinf(mn) || isnan(mn)) {                             // every trial clashes: growth fails (side_chain_builder.py:187)
+    if (isinf(mn) || isnan(mn) || (a.term_overflow && a.term_overflow[set])) {   // every trial clashes: growth fails (side_chain_builder.py:187)
         if (tid == 0) {
             a.alive[set] = 0;
             if (a.n_dead) atomicAdd(a.n_dead, 1);
@@ -1038,6 +1075,10 @@ __global__ void __launch_bounds__(128) select_kernel(SelectArgs a) {
         const int atom = st.sc_start + tid;
         p.w = (float)a.s.charge[atom];
         a.env[(long long)set * a.s.n_atoms + a.s.slot_of_atom[atom]] = p;
+        if (a.gcoords) {
+            float *g = a.gcoords + ((long long)set * a.s.n_atoms + atom) * 3;
+            g[0] = p.x; g[1] = p.y; g[2] = p.z;
+        }
     }
 }
 
@@ -1146,14 +1187,22 @@ __global__ void input_energy_reduce_kernel(int n_rows, const double2 *rows, int 
     if (threadIdx.x == 0) out[0] = s_cl[0] ? CUDART_INF : s_sum[0];
 }
 
-__global__ void init_state_kernel(int n_sets, unsigned char *alive, double *e_acc, const double *e_input) {
+__global__ void init_state_kernel(int n_sets, unsigned char *alive, double *e_acc, const double *e_input, const double *e_term,
+                                  int *term_overflow) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_sets) { alive[i] = 1; e_acc[i] = e_input[0]; }
+    if (i < n_sets) {
+        alive[i] = 1; e_acc[i] = e_term ? e_input[0] + e_term[0] : e_input[0];
+        if (term_overflow) term_overflow[i] = 0;
+    }
 }
 
-__global__ void finish_kernel(int n_sets, const unsigned char *alive, const double *e_acc, double *energy, unsigned char *ok) {
+__global__ void finish_kernel(int n_sets, const unsigned char *alive, const double *e_acc, double *energy, unsigned char *ok,
+                              const int *term_overflow) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_sets) { ok[i] = alive[i]; energy[i] = alive[i] ? e_acc[i] : CUDART_NAN; }
+    if (i < n_sets) {
+        ok[i] = (term_overflow && term_overflow[i]) ? 2 : alive[i];
+        energy[i] = alive[i] ? e_acc[i] : CUDART_NAN;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1175,7 +1224,7 @@ struct mcsce_handle_s {
     SysDev d{};
     bool has_sys = false, has_bb = false;
     bool warned_screen_limit = false;
-    TileRule rule{SCORE_R, 0, 0.4f};       // tuning knobs: MCSCE_B200_TILE_ROWS / _TILE_PACKED / _TILE_OVERHEAD
+    TileRule rule{SCORE_R, 1, 0.4f};       // packed 2-row tiles; tuning knobs: MCSCE_B200_TILE_ROWS / _TILE_PACKED / _TILE_OVERHEAD
     // host mirrors needed for launch geometry
     std::vector<StepDev> steps;
     std::vector<TmplDev> tmpl_host;
@@ -1198,7 +1247,11 @@ struct mcsce_handle_s {
     // A lane = what one group of conformers in flight needs: a main stream (lane 0: the caller's), a second stream for
     // the placement of the next residue and the special-pair kernel, their events, the call's parameter block.  Big calls
     // run two groups side by side so that the launch tails and the small kernels of one hide under the other's scoring pass.
+    std::vector<float> input_xyz_host;               // backbone of the last set_backbone (near lists of the hydrophobic PMF)
     struct Lane {
+        // buffers of the coordinate-based term (grow-only): growth-order coordinates, per-trial values, mask, overflow flags
+        float *hp_gcoords = nullptr; double *hp_v = nullptr, *hp_v_init = nullptr; unsigned char *hp_mask = nullptr; int *hp_ovf = nullptr;
+        size_t hp_cap_conf = 0, hp_cap_atoms = 0, hp_cap_trials = 0;
         cudaStream_t main = nullptr, aux = nullptr;
         std::vector<cudaEvent_t> evP, evQ, evS;
         cudaEvent_t ev0 = nullptr, done = nullptr;
@@ -1210,7 +1263,7 @@ struct mcsce_handle_s {
     // optional per-kernel-class device timing (CUDA events on the launch stream)
     bool profiling = false;
     bool capturing = false;
-    std::vector<cudaEvent_t> ev[4];     // 0 place, 1 score_generic, 2 score_special, 3 select: begin/end pairs
+    std::vector<cudaEvent_t> ev[5];     // 0 place, 1 score_generic, 2 score_special, 3 select, 4 hpmf: begin/end pairs
 };
 
 struct ProfScope {
@@ -1305,6 +1358,11 @@ extern "C" int mcsce_destroy(mcsce_handle h) {
         if (ln.main) cudaStreamDestroy(ln.main);
         if (ln.d_n_dead) cudaFree(ln.d_n_dead);
         if (ln.d_call) cudaFree(ln.d_call);
+        if (ln.hp_gcoords) cudaFree(ln.hp_gcoords);
+        if (ln.hp_v) cudaFree(ln.hp_v);
+        if (ln.hp_v_init) cudaFree(ln.hp_v_init);
+        if (ln.hp_mask) cudaFree(ln.hp_mask);
+        if (ln.hp_ovf) cudaFree(ln.hp_ovf);
     }
     if (h->d_steps) cudaFree(h->d_steps);
     if (h->d_input_energy) cudaFree(h->d_input_energy);
@@ -1388,7 +1446,6 @@ extern "C" int mcsce_set_system(mcsce_handle h, const mcsce_system_desc *s) {
     }
     if (upload(h, P, tm.data(), tm.size(), &d.tmpl)) return -1;
     h->tmpl_host = tm;
-
     h->steps.assign(s->n_res, StepDev{});
     h->step_n_sp_env.assign(s->n_res, 0);
     for (int i = 0; i < s->n_res; ++i) {
@@ -1591,6 +1648,7 @@ extern "C" int mcsce_set_backbone(mcsce_handle h, const mcsce_backbone_desc *b) 
     }
     if (ensure_dyn_smem(select_kernel, sizeof(double) * 2 * (size_t)h->max_trials, "mcsce_set_backbone")) return -1;
     CK(cudaMemcpy(h->d_steps, h->steps.data(), sizeof(StepDev) * d.n_res, cudaMemcpyHostToDevice));
+    h->input_xyz_host.assign(b->input_xyz, b->input_xyz + (size_t)d.n_input * 3);
     std::vector<int> scr_off, scr_slots, scr_prefix;
     if (build_screen_lists(h, b, scr_off, scr_slots, scr_prefix)) return -1;
     if (dbg) fprintf(stderr, "[mcsce_b200] set_backbone: +screen lists (host) %.2f ms\n", ms_since(t_start));
@@ -1920,6 +1978,104 @@ extern "C" int mcsce_select(mcsce_handle h, int n_sets, int n_trials, const doub
     return 0;
 }
 
+// Per grown residue, the atoms already placed that can come within `range` of any of its side-chain atoms, whatever the chi
+// angles of either: input atoms by their position, side-chain atoms of earlier residues by their CA and reach bound.  Complete
+// (unlike the clash screen's lists, which only have to be likely): the hydrophobic PMF visits no other atom for its surface terms.
+// Upper bound of |atom - CA| over all chi angles, per template atom, for the first n_rot rotations of the template (the ones
+// a residue applies).  Rotation k turns its moving set about the axis (axis_from[k] -> axis_to[k]) through the pivot
+// axis_to[k]; atoms on the axis stay put.  Every other rotation moves an atom and the pivot of the last rotation that moves it
+// together, so |atom - pivot| is a template constant and  bound(atom) <= bound(pivot) + |atom - pivot|.  An axis through CA
+// (chi1) keeps the distance to CA itself.  2 % + 0.05 A of slack for the float32 arithmetic of K1.
+static void reach_bounds(const TmplDev &o, int n_rot, float *out) {
+    auto dist = [&](int a, int b) {
+        const float x = o.xyz[a][0] - o.xyz[b][0], y = o.xyz[a][1] - o.xyz[b][1], z = o.xyz[a][2] - o.xyz[b][2];
+        return sqrtf(x * x + y * y + z * z);
+    };
+    auto norm = [&](int a) { return sqrtf(o.xyz[a][0] * o.xyz[a][0] + o.xyz[a][1] * o.xyz[a][1] + o.xyz[a][2] * o.xyz[a][2]); };
+    float far = 0.f;
+    for (int a = 0; a < o.n_atoms; ++a) far = std::max(far, norm(a));
+    std::vector<float> bound(MAX_TMPL, -1.f);
+    std::function<float(int, int)> rec = [&](int a, int depth) -> float {
+        if (bound[a] >= 0.f) return bound[a];
+        int m = -1;
+        for (int k = 0; k < n_rot; ++k) if (((o.move[k] >> a) & 1u) && a != o.axis_to[k] && a != o.axis_from[k]) m = k;
+        float b;
+        if (m < 0) b = norm(a);
+        else if (norm(o.axis_from[m]) < 1e-4f || norm(o.axis_to[m]) < 1e-4f) b = norm(a);       // the axis passes through CA
+        else if (depth > MAX_ROT + 2) return 3.f * far + 3.f;       // rotation programs that are not nested chains: a loose bound
+        else b = rec(o.axis_to[m], depth + 1) + dist(a, o.axis_to[m]);
+        return bound[a] = b;
+    };
+    for (int a = 0; a < MAX_TMPL; ++a) out[a] = a < o.n_atoms ? 1.02f * rec(a, 0) + 0.05f : 0.f;
+}
+
+// Per grown residue, the atoms already placed that can come within `range` of any of its side-chain atoms, whatever the chi
+// angles of either: input atoms by their position, side-chain atoms of earlier residues by their CA and reach bound.  Complete
+// (unlike the clash screen's lists, which only have to be likely): the hydrophobic PMF visits no other atom for its surface terms.
+static int ensure_hpmf_near_lists(mcsce_handle h, mcsce_hpmf hp) {
+    if (mcsce_hpmf_near_version(hp) == h->table_version) return 0;
+    const SysDev &d = h->d;
+    if (mcsce_hpmf_n_atoms(hp) != d.n_atoms) return fail("the hpmf handle was created for another atom list");
+    const double range = mcsce_hpmf_sasa_range(hp) + 0.01;
+    std::vector<float> cx((size_t)d.n_atoms * 3, 0.f), rad(d.n_atoms, 0.f), reach(d.n_res, 0.f);
+    for (int a = 0; a < d.n_input; ++a) for (int k = 0; k < 3; ++k) cx[(size_t)a * 3 + k] = h->input_xyz_host[(size_t)a * 3 + k];
+    float bound[MAX_TMPL];
+    for (int j = 0; j < d.n_res; ++j) {
+        const StepDev &sj = h->steps[j];
+        if (sj.kind == 0) continue;
+        const TmplDev &tm = h->tmpl_host[sj.type];
+        reach_bounds(tm, sj.kind == 2 ? std::min(sj.n_chi, tm.n_chi) : 0, bound);
+        for (int p = 0; p < tm.n_atoms; ++p) {
+            const int k = tm.sc_rank[p];
+            if (k < 0 || k >= sj.n_sc) continue;
+            const int a = sj.sc_start + k;
+            for (int q = 0; q < 3; ++q) cx[(size_t)a * 3 + q] = sj.ca[q];
+            rad[a] = bound[p];
+            reach[j] = std::max(reach[j], rad[a]);
+        }
+    }
+    const double range2 = mcsce_hpmf_pair_range(hp) + 0.01;       // carbon pairs: the Gaussian cutoff
+    std::vector<int> off(d.n_res + 1, 0), atoms, off2(d.n_res + 1, 0), atoms2;
+    for (int i = 0; i < d.n_res; ++i) {
+        off[i] = (int)atoms.size(); off2[i] = (int)atoms2.size();
+        const StepDev &si = h->steps[i];
+        if (si.kind != 2) continue;
+        for (int a = 0; a < si.sc_start; ++a) {
+            const float dx = cx[(size_t)a * 3] - si.ca[0], dy = cx[(size_t)a * 3 + 1] - si.ca[1], dz = cx[(size_t)a * 3 + 2] - si.ca[2];
+            const double d2 = (double)dx * dx + (double)dy * dy + (double)dz * dz;
+            const double lim = (double)reach[i] + rad[a] + range, lim2 = (double)reach[i] + rad[a] + range2;
+            if (d2 < lim * lim) atoms.push_back(a);
+            if (d2 < lim2 * lim2) atoms2.push_back(a);
+        }
+    }
+    off[d.n_res] = (int)atoms.size(); off2[d.n_res] = (int)atoms2.size();
+    if (atoms.empty()) atoms.push_back(0);
+    if (atoms2.empty()) atoms2.push_back(0);
+    return mcsce_hpmf_set_near_lists(hp, h->table_version, d.n_res, off.data(), atoms.data(), off2.data(), atoms2.data());
+}
+
+static int ensure_hpmf_buffers(mcsce_handle h, mcsce_handle_s::Lane &ln, int n_conf, cudaStream_t st) {
+    const size_t na = (size_t)h->d.n_atoms, nt = (size_t)std::max(1, h->max_trials);
+    if ((size_t)n_conf <= ln.hp_cap_conf && na <= ln.hp_cap_atoms && nt <= ln.hp_cap_trials) return 0;
+    CK(cudaDeviceSynchronize());
+    if (ln.hp_gcoords) cudaFree(ln.hp_gcoords);
+    if (ln.hp_v) cudaFree(ln.hp_v);
+    if (ln.hp_mask) cudaFree(ln.hp_mask);
+    if (ln.hp_ovf) cudaFree(ln.hp_ovf);
+    ln.hp_gcoords = nullptr; ln.hp_v = nullptr; ln.hp_mask = nullptr; ln.hp_ovf = nullptr; ln.hp_cap_conf = 0;
+    const size_t C = std::max<size_t>(n_conf, ln.hp_cap_conf), A = std::max(na, ln.hp_cap_atoms), T = std::max(nt, ln.hp_cap_trials);
+    CK(cudaMalloc((void **)&ln.hp_gcoords, C * A * 3 * sizeof(float)));
+    CK(cudaMalloc((void **)&ln.hp_v, C * T * sizeof(double)));
+    CK(cudaMalloc((void **)&ln.hp_mask, C * T));
+    CK(cudaMalloc((void **)&ln.hp_ovf, C * sizeof(int)));
+    if (!ln.hp_v_init) CK(cudaMalloc((void **)&ln.hp_v_init, sizeof(double)));
+    ln.hp_cap_conf = C; ln.hp_cap_atoms = A; ln.hp_cap_trials = T;
+    (void)st;
+    return 0;
+}
+
+__global__ void gather_kernel(SysDev s, int n_sets, const float4 *env, float *coords);
+
 // Enqueue of one growth (environment init, then K1 / K2s / screen / K2 / K3 for every grown residue) on `st` + `aux`, as a
 // stepper: begin(), residue(i) for every residue in order, so that several conformer groups (lanes) can be enqueued
 // interleaved residue by residue - the occasional read-back of the number of dead conformers (`resync`, never while
@@ -1927,6 +2083,7 @@ extern "C" int mcsce_select(mcsce_handle h, int n_sets, int n_trials, const doub
 struct GrowthEnqueue {
     mcsce_handle h; mcsce_grow_opts o; Workspace w; mcsce_handle_s::Lane *ln; cudaStream_t st, aux; bool resync;
     int groups;                 // conformer groups in flight: the environment split is chosen for all of them together
+    mcsce_hpmf hp = nullptr;    // coordinate-based term (hydrophobic PMF) of this growth, or null
     int prev = -1, prev2 = -1, count = 0, ms_alloc = 1, n_alive = 0;
     long long trial_stride = 1, chi_set_stride = 0;
 
@@ -1944,7 +2101,19 @@ struct GrowthEnqueue {
         trial_stride = std::max(1, h->max_trial_atoms);
         chi_set_stride = (long long)d.n_trials_total * MAX_CHI;
         if (mcsce_init_env(h, C, (float *)w.env, (void *)st)) return -1;
-        init_state_kernel<<<(C + 255) / 256, 256, 0, st>>>(C, w.alive, w.e_acc, h->d_input_energy);   // starts from the input atoms' energy (:149)
+        hp = (mcsce_hpmf)o.hpmf;
+        if (hp) {
+            // coordinate-based term: growth-order copy of the conformers for its kernels, its level-0 value (input atoms alone)
+            if (ensure_hpmf_near_lists(h, hp) || ensure_hpmf_buffers(h, *ln, C, st)) return -1;
+            const long long n = (long long)C * d.n_atoms;
+            gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d, C, w.env, ln->hp_gcoords);
+            h->launches += 1;
+            ProfScope ps(h, 4, st);
+            if (mcsce_hpmf_growth_begin(hp, (int)(ln - h->lane), ln->hp_gcoords, d.n_input, ln->hp_v_init, st)) return fail(mcsce_last_error());
+            h->launches += 4;
+        }
+        init_state_kernel<<<(C + 255) / 256, 256, 0, st>>>(C, w.alive, w.e_acc, h->d_input_energy, hp ? ln->hp_v_init : nullptr,
+                                                           hp ? ln->hp_ovf : nullptr);   // starts from the input atoms' energy (:149)
         h->launches += 1;
         // Two streams: `st` runs the generic-pair kernel and the selection of every residue in order; `aux` runs the
         // placement of the next residue (independent of the pending selection) and the special-pair kernel.
@@ -2012,6 +2181,16 @@ struct GrowthEnqueue {
         a.pairs_computed_per_kept = (long long)n_per * n_active;
         a.pairs_computed_per_set = (dedup ? (long long)sd.n_fix * n_active : 0) + (long long)T * sd.n_sp
                                    + (screen ? (long long)T * n_per * h->scr_len[i] / 2 : 0);
+        if (hp) {
+            // hydrophobic PMF of (conformer so far + trial) for every trial that passed the clash filter (libenergy.py:806-808):
+            // the environment's areas / weights / fields are carried from residue to residue, each trial adds its own terms
+            a.extra = ln->hp_v; a.gcoords = ln->hp_gcoords; a.term_overflow = ln->hp_ovf;
+            ProfScope ps(h, 4, st);
+            finite_mask_kernel<<<dim3((T + 127) / 128, C), 128, 0, st>>>(a, ln->hp_mask);
+            if (mcsce_hpmf_growth_step(hp, (int)(ln - h->lane), i, C, ln->hp_gcoords, sd.sc_start, sd.n_sc, T, trial, trial_stride,
+                                       ln->hp_mask, ln->hp_v, ln->hp_ovf, st)) return fail(mcsce_last_error());
+            h->launches += 5;
+        }
         { ProfScope ps(h, 3, st); select_kernel<<<C, 128, sizeof(double) * 2 * T, st>>>(a); }
         h->launches += 1;
         CK(cudaEventRecord(ln->evS[i], st));
@@ -2056,10 +2235,10 @@ static int prepare_lane(mcsce_handle h, mcsce_handle_s::Lane &ln, bool own_main)
 }
 
 static int finish_growth(mcsce_handle h, int C, const Workspace &w, float *d_coords, double *d_energy, uint8_t *d_ok,
-                         cudaStream_t st) {
+                         cudaStream_t st, const int *term_overflow = nullptr) {
     const long long n = (long long)C * h->d.n_atoms;
     gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->d, C, w.env, d_coords);
-    finish_kernel<<<(C + 255) / 256, 256, 0, st>>>(C, w.alive, w.e_acc, d_energy, d_ok);
+    finish_kernel<<<(C + 255) / 256, 256, 0, st>>>(C, w.alive, w.e_acc, d_energy, d_ok, term_overflow);
     h->launches += 2;
     CK(cudaGetLastError());
     return 0;
@@ -2090,7 +2269,8 @@ extern "C" int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *o, void *d_work
         pairs += (long long)sd.n_trials * sd.n_sc * n_active;
         ++grow_steps;
     }
-    const bool use_graph = !o->no_graph && !h->profiling && grow_steps > 0 && (pairs * C) / grow_steps < 300000000LL;
+    // (the coordinate-based term sizes its buffers at the first step of a growth: not capturable)
+    const bool use_graph = !o->no_graph && !o->hpmf && !h->profiling && grow_steps > 0 && (pairs * C) / grow_steps < 300000000LL;
     if (use_graph) {
         Workspace w = carve(h, C, h->max_trials, h->max_trial_atoms, d_workspace);
         std::vector<long long> key = {h->table_version, C, (long long)(size_t)d_workspace, (long long)workspace_bytes,
@@ -2137,7 +2317,7 @@ extern "C" int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *o, void *d_work
         Workspace w = carve(h, C, h->max_trials, h->max_trial_atoms, d_workspace);
         // while the per-class event timing is on, everything goes to one stream so that each kernel is timed alone
         if (enqueue_growth(h, o, w, h->lane[0], st, h->profiling ? st : h->lane[0].aux, true)) return -1;
-        return finish_growth(h, C, w, d_coords, d_energy, d_ok, st);
+        return finish_growth(h, C, w, d_coords, d_energy, d_ok, st, o->hpmf ? h->lane[0].hp_ovf : nullptr);
     }
     // G groups of conformers, each a complete growth on its own pair of streams; group 0 on the caller's stream.  The groups
     // are enqueued interleaved, residue by residue, and share one environment-split rule (that of the whole call).
@@ -2172,7 +2352,8 @@ extern "C" int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *o, void *d_work
         for (auto &g : ge) if (g.residue(i)) return -1;
     CK(cudaGetLastError());
     for (int g = G - 1; g >= 0; --g) {
-        if (finish_growth(h, cgs[g], ge[g].w, d_coords + (size_t)c0s[g] * d.n_atoms * 3, d_energy + c0s[g], d_ok + c0s[g], ge[g].st)) return -1;
+        if (finish_growth(h, cgs[g], ge[g].w, d_coords + (size_t)c0s[g] * d.n_atoms * 3, d_energy + c0s[g], d_ok + c0s[g], ge[g].st,
+                          o->hpmf ? h->lane[g].hp_ovf : nullptr)) return -1;
         if (g > 0) { CK(cudaEventRecord(h->lane[g].done, ge[g].st)); CK(cudaStreamWaitEvent(st, h->lane[g].done, 0)); }
     }
     return 0;
@@ -2195,6 +2376,12 @@ extern "C" int mcsce_grow_host(mcsce_handle h, const mcsce_grow_opts *o, void *d
     CK(cudaMemcpyAsync(h_energy, de, (size_t)o->n_conf * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(h_ok, dk, (size_t)o->n_conf, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    if (o->hpmf) {
+        int n_over = 0;
+        for (int i = 0; i < o->n_conf; ++i) n_over += h_ok[i] == 2;
+        if (n_over) return fail("hydrophobic PMF: a neighbour-list capacity was exceeded for " + std::to_string(n_over) +
+                                " conformers (ok = 2); the other conformers are complete");
+    }
     return 0;
 }
 
@@ -2291,7 +2478,7 @@ extern "C" int mcsce_profile(mcsce_handle h, int enable, double *ms_by_class, in
     }
     h->profiling = false;
     CK(cudaDeviceSynchronize());
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 5; ++c) {
         double ms = 0.0;
         for (size_t i = 0; i + 1 < h->ev[c].size(); i += 2) {
             float t = 0.f;

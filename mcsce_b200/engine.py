@@ -193,11 +193,13 @@ class GrowthEngine:
 
     def grow(self, n_conf, beta, seed=0, conf_id0=0, noise_deg=0.5, chis=None, uniforms=None, dump=False,
              env_split=0, host_out=False, stream=None, no_dedup=False, no_graph=False, no_screen=False, oris=None,
-             out_ptrs=None):
+             out_ptrs=None, hpmf=None):
         """Grow ``n_conf`` conformers.  Returns dict(coords (C,N,3) f32 growth order, energy (C,) f64,
         ok (C,) uint8 [, trial_energy, chis, selected]); torch CUDA tensors, or NumPy arrays (pinned
         staging inside the C call) with ``host_out``.  ``out_ptrs`` = (coords, energy, ok) raw device addresses: the
-        results are stored there instead (e.g. this rank's slice of rank 0's peer-mapped buffer, ``sharding.PeerResults``)."""
+        results are stored there instead (e.g. this rank's slice of rank 0's peer-mapped buffer, ``sharding.PeerResults``).
+        ``hpmf``: a :class:`mcsce_b200.hpmf.HpmfCalculator` for this atom list - adds the hydrophobic PMF of (conformer so far
+        + trial) to every trial that passed the clash filter, inside the fused loop (``terms=[..., "hpmf"]``)."""
         torch = self.torch
         assert self._has_backbone, "set_backbone first"
         if any(st.kind == "grow" and st.chi_mean is None for st in self.system.steps):
@@ -210,6 +212,10 @@ class GrowthEngine:
         o.no_graph = 1 if no_graph else 0
         o.no_screen = 1 if no_screen else 0
         keep = []
+        if hpmf is not None:
+            assert hpmf.n_atoms == N, "the hpmf calculator was built for another atom list"
+            o.hpmf = hpmf.h.value if hasattr(hpmf.h, "value") else int(hpmf.h)
+            keep.append(hpmf)
         if chis is not None:
             ch = torch.as_tensor(np.ascontiguousarray(chis, np.float64), device=self.device)
             assert ch.numel() == C_ * self.n_trials_total * MAX_CHI, "chis must be (n_conf, n_trials_total, MAX_CHI)"
@@ -434,8 +440,8 @@ class GrowthEngine:
         check(self.lib.mcsce_profile(self.h, 1, None, None))
 
     def profile_end(self):
-        """{kernel class: (milliseconds, launches)} for place / score_generic / score_special / select."""
-        ms = (C.c_double * 4)(); n = (C.c_int64 * 4)()
+        """{kernel class: (milliseconds, launches)} for place / score_generic / score_special / select / hpmf."""
+        ms = (C.c_double * 5)(); n = (C.c_int64 * 5)()
         check(self.lib.mcsce_profile(self.h, 0, ms, n))
-        names = ("place_trials", "score_generic", "score_special", "select")
+        names = ("place_trials", "score_generic", "score_special", "select", "hpmf")
         return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(names)}
