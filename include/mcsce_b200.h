@@ -292,6 +292,10 @@ int mcsce_hpmf_trials(mcsce_hpmf h, int n_conf, const float *d_coords, int first
  * every call of this function - with 0 or 1 - forgets the kept state, so a new growth starts with one.  */
 int mcsce_hpmf_carry(mcsce_hpmf h, int enable);
 
+/* diagnostics: key 0 = which kernel evaluates the trials inside mcsce_grow (1, default: one block per conformer, a warp per
+ * trial; 0: one block per (trial, conformer) - the kernel behind mcsce_hpmf_trials); same numbers to 1e-13 */
+int mcsce_hpmf_set_option(mcsce_hpmf h, int key, int value);
+
 /* per-kernel device time of the last mcsce_hpmf_energy call: ms[0] = SASA kernel, ms[1] = carbon-pair kernel
  * (CUDA events on the launch stream; synchronises) */
 int mcsce_hpmf_last_ms(mcsce_hpmf h, double *ms);

@@ -105,6 +105,7 @@ SYMBOLS = {
     "mcsce_hpmf_trials": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),
     "mcsce_hpmf_carry": (C.c_int, [C.c_void_p, C.c_int]),
+    "mcsce_hpmf_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "mcsce_hpmf_last_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "mcsce_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int]),
 }

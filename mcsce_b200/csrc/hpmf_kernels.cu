@@ -55,15 +55,33 @@ __device__ __forceinline__ float dist2_fast(float ax, float ay, float az, float 
     return fmaf(z, z, fmaf(y, y, x * x));
 }
 
-// one factor of the product: atom i (P_i, S_i, R_i) shadowed by partner j (pi (R_j + R_s), R_j) at distance d < thr
+// one factor of the product: atom i (P_i, S_i, R_i) shadowed by partner j (pi (R_j + R_s), R_j) at distance d < thr:
+//   1 - P_i p_ij b_ij / S_i ,  b_ij = pi (R_j + R_s) (thr - d) (1 + (R_j - R_i) / (d + 1e-8))          (libsasa.py:100-105)
+// The two float64 divisions (by d and by S_i) were 2/3 of the instructions of the per-trial kernels; the reciprocal of d comes
+// from the float32 MUFU result refined by two Newton steps in float64 (relative error < 1e-15), 1/S_i is a per-type constant
+// (one more rounding, 1e-16).  Surface areas stay within 1e-12 relative of the reference's (the tests ask 1e-9).
+__device__ __forceinline__ double recip_f64(double x) {
+    double y = (double)__frcp_rn((float)x);
+    y = y * (2.0 - x * y);
+    return y * (2.0 - x * y);
+}
 __device__ __forceinline__ double sasa_term(double Pi, double Si, double Ri, double piRRs_j, double Rj, double thr, float d,
                                             double pij) {
     // dij + 1e-8 stays float32 in the reference (float32 array + Python scalar)
     const double dd = (double)__fadd_rn(d, 1e-8f);
-    const double bij = __dmul_rn(__dmul_rn(piRRs_j, __dsub_rn(thr, (double)d)),
-                                 __dadd_rn(1.0, __ddiv_rn(__dsub_rn(Rj, Ri), dd)));
-    return __dsub_rn(1.0, __ddiv_rn(__dmul_rn(__dmul_rn(Pi, pij), bij), Si));
+    const double bij = (piRRs_j * (thr - (double)d)) * (1.0 + (Rj - Ri) * recip_f64(dd));
+    return 1.0 - ((Pi * pij) * bij) * recip_f64(Si);
 }
+// both factors of a pair at once: (i shadowed by j, j shadowed by i); invS = 1 / S per type
+__device__ __forceinline__ void sasa_term_pair(double Pi, double invSi, double Ri, double piRRs_i, double Pj, double invSj, double Rj,
+                                               double piRRs_j, double thr, float d, double pij, double &t_ij, double &t_ji) {
+    const double dd = (double)__fadd_rn(d, 1e-8f);
+    const double gap = thr - (double)d, q = (Rj - Ri) * recip_f64(dd);
+    t_ij = 1.0 - ((Pi * pij) * ((piRRs_j * gap) * (1.0 + q))) * invSi;
+    t_ji = 1.0 - ((Pj * pij) * ((piRRs_i * gap) * (1.0 - q))) * invSj;
+}
+// tanh of a surface area: exactly 1 in float64 beyond 19.07 (1 - tanh x < 2^-54), which most exposed carbons are
+__device__ __forceinline__ double tanh_area(double a) { return a > 19.07 ? 1.0 : tanh(a); }
 
 // nt_lim: only the first nt_lim typed atoms exist (a partially grown structure); n_typed for a whole one
 __global__ void __launch_bounds__(HT) sasa_kernel(HpmfDev s, const float *__restrict__ coords, double *__restrict__ sasa,
@@ -154,7 +172,7 @@ __global__ void __launch_bounds__(HT) hpmf_pair_kernel(HpmfDev s, const float *_
         const float *p = coords + (base + s.typed_atom[c]) * 3;
         xi = p[0]; yi = p[1]; zi = p[2];
         const double a = sa[c];
-        wi = (a > s.sa_threshold && xi <= ABSENT_X) ? tanh(a) : 0.0;
+        wi = (a > s.sa_threshold && xi <= ABSENT_X) ? tanh_area(a) : 0.0;
     }
     const bool want_field = f_out != nullptr && i < nc_lim;
     double acc = 0.0;
@@ -165,7 +183,7 @@ __global__ void __launch_bounds__(HT) hpmf_pair_kernel(HpmfDev s, const float *_
             const int c = s.carbon[jl];
             const float *p = coords + (base + s.typed_atom[c]) * 3;
             const double a = sa[c];
-            const double w = (a > s.sa_threshold && p[0] <= ABSENT_X) ? tanh(a) : 0.0;
+            const double w = (a > s.sa_threshold && p[0] <= ABSENT_X) ? tanh_area(a) : 0.0;
             sw[tid] = w;
             sp[tid] = make_float4(p[0], p[1], p[2], w == 0.0 ? 0.f : 1.f);
         }
@@ -308,7 +326,7 @@ __global__ void __launch_bounds__(HT, MINB) hpmf_trial_kernel(
             const int ck = carbon_ord[k];
             if (ck >= 0) {
                 const double a = sa[k] * f;
-                const double w = a > s.sa_threshold ? tanh(a) : 0.0;
+                const double w = a > s.sa_threshold ? tanh_area(a) : 0.0;
                 const double del = w - w0c[ck];
                 if (del != 0.0) {
                     acc += del * f0c[ck];
@@ -352,7 +370,7 @@ __global__ void __launch_bounds__(HT, MINB) hpmf_trial_kernel(
         const int ck = carbon_ord[e1 + tid];
         if (ck >= 0) {
             const double a = __dmul_rn(s_S[ti], prod);
-            tw[ck - c1] = a > s.sa_threshold ? tanh(a) : 0.0;
+            tw[ck - c1] = a > s.sa_threshold ? tanh_area(a) : 0.0;
             tc[ck - c1] = make_float4(me.x, me.y, me.z, 0.f);
         }
     }
@@ -416,6 +434,328 @@ __global__ void __launch_bounds__(HT, MINB) hpmf_trial_kernel(
 
 
 // ------------------------------------------------------------------------------------------------
+// the same per-trial evaluation, one block per CONFORMER and one warp per trial (the growth's kernel)
+// ------------------------------------------------------------------------------------------------
+// hpmf_trial_kernel spends a block per (trial, conformer): every block reloads the type tables, gathers the environment atoms
+// through two index tables and evaluates the float64 surface factors under heavy divergence (a few lanes of every warp are in
+// range) - 262 us per residue at 256 conformers of config 3, 14 us per block for ~3000 instructions of work.  Here a block
+// takes a conformer: the residue's environment lists are staged in shared memory once (typed atoms in surface range with their
+// areas; the EXPOSED carbons in Gaussian range with their weights, compacted in order), then each warp takes trials in turn:
+//   pass A  lanes over the staged atoms, float32 range test against the trial's <= 16 typed atoms -> (atom, bit mask) hit list
+//   pass B  lanes over the hit list (dense: every lane has work): exact distances, float64 factors for both surface products
+//   phase 2 the trial's own atoms, lane = atom;  phase 3 Gaussian sums, lanes over the staged carbons / the changed carbons
+// Same terms in the same arithmetic as hpmf_trial_kernel (float64 products are taken in another order: 1e-13 relative).
+#define CT_WARPS 8
+#define CT_THREADS (CT_WARPS * 32)
+#define CT_TRIALS 1024         // trials per residue the kernel indexes (the reference's largest set: 729)
+#define CT_NEAR 768            // staged typed atoms in surface range (more: the block falls back to global reads)
+#define CT_CARB 768            // staged exposed carbons in Gaussian range (more: global reads)
+#define CT_HITS 192            // (atom, mask) pairs one trial can hit
+#define CT_LIST 160            // environment carbons whose weight one trial changes
+
+struct ConfTrialArgs {
+    HpmfDev s;
+    const float *coords; const float4 *trial4; long long trial4_stride; const unsigned char *mask;
+    int first_new, n_new, n_trials, e1, m, c1, mc;
+    const int *carbon_ord; const double *sa_env, *w0, *f0, *v0; double *out;
+    int *overflow, *overflow_conf;
+    const int *near; int n_near; const int *clist; int n_clist;
+    const float4 *cpos;
+    float4 *scratch_pos; double *scratch_w;          // [conformer][n_carbon] exposed carbons beyond the shared-memory stage
+};
+
+struct ConfTrialSmem {
+    double thr[MAX_SASA_TYPES * MAX_SASA_TYPES];
+    double R[MAX_SASA_TYPES], piRRs[MAX_SASA_TYPES], P[MAX_SASA_TYPES], S[MAX_SASA_TYPES], invS[MAX_SASA_TYPES];
+    float4 near_pos[CT_NEAR];      // x, y, z, type (int bits; -1 = absent)
+    double near_sa[CT_NEAR];
+    float4 carb_pos[CT_CARB];
+    double carb_w[CT_CARB];
+    int trials[CT_TRIALS];         // the conformer's trials that passed the clash filter, ascending
+    int n_active, n_carb;
+    int warp_cnt[CT_WARPS];
+    // per warp
+    float4 ta[CT_WARPS][MAX_NEW_T];
+    float4 tc[CT_WARPS][MAX_NEW_C];
+    double tw[CT_WARPS][MAX_NEW_C];
+    int hit_q[CT_WARPS][CT_HITS];
+    unsigned hit_m[CT_WARPS][CT_HITS];
+    float4 lpos[CT_WARPS][CT_LIST];
+    double ldel[CT_WARPS][CT_LIST];
+};
+
+__device__ __forceinline__ double warp_sum_fixed(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+__global__ void __launch_bounds__(CT_THREADS, 2) hpmf_trials_conf_kernel(ConfTrialArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ConfTrialSmem &sm = *reinterpret_cast<ConfTrialSmem *>(smem_raw);
+    const HpmfDev &s = a.s;
+    const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = s.n_types;
+    const int T = a.n_trials, e1 = a.e1, m = a.m, c1 = a.c1, mc = a.mc;
+    const unsigned char *mask = a.mask ? a.mask + (long long)c * T : nullptr;
+    double *out = a.out + (long long)c * T;
+    const float *cbase = a.coords + (long long)c * s.n_atoms * 3;
+    const double *sa = a.sa_env + (long long)c * s.n_typed;
+    const double *w0c = a.w0 + (long long)c * s.n_carbon, *f0c = a.f0 + (long long)c * s.n_carbon;
+    const float cut2 = HPMF_CUTOFF * HPMF_CUTOFF;
+
+    // ---- the conformer's active trials (ordered compaction of the mask), zeros for the others ----
+    if (tid == 0) { sm.n_active = 0; sm.n_carb = 0; }
+    __syncthreads();
+    for (int t0 = 0; t0 < T; t0 += CT_THREADS) {
+        const int t = t0 + tid;
+        const bool on = t < T && (!mask || mask[t]);
+        if (t < T && !on) out[t] = 0.0;
+        const unsigned b = __ballot_sync(0xffffffffu, on);
+        if (lane == 0) sm.warp_cnt[warp] = __popc(b);
+        __syncthreads();
+        int base = sm.n_active;
+        for (int w = 0; w < warp; ++w) base += sm.warp_cnt[w];
+        if (on) sm.trials[base + __popc(b & ((1u << lane) - 1u))] = t;
+        __syncthreads();
+        if (tid == 0) { int tot = 0; for (int w = 0; w < CT_WARPS; ++w) tot += sm.warp_cnt[w]; sm.n_active += tot; }
+        __syncthreads();
+    }
+    const int n_active = sm.n_active;
+    if (n_active == 0) return;
+
+    // ---- tables and the residue's environment lists, once per conformer ----
+    for (int k = tid; k < nt * nt; k += CT_THREADS) sm.thr[k] = s.thr[k];
+    if (tid < nt) {
+        sm.R[tid] = s.R[tid]; sm.piRRs[tid] = s.piRRs[tid]; sm.P[tid] = s.P[tid]; sm.S[tid] = s.S[tid];
+        sm.invS[tid] = recip_f64(s.S[tid]);
+    }
+    const int n_near = a.near ? a.n_near : e1;
+    for (int q = tid; q < min(n_near, CT_NEAR); q += CT_THREADS) {
+        const int k = a.near ? a.near[q] : q;
+        float4 v = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+        double area = 0.0;
+        if (k < e1) {
+            const float *p = cbase + (long long)s.typed_atom[k] * 3;
+            if (p[0] <= ABSENT_X) { v = make_float4(p[0], p[1], p[2], __int_as_float(s.type_of[k])); area = sa[k]; }
+        }
+        sm.near_pos[q] = v; sm.near_sa[q] = area;
+    }
+    {   // exposed carbons in Gaussian range, in list order
+        const int n3 = a.clist ? a.n_clist : c1;
+        const float4 *cposc = a.cpos + (long long)c * s.n_carbon;
+        float4 *spos = a.scratch_pos + (long long)c * s.n_carbon;
+        double *sw = a.scratch_w + (long long)c * s.n_carbon;
+        for (int q0 = 0; q0 < n3; q0 += CT_THREADS) {
+            const int q = q0 + tid;
+            int ck = -1; double w = 0.0;
+            if (q < n3) { ck = a.clist ? a.clist[q] : q; if (ck < c1) w = w0c[ck]; }
+            const bool on = w != 0.0;
+            const unsigned b = __ballot_sync(0xffffffffu, on);
+            if (lane == 0) sm.warp_cnt[warp] = __popc(b);
+            __syncthreads();
+            int base = sm.n_carb;
+            for (int ww = 0; ww < warp; ++ww) base += sm.warp_cnt[ww];
+            if (on) {
+                const int idx = base + __popc(b & ((1u << lane) - 1u));
+                const float4 p = cposc[ck];
+                if (idx < CT_CARB) { sm.carb_pos[idx] = p; sm.carb_w[idx] = w; }
+                else { spos[idx] = p; sw[idx] = w; }
+            }
+            __syncthreads();
+            if (tid == 0) { int tot = 0; for (int ww = 0; ww < CT_WARPS; ++ww) tot += sm.warp_cnt[ww]; sm.n_carb += tot; }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    const int n_carb = sm.n_carb;
+    const float4 *spos = a.scratch_pos + (long long)c * s.n_carbon;
+    const double *sw = a.scratch_w + (long long)c * s.n_carbon;
+
+    // ---- trials, one per warp at a time ----
+    float4 *ta = sm.ta[warp]; float4 *tc = sm.tc[warp]; double *tw = sm.tw[warp];
+    int *hit_q = sm.hit_q[warp]; unsigned *hit_m = sm.hit_m[warp];
+    float4 *lpos = sm.lpos[warp]; double *ldel = sm.ldel[warp];
+    for (int it = warp; it < n_active; it += CT_WARPS) {
+        const int t = sm.trials[it];
+        __syncwarp();
+        int tb0 = -1, tb1 = -1, tb2 = -1, tb3 = -1;
+        if (lane < m) {
+            const int g = e1 + lane;
+            const float4 q = a.trial4[(long long)c * a.trial4_stride + (long long)t * a.n_new + (s.typed_atom[g] - a.first_new)];
+            ta[lane] = make_float4(q.x, q.y, q.z, __int_as_float(s.type_of[g]));
+            tb0 = s.bonded[g * MAXB]; tb1 = s.bonded[g * MAXB + 1]; tb2 = s.bonded[g * MAXB + 2]; tb3 = s.bonded[g * MAXB + 3];
+        }
+        if (lane < MAX_NEW_C) { tw[lane] = 0.0; tc[lane] = make_float4(0.f, 0.f, 0.f, 0.f); }
+        __syncwarp();
+        // pass A: which staged atoms have a trial atom within the (padded) surface range
+        int n_hits = 0;
+        for (int q0 = 0; q0 < n_near; q0 += 32) {
+            const int q = q0 + lane;
+            unsigned bits = 0;
+            if (q < n_near) {
+                float4 p;
+                if (q < CT_NEAR) p = sm.near_pos[q];
+                else {
+                    const int k = a.near ? a.near[q] : q;
+                    p = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+                    if (k < e1) { const float *g = cbase + (long long)s.typed_atom[k] * 3; if (g[0] <= ABSENT_X) p = make_float4(g[0], g[1], g[2], 0.f); }
+                }
+                if (__float_as_int(p.w) >= 0)
+#pragma unroll
+                    for (int n = 0; n < MAX_NEW_T; ++n)
+                        if (n < m) { const float4 u = ta[n]; if (dist2_fast(p.x, p.y, p.z, u.x, u.y, u.z) < s.pre2) bits |= 1u << n; }
+            }
+            const unsigned b = __ballot_sync(0xffffffffu, bits != 0);
+            if (bits != 0) {
+                const int idx = n_hits + __popc(b & ((1u << lane) - 1u));
+                if (idx < CT_HITS) { hit_q[idx] = q; hit_m[idx] = bits; }
+            }
+            n_hits += __popc(b);
+        }
+        bool over = n_hits > CT_HITS;
+        n_hits = min(n_hits, CT_HITS);
+        __syncwarp();
+        // pass B: the factors of both surface products, lanes over the hit list
+        double tp[MAX_NEW_T];
+#pragma unroll
+        for (int n = 0; n < MAX_NEW_T; ++n) tp[n] = 1.0;
+        double acc = 0.0;
+        int n_list = 0;
+        for (int h0 = 0; h0 < n_hits; h0 += 32) {
+            const int hh = h0 + lane;
+            const bool have = hh < n_hits;
+            double f = 1.0;
+            int k = -1; float xk = 0.f, yk = 0.f, zk = 0.f; double area = 0.0;
+            if (have) {
+                const int q = hit_q[hh];
+                const unsigned bits = hit_m[hh];
+                k = a.near ? a.near[q] : q;
+                int tk;
+                if (q < CT_NEAR) { const float4 p = sm.near_pos[q]; xk = p.x; yk = p.y; zk = p.z; tk = __float_as_int(p.w); area = sm.near_sa[q]; }
+                else { const float *g = cbase + (long long)s.typed_atom[k] * 3; xk = g[0]; yk = g[1]; zk = g[2]; tk = s.type_of[k]; area = sa[k]; }
+                const int4 bk = *reinterpret_cast<const int4 *>(s.bonded + (long long)k * MAXB);
+#pragma unroll
+                for (int n = 0; n < MAX_NEW_T; ++n) {
+                    if ((bits >> n) & 1u) {
+                        const float4 u = ta[n];
+                        const float d = __fsqrt_rn(norm2_f32(xk, yk, zk, u.x, u.y, u.z));
+                        const int tn = __float_as_int(u.w);
+                        const double thr = sm.thr[tk * nt + tn];
+                        if ((double)d < thr) {
+                            const int g = e1 + n;
+                            const double pij = (g == bk.x || g == bk.y || g == bk.z || g == bk.w) ? s.pij_bonded : s.pij_non_bonded;
+                            double t_kn, t_nk;
+                            sasa_term_pair(sm.P[tk], sm.invS[tk], sm.R[tk], sm.piRRs[tk], sm.P[tn], sm.invS[tn], sm.R[tn], sm.piRRs[tn],
+                                           thr, d, pij, t_kn, t_nk);
+                            f *= t_kn; tp[n] *= t_nk;
+                        }
+                    }
+                }
+            }
+            double del = 0.0;
+            if (have && f != 1.0) {
+                const int ck = a.carbon_ord[k];
+                if (ck >= 0) {
+                    const double ar = area * f;
+                    const double w = ar > s.sa_threshold ? tanh_area(ar) : 0.0;
+                    del = w - w0c[ck];
+                    if (del != 0.0) acc += del * f0c[ck];
+                }
+            }
+            const unsigned b = __ballot_sync(0xffffffffu, del != 0.0);
+            if (del != 0.0) {
+                const int idx = n_list + __popc(b & ((1u << lane) - 1u));
+                if (idx < CT_LIST) { lpos[idx] = make_float4(xk, yk, zk, 0.f); ldel[idx] = del; }
+            }
+            n_list += __popc(b);
+        }
+        over |= n_list > CT_LIST;
+        const int L = min(n_list, CT_LIST);
+        // products over the lanes, per trial atom (fixed butterfly order)
+#pragma unroll
+        for (int n = 0; n < MAX_NEW_T; ++n) {
+            if (n < m) {
+                double v = tp[n];
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) v *= __shfl_xor_sync(0xffffffffu, v, off);
+                tp[n] = v;
+            }
+        }
+        // phase 2: the trial's atoms among themselves -> their areas and weights (lane = trial atom)
+        {
+            double prod = 1.0;
+#pragma unroll
+            for (int n = 0; n < MAX_NEW_T; ++n) if (n == lane) prod = tp[n];
+            if (lane < m) {
+                const float4 me = ta[lane];
+                const int ti = __float_as_int(me.w);
+                for (int n = 0; n < m; ++n) {
+                    if (n == lane) continue;
+                    const float4 q = ta[n];
+                    const float d = __fsqrt_rn(norm2_f32(me.x, me.y, me.z, q.x, q.y, q.z));
+                    const int tn = __float_as_int(q.w);
+                    const double thr = sm.thr[ti * nt + tn];
+                    if ((double)d < thr) {
+                        const int g = e1 + n;
+                        const bool bonded = g == tb0 || g == tb1 || g == tb2 || g == tb3;
+                        prod = __dmul_rn(prod, sasa_term(sm.P[ti], sm.S[ti], sm.R[ti], sm.piRRs[tn], sm.R[tn], thr, d,
+                                                         bonded ? s.pij_bonded : s.pij_non_bonded));
+                    }
+                }
+                const int ck = a.carbon_ord[e1 + lane];
+                if (ck >= 0) {
+                    const double ar = __dmul_rn(sm.S[ti], prod);
+                    tw[ck - c1] = ar > s.sa_threshold ? tanh_area(ar) : 0.0;
+                    tc[ck - c1] = make_float4(me.x, me.y, me.z, 0.f);
+                }
+            }
+        }
+        __syncwarp();
+        // phase 3a: trial carbons x exposed environment carbons (weights of the environment alone)
+        for (int q = lane; q < n_carb; q += 32) {
+            float4 p; double wk;
+            if (q < CT_CARB) { p = sm.carb_pos[q]; wk = sm.carb_w[q]; } else { p = spos[q]; wk = sw[q]; }
+            for (int n = 0; n < mc; ++n) {
+                const double wn = tw[n];
+                const float4 u = tc[n];
+                if (wn != 0.0 && dist2_fast(p.x, p.y, p.z, u.x, u.y, u.z) < cut2)
+                    acc += wn * wk * gauss3(s, __fsqrt_rn(norm2_f32(p.x, p.y, p.z, u.x, u.y, u.z)));
+            }
+        }
+        // phase 3b: the changed environment carbons: with the trial carbons, and among themselves
+        for (int i = lane; i < L; i += 32) {
+            const float4 pa = lpos[i];
+            const double da = ldel[i];
+            for (int n = 0; n < mc; ++n) {
+                const double wn = tw[n];
+                const float4 u = tc[n];
+                if (wn != 0.0 && dist2_fast(pa.x, pa.y, pa.z, u.x, u.y, u.z) < cut2)
+                    acc += wn * da * gauss3(s, __fsqrt_rn(norm2_f32(pa.x, pa.y, pa.z, u.x, u.y, u.z)));
+            }
+            for (int j = i + 1; j < L; ++j) {
+                const float4 pb = lpos[j];
+                if (dist2_fast(pa.x, pa.y, pa.z, pb.x, pb.y, pb.z) < cut2)
+                    acc += da * ldel[j] * gauss3(s, __fsqrt_rn(norm2_f32(pa.x, pa.y, pa.z, pb.x, pb.y, pb.z)));
+            }
+        }
+        // phase 3c: trial carbons among themselves
+        if (lane < mc) {
+            const float4 pa = tc[lane];
+            for (int j = lane + 1; j < mc; ++j) {
+                const float4 pb = tc[j];
+                if (tw[lane] != 0.0 && tw[j] != 0.0 && dist2_fast(pa.x, pa.y, pa.z, pb.x, pb.y, pb.z) < cut2)
+                    acc += tw[lane] * tw[j] * gauss3(s, __fsqrt_rn(norm2_f32(pa.x, pa.y, pa.z, pb.x, pb.y, pb.z)));
+            }
+        }
+        acc = warp_sum_fixed(acc);
+        if (lane == 0) {
+            out[t] = a.v0[c] + acc;
+            if (over) { atomicExch(a.overflow, 1); if (a.overflow_conf) a.overflow_conf[c] = 1; }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // carrying the environment state from one growth step to the next
 // ------------------------------------------------------------------------------------------------
 // Between two steps the environment only gains the atoms [L, F): the side chain selected at the previous step (and
@@ -454,50 +794,67 @@ __global__ void __launch_bounds__(HT) hpmf_extend_kernel(
     double tp[MAX_NEW_T];
 #pragma unroll
     for (int n = 0; n < MAX_NEW_T; ++n) tp[n] = 1.0;
-    for (int k = tid; k < eL; k += HT) {
-        const float *p = cbase + (long long)s.typed_atom[k] * 3;
-        const float xk = p[0], yk = p[1], zk = p[2];
-        if (xk > ABSENT_X) continue;
-        int tk = -1, b0 = -1, b1 = -1, b2 = -1, b3 = -1;
-        double f = 1.0;
+    // (the list of changed carbons is filled in atom order - ballots and a scan over the warps, no atomics - so that the
+    //  float64 sums taken over it later do not depend on the scheduling: repeated runs are bitwise identical)
+    __shared__ int s_wcnt[HT / 32];
+    for (int k0 = 0; k0 < eL; k0 += HT) {
+        const int k = k0 + tid;
+        double del = 0.0; float xk = 0.f, yk = 0.f, zk = 0.f; int ck = -1;
+        if (k < eL) {
+            const float *p = cbase + (long long)s.typed_atom[k] * 3;
+            xk = p[0]; yk = p[1]; zk = p[2];
+            if (xk <= ABSENT_X) {
+                int tk = -1, b0 = -1, b1 = -1, b2 = -1, b3 = -1;
+                double f = 1.0;
 #pragma unroll
-        for (int n = 0; n < MAX_NEW_T; ++n) {
-            if (n < m) {
-                const float4 q = ta[n];
-                if (dist2_fast(xk, yk, zk, q.x, q.y, q.z) < s.pre2) {
-                    const float d = __fsqrt_rn(norm2_f32(xk, yk, zk, q.x, q.y, q.z));
-                    if (tk < 0) {
-                        tk = s.type_of[k];
-                        b0 = s.bonded[k * MAXB]; b1 = s.bonded[k * MAXB + 1]; b2 = s.bonded[k * MAXB + 2]; b3 = s.bonded[k * MAXB + 3];
+                for (int n = 0; n < MAX_NEW_T; ++n) {
+                    if (n < m) {
+                        const float4 q = ta[n];
+                        if (dist2_fast(xk, yk, zk, q.x, q.y, q.z) < s.pre2) {
+                            const float d = __fsqrt_rn(norm2_f32(xk, yk, zk, q.x, q.y, q.z));
+                            if (tk < 0) {
+                                tk = s.type_of[k];
+                                b0 = s.bonded[k * MAXB]; b1 = s.bonded[k * MAXB + 1]; b2 = s.bonded[k * MAXB + 2]; b3 = s.bonded[k * MAXB + 3];
+                            }
+                            const int tn = __float_as_int(q.w);
+                            const double thr = s_thr[tk * nt + tn];
+                            if ((double)d < thr) {
+                                const int g = eL + n;
+                                const double pij = (g == b0 || g == b1 || g == b2 || g == b3) ? s.pij_bonded : s.pij_non_bonded;
+                                f = __dmul_rn(f, sasa_term(s_P[tk], s_S[tk], s_R[tk], s_piRRs[tn], s_R[tn], thr, d, pij));
+                                tp[n] = __dmul_rn(tp[n], sasa_term(s_P[tn], s_S[tn], s_R[tn], s_piRRs[tk], s_R[tk], thr, d, pij));
+                            }
+                        }
                     }
-                    const int tn = __float_as_int(q.w);
-                    const double thr = s_thr[tk * nt + tn];
-                    if ((double)d < thr) {
-                        const int g = eL + n;
-                        const double pij = (g == b0 || g == b1 || g == b2 || g == b3) ? s.pij_bonded : s.pij_non_bonded;
-                        f = __dmul_rn(f, sasa_term(s_P[tk], s_S[tk], s_R[tk], s_piRRs[tn], s_R[tn], thr, d, pij));
-                        tp[n] = __dmul_rn(tp[n], sasa_term(s_P[tn], s_S[tn], s_R[tn], s_piRRs[tk], s_R[tk], thr, d, pij));
+                }
+                if (f != 1.0) {
+                    const double a = sa[k] * f;
+                    sa[k] = a;
+                    ck = carbon_ord[k];
+                    if (ck >= 0) {
+                        const double w = a > s.sa_threshold ? tanh_area(a) : 0.0;
+                        del = w - w0c[ck];
+                        if (del != 0.0) w0c[ck] = w;
                     }
                 }
             }
         }
-        if (f != 1.0) {
-            const double a = sa[k] * f;
-            sa[k] = a;
-            const int ck = carbon_ord[k];
-            if (ck >= 0) {
-                const double w = a > s.sa_threshold ? tanh(a) : 0.0;
-                const double del = w - w0c[ck];
-                if (del != 0.0) {
-                    w0c[ck] = w;
-                    const int idx = atomicAdd(&ln, 1);
-                    if (idx < EXT_LIST) {
-                        const long long o = (long long)c * EXT_LIST + idx;
-                        ext_pos[o] = make_float4(xk, yk, zk, 0.f); ext_del[o] = del; ext_ck[o] = ck;
-                    }
-                }
+        const bool on = del != 0.0;
+        const unsigned bal = __ballot_sync(0xffffffffu, on);
+        if ((tid & 31) == 0) s_wcnt[tid >> 5] = __popc(bal);
+        __syncthreads();
+        int base = ln;
+        for (int w = 0; w < (tid >> 5); ++w) base += s_wcnt[w];
+        if (on) {
+            const int idx = base + __popc(bal & ((1u << (tid & 31)) - 1u));
+            if (idx < EXT_LIST) {
+                const long long o = (long long)c * EXT_LIST + idx;
+                ext_pos[o] = make_float4(xk, yk, zk, 0.f); ext_del[o] = del; ext_ck[o] = ck;
             }
         }
+        __syncthreads();
+        if (tid == 0) { int tot = 0; for (int w = 0; w < HT / 32; ++w) tot += s_wcnt[w]; ln += tot; }
+        __syncthreads();
     }
 #pragma unroll
     for (int n = 0; n < MAX_NEW_T; ++n) {
@@ -533,7 +890,7 @@ __global__ void __launch_bounds__(HT) hpmf_extend_kernel(
         const double a = absent ? 0.0 : __dmul_rn(s_S[ti], prod);
         sa[eL + tid] = a;
         const int ck = carbon_ord[eL + tid];
-        if (ck >= 0) w0c[ck] = a > s.sa_threshold ? tanh(a) : 0.0;
+        if (ck >= 0) w0c[ck] = a > s.sa_threshold ? tanh_area(a) : 0.0;
     }
     if (tid == 0) {
         ext_n[c] = min(ln, EXT_LIST);
@@ -690,6 +1047,8 @@ struct EnvState {
     size_t ext_cap = 0;
     double *d_partial_new = nullptr;        // [C*tiles*EXT_NEW_C] per-tile sums of the new carbons' fields
     float4 *d_cpos = nullptr;               // [C*n_carbon] packed carbon positions
+    float4 *d_scr_pos = nullptr;            // [C*n_carbon] exposed carbons beyond the per-conformer kernel's shared-memory stage
+    double *d_scr_w = nullptr;
     // carried state: the level (first atom not yet part of the state) the buffers describe
     int state_level = 0, state_nconf = 0;
     const float *state_coords = nullptr;
@@ -706,6 +1065,7 @@ struct mcsce_hpmf_s {
     const int *d_carbon_ord = nullptr;
     int *d_overflow = nullptr;
     bool carry = false;
+    int growth_trial_kernel = 1;            // 1: per-conformer kernel inside mcsce_grow (hpmf_trials_conf_kernel); 0: per-trial kernel
     EnvState es[HPMF_STATES];
     // inside mcsce_grow: per-residue lists of typed environment atoms within SASA range of the residue's side chain
     int *d_near = nullptr, *d_near_c = nullptr;   // typed atoms in SASA range / carbon ordinals in Gaussian range
@@ -801,6 +1161,8 @@ extern "C" int mcsce_hpmf_destroy(mcsce_hpmf h) {
         if (e.d_ext) cudaFree(e.d_ext);
         if (e.d_partial_new) cudaFree(e.d_partial_new);
         if (e.d_cpos) cudaFree(e.d_cpos);
+        if (e.d_scr_pos) cudaFree(e.d_scr_pos);
+        if (e.d_scr_w) cudaFree(e.d_scr_w);
     }
     if (h->d_near) cudaFree(h->d_near);
     if (h->d_near_c) cudaFree(h->d_near_c);
@@ -906,8 +1268,12 @@ static int hpmf_trials_impl(mcsce_hpmf h, EnvState &es, bool carry, int n_conf, 
             es.partial_cap = need_partial;
         }
         if (es.d_cpos) HCK(cudaFree(es.d_cpos));
-        es.d_cpos = nullptr;
+        if (es.d_scr_pos) HCK(cudaFree(es.d_scr_pos));
+        if (es.d_scr_w) HCK(cudaFree(es.d_scr_w));
+        es.d_cpos = nullptr; es.d_scr_pos = nullptr; es.d_scr_w = nullptr;
         HCK(cudaMalloc(&es.d_cpos, (size_t)n_conf * std::max(1, v.n_carbon) * sizeof(float4)));
+        HCK(cudaMalloc(&es.d_scr_pos, (size_t)n_conf * std::max(1, v.n_carbon) * sizeof(float4)));
+        HCK(cudaMalloc(&es.d_scr_w, (size_t)n_conf * std::max(1, v.n_carbon) * sizeof(double)));
     }
     double *sa_env = es.d_env_state;
     double *w0 = sa_env + (size_t)n_conf * v.n_typed;
@@ -952,7 +1318,21 @@ static int hpmf_trials_impl(mcsce_hpmf h, EnvState &es, bool carry, int n_conf, 
     es.state_level = first_new; es.state_nconf = n_conf; es.state_coords = d_coords;
     if (c1 > 0) hpmf_pack_carbons_kernel<<<dim3((c1 + 127) / 128, n_conf), 128, 0, st>>>(v, d_coords, c1, es.d_cpos);
     // every trial on top of it
-    {
+    if (x.trial4 && h->growth_trial_kernel && n_trials <= CT_TRIALS) {
+        ConfTrialArgs a{};
+        a.s = v; a.coords = d_coords; a.trial4 = x.trial4; a.trial4_stride = x.trial4_stride; a.mask = d_mask;
+        a.first_new = first_new; a.n_new = n_new; a.n_trials = n_trials; a.e1 = e1; a.m = m; a.c1 = c1; a.mc = mc;
+        a.carbon_ord = h->d_carbon_ord; a.sa_env = sa_env; a.w0 = w0; a.f0 = f0; a.v0 = v0; a.out = d_v;
+        a.overflow = h->d_overflow; a.overflow_conf = x.overflow_conf;
+        a.near = x.near; a.n_near = x.n_near; a.clist = x.clist; a.n_clist = x.n_clist;
+        a.cpos = es.d_cpos; a.scratch_pos = es.d_scr_pos; a.scratch_w = es.d_scr_w;
+        static bool attr_set = false;
+        if (!attr_set) {
+            HCK(cudaFuncSetAttribute(hpmf_trials_conf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ConfTrialSmem)));
+            attr_set = true;
+        }
+        hpmf_trials_conf_kernel<<<n_conf, CT_THREADS, sizeof(ConfTrialSmem), st>>>(a);
+    } else {
         static int minb = -1;                 // tuning knob: resident blocks per SM the kernel is compiled for
         if (minb < 0) { const char *e = getenv("MCSCE_B200_HPMF_MINB"); minb = e ? atoi(e) : TRIAL_MINB_DEFAULT; }
         const dim3 grid(n_trials, n_conf);
@@ -1073,6 +1453,12 @@ int mcsce_hpmf_growth_step(mcsce_hpmf h, int lane, int residue, int n_conf, cons
         x.clist = h->d_near_c + h->near_c_off[residue]; x.n_clist = h->near_c_off[residue + 1] - h->near_c_off[residue];
     }
     return hpmf_trials_impl(h, h->es[lane + 1], true, n_conf, d_coords, first_new, n_new, n_trials, nullptr, d_mask, d_v, st, x);
+}
+
+extern "C" int mcsce_hpmf_set_option(mcsce_hpmf h, int key, int value) {
+    if (!h) return mcsce_fail_shared("mcsce_hpmf_set_option: null handle");
+    if (key == 0) { h->growth_trial_kernel = value ? 1 : 0; return 0; }
+    return mcsce_fail_shared("mcsce_hpmf_set_option: unknown key");
 }
 
 extern "C" int mcsce_hpmf_carry(mcsce_hpmf h, int enable) {

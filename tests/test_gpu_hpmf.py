@@ -475,8 +475,9 @@ def test_fused_growth_with_hpmf_equals_the_host_driven_loop(which, n_conf):
             fin = np.isfinite(ref)
             # (the lj/coulomb part differs at float32-sum level between the two loops: the fused one scores the chi-independent
             #  atoms once per residue, the single-kernel entry point scores them in every trial; the hpmf part is the same
-            #  arithmetic - with and without the residue lists it agrees to 2e-13, tools/diag_hpmf_lists.py)
-            assert np.allclose(got[fin], ref[fin], rtol=2e-6, atol=1e-5), (which, c, i, np.abs(got[fin] - ref[fin]).max())
+            #  arithmetic - with and without the residue lists it agrees to 2e-13, tools/diag_hpmf_lists.py.  The float32 error
+            #  scales with the size of the partial sums, not of the total: half the north-star absolute tolerance is allowed)
+            assert np.allclose(got[fin], ref[fin], rtol=2e-6, atol=5e-4), (which, c, i, np.abs(got[fin] - ref[fin]).max())
             n_cmp += int(fin.sum())
     assert n_cmp > 100
     ok = ok_f.astype(bool)
@@ -503,3 +504,22 @@ def test_fused_hpmf_growth_in_two_conformer_groups():
         assert np.array_equal(part["coords"], xyz[lo:lo + half])
     again = eng.grow(n, beta, seed=5, hpmf=calc, env_split=1, host_out=True)
     assert np.array_equal(again["energy"], e, equal_nan=True)
+
+
+def test_per_conformer_trial_kernel_equals_per_trial_kernel():
+    """Inside mcsce_grow the trials of a conformer are evaluated by one block (a warp per trial, the residue's lists staged in
+    shared memory); ``mcsce_hpmf_set_option(h, 0, 0)`` switches the growth back to the block-per-trial kernel that
+    ``mcsce_hpmf_trials`` runs (pinned against whole-structure evaluations above): same selections, energies to 1e-12."""
+    s, sysm, eng = _workload(3)
+    calc = _calc_for(sysm, eng)
+    beta = 1.0 / (300 * 0.008314462)
+    u = np.random.default_rng(2).random((6, sysm.n_res))
+    a = eng.grow(6, beta, seed=4, uniforms=u, dump=True, hpmf=calc)
+    assert calc.lib.mcsce_hpmf_set_option(calc.h, 0, 0) == 0
+    b = eng.grow(6, beta, seed=4, uniforms=u, dump=True, hpmf=calc)
+    assert calc.lib.mcsce_hpmf_set_option(calc.h, 0, 1) == 0
+    assert np.array_equal(a["selected"].cpu().numpy(), b["selected"].cpu().numpy())
+    ta, tb = a["trial_energy"].cpu().numpy(), b["trial_energy"].cpu().numpy()
+    assert np.array_equal(np.isfinite(ta), np.isfinite(tb))
+    fin = np.isfinite(ta)
+    assert fin.sum() > 10000 and np.allclose(ta[fin], tb[fin], rtol=1e-12, atol=1e-10)
