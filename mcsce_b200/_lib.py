@@ -12,6 +12,8 @@ from pathlib import Path
 import os
 
 LIB_PATH = Path(os.environ.get("MCSCE_B200_LIB") or (Path(__file__).resolve().parent / "libmcsce_b200.so"))
+if os.environ.get("MCSCE_B200_LIB"):          # build variants for timing experiments (tools/)
+    LIB_PATH = Path(os.environ["MCSCE_B200_LIB"])
 
 MAX_CLS, MAX_SP_ENV, MAX_CHI, MAX_CHI_ROT, MAX_TMPL, MAX_SC = 64, 16, 6, 5, 32, 28
 

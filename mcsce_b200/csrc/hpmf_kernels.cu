@@ -292,49 +292,65 @@ __global__ void __launch_bounds__(HT, MINB) hpmf_trial_kernel(
     // (with a near list only the typed atoms that can be in SASA range of the side chain are visited - a complete list,
     //  built from rigorous reach bounds, so the factors found are the same; the order of the float64 products per trial
     //  atom is the list's ascending order either way)
+    // (the list of changed carbons is filled in scan order - ballots and a scan over the warps, no atomics - so that the float64
+    //  sums over it do not depend on the scheduling: the same call gives the same bits)
+    __shared__ int s_wcnt[HT / 32];
     const int n_scan = near ? n_near : e1;
-    for (int q0 = tid; q0 < n_scan; q0 += HT) {
-        const int k = near ? near[q0] : q0;
-        if (k >= e1) continue;
-        const float *p = cbase + (long long)s.typed_atom[k] * 3;
-        const float xk = p[0], yk = p[1], zk = p[2];
-        if (xk > ABSENT_X) continue;
-        int tk = -1, b0 = -1, b1 = -1, b2 = -1, b3 = -1;
-        double f = 1.0;
+    for (int qb = 0; qb < n_scan; qb += HT) {
+        const int q0 = qb + tid;
+        double del = 0.0; float xk = 0.f, yk = 0.f, zk = 0.f;
+        const int k = q0 < n_scan ? (near ? near[q0] : q0) : e1;
+        if (k < e1) {
+            const float *p = cbase + (long long)s.typed_atom[k] * 3;
+            xk = p[0]; yk = p[1]; zk = p[2];
+            if (xk <= ABSENT_X) {
+                int tk = -1, b0 = -1, b1 = -1, b2 = -1, b3 = -1;
+                double f = 1.0;
 #pragma unroll
-        for (int n = 0; n < MAX_NEW_T; ++n) {
-            if (n < m) {
-                const float4 q = ta[n];
-                if (dist2_fast(xk, yk, zk, q.x, q.y, q.z) < s.pre2) {
-                    const float d = __fsqrt_rn(norm2_f32(xk, yk, zk, q.x, q.y, q.z));
-                    if (tk < 0) {
-                        tk = s.type_of[k];
-                        b0 = s.bonded[k * MAXB]; b1 = s.bonded[k * MAXB + 1]; b2 = s.bonded[k * MAXB + 2]; b3 = s.bonded[k * MAXB + 3];
+                for (int n = 0; n < MAX_NEW_T; ++n) {
+                    if (n < m) {
+                        const float4 q = ta[n];
+                        if (dist2_fast(xk, yk, zk, q.x, q.y, q.z) < s.pre2) {
+                            const float d = __fsqrt_rn(norm2_f32(xk, yk, zk, q.x, q.y, q.z));
+                            if (tk < 0) {
+                                tk = s.type_of[k];
+                                b0 = s.bonded[k * MAXB]; b1 = s.bonded[k * MAXB + 1]; b2 = s.bonded[k * MAXB + 2]; b3 = s.bonded[k * MAXB + 3];
+                            }
+                            const int tn = __float_as_int(q.w);
+                            const double thr = s_thr[tk * nt + tn];
+                            if ((double)d < thr) {
+                                const int g = e1 + n;
+                                const double pij = (g == b0 || g == b1 || g == b2 || g == b3) ? s.pij_bonded : s.pij_non_bonded;
+                                f = __dmul_rn(f, sasa_term(s_P[tk], s_S[tk], s_R[tk], s_piRRs[tn], s_R[tn], thr, d, pij));
+                                tp[n] = __dmul_rn(tp[n], sasa_term(s_P[tn], s_S[tn], s_R[tn], s_piRRs[tk], s_R[tk], thr, d, pij));
+                            }
+                        }
                     }
-                    const int tn = __float_as_int(q.w);
-                    const double thr = s_thr[tk * nt + tn];
-                    if ((double)d < thr) {
-                        const int g = e1 + n;
-                        const double pij = (g == b0 || g == b1 || g == b2 || g == b3) ? s.pij_bonded : s.pij_non_bonded;
-                        f = __dmul_rn(f, sasa_term(s_P[tk], s_S[tk], s_R[tk], s_piRRs[tn], s_R[tn], thr, d, pij));
-                        tp[n] = __dmul_rn(tp[n], sasa_term(s_P[tn], s_S[tn], s_R[tn], s_piRRs[tk], s_R[tk], thr, d, pij));
+                }
+                if (f != 1.0) {
+                    const int ck = carbon_ord[k];
+                    if (ck >= 0) {
+                        const double a = sa[k] * f;
+                        const double w = a > s.sa_threshold ? tanh_area(a) : 0.0;
+                        del = w - w0c[ck];
+                        if (del != 0.0) acc += del * f0c[ck];
                     }
                 }
             }
         }
-        if (f != 1.0) {
-            const int ck = carbon_ord[k];
-            if (ck >= 0) {
-                const double a = sa[k] * f;
-                const double w = a > s.sa_threshold ? tanh_area(a) : 0.0;
-                const double del = w - w0c[ck];
-                if (del != 0.0) {
-                    acc += del * f0c[ck];
-                    const int idx = atomicAdd(&ln, 1);
-                    if (idx < MAX_LIST) { lpos[idx] = make_float4(xk, yk, zk, 0.f); ldel[idx] = del; }
-                }
-            }
+        const bool on = del != 0.0;
+        const unsigned bal = __ballot_sync(0xffffffffu, on);
+        if ((tid & 31) == 0) s_wcnt[tid >> 5] = __popc(bal);
+        __syncthreads();
+        int base = ln;
+        for (int w = 0; w < (tid >> 5); ++w) base += s_wcnt[w];
+        if (on) {
+            const int idx = base + __popc(bal & ((1u << (tid & 31)) - 1u));
+            if (idx < MAX_LIST) { lpos[idx] = make_float4(xk, yk, zk, 0.f); ldel[idx] = del; }
         }
+        __syncthreads();
+        if (tid == 0) { int tot = 0; for (int w = 0; w < HT / 32; ++w) tot += s_wcnt[w]; ln += tot; }
+        __syncthreads();
     }
     // block-wide products for the trial atoms
 #pragma unroll
@@ -445,6 +461,9 @@ __global__ void __launch_bounds__(HT, MINB) hpmf_trial_kernel(
 //   pass B  lanes over the hit list (dense: every lane has work): exact distances, float64 factors for both surface products
 //   phase 2 the trial's own atoms, lane = atom;  phase 3 Gaussian sums, lanes over the staged carbons / the changed carbons
 // Same terms in the same arithmetic as hpmf_trial_kernel (float64 products are taken in another order: 1e-13 relative).
+// Measured alternatives (round 2, config 3, ms per 2048 conformers with the term / without = 540): this kernel 893; a version
+// with a bounding-sphere prefilter, one (atom, trial atom) pair per lane in pass B and 16 warps per block 995 (8 warps 1185):
+// the denser lanes did not pay for the extra list passes.
 #define CT_WARPS 8
 #define CT_THREADS (CT_WARPS * 32)
 #define CT_TRIALS 1024         // trials per residue the kernel indexes (the reference's largest set: 729)
