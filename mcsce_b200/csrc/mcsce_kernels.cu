@@ -1220,7 +1220,10 @@ struct mcsce_handle_s {
     int sm_count = 148;
     std::vector<void *> sys_allocs;
     char *bb_slab = nullptr;              // backbone-dependent tables: one grow-only device allocation, refilled by set_backbone
+    char *bb_stage = nullptr;             // its pinned host image: one copy per backbone
     size_t bb_cap = 0;
+    const double2 *d_bb_rows = nullptr, *d_bb_pairs = nullptr;   // scratch of the input-atom energy (inside the slab)
+    cudaEvent_t bb_ready = nullptr;       // recorded when set_backbone's copies and kernels are enqueued
     SysDev d{};
     bool has_sys = false, has_bb = false;
     bool warned_screen_limit = false;
@@ -1339,6 +1342,7 @@ extern "C" int mcsce_create(mcsce_handle *out, int device) {
     if (const char *e = getenv("MCSCE_B200_TILE_OVERHEAD")) h->rule.overhead = (float)atof(e);
     CK(cudaMalloc((void **)&h->d_input_energy, sizeof(double)));
     CK(cudaMallocHost((void **)&h->h_n_dead, sizeof(int) * MAX_LANES));
+    CK(cudaEventCreateWithFlags(&h->bb_ready, cudaEventDisableTiming));
     *out = h;
     return 0;
 }
@@ -1348,6 +1352,8 @@ extern "C" int mcsce_destroy(mcsce_handle h) {
     cudaSetDevice(h->device);
     free_pool(h->sys_allocs);
     if (h->bb_slab) cudaFree(h->bb_slab);
+    if (h->bb_stage) cudaFreeHost(h->bb_stage);
+    if (h->bb_ready) cudaEventDestroy(h->bb_ready);
     for (auto &ln : h->lane) {
         for (auto e : ln.evP) cudaEventDestroy(e);
         for (auto e : ln.evQ) cudaEventDestroy(e);
@@ -1364,7 +1370,6 @@ extern "C" int mcsce_destroy(mcsce_handle h) {
         if (ln.hp_mask) cudaFree(ln.hp_mask);
         if (ln.hp_ovf) cudaFree(ln.hp_ovf);
     }
-    if (h->d_steps) cudaFree(h->d_steps);
     if (h->d_input_energy) cudaFree(h->d_input_energy);
     if (h->d_pairs) cudaFree(h->d_pairs);
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
@@ -1475,9 +1480,7 @@ extern "C" int mcsce_set_system(mcsce_handle h, const mcsce_system_desc *s) {
     if (upload(h, P, s->bb_i, s->n_bb_pairs, &d.bb_i)) return -1;
     if (upload(h, P, s->bb_j, s->n_bb_pairs, &d.bb_j)) return -1;
     if (upload(h, P, s->bb_coef, (size_t)s->n_bb_pairs * 4, &d.bb_coef)) return -1;
-    if (h->d_steps) { cudaFree(h->d_steps); h->d_steps = nullptr; }
-    CK(cudaMalloc((void **)&h->d_steps, sizeof(StepDev) * std::max(1, s->n_res)));
-    d.steps = h->d_steps;
+    d.steps = nullptr;                   // filled by set_backbone (the per-step records carry backbone-dependent fields)
     h->has_sys = true;
     return 0;
 }
@@ -1486,9 +1489,24 @@ static int launch_place(mcsce_handle h, int step, int n_sets, int n_rows, const 
                         long long row_off, double *chis_out, float4 *trial, long long trial_stride,
                         const unsigned char *alive, cudaStream_t st, const double *ori_in = nullptr);
 
-__global__ void store_rigid_kernel(const float4 *src, int sc_start, int n_sc, float *rigid) {
-    const int k = threadIdx.x;
-    if (k < n_sc) { rigid[(sc_start + k) * 3] = src[k].x; rigid[(sc_start + k) * 3 + 1] = src[k].y; rigid[(sc_start + k) * 3 + 2] = src[k].z; }
+// GLY/ALA side chains have no chi: the template is placed once per backbone and shared by every conformer
+// (side_chain_builder.py:164-168).  One block per residue, lane = template atom; same arithmetic as K1's placement step.
+__global__ void __launch_bounds__(32) place_rigid_kernel(SysDev s, float *rigid) {
+    const StepDev &st = s.steps[blockIdx.x];
+    if (st.kind != 1) return;
+    const TmplDev &tm = s.tmpl[st.type];
+    const int lane = threadIdx.x;
+    if (lane >= tm.n_atoms) return;
+    const int rank = tm.sc_rank[lane];
+    if (rank < 0 || rank >= st.n_sc) return;
+    double ox, oy, oz;
+    quat_rotate(st.q1[0], st.q1[1], st.q1[2], st.q1[3], (double)tm.xyz[lane][0], (double)tm.xyz[lane][1], (double)tm.xyz[lane][2], ox, oy, oz);
+    const float rx = __double2float_rn(ox), ry = __double2float_rn(oy), rz = __double2float_rn(oz);
+    quat_rotate(st.q2[0], st.q2[1], st.q2[2], st.q2[3], (double)rx, (double)ry, (double)rz, ox, oy, oz);
+    float *o = rigid + (size_t)(st.sc_start + rank) * 3;
+    o[0] = __double2float_rn(__dadd_rn(ox, (double)st.ca[0]));
+    o[1] = __double2float_rn(__dadd_rn(oy, (double)st.ca[1]));
+    o[2] = __double2float_rn(__dadd_rn(oz, (double)st.ca[2]));
 }
 
 // Neighbour screen lists.  A trial that clashes with any atom is +inf no matter what else it touches, and most clashes
@@ -1647,18 +1665,20 @@ extern "C" int mcsce_set_backbone(mcsce_handle h, const mcsce_backbone_desc *b) 
         }
     }
     if (ensure_dyn_smem(select_kernel, sizeof(double) * 2 * (size_t)h->max_trials, "mcsce_set_backbone")) return -1;
-    CK(cudaMemcpy(h->d_steps, h->steps.data(), sizeof(StepDev) * d.n_res, cudaMemcpyHostToDevice));
     h->input_xyz_host.assign(b->input_xyz, b->input_xyz + (size_t)d.n_input * 3);
     std::vector<int> scr_off, scr_slots, scr_prefix;
     if (build_screen_lists(h, b, scr_off, scr_slots, scr_prefix)) return -1;
     if (dbg) fprintf(stderr, "[mcsce_b200] set_backbone: +screen lists (host) %.2f ms\n", ms_since(t_start));
-    // all backbone-dependent device tables live in one grow-only allocation (no cudaMalloc/cudaFree per backbone)
+    // All backbone-dependent device tables live in one grow-only allocation and travel in ONE copy from a pinned staging
+    // buffer (no cudaMalloc/cudaFree per backbone, no per-table synchronous copies); the kernels that finish the tables
+    // (GLY/ALA placement, input-atom energy) follow on the same stream - nothing here waits for the device again.
     float *rigid = nullptr;
     {
-        std::vector<float> nanv((size_t)d.n_atoms * 3, NAN);
         struct Item { const void *src; size_t bytes; const void **dst; };
         const size_t nt6 = (size_t)b->n_trials_total * MAX_CHI;
+        const void *steps_dst = nullptr, *rigid_dst = nullptr;
         const Item items[] = {
+            {h->steps.data(), sizeof(StepDev) * (size_t)d.n_res, &steps_dst},
             {b->chi_mean, nt6 * sizeof(double), (const void **)&d.chi_mean},
             {b->chi_sigma, nt6 * sizeof(double), (const void **)&d.chi_sigma},
             {b->prob, (size_t)b->n_trials_total * sizeof(double), (const void **)&d.prob},
@@ -1666,51 +1686,44 @@ extern "C" int mcsce_set_backbone(mcsce_handle h, const mcsce_backbone_desc *b) 
             {scr_off.data(), scr_off.size() * sizeof(int), (const void **)&d.scr_off},
             {scr_slots.data(), scr_slots.size() * sizeof(int), (const void **)&d.scr_slot},
             {scr_prefix.data(), scr_prefix.size() * sizeof(int), (const void **)&d.scr_prefix},
-            {nanv.data(), nanv.size() * sizeof(float), (const void **)&d.rigid_xyz},
+            {nullptr, (size_t)d.n_atoms * 3 * sizeof(float), &rigid_dst},                  // rigid_xyz: NaN = not a rigid atom
+            {nullptr, sizeof(double2) * (size_t)std::max(1, d.n_input), (const void **)&h->d_bb_rows},    // input-energy scratch
+            {nullptr, sizeof(double2) * (size_t)std::max(1, d.n_bb_pairs), (const void **)&h->d_bb_pairs},
         };
         size_t need = 0;
         for (const Item &it : items) need += (std::max<size_t>(it.bytes, 1) + 255) / 256 * 256;
         if (need > h->bb_cap) {
             if (h->bb_slab) cudaFree(h->bb_slab);
-            h->bb_slab = nullptr; h->bb_cap = 0;
+            if (h->bb_stage) cudaFreeHost(h->bb_stage);
+            h->bb_slab = nullptr; h->bb_stage = nullptr; h->bb_cap = 0;
             CK(cudaMalloc((void **)&h->bb_slab, need + need / 4));
+            CK(cudaMallocHost((void **)&h->bb_stage, need + need / 4));
             h->bb_cap = need + need / 4;
         }
-        size_t used = 0;
+        size_t used = 0, copy_bytes = 0;
         for (const Item &it : items) {
             char *p = h->bb_slab + used;
+            if (it.src) { memcpy(h->bb_stage + used, it.src, it.bytes); }
+            else if (it.dst == &rigid_dst) {
+                float *f = reinterpret_cast<float *>(h->bb_stage + used);
+                for (size_t k = 0; k < (size_t)d.n_atoms * 3; ++k) f[k] = NAN;
+            }
             used += (std::max<size_t>(it.bytes, 1) + 255) / 256 * 256;
-            if (it.bytes) CK(cudaMemcpy(p, it.src, it.bytes, cudaMemcpyHostToDevice));
+            if (it.src || it.dst == &rigid_dst) copy_bytes = used;
             *it.dst = p;
         }
+        CK(cudaMemcpyAsync(h->bb_slab, h->bb_stage, copy_bytes, cudaMemcpyHostToDevice, 0));
+        d.steps = reinterpret_cast<const StepDev *>(steps_dst);
+        d.rigid_xyz = reinterpret_cast<const float *>(rigid_dst);
         rigid = const_cast<float *>(d.rigid_xyz);
     }
     if (dbg) fprintf(stderr, "[mcsce_b200] set_backbone: +tables %.2f ms\n", ms_since(t_start));
-    // GLY/ALA side chains have no chi: placed once per backbone with K1 (zero rotations) and shared
-    // by every conformer (side_chain_builder.py:164-168)
-    {
-        float4 *tmp = nullptr;
-        CK(cudaMalloc((void **)&tmp, sizeof(float4) * MAX_SC));
-        for (int i = 0; i < d.n_res; ++i) {
-            if (h->steps[i].kind != 1) continue;
-            if (launch_place(h, i, 1, 1, nullptr, 0, 0, nullptr, tmp, 0, nullptr, 0)) { cudaFree(tmp); return -1; }
-            store_rigid_kernel<<<1, 32>>>(tmp, h->steps[i].sc_start, h->steps[i].n_sc, rigid);
-            h->launches += 1;
-        }
-        CK(cudaDeviceSynchronize());
-        cudaFree(tmp);
-    }
-    if (dbg) fprintf(stderr, "[mcsce_b200] set_backbone: +rigid side chains %.2f ms\n", ms_since(t_start));
-    {   // energy of the input atoms alone (side_chain_builder.py:149): a constant of the backbone, every conformer starts from it
-        double2 *rows = nullptr, *pairs = nullptr;
-        CK(cudaMalloc((void **)&rows, sizeof(double2) * std::max(1, d.n_input)));
-        CK(cudaMalloc((void **)&pairs, sizeof(double2) * std::max(1, d.n_bb_pairs)));
-        const int rc = launch_input_energy(h, rows, pairs, h->d_input_energy, 0);
-        cudaDeviceSynchronize();
-        cudaFree(rows); cudaFree(pairs);
-        if (rc) return -1;
-    }
-    if (dbg) fprintf(stderr, "[mcsce_b200] set_backbone: +input energy %.2f ms\n", ms_since(t_start));
+    place_rigid_kernel<<<std::max(1, d.n_res), 32>>>(d, rigid);
+    h->launches += 1;
+    // energy of the input atoms alone (side_chain_builder.py:149): a constant of the backbone, every conformer starts from it
+    if (launch_input_energy(h, const_cast<double2 *>(h->d_bb_rows), const_cast<double2 *>(h->d_bb_pairs), h->d_input_energy, 0)) return -1;
+    CK(cudaEventRecord(h->bb_ready, 0));      // growths on other streams wait for the tables (mcsce_grow)
+    if (dbg) fprintf(stderr, "[mcsce_b200] set_backbone: +rigid side chains, input energy enqueued %.2f ms\n", ms_since(t_start));
     h->has_bb = true;
     return 0;
 }
@@ -1812,18 +1825,16 @@ static int launch_input_energy(mcsce_handle h, double2 *rows, double2 *pairs, do
 extern "C" int mcsce_input_energy(mcsce_handle h, double *d_energy, void *stream) {
     if (!h || !h->has_bb) return fail("set_system/set_backbone first");
     CK(cudaSetDevice(h->device));
-    double2 *rows = nullptr, *pairs = nullptr;
-    CK(cudaMalloc((void **)&rows, sizeof(double2) * std::max(1, h->d.n_input)));
-    CK(cudaMalloc((void **)&pairs, sizeof(double2) * std::max(1, h->d.n_bb_pairs)));
-    int rc = launch_input_energy(h, rows, pairs, d_energy, (cudaStream_t)stream);
-    cudaStreamSynchronize((cudaStream_t)stream);
-    cudaFree(rows); cudaFree(pairs);
-    return rc;
+    // the value is a constant of the backbone, computed by set_backbone: hand out a copy
+    CK(cudaStreamWaitEvent((cudaStream_t)stream, h->bb_ready, 0));
+    CK(cudaMemcpyAsync(d_energy, h->d_input_energy, sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
 }
 
 extern "C" int mcsce_init_env(mcsce_handle h, int n_env_sets, float *d_env, void *stream) {
     if (!h || !h->has_bb) return fail("set_system/set_backbone first");
     CK(cudaSetDevice(h->device));
+    if (!h->capturing) CK(cudaStreamWaitEvent((cudaStream_t)stream, h->bb_ready, 0));
     const long long n = (long long)n_env_sets * h->d.n_atoms;
     init_env_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->d, n_env_sets, (float4 *)d_env);
     h->launches += 1;
@@ -1899,6 +1910,7 @@ extern "C" int mcsce_place_trials_replay(mcsce_handle h, int residue, int n_rows
     if (h->steps[residue].kind == 0) return fail("residue is retained: nothing to place");
     if (!d_chis) return fail("mcsce_place_trials: chi rows are required");
     CK(cudaSetDevice(h->device));
+    CK(cudaStreamWaitEvent((cudaStream_t)stream, h->bb_ready, 0));
     return launch_place(h, residue, 1, n_rows, d_chis, 0, 0, nullptr, (float4 *)d_xyz, 0, nullptr, (cudaStream_t)stream, d_ori);
 }
 
@@ -1920,6 +1932,7 @@ extern "C" int mcsce_score_trials(mcsce_handle h, int residue, int n_env_sets, i
     if (!h || !h->has_bb) return fail("set_system/set_backbone first");
     if (residue < 0 || residue >= h->d.n_res || h->steps[residue].kind != 2) return fail("residue is not a grown residue");
     CK(cudaSetDevice(h->device));
+    CK(cudaStreamWaitEvent((cudaStream_t)stream, h->bb_ready, 0));
     const int split = choose_split(h, residue, n_env_sets, trials_per_env, env_split);
     const size_t n = (size_t)n_env_sets * trials_per_env;
     const size_t need = align_up(n * split * sizeof(double2)) + align_up(n * sizeof(double2));
@@ -2255,6 +2268,7 @@ extern "C" int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *o, void *d_work
     if (workspace_bytes < mcsce_workspace_bytes(h, o->n_conf)) return fail("workspace too small: call mcsce_workspace_bytes");
     cudaStream_t st = (cudaStream_t)stream;
     const int C = o->n_conf;
+    CK(cudaStreamWaitEvent(st, h->bb_ready, 0));       // set_backbone's copy and table kernels run on the default stream
     if (prepare_lane(h, h->lane[0], false)) return -1;
 
     // Launch-bound runs (little work per residue: few conformers and/or a small protein) replay a captured CUDA graph of
