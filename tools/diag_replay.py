@@ -7,7 +7,7 @@ import numpy as np, bench
 from mcsce_b200.engine import GrowthEngine
 from oracle.growth_c import COracle
 wl = sys.argv[1] if len(sys.argv) > 1 else "cfg3"
-s, sysm, n_conf, desc = bench.build_workload(wl)
+s, sysm, n_conf, mode, desc = bench.build_workload(wl)
 eng = GrowthEngine(0).set_system(sysm).set_backbone(s.coords)
 co = COracle(sysm, s.coords)
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 6

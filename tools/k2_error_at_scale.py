@@ -9,7 +9,7 @@ from mcsce_b200.engine import GrowthEngine
 from oracle.growth_c import COracle
 wl = sys.argv[1] if len(sys.argv) > 1 else "cfg3"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 12
-s, sysm, n_conf, desc = bench.build_workload(wl)
+s, sysm, n_conf, mode, desc = bench.build_workload(wl)
 eng = GrowthEngine(0).set_system(sysm).set_backbone(s.coords)
 co = COracle(sysm, s.coords)
 out = eng.grow(n, bench.BETA, seed=7, dump=True, no_graph=True)
