@@ -1212,7 +1212,8 @@ __global__ void finish_kernel(int n_sets, const unsigned char *alive, const doub
 #define MAX_LANES 4
 #endif
 #ifndef LANE_LIMIT
-#define LANE_LIMIT 2                    // conformer groups in flight at most (3 and 4 measured: see DESIGN)
+#define LANE_LIMIT 4                    // conformer groups in flight at most (round 2, interleaved enqueue: 2 / 3 / 4 groups
+                                        // 77.7 / 76.0 / 74.8 ms at 256 conformers of config 3, 539.9 / 537.2 / 536.0 ms at 2048)
 #endif
 
 struct mcsce_handle_s {
@@ -2221,13 +2222,13 @@ static int enqueue_growth(mcsce_handle h, const mcsce_grow_opts *o, const Worksp
     return 0;
 }
 
-// conformer groups in flight for one call: two when each holds at least 96 conformers.  The groups share the environment
+// conformer groups in flight for one call: up to four, each of at least 48 conformers.  The groups share the environment
 // split of the whole call (GrowthEnqueue::groups), so a call's result does not depend on the grouping.
 static int lane_count(const mcsce_handle h, int n_conf) {
     int g = 1;
     if (const char *e = getenv("MCSCE_B200_LANES")) { g = atoi(e); g = std::max(1, std::min(g, MAX_LANES)); }   // tuning knob
     else g = LANE_LIMIT;
-    int per_lane = 96;
+    int per_lane = 48;
     if (const char *e = getenv("MCSCE_B200_LANE_MIN")) per_lane = std::max(1, atoi(e));          // tuning knob
     while (g > 1 && n_conf / g < per_lane) --g;
     return g;
