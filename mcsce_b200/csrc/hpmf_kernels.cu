@@ -11,7 +11,7 @@
 // of 128.  Numerics follow the reference: pair difference, squared norm and square root in float32 (np.linalg.norm
 // of a float32 array: x*x, add.reduce over three elements, sqrt), everything after that in float64, the product
 // over partners in ascending partner order.  Pairs that cannot pass the distance test are rejected on the float32
-// squared distance; Gaussian terms beyond 18 A (< 2e-22 each) are dropped.
+// squared distance; Gaussian terms beyond HPMF_CUTOFF (14 A: < 4.5e-10 each) are dropped.
 
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -30,7 +30,11 @@ int mcsce_fail_shared(const std::string &m);
 #define HT 128                 // threads per block = atoms per tile
 #define MAXB MCSCE_SASA_MAX_BONDS
 #define MAX_SASA_TYPES 32
-#define HPMF_CUTOFF 18.0f
+#ifndef HPMF_CUTOFF
+#define HPMF_CUTOFF 14.0f      // carbon pairs beyond this are dropped: each term is below 0.091 exp(-((14 - 7.117)/1.574)^2) = 4.5e-10,
+                               // a few thousand of them stay five orders of magnitude under the 1e-3 tolerance (18 A before:
+                               // < 2e-22 each, twice the pairs - the Gaussian sums were 40 % of the per-trial kernel, ncu)
+#endif
 #define ABSENT_X 1.0e14f       // x beyond this = atom not placed (the growth parks unplaced atoms at 1e15)
 
 struct HpmfDev {
@@ -467,8 +471,8 @@ __global__ void __launch_bounds__(HT, MINB) hpmf_trial_kernel(
 #define CT_WARPS 8
 #define CT_THREADS (CT_WARPS * 32)
 #define CT_TRIALS 1024         // trials per residue the kernel indexes (the reference's largest set: 729)
-#define CT_NEAR 768            // staged typed atoms in surface range (more: the block falls back to global reads)
-#define CT_CARB 768            // staged exposed carbons in Gaussian range (more: global reads)
+#define CT_NEAR 896            // staged typed atoms in surface range of the residue (more: the conformer is given up, ok = 2)
+#define CT_CARB 640            // staged exposed carbons in Gaussian range (more: global reads)
 #define CT_HITS 192            // (atom, mask) pairs one trial can hit
 #define CT_LIST 160            // environment carbons whose weight one trial changes
 
@@ -481,13 +485,19 @@ struct ConfTrialArgs {
     const int *near; int n_near; const int *clist; int n_clist;
     const float4 *cpos;
     float4 *scratch_pos; double *scratch_w;          // [conformer][n_carbon] exposed carbons beyond the shared-memory stage
+    // The lists come from bounds that hold for every conformer; with the conformer's own coordinates they shrink to the atoms
+    // within reach of the residue: centre = its CA, r2_near = (reach + surface range)^2, r2_carb = (reach + Gaussian cutoff)^2
+    // (r2 <= 0: no filter).
+    float cax, cay, caz, r2_near, r2_carb;
 };
 
 struct ConfTrialSmem {
     double thr[MAX_SASA_TYPES * MAX_SASA_TYPES];
     double R[MAX_SASA_TYPES], piRRs[MAX_SASA_TYPES], P[MAX_SASA_TYPES], S[MAX_SASA_TYPES], invS[MAX_SASA_TYPES];
-    float4 near_pos[CT_NEAR];      // x, y, z, type (int bits; -1 = absent)
+    float4 near_pos[CT_NEAR];      // x, y, z, type (int bits): the typed atoms in surface range of the residue, compacted in order
     double near_sa[CT_NEAR];
+    int near_k[CT_NEAR];           // their typed index
+    int n_near;
     float4 carb_pos[CT_CARB];
     double carb_w[CT_CARB];
     int trials[CT_TRIALS];         // the conformer's trials that passed the clash filter, ascending
@@ -548,17 +558,41 @@ __global__ void __launch_bounds__(CT_THREADS, 2) hpmf_trials_conf_kernel(ConfTri
         sm.R[tid] = s.R[tid]; sm.piRRs[tid] = s.piRRs[tid]; sm.P[tid] = s.P[tid]; sm.S[tid] = s.S[tid];
         sm.invS[tid] = recip_f64(s.S[tid]);
     }
-    const int n_near = a.near ? a.n_near : e1;
-    for (int q = tid; q < min(n_near, CT_NEAR); q += CT_THREADS) {
-        const int k = a.near ? a.near[q] : q;
-        float4 v = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-        double area = 0.0;
-        if (k < e1) {
-            const float *p = cbase + (long long)s.typed_atom[k] * 3;
-            if (p[0] <= ABSENT_X) { v = make_float4(p[0], p[1], p[2], __int_as_float(s.type_of[k])); area = sa[k]; }
+    {   // typed atoms in surface range: present, and (with the conformer's own coordinates) within reach of the residue
+        const int n0 = a.near ? a.n_near : e1;
+        if (tid == 0) sm.n_near = 0;
+        __syncthreads();
+        for (int q0 = 0; q0 < n0; q0 += CT_THREADS) {
+            const int q = q0 + tid;
+            int k = -1; float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            bool on = false;
+            if (q < n0) {
+                k = a.near ? a.near[q] : q;
+                if (k < e1) {
+                    const float *p = cbase + (long long)s.typed_atom[k] * 3;
+                    v = make_float4(p[0], p[1], p[2], 0.f);
+                    on = v.x <= ABSENT_X && (a.r2_near <= 0.f || dist2_fast(v.x, v.y, v.z, a.cax, a.cay, a.caz) < a.r2_near);
+                }
+            }
+            const unsigned b = __ballot_sync(0xffffffffu, on);
+            if (lane == 0) sm.warp_cnt[warp] = __popc(b);
+            __syncthreads();
+            int base = sm.n_near;
+            for (int ww = 0; ww < warp; ++ww) base += sm.warp_cnt[ww];
+            if (on) {
+                const int idx = base + __popc(b & ((1u << lane) - 1u));
+                if (idx < CT_NEAR) {
+                    v.w = __int_as_float(s.type_of[k]);
+                    sm.near_pos[idx] = v; sm.near_sa[idx] = sa[k]; sm.near_k[idx] = k;
+                }
+            }
+            __syncthreads();
+            if (tid == 0) { int tot = 0; for (int ww = 0; ww < CT_WARPS; ++ww) tot += sm.warp_cnt[ww]; sm.n_near += tot; }
+            __syncthreads();
         }
-        sm.near_pos[q] = v; sm.near_sa[q] = area;
     }
+    const int n_near = min(sm.n_near, CT_NEAR);
+    const bool near_over = sm.n_near > CT_NEAR;
     {   // exposed carbons in Gaussian range, in list order
         const int n3 = a.clist ? a.n_clist : c1;
         const float4 *cposc = a.cpos + (long long)c * s.n_carbon;
@@ -567,7 +601,14 @@ __global__ void __launch_bounds__(CT_THREADS, 2) hpmf_trials_conf_kernel(ConfTri
         for (int q0 = 0; q0 < n3; q0 += CT_THREADS) {
             const int q = q0 + tid;
             int ck = -1; double w = 0.0;
-            if (q < n3) { ck = a.clist ? a.clist[q] : q; if (ck < c1) w = w0c[ck]; }
+            float4 pc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (q < n3) {
+                ck = a.clist ? a.clist[q] : q;
+                if (ck < c1) {
+                    w = w0c[ck];
+                    if (w != 0.0) { pc = cposc[ck]; if (a.r2_carb > 0.f && !(dist2_fast(pc.x, pc.y, pc.z, a.cax, a.cay, a.caz) < a.r2_carb)) w = 0.0; }
+                }
+            }
             const bool on = w != 0.0;
             const unsigned b = __ballot_sync(0xffffffffu, on);
             if (lane == 0) sm.warp_cnt[warp] = __popc(b);
@@ -576,9 +617,8 @@ __global__ void __launch_bounds__(CT_THREADS, 2) hpmf_trials_conf_kernel(ConfTri
             for (int ww = 0; ww < warp; ++ww) base += sm.warp_cnt[ww];
             if (on) {
                 const int idx = base + __popc(b & ((1u << lane) - 1u));
-                const float4 p = cposc[ck];
-                if (idx < CT_CARB) { sm.carb_pos[idx] = p; sm.carb_w[idx] = w; }
-                else { spos[idx] = p; sw[idx] = w; }
+                if (idx < CT_CARB) { sm.carb_pos[idx] = pc; sm.carb_w[idx] = w; }
+                else { spos[idx] = pc; sw[idx] = w; }
             }
             __syncthreads();
             if (tid == 0) { int tot = 0; for (int ww = 0; ww < CT_WARPS; ++ww) tot += sm.warp_cnt[ww]; sm.n_carb += tot; }
@@ -606,23 +646,35 @@ __global__ void __launch_bounds__(CT_THREADS, 2) hpmf_trials_conf_kernel(ConfTri
         }
         if (lane < MAX_NEW_C) { tw[lane] = 0.0; tc[lane] = make_float4(0.f, 0.f, 0.f, 0.f); }
         __syncwarp();
-        // pass A: which staged atoms have a trial atom within the (padded) surface range
+        // pass A: which staged atoms have a trial atom within the (padded) surface range.  The list is in sequence order, so
+        // the 32 atoms of an iteration are neighbours in space: a test against the trial's bounding sphere lets whole
+        // iterations skip the per-atom tests.
+        float bx, by, bz, brad2;
+        {
+            float sx = lane < m ? ta[lane].x : 0.f, sy = lane < m ? ta[lane].y : 0.f, sz = lane < m ? ta[lane].z : 0.f;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                sx += __shfl_xor_sync(0xffffffffu, sx, off); sy += __shfl_xor_sync(0xffffffffu, sy, off); sz += __shfl_xor_sync(0xffffffffu, sz, off);
+            }
+            bx = sx / (float)m; by = sy / (float)m; bz = sz / (float)m;
+            float r = lane < m ? sqrtf(dist2_fast(bx, by, bz, ta[lane].x, ta[lane].y, ta[lane].z)) : 0.f;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, off));
+            const float brad = r * 1.0001f + sqrtf(s.pre2) + 1.0e-3f;
+            brad2 = brad * brad;
+        }
         int n_hits = 0;
         for (int q0 = 0; q0 < n_near; q0 += 32) {
             const int q = q0 + lane;
             unsigned bits = 0;
-            if (q < n_near) {
-                float4 p;
-                if (q < CT_NEAR) p = sm.near_pos[q];
-                else {
-                    const int k = a.near ? a.near[q] : q;
-                    p = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-                    if (k < e1) { const float *g = cbase + (long long)s.typed_atom[k] * 3; if (g[0] <= ABSENT_X) p = make_float4(g[0], g[1], g[2], 0.f); }
-                }
-                if (__float_as_int(p.w) >= 0)
+            float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+            bool in = false;
+            if (q < n_near) { p = sm.near_pos[q]; in = dist2_fast(p.x, p.y, p.z, bx, by, bz) < brad2; }
+            if (!__any_sync(0xffffffffu, in)) continue;
+            if (in) {
 #pragma unroll
-                    for (int n = 0; n < MAX_NEW_T; ++n)
-                        if (n < m) { const float4 u = ta[n]; if (dist2_fast(p.x, p.y, p.z, u.x, u.y, u.z) < s.pre2) bits |= 1u << n; }
+                for (int n = 0; n < MAX_NEW_T; ++n)
+                    if (n < m) { const float4 u = ta[n]; if (dist2_fast(p.x, p.y, p.z, u.x, u.y, u.z) < s.pre2) bits |= 1u << n; }
             }
             const unsigned b = __ballot_sync(0xffffffffu, bits != 0);
             if (bits != 0) {
@@ -631,7 +683,7 @@ __global__ void __launch_bounds__(CT_THREADS, 2) hpmf_trials_conf_kernel(ConfTri
             }
             n_hits += __popc(b);
         }
-        bool over = n_hits > CT_HITS;
+        bool over = n_hits > CT_HITS || near_over;
         n_hits = min(n_hits, CT_HITS);
         __syncwarp();
         // pass B: the factors of both surface products, lanes over the hit list
@@ -648,10 +700,9 @@ __global__ void __launch_bounds__(CT_THREADS, 2) hpmf_trials_conf_kernel(ConfTri
             if (have) {
                 const int q = hit_q[hh];
                 const unsigned bits = hit_m[hh];
-                k = a.near ? a.near[q] : q;
+                k = sm.near_k[q];
                 int tk;
-                if (q < CT_NEAR) { const float4 p = sm.near_pos[q]; xk = p.x; yk = p.y; zk = p.z; tk = __float_as_int(p.w); area = sm.near_sa[q]; }
-                else { const float *g = cbase + (long long)s.typed_atom[k] * 3; xk = g[0]; yk = g[1]; zk = g[2]; tk = s.type_of[k]; area = sa[k]; }
+                { const float4 p = sm.near_pos[q]; xk = p.x; yk = p.y; zk = p.z; tk = __float_as_int(p.w); area = sm.near_sa[q]; }
                 const int4 bk = *reinterpret_cast<const int4 *>(s.bonded + (long long)k * MAXB);
 #pragma unroll
                 for (int n = 0; n < MAX_NEW_T; ++n) {
@@ -810,6 +861,20 @@ __global__ void __launch_bounds__(HT) hpmf_extend_kernel(
     }
     if (tid == 0) ln = 0;
     __syncthreads();
+    // bounding sphere of the new atoms (padded by the surface range): atoms outside it skip the per-atom tests, and as the
+    // environment is walked in sequence order whole warps do
+    __shared__ float s_sph[4];
+    if (tid == 0) {
+        float cx = 0.f, cy = 0.f, cz = 0.f; int cnt = 0;
+        for (int n = 0; n < m; ++n) if (ta[n].x <= ABSENT_X) { cx += ta[n].x; cy += ta[n].y; cz += ta[n].z; ++cnt; }
+        if (cnt) { cx /= cnt; cy /= cnt; cz /= cnt; }
+        float r = 0.f;
+        for (int n = 0; n < m; ++n) if (ta[n].x <= ABSENT_X) r = fmaxf(r, sqrtf(dist2_fast(cx, cy, cz, ta[n].x, ta[n].y, ta[n].z)));
+        r = cnt ? r * 1.0001f + sqrtf(s.pre2) + 1.0e-3f : -1.f;
+        s_sph[0] = cx; s_sph[1] = cy; s_sph[2] = cz; s_sph[3] = r < 0.f ? -1.f : r * r;
+    }
+    __syncthreads();
+    const float sx = s_sph[0], sy = s_sph[1], sz = s_sph[2], sr2 = s_sph[3];
     double tp[MAX_NEW_T];
 #pragma unroll
     for (int n = 0; n < MAX_NEW_T; ++n) tp[n] = 1.0;
@@ -822,7 +887,7 @@ __global__ void __launch_bounds__(HT) hpmf_extend_kernel(
         if (k < eL) {
             const float *p = cbase + (long long)s.typed_atom[k] * 3;
             xk = p[0]; yk = p[1]; zk = p[2];
-            if (xk <= ABSENT_X) {
+            if (xk <= ABSENT_X && dist2_fast(xk, yk, zk, sx, sy, sz) < sr2) {
                 int tk = -1, b0 = -1, b1 = -1, b2 = -1, b3 = -1;
                 double f = 1.0;
 #pragma unroll
@@ -1249,6 +1314,7 @@ extern "C" int mcsce_hpmf_energy(mcsce_hpmf h, int n_struct, const float *d_coor
 // Per-trial V_hpmf of one growth step.  `es`: the environment state this growth carries; `carry`: extend it from the
 // previous step instead of re-deriving it.  Buffers grow here (stream synchronised when they do: only at a growth's first step).
 struct TrialStepExtra {
+    float ca[3] = {0.f, 0.f, 0.f}; float reach = -1.f;                  // the residue's CA and reach bound (< 0: lists are not filtered)
     const float4 *trial4 = nullptr; long long trial4_stride = 0;      // the growth's own trial buffer instead of d_trial
     const int *near = nullptr; int n_near = 0;                          // typed atoms in SASA range of the residue (complete list)
     const int *clist = nullptr; int n_clist = 0;                        // carbons in Gaussian range of the residue (complete list)
@@ -1345,6 +1411,11 @@ static int hpmf_trials_impl(mcsce_hpmf h, EnvState &es, bool carry, int n_conf, 
         a.overflow = h->d_overflow; a.overflow_conf = x.overflow_conf;
         a.near = x.near; a.n_near = x.n_near; a.clist = x.clist; a.n_clist = x.n_clist;
         a.cpos = es.d_cpos; a.scratch_pos = es.d_scr_pos; a.scratch_w = es.d_scr_w;
+        a.cax = x.ca[0]; a.cay = x.ca[1]; a.caz = x.ca[2]; a.r2_near = -1.f; a.r2_carb = -1.f;
+        if (x.reach >= 0.f) {
+            const float rn = x.reach + sqrtf(v.pre2) + 0.01f, rc = x.reach + HPMF_CUTOFF + 0.01f;
+            a.r2_near = rn * rn; a.r2_carb = rc * rc;
+        }
         static bool attr_set = false;
         if (!attr_set) {
             HCK(cudaFuncSetAttribute(hpmf_trials_conf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ConfTrialSmem)));
@@ -1460,11 +1531,12 @@ int mcsce_hpmf_growth_begin(mcsce_hpmf h, int lane, const float *d_coords, int n
 // One residue of a growth: V_hpmf(environment + trial) for the masked (conformer, trial) pairs, into d_v [n_conf*n_trials].
 int mcsce_hpmf_growth_step(mcsce_hpmf h, int lane, int residue, int n_conf, const float *d_coords, int first_new, int n_new,
                            int n_trials, const float4 *d_trial4, long long trial4_stride, const uint8_t *d_mask, double *d_v,
-                           int *d_overflow_conf, cudaStream_t st) {
+                           int *d_overflow_conf, cudaStream_t st, const float *ca, float reach) {
     if (!h || lane < 0 || lane + 1 >= HPMF_STATES) return mcsce_fail_shared("mcsce_hpmf_growth_step: bad arguments");
     HCK(cudaSetDevice(h->device));
     TrialStepExtra x;
     x.trial4 = d_trial4; x.trial4_stride = trial4_stride; x.overflow_conf = d_overflow_conf;
+    if (ca) { x.ca[0] = ca[0]; x.ca[1] = ca[1]; x.ca[2] = ca[2]; x.reach = reach; }
     static int no_lists = -1;                 // diagnostic knob: visit every environment atom instead of the residue's lists
     if (no_lists < 0) { const char *e = getenv("MCSCE_B200_HPMF_NO_LISTS"); no_lists = e ? atoi(e) : 0; }
     if (h->d_near && !no_lists && residue + 1 < (int)h->near_off.size()) {

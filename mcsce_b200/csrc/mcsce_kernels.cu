@@ -40,7 +40,7 @@ double mcsce_hpmf_sasa_range(mcsce_hpmf h);
 int mcsce_hpmf_growth_begin(mcsce_hpmf h, int lane, const float *d_coords, int n_input, double *d_v_init, cudaStream_t st);
 int mcsce_hpmf_growth_step(mcsce_hpmf h, int lane, int residue, int n_conf, const float *d_coords, int first_new, int n_new,
                            int n_trials, const float4 *d_trial4, long long trial4_stride, const uint8_t *d_mask, double *d_v,
-                           int *d_overflow_conf, cudaStream_t st);
+                           int *d_overflow_conf, cudaStream_t st, const float *ca, float reach);
 
 #define MAX_CLS MCSCE_MAX_CLS
 #define MAX_SP_ENV MCSCE_MAX_SP_ENV
@@ -1252,6 +1252,7 @@ struct mcsce_handle_s {
     // the placement of the next residue and the special-pair kernel, their events, the call's parameter block.  Big calls
     // run two groups side by side so that the launch tails and the small kernels of one hide under the other's scoring pass.
     std::vector<float> input_xyz_host;               // backbone of the last set_backbone (near lists of the hydrophobic PMF)
+    std::vector<float> hp_reach;                     // per residue: upper bound of |side-chain atom - CA| (reach_bounds)
     struct Lane {
         // buffers of the coordinate-based term (grow-only): growth-order coordinates, per-trial values, mask, overflow flags
         float *hp_gcoords = nullptr; double *hp_v = nullptr, *hp_v_init = nullptr; unsigned char *hp_mask = nullptr; int *hp_ovf = nullptr;
@@ -2049,6 +2050,7 @@ static int ensure_hpmf_near_lists(mcsce_handle h, mcsce_hpmf hp) {
         }
     }
     const double range2 = mcsce_hpmf_pair_range(hp) + 0.01;       // carbon pairs: the Gaussian cutoff
+    h->hp_reach = reach;
     std::vector<int> off(d.n_res + 1, 0), atoms, off2(d.n_res + 1, 0), atoms2;
     for (int i = 0; i < d.n_res; ++i) {
         off[i] = (int)atoms.size(); off2[i] = (int)atoms2.size();
@@ -2202,7 +2204,7 @@ struct GrowthEnqueue {
             ProfScope ps(h, 4, st);
             finite_mask_kernel<<<dim3((T + 127) / 128, C), 128, 0, st>>>(a, ln->hp_mask);
             if (mcsce_hpmf_growth_step(hp, (int)(ln - h->lane), i, C, ln->hp_gcoords, sd.sc_start, sd.n_sc, T, trial, trial_stride,
-                                       ln->hp_mask, ln->hp_v, ln->hp_ovf, st)) return fail(mcsce_last_error());
+                                       ln->hp_mask, ln->hp_v, ln->hp_ovf, st, sd.ca, h->hp_reach[i])) return fail(mcsce_last_error());
             h->launches += 5;
         }
         { ProfScope ps(h, 3, st); select_kernel<<<C, 128, sizeof(double) * 2 * T, st>>>(a); }
