@@ -213,3 +213,29 @@ def test_chains_that_restart_their_numbering_are_rejected():
     s.cols["resseq"] = num
     with pytest.raises(ValueError):
         build_system(s)
+
+
+def test_synthetic_rotamer_library_is_opt_in(monkeypatch, tmp_path):
+    """Production entry points must not silently sample from the seeded synthetic library (random priors): without
+    $MCSCE_ROTAMER_LIB or a library under the package data directory the default path raises; the stand-in that tests and
+    bench.py use needs MCSCE_B200_ALLOW_SYNTHETIC=1 and warns."""
+    import warnings
+
+    from mcsce_b200.core import rotamer_library as rl
+
+    monkeypatch.delenv("MCSCE_ROTAMER_LIB", raising=False)
+    monkeypatch.delenv(rl.ALLOW_SYNTHETIC_ENV, raising=False)
+    with pytest.raises(FileNotFoundError):
+        rl.default_library_path()
+    monkeypatch.setenv(rl.ALLOW_SYNTHETIC_ENV, "1")
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        p = rl.default_library_path()
+    assert p.exists() and any("SYNTHETIC" in str(x.message) for x in w)
+    monkeypatch.setenv("MCSCE_ROTAMER_LIB", str(tmp_path / "missing.lib"))
+    with pytest.raises(FileNotFoundError):
+        rl.default_library_path()
+    real = tmp_path / "ALL.bbdep.rotamers.lib"
+    real.write_text("# stand-in\n")
+    monkeypatch.setenv("MCSCE_ROTAMER_LIB", str(real))
+    assert rl.default_library_path() == real
