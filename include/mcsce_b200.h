@@ -113,7 +113,12 @@ typedef struct {
     int32_t env_split;             /* >0 forces the environment split factor; 0 = automatic      */
     int32_t no_dedup;              /* 1: score the chi-independent side-chain atoms (HA, CB, ...) in every trial like the
                                       reference does, instead of once per residue (same result, more work) */
-    int32_t no_graph;              /* 1: never replay a cached CUDA graph (launch-bound runs do by default) */
+    int32_t no_graph;              /* which driver runs the growth.  0: automatic - launch-bound runs (little work per residue) go to
+                                      the persistent cluster kernel (one launch: a thread-block cluster per conformer loops over
+                                      the residues on the device), everything else to the per-kernel path; 1: always the per-kernel
+                                      path; 2: launch-bound runs replay a cached CUDA graph of the per-kernel path instead;
+                                      3: the persistent cluster kernel whatever the size (falls back if the conformer's
+                                      environment does not fit one SM's shared memory) */
     int32_t no_screen;             /* 1: score every trial against the whole environment; by default a short clash-only pass over
                                       the atoms near the residue runs first and trials it rejects (+inf either way) are not scored */
     /* optional replay input, used with d_chis (parity runs): the dihedral rotate_sidechain measured before each chi

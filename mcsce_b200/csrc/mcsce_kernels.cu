@@ -1206,6 +1206,11 @@ __global__ void finish_kernel(int n_sets, const unsigned char *alive, const doub
 }
 
 // ------------------------------------------------------------------------------------------------
+// K0: the whole growth in one kernel, a thread-block cluster per conformer (launch-bound runs)
+// ------------------------------------------------------------------------------------------------
+#include "grow_cluster.cuh"
+
+// ------------------------------------------------------------------------------------------------
 // host side: handle, table upload, launch logic
 // ------------------------------------------------------------------------------------------------
 #ifndef MAX_LANES
@@ -1264,6 +1269,15 @@ struct mcsce_handle_s {
         int *d_n_dead = nullptr;
     } lane[MAX_LANES];
     double *d_input_energy = nullptr;         // energy of the input atoms alone: a constant of the backbone, computed in set_backbone
+    // persistent cluster growth (grow_cluster.cuh): layout of the shared-memory environment image, cached launch plan
+    const int *d_pstart = nullptr;            // [n_cls+1] even-padded class starts
+    const int *d_aoff = nullptr;              // [n_res+1] first trial atom of every residue (all trials of a conformer in one block)
+    long long trial_atoms_total = 0;
+    int env_pairs = 0;
+    long long gc_plan_key[2] = {-1, -1};      // (table_version, n_conf) the cached plan was made for
+    int gc_S = 0, gc_threads = 0, gc_grid = 0;
+    size_t gc_smem = 0;
+    long long persistent_launches = 0;
     const CallParams *cur_call = nullptr;     // parameter block of the lane being enqueued (read by launch_place)
     // optional per-kernel-class device timing (CUDA events on the launch stream)
     bool profiling = false;
@@ -1422,6 +1436,12 @@ extern "C" int mcsce_set_system(mcsce_handle h, const mcsce_system_desc *s) {
             for (int c = 0; c < s->n_cls; ++c)
                 pre[(size_t)i * (s->n_cls + 1) + c + 1] = pre[(size_t)i * (s->n_cls + 1) + c] + s->cls_active[(size_t)i * s->n_cls + c];
         if (upload(h, P, pre.data(), pre.size(), &d.cls_prefix)) return -1;
+    }
+    {   // shared-memory environment image of the persistent growth: every class segment starts at an even position
+        std::vector<int> ps(s->n_cls + 1, 0);
+        for (int c = 0; c < s->n_cls; ++c) ps[c + 1] = ps[c] + ((s->cls_start[c + 1] - s->cls_start[c] + 1) & ~1);
+        h->env_pairs = ps[s->n_cls] / 2;
+        if (upload(h, P, ps.data(), ps.size(), &h->d_pstart)) return -1;
     }
     h->slot_of_atom.assign(s->slot_of_atom, s->slot_of_atom + s->n_atoms);
     h->cls_of_atom.assign(s->cls_of_atom, s->cls_of_atom + s->n_atoms);
@@ -1667,6 +1687,14 @@ extern "C" int mcsce_set_backbone(mcsce_handle h, const mcsce_backbone_desc *b) 
         }
     }
     if (ensure_dyn_smem(select_kernel, sizeof(double) * 2 * (size_t)h->max_trials, "mcsce_set_backbone")) return -1;
+    std::vector<int> aoff((size_t)d.n_res + 1, 0);       // persistent growth: where a residue's placed trials start
+    h->trial_atoms_total = 0;
+    for (int i = 0; i < d.n_res; ++i) {
+        const StepDev &o = h->steps[i];
+        aoff[i] = (int)std::min<long long>(h->trial_atoms_total, 0x7fffffffLL);
+        if (o.kind == 2 && o.n_trials > 0) h->trial_atoms_total += (long long)o.n_trials * o.n_sc;
+    }
+    aoff[d.n_res] = (int)std::min<long long>(h->trial_atoms_total, 0x7fffffffLL);
     h->input_xyz_host.assign(b->input_xyz, b->input_xyz + (size_t)d.n_input * 3);
     std::vector<int> scr_off, scr_slots, scr_prefix;
     if (build_screen_lists(h, b, scr_off, scr_slots, scr_prefix)) return -1;
@@ -1688,6 +1716,7 @@ extern "C" int mcsce_set_backbone(mcsce_handle h, const mcsce_backbone_desc *b) 
             {scr_off.data(), scr_off.size() * sizeof(int), (const void **)&d.scr_off},
             {scr_slots.data(), scr_slots.size() * sizeof(int), (const void **)&d.scr_slot},
             {scr_prefix.data(), scr_prefix.size() * sizeof(int), (const void **)&d.scr_prefix},
+            {aoff.data(), aoff.size() * sizeof(int), (const void **)&h->d_aoff},
             {nullptr, (size_t)d.n_atoms * 3 * sizeof(float), &rigid_dst},                  // rigid_xyz: NaN = not a rigid atom
             {nullptr, sizeof(double2) * (size_t)std::max(1, d.n_input), (const void **)&h->d_bb_rows},    // input-energy scratch
             {nullptr, sizeof(double2) * (size_t)std::max(1, d.n_bb_pairs), (const void **)&h->d_bb_pairs},
@@ -1798,6 +1827,28 @@ static Workspace carve(const mcsce_handle h, int n_conf, int max_trials, int max
 }
 
 static int lane_count(const mcsce_handle h, int n_conf);
+static size_t gc_workspace_bytes(const mcsce_handle h, int C);
+// Launch-bound runs: little pair work per residue (few conformers and/or a small protein), where launch latencies and tails
+// of the per-kernel path outweigh the arithmetic.
+static bool launch_bound(const mcsce_handle h, int C, long long *grow_steps_out = nullptr) {
+    const SysDev &d = h->d;
+    long long grow_steps = 0, pairs = 0;
+    for (int i = 0; i < d.n_res; ++i) {
+        const StepDev &sd = h->steps[i];
+        if (sd.kind != 2 || sd.n_trials <= 0) continue;
+        long long n_active = 0;
+        for (int c = 0; c < d.n_cls; ++c) n_active += h->cls_active[(size_t)i * d.n_cls + c];
+        pairs += (long long)sd.n_trials * sd.n_sc * n_active;
+        ++grow_steps;
+    }
+    if (grow_steps_out) *grow_steps_out = grow_steps;
+    return grow_steps > 0 && (pairs * C) / grow_steps < 300000000LL;
+}
+static int persistent_knob() {               // MCSCE_B200_PERSISTENT: 0 = never picked automatically, 1 = launch-bound runs (default), 2 = always
+    if (const char *e = getenv("MCSCE_B200_PERSISTENT")) return atoi(e);
+    return 1;
+}
+#define GC_MAX_WORKSPACE (2048LL << 20)      // the up-front placement is for launch-bound runs: beyond 2 GB the per-kernel path serves
 
 extern "C" size_t mcsce_workspace_bytes(mcsce_handle h, int n_conf) {
     if (!h || !h->has_bb || n_conf <= 0) return 0;
@@ -1811,6 +1862,9 @@ extern "C" size_t mcsce_workspace_bytes(mcsce_handle h, int n_conf) {
         }
         whole = std::max(whole, sum);
     }
+    // the persistent cluster growth (launch-bound runs) places every trial up front
+    const size_t pers = gc_workspace_bytes(h, n_conf);
+    if (pers <= (size_t)GC_MAX_WORKSPACE && (launch_bound(h, n_conf) || persistent_knob() >= 2)) whole = std::max(whole, pers);
     return whole;
 }
 
@@ -2260,6 +2314,117 @@ static int finish_growth(mcsce_handle h, int C, const Workspace &w, float *d_coo
     return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Persistent cluster growth (grow_cluster.cuh): launch plan and launch.  Returns 1 when the call was served, 0 when this
+// path cannot take it (the caller falls back to the graph / direct path), -1 on error.
+// ------------------------------------------------------------------------------------------------
+static size_t gc_smem_bytes(const mcsce_handle h) {
+    const size_t T = (size_t)std::max(1, h->max_trials);
+    const size_t b = (size_t)h->env_pairs * 32 + (size_t)GC_SE * 8 + T * 16 + GC_SE;
+    return (b + 15) / 16 * 16;
+}
+// device workspace of the persistent growth: every trial of every residue placed up front, their special-pair sums, and the
+// double-buffered per-trial sums of the residue in hand
+static size_t gc_workspace_bytes(const mcsce_handle h, int C) {
+    return align_up((size_t)C * (size_t)std::max<long long>(1, h->trial_atoms_total) * sizeof(float4)) +
+           align_up((size_t)C * (size_t)std::max(1, h->d.n_trials_total) * sizeof(double2)) +
+           align_up((size_t)C * 2 * ((size_t)std::max(1, h->max_trials) + 1) * sizeof(double2));
+}
+
+static int gc_make_plan(mcsce_handle h, int C) {
+    int max_s = 16, thr_override = 0;
+    if (const char *e = getenv("MCSCE_B200_CLUSTER_MAX")) max_s = std::max(1, std::min(16, atoi(e)));     // tuning knobs
+    if (const char *e = getenv("MCSCE_B200_CLUSTER_THREADS")) thr_override = std::max(64, std::min(GC_MAX_THREADS, atoi(e) / 32 * 32));
+    const long long key1 = (long long)C | ((long long)max_s << 32) | ((long long)thr_override << 40);
+    if (h->gc_plan_key[0] == h->table_version && h->gc_plan_key[1] == key1) return h->gc_S > 0 ? 1 : 0;
+    h->gc_plan_key[0] = h->table_version; h->gc_plan_key[1] = key1; h->gc_S = 0;
+    cudaFuncAttributes fa;
+    CK(cudaFuncGetAttributes(&fa, grow_cluster_kernel));
+    static bool np_set = false;
+    if (!np_set) { CK(cudaFuncSetAttribute(grow_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)); np_set = true; }
+    for (int S = max_s; S >= 1; S >>= 1) {
+        if (S > 1 && (long long)C * S > h->sm_count) continue;        // CTAs are added to a conformer only while SMs are spare
+        int threads = (long long)C * S <= h->sm_count ? 512 : 256;    // one CTA per SM: 16 warps; otherwise two CTAs of 8
+        if (thr_override) threads = thr_override;
+        const size_t smem = gc_smem_bytes(h);
+        if (smem + fa.sharedSizeBytes > (size_t)227 * 1024) return 0;  // the environment image does not fit one SM
+        CK(cudaFuncSetAttribute(grow_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int grid = 0;
+        if (S > 1) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(C * S)); cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = smem;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)S; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int n_active = 0;
+            if (cudaOccupancyMaxActiveClusters(&n_active, grow_cluster_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); continue; }
+            if (n_active < C) continue;                                // every conformer's cluster must be resident at once
+            grid = C * S;
+        } else {
+            int per_sm = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grow_cluster_kernel, threads, smem));
+            if (per_sm < 1) return 0;
+            grid = (int)std::min<long long>(C, (long long)per_sm * h->sm_count);
+        }
+        h->gc_S = S; h->gc_threads = threads; h->gc_grid = grid; h->gc_smem = smem;
+        return 1;
+    }
+    return 0;
+}
+
+static int grow_persistent(mcsce_handle h, const mcsce_grow_opts *o, void *d_workspace, size_t workspace_bytes, float *d_coords,
+                           double *d_energy, uint8_t *d_ok, cudaStream_t st) {
+    const int C = o->n_conf;
+    const int rc = gc_make_plan(h, C);
+    if (rc <= 0) return rc;
+    const SysDev &d = h->d;
+    ClusterArgs a{};
+    a.s = d; a.cp = CallParams{o->seed, o->conf_id0, o->beta, o->noise_deg};
+    a.n_conf = C; a.cluster = h->gc_S; a.dedup_ok = o->no_dedup ? 0 : 1; a.max_trials = std::max(1, h->max_trials);
+    a.env_pairs = h->env_pairs; a.pstart = h->d_pstart;
+    if (h->trial_atoms_total >= 0x7fffffffLL) return 0;
+    a.trial_stride = std::max<long long>(1, h->trial_atoms_total); a.aoff = h->d_aoff;
+    const size_t need = gc_workspace_bytes(h, C);
+    if (need > workspace_bytes || need > (size_t)GC_MAX_WORKSPACE) return 0;
+    const size_t trial_bytes = align_up((size_t)C * (size_t)a.trial_stride * sizeof(float4));
+    const size_t sp_bytes = align_up((size_t)C * (size_t)std::max(1, d.n_trials_total) * sizeof(double2));
+    a.trial = (float4 *)d_workspace; a.sp = (double2 *)((char *)d_workspace + trial_bytes);
+    a.partial = (double2 *)((char *)d_workspace + trial_bytes + sp_bytes);
+    a.chis_in = o->d_chis; a.ori_in = o->d_chis ? o->d_ori : nullptr; a.uniform = o->d_uniform;
+    a.chis_out = o->d_chis_out; a.trial_energy = o->d_trial_energy; a.selected = o->d_selected;
+    a.coords = d_coords; a.energy = d_energy; a.ok = d_ok; a.e_input = h->d_input_energy; a.pair_counter = h->d_pairs;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)h->gc_grid); cfg.blockDim = dim3((unsigned)h->gc_threads); cfg.dynamicSmemBytes = h->gc_smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    if (h->gc_S > 1) {
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)h->gc_S; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+    }
+    CK(cudaFuncSetAttribute(grow_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->gc_smem));
+    static long long *d_dbg = nullptr;
+    const bool debug = getenv("MCSCE_B200_GC_DEBUG") != nullptr;
+    if (debug) {
+        if (!d_dbg) CK(cudaMalloc((void **)&d_dbg, 16 * sizeof(long long)));
+        CK(cudaMemsetAsync(d_dbg, 0, 16 * sizeof(long long), st));
+        a.debug = d_dbg;
+    }
+    CK(cudaLaunchKernelEx(&cfg, grow_cluster_kernel, a));
+    h->launches += 1; h->persistent_launches += 1;
+    if (debug) {
+        long long t[16];
+        CK(cudaStreamSynchronize(st));
+        CK(cudaMemcpy(t, d_dbg, sizeof(t), cudaMemcpyDeviceToHost));
+        static const char *nm[10] = {"init", "K1", "K2s", "prep", "generic", "reduce", "barrier", "select-min", "weights+scan", "append"};
+        fprintf(stderr, "[mcsce_b200] persistent growth C=%d cluster=%d threads=%d smem=%zu, kclocks of conformer 0:", C, h->gc_S, h->gc_threads, h->gc_smem);
+        for (int k = 0; k < 10; ++k) fprintf(stderr, " %s %.1f", nm[k], t[k] * 1e-3);
+        fprintf(stderr, "\n");
+    }
+    return 1;
+}
+
 extern "C" int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *o, void *d_workspace, size_t workspace_bytes,
                           float *d_coords, double *d_energy, uint8_t *d_ok, void *stream) {
     if (!h || !o) return fail("null argument");
@@ -2277,17 +2442,18 @@ extern "C" int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *o, void *d_work
     // Launch-bound runs (little work per residue: few conformers and/or a small protein) replay a captured CUDA graph of
     // the whole growth instead of ~4 launches + 7 event calls per residue; the graph is cached per (tables, n_conf,
     // buffers, options).  Large runs enqueue directly and may re-derive the environment split while conformers die.
-    long long grow_steps = 0, pairs = 0;
-    for (int i = 0; i < d.n_res; ++i) {
-        const StepDev &sd = h->steps[i];
-        if (sd.kind != 2 || sd.n_trials <= 0) continue;
-        long long n_active = 0;
-        for (int c = 0; c < d.n_cls; ++c) n_active += h->cls_active[(size_t)i * d.n_cls + c];
-        pairs += (long long)sd.n_trials * sd.n_sc * n_active;
-        ++grow_steps;
-    }
+    long long grow_steps = 0;
+    const bool small = launch_bound(h, C, &grow_steps);
     // (the coordinate-based term sizes its buffers at the first step of a growth: not capturable)
-    const bool use_graph = !o->no_graph && !o->hpmf && !h->profiling && grow_steps > 0 && (pairs * C) / grow_steps < 300000000LL;
+    // o->no_graph: 0 = automatic, 1 = the direct per-kernel path, 2 = a replayed graph wherever the automatic choice is a
+    // launch-bound path, 3 = the persistent cluster kernel whatever the size (if the environment fits shared memory)
+    const bool plain = !o->hpmf && !h->profiling && grow_steps > 0;
+    const int persistent = persistent_knob();
+    if (plain && (o->no_graph == 3 || (o->no_graph == 0 && ((small && persistent >= 1) || persistent >= 2)))) {
+        const int rc = grow_persistent(h, o, d_workspace, workspace_bytes, d_coords, d_energy, d_ok, st);
+        if (rc != 0) return rc < 0 ? -1 : 0;
+    }
+    const bool use_graph = (o->no_graph == 0 || o->no_graph == 2) && plain && small;
     if (use_graph) {
         Workspace w = carve(h, C, h->max_trials, h->max_trial_atoms, d_workspace);
         std::vector<long long> key = {h->table_version, C, (long long)(size_t)d_workspace, (long long)workspace_bytes,

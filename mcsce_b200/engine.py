@@ -209,7 +209,7 @@ class GrowthEngine:
         o = GrowOpts()
         o.n_conf, o.conf_id0, o.seed, o.beta, o.noise_deg, o.env_split = C_, int(conf_id0), int(seed), float(beta), float(noise_deg), int(env_split)
         o.no_dedup = 1 if no_dedup else 0
-        o.no_graph = 1 if no_graph else 0
+        o.no_graph = int(no_graph)          # False/0 automatic, True/1 direct per-kernel path, 2 graph replay, 3 persistent cluster kernel
         o.no_screen = 1 if no_screen else 0
         keep = []
         if hpmf is not None:

@@ -406,7 +406,8 @@ def test_one_engine_serves_systems_of_different_size_in_turn():
 
 
 def test_cuda_graph_replay_equals_direct_launches():
-    """Launch-bound growths replay a cached CUDA graph; seeds, conformer offsets and beta are read from a device
+    """With no_graph=2 launch-bound growths replay a cached CUDA graph of the per-kernel path (the automatic choice is the
+    persistent cluster kernel, tests/test_gpu_persistent.py); seeds, conformer offsets and beta are read from a device
     parameter block, so one graph serves every call with the same buffers."""
     case, s, sysm, eng = engine_for("helix76")
     ref = {}
@@ -417,17 +418,17 @@ def test_cuda_graph_replay_equals_direct_launches():
         ref[(seed, cid)] = (o["energy"].cpu().numpy().copy(), o["coords"].cpu().numpy().copy(), o["ok"].cpu().numpy().copy())
     for rep in range(2):                     # second round replays the cached graph
         for (seed, cid), (e, x, k) in ref.items():
-            o = eng.grow(16, case.beta, seed=seed, conf_id0=cid)
+            o = eng.grow(16, case.beta, seed=seed, conf_id0=cid, no_graph=2)
             assert np.array_equal(o["energy"].cpu().numpy(), e, equal_nan=True)
             assert np.array_equal(o["coords"].cpu().numpy(), x) and np.array_equal(o["ok"].cpu().numpy(), k)
-    hot = eng.grow(16, 2 * case.beta, seed=1)            # beta comes from the parameter block too
+    hot = eng.grow(16, 2 * case.beta, seed=1, no_graph=2)            # beta comes from the parameter block too
     assert not np.array_equal(hot["energy"].cpu().numpy(), ref[(1, 0)][0], equal_nan=True)
     # a new backbone invalidates the graph
     eng.set_backbone(s.coords + np.float32(0.25))
-    moved = eng.grow(16, case.beta, seed=1)
+    moved = eng.grow(16, case.beta, seed=1, no_graph=2)
     assert np.abs(moved["coords"].cpu().numpy()[:, :sysm.n_input] - (s.coords + np.float32(0.25))).max() == 0
     eng.set_backbone(s.coords)
-    back = eng.grow(16, case.beta, seed=1)
+    back = eng.grow(16, case.beta, seed=1, no_graph=2)
     assert np.array_equal(back["energy"].cpu().numpy(), ref[(1, 0)][0], equal_nan=True)
 
 

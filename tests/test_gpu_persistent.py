@@ -1,0 +1,130 @@
+"""K0, the persistent cluster kernel (one launch per growth: a thread-block cluster per conformer loops over the residues on the
+device; ``mcsce_grow_opts.no_graph``: 0 picks it for launch-bound runs, 3 forces it) against the per-kernel path (1) and the
+replayed graph (2): same Philox streams, same arithmetic per pair - selections, success flags and coordinates identical,
+energies equal up to the float32 partial sums' grouping.  Cluster sizes 1-16 and both block sizes are forced through the
+tuning variables; the oracle replays follow in tests/test_gpu_parity.py / test_gpu_scale.py (their small fixtures take this
+path by default)."""
+import os
+
+import numpy as np
+import pytest
+
+from golden_utils import GoldenCase, library
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(name):
+    from mcsce_b200.engine import GrowthEngine
+    from mcsce_b200.system import build_system
+
+    case = GoldenCase(name)
+    lib, ptm = library()
+    s = case.structure()
+    sysm = build_system(s, terms=case.terms, retain_idxs=case.retain, rotamer_library=lib, ptm_library=ptm)
+    return case, sysm, GrowthEngine(0).set_system(sysm).set_backbone(s.coords)
+
+
+def _np(out):
+    return {k: out[k].cpu().numpy().copy() for k in ("energy", "ok", "selected", "trial_energy", "chis", "coords")}
+
+
+def _same_growth(a, b, tag):
+    assert np.array_equal(a["ok"], b["ok"]), tag
+    assert np.array_equal(a["selected"], b["selected"]), tag
+    wrote = a["chis"] != 0        # (the persistent kernel places every residue's trials up front, also past a failed residue)
+    assert np.array_equal(a["chis"][wrote], b["chis"][wrote]), tag
+    ta, tb = a["trial_energy"], b["trial_energy"]
+    assert np.array_equal(np.isnan(ta), np.isnan(tb)), tag
+    both = ~np.isnan(ta)
+    assert np.array_equal(np.isinf(ta[both]), np.isinf(tb[both])), tag
+    fin = both & np.isfinite(ta)
+    # float32 partial sums are grouped differently (whole class segments vs 1024-atom tiles): ~1e-7 of the d^-12 / d^-6 /
+    # Coulomb sums, which are 1e2-1e3 kJ/mol before they cancel (measured: up to 1.2e-4 kJ/mol, 0.12x the north-star tolerance)
+    assert np.allclose(ta[fin], tb[fin], rtol=2e-6, atol=5e-4), (tag, float(np.abs(ta[fin] - tb[fin]).max()))
+    ok = a["ok"].astype(bool)
+    assert np.allclose(a["energy"][ok], b["energy"][ok], rtol=2e-6, atol=2e-3), tag
+    assert np.array_equal(a["coords"][ok], b["coords"][ok]), tag       # same selections of bit-identical placements
+
+
+@pytest.fixture
+def knobs():
+    saved = {k: os.environ.get(k) for k in ("MCSCE_B200_CLUSTER_MAX", "MCSCE_B200_CLUSTER_THREADS")}
+    yield
+    for k, v in saved.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
+
+
+@pytest.mark.parametrize("name", ["pep12", "ptm18", "twochain", "fix12", "bundle40", "helix76"])
+def test_persistent_kernel_equals_per_kernel_path(name, knobs):
+    case, sysm, eng = _engine(name)
+    for n_conf, cmax, threads in ((1, 16, 512), (1, 4, 256), (3, 16, 512), (5, 2, 512), (40, 1, 512), (40, 4, 256),
+                                  (200, 1, 256), (333, 1, 256)):
+        os.environ["MCSCE_B200_CLUSTER_MAX"] = str(cmax)
+        os.environ["MCSCE_B200_CLUSTER_THREADS"] = str(threads)
+        rng = np.random.default_rng(n_conf)
+        u = rng.random((n_conf, sysm.n_res))
+        a = _np(eng.grow(n_conf, case.beta, seed=11, conf_id0=7, uniforms=u, dump=True, no_graph=1, no_screen=True))
+        eng.counters(reset=True)
+        b = _np(eng.grow(n_conf, case.beta, seed=11, conf_id0=7, uniforms=u, dump=True, no_graph=3))
+        launches = eng.counters(reset=True)[0]
+        assert launches == 1, launches                                  # one kernel for the whole ensemble
+        _same_growth(a, b, (name, n_conf, cmax, threads))
+        # device uniforms (Philox) and the chi-independent atoms in every trial
+        c = _np(eng.grow(n_conf, case.beta, seed=3, dump=True, no_graph=1, no_screen=True, no_dedup=True))
+        d = _np(eng.grow(n_conf, case.beta, seed=3, dump=True, no_graph=3, no_dedup=True))
+        _same_growth(c, d, (name, n_conf, cmax, threads, "philox"))
+
+
+def test_automatic_choice_and_graph_replay(knobs):
+    """Launch-bound runs take the persistent kernel on their own; no_graph=2 still replays the graph, bit-identical to the
+    per-kernel path."""
+    case, sysm, eng = _engine("helix76")
+    a = _np(eng.grow(8, case.beta, seed=5, dump=True, no_graph=1, no_screen=True))
+    eng.counters(reset=True)
+    b = _np(eng.grow(8, case.beta, seed=5, dump=True))
+    assert eng.counters(reset=True)[0] == 1
+    _same_growth(a, b, "auto")
+    g = _np(eng.grow(8, case.beta, seed=5, dump=True, no_graph=2))
+    assert eng.counters(reset=True)[0] > 100
+    for k in ("ok", "selected", "coords"):
+        assert np.array_equal(a[k], g[k]), k
+    assert np.array_equal(a["energy"], g["energy"], equal_nan=True)
+
+
+@pytest.mark.parametrize("cmax", [1, 8])
+def test_persistent_kernel_replays_the_reference(cmax, knobs):
+    """The reference's chi rows, measured dihedrals and uniforms through the persistent kernel (one CTA, and a cluster of up to 8
+    CTAs per conformer): every per-trial energy within the north-star tolerance, every clash flag and selection identical."""
+    from test_gpu_parity import ALL_CASES, _replay_feed
+
+    os.environ["MCSCE_B200_CLUSTER_MAX"] = str(cmax)
+    for name in ALL_CASES:
+        case, sysm, eng = _engine(name)
+        feeds = [_replay_feed(case, c, sysm, eng, with_ori=True) for c in range(case.n_conf)]
+        eng.counters(reset=True)
+        out = eng.grow(case.n_conf, case.beta, chis=np.stack([f[0] for f in feeds]), uniforms=np.stack([f[1] for f in feeds]),
+                       oris=np.stack([f[2] for f in feeds]), dump=True, no_graph=3)
+        assert eng.counters(reset=True)[0] == 1, name
+        te = out["trial_energy"].cpu().numpy(); sel = out["selected"].cpu().numpy()
+        ok = out["ok"].cpu().numpy(); energy = out["energy"].cpu().numpy()
+        worst = 0.0
+        for c in range(case.n_conf):
+            gold = case.conf(c)
+            assert bool(ok[c]) == bool(gold["ok"])
+            for i, g in case.steps_by_level(c).items():
+                o = eng.trial_off[i]
+                got, ref = te[c, o:o + len(g["energies"])], g["energies"]
+                assert np.array_equal(np.isinf(got), np.isinf(ref)), (name, c, i)
+                fin = ~np.isinf(ref)
+                if fin.any():
+                    worst = max(worst, float((np.abs(got[fin] - ref[fin]) / np.maximum(1e-3, 1e-5 * np.abs(ref[fin]))).max()))
+                if "selected" in g:
+                    assert sel[c, i] == int(g["selected"]), (name, c, i)
+            if gold["ok"]:
+                assert abs(energy[c] - float(gold["energy"])) <= 1e-3 + 1e-5 * abs(float(gold["energy"]))
+        print("persistent replay %s (cluster <= %d): worst = %.3f x tolerance" % (name, cmax, worst))
+        assert worst < 0.5, (name, worst)
