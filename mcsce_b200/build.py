@@ -31,7 +31,7 @@ def _stale(target, sources):
 
 def build_cuda(force=False, verbose=False):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    deps = CU_SOURCES + [ROOT / "include" / "mcsce_b200.h"]
+    deps = CU_SOURCES + [ROOT / "include" / "mcsce_b200.h"] + sorted((PKG / "csrc").glob("*.cuh"))    # (headers included by the sources)
     if not force and not _stale(LIB, deps):
         return LIB
     if not os.path.exists(nvcc):

@@ -161,7 +161,9 @@ def _grow(backbone_coords, beta, n_conf):
     parts = []
     # one rank: results straight into pinned host memory; several ranks: keep them on the device for the gather.
     # Big requests are grown in chunks so that the device workspace and the pinned staging stay bounded.  Conformer
-    # streams (Philox) are keyed by the global conformer id, so the result does not depend on chunking or sharding.
+    # streams (Philox) are keyed by the global conformer id, so every conformer sees the same trial rows and uniforms whatever
+    # the chunking or sharding; its energies agree to the float32 grouping of the pair sums, which follows the launch geometry
+    # (cluster size of the persistent kernel, environment split of the per-kernel path).
     hpmf = _state.get("hpmf")
     for c0 in range(lo, hi, MAX_CONFORMERS_PER_LAUNCH):
         n = min(MAX_CONFORMERS_PER_LAUNCH, hi - c0)

@@ -26,6 +26,26 @@
 #define GC_BATCH 2048              // trial atoms scored between two block barriers
 #define GC_SE 4096                 // per-atom partial sums held between them (atoms x environment shares)
 #define GC_K1_ROWS 5               // K1: trial rows a warp takes at a time (5 rows x 6 chi columns = 30 lanes of scalar work)
+#define GC_TRIAL_PF 512            // trial atoms of the next residue staged in shared memory ahead of time (more: read from L2)
+
+// What the residue loop needs of one residue.  It is copied into shared memory one residue ahead with asynchronous copies
+// (LDGSTS) issued in the shadow of the cluster barrier, so the loop's dependent table reads are shared-memory reads instead
+// of a chain of L2 round trips (~1000 clocks each; measured: half of the scoring phase of a 1-conformer run).
+struct __align__(16) GcStage {
+    StepDev st;
+    int prefix[MAX_CLS + 1];       // row of cls_prefix: atoms of every class present when the residue grows
+    int cls[MAX_SC], slot[MAX_SC]; // of its side-chain atoms
+    double q[MAX_SC];              // their charges
+    int n_tb;                      // trial atoms staged (0: more than GC_TRIAL_PF, read from global memory)
+};
+static_assert(sizeof(StepDev) % 16 == 0, "StepDev is copied in 16-byte pieces");
+
+__device__ __forceinline__ void gc_ldgsts(void *dst, const void *src, int bytes) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    if (bytes == 16) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(d), "l"(src));
+    else if (bytes == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d), "l"(src));
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(d), "l"(src));
+}
 
 struct ClusterArgs {
     SysDev s;
@@ -59,25 +79,33 @@ __device__ __forceinline__ void gc_cluster_sync(int cluster) {
 // position P of an atom inside the pair-interleaved image -> index of its x in the float view (y +2, z +4, q +6)
 __device__ __forceinline__ int gc_flat(int P) { return 8 * (P >> 1) + (P & 1); }
 
-// generic pairs of this thread's RR trial atoms against share j of esplit of every active class segment
+// generic pairs of this thread's RR trial atoms against share j of esplit of the active environment: the active pairs of
+// all classes form one sequence (s_pp = its per-class prefix), a share is a contiguous run of it, so a unit walks only the
+// classes its run touches
 template <int RR>
 __device__ __forceinline__ void gc_score_unit(const ClusterArgs &a, const float4 *__restrict__ s_env, const int *s_pstart,
-                                              const int *s_act, int j, int esplit, const float2 (&nx)[SCORE_R],
+                                              const int *s_pp, const float *s_cthr, const double *s_cA, const double *s_cB,
+                                              int j, int esplit, const float2 (&nx)[SCORE_R],
                                               const float2 (&ny)[SCORE_R], const float2 (&nz)[SCORE_R], const int (&ci)[SCORE_R],
                                               double (&e_lj)[SCORE_R], double (&e_c)[SCORE_R], bool (&clash)[SCORE_R]) {
     const int n_cls = a.s.n_cls;
-    for (int c = 0; c < n_cls; ++c) {
-        const int act = s_act[c];
-        if (act <= 0) continue;
-        const int P0 = s_pstart[c] >> 1, P1 = (s_pstart[c] + act + 1) >> 1;
-        const int q0 = P0 + (int)(((long long)(P1 - P0) * j) / esplit), q1 = P0 + (int)(((long long)(P1 - P0) * (j + 1)) / esplit);
-        if (q0 >= q1) continue;
+    const int total = s_pp[n_cls];
+    const int g0 = (int)(((unsigned)total * (unsigned)j) / (unsigned)esplit), g1 = (int)(((unsigned)total * (unsigned)(j + 1)) / (unsigned)esplit);
+    int c = 0;
+    if (esplit > 1) { int c_lo = 0, c_hi = n_cls; while (c_hi - c_lo > 1) { const int m = (c_lo + c_hi) >> 1; if (s_pp[m] <= g0) c_lo = m; else c_hi = m; } c = c_lo; }
+    for (; c < n_cls; ++c) {
+        const int b = s_pp[c];
+        if (b >= g1) break;
+        const int lo = max(g0, b), hi = min(g1, s_pp[c + 1]);
+        if (lo >= hi) continue;
+        const int P0 = s_pstart[c] >> 1;
+        const int q0 = P0 + lo - b, q1 = P0 + hi - b;
         float thr2[SCORE_R];
         double A[SCORE_R], B[SCORE_R], E6[SCORE_R], E3[SCORE_R], EC[SCORE_R];
 #pragma unroll
         for (int r = 0; r < RR; ++r) {
             const int idx = ci[r] * n_cls + c;
-            thr2[r] = __ldg(&a.s.cls_thr2f[idx]); A[r] = __ldg(&a.s.cls_A[idx]); B[r] = __ldg(&a.s.cls_B[idx]);
+            thr2[r] = s_cthr[idx]; A[r] = s_cA[idx]; B[r] = s_cB[idx];
             E6[r] = 0.0; E3[r] = 0.0; EC[r] = 0.0;
         }
         score_segment<RR>(s_env, q0, q1, nx, ny, nz, thr2, E6, E3, EC, clash);
@@ -90,7 +118,8 @@ __device__ __forceinline__ void gc_score_unit(const ClusterArgs &a, const float4
 
 __global__ void __launch_bounds__(GC_MAX_THREADS, 1) grow_cluster_kernel(ClusterArgs a) {
     extern __shared__ float4 gc_dyn[];
-    __shared__ int s_pstart[MAX_CLS + 1], s_act[MAX_CLS];
+    __shared__ int s_pstart[MAX_CLS + 1], s_act[MAX_CLS], s_pp[MAX_CLS + 1], s_cstart[MAX_CLS + 1];
+    __shared__ GcStage s_stage[2];
     __shared__ float4 s_save[MAX_SP_ENV];
     __shared__ int s_savepos[MAX_SP_ENV];
     __shared__ double s_red[GC_MAX_THREADS / 32];
@@ -108,11 +137,24 @@ __global__ void __launch_bounds__(GC_MAX_THREADS, 1) grow_cluster_kernel(Cluster
     float4 *s_env = gc_dyn;                                             // [2*env_pairs]
     float *s_flat = reinterpret_cast<float *>(s_env);
     double *s_e = reinterpret_cast<double *>(s_env + 2 * a.env_pairs);  // [GC_SE] per-atom energies of a batch, one per environment share
-    double *s_E = s_e + GC_SE;                                          // [Tmax] per-trial energies (selection)
-    double *s_w = s_E + Tmax;                                           // [Tmax] Boltzmann weights, then their running sums
-    unsigned char *s_cl = reinterpret_cast<unsigned char *>(s_w + Tmax);   // [GC_SE]
+    const int Tpad = (Tmax + 1) & ~1;                                   // keeps every array below 16-byte aligned
+    double *s_E = s_e + GC_SE;                                          // [Tpad] per-trial energies (selection)
+    double *s_w = s_E + Tpad;                                           // [Tpad] Boltzmann weights
+    double *s_prob2 = s_w + Tpad;                                       // [2][Tpad] staged prior weights
+    double2 *s_sp2 = reinterpret_cast<double2 *>(s_prob2 + 2 * Tpad);   // [2][Tpad] staged special-pair sums of this CTA's trials
+    float4 *s_tb2 = reinterpret_cast<float4 *>(s_sp2 + 2 * Tpad);       // [2][GC_TRIAL_PF] staged trial atoms of this CTA's trials
+    double *s_cA = reinterpret_cast<double *>(s_tb2 + 2 * GC_TRIAL_PF); // [n_cls^2] class-pair constants (A/d^12 - B/d^6)
+    double *s_cB = s_cA + n_cls * n_cls;
+    float *s_cthr = reinterpret_cast<float *>(s_cB + n_cls * n_cls);    // [n_cls^2] exact float32 clash thresholds (squared)
+    unsigned char *s_cl = reinterpret_cast<unsigned char *>(s_cthr + ((n_cls * n_cls + 3) & ~3));   // [GC_SE]
+    unsigned char *s_kind = s_cl + GC_SE;                               // [n_res] 2 = grown here, 1 = rigid side chain, 0 = nothing to do
 
-    for (int c = tid; c <= n_cls; c += nthr) s_pstart[c] = a.pstart[c];
+    for (int c = tid; c <= n_cls; c += nthr) { s_pstart[c] = a.pstart[c]; s_cstart[c] = a.s.cls_start[c]; }
+    for (int i = tid; i < n_cls * n_cls; i += nthr) { s_cA[i] = a.s.cls_A[i]; s_cB[i] = a.s.cls_B[i]; s_cthr[i] = a.s.cls_thr2f[i]; }
+    for (int i = tid; i < a.s.n_res; i += nthr) {
+        const int k = a.s.steps[i].kind;
+        s_kind[i] = (unsigned char)((k == 2 && a.s.steps[i].n_trials <= 0) ? 0 : k);
+    }
     const bool dbg = a.debug != nullptr && blockIdx.x == 0 && tid == 0;
     long long t_last = dbg ? clock64() : 0;
 
@@ -271,36 +313,86 @@ __global__ void __launch_bounds__(GC_MAX_THREADS, 1) grow_cluster_kernel(Cluster
         GC_TICK(2);
 
         // ---- the residue loop: generic pairs -> one cluster barrier -> selection -> append ----
+        // stage_issue: asynchronous copies of everything the loop reads of residue nx into stage buffer b (all threads)
+        auto stage_issue = [&](int b, int nx) {
+            const StepDev *gs = a.s.steps + nx;
+            const int n_sc_n = gs->n_sc, sc0 = gs->sc_start, Tn = gs->n_trials, toff = gs->trial_off;
+            const int tn_lo = (int)(((long long)Tn * rank) / S), ntn = (int)(((long long)Tn * (rank + 1)) / S) - tn_lo;
+            GcStage &sg = s_stage[b];
+            const int n_tb = (ntn * n_sc_n <= GC_TRIAL_PF) ? ntn * n_sc_n : 0;
+            if (tid == 0) sg.n_tb = n_tb;
+            const int o1 = (int)(sizeof(StepDev) / 16), o2 = o1 + n_cls + 1, o3 = o2 + n_sc_n, o4 = o3 + n_sc_n, o5 = o4 + n_sc_n,
+                      o6 = o5 + Tn, o7 = o6 + ntn, o8 = o7 + n_tb;
+            const float4 *tb_n = tb_all + a.aoff[nx] + (long long)tn_lo * n_sc_n;
+            for (int it = tid; it < o8; it += nthr) {
+                if (it < o1) gc_ldgsts(reinterpret_cast<char *>(&sg.st) + 16 * it, reinterpret_cast<const char *>(gs) + 16 * it, 16);
+                else if (it < o2) gc_ldgsts(&sg.prefix[it - o1], a.s.cls_prefix + nx * (n_cls + 1) + (it - o1), 4);
+                else if (it < o3) gc_ldgsts(&sg.cls[it - o2], a.s.cls_of_atom + sc0 + (it - o2), 4);
+                else if (it < o4) gc_ldgsts(&sg.slot[it - o3], a.s.slot_of_atom + sc0 + (it - o3), 4);
+                else if (it < o5) gc_ldgsts(&sg.q[it - o4], a.s.charge + sc0 + (it - o4), 8);
+                else if (it < o6) gc_ldgsts(&s_prob2[b * Tpad + (it - o5)], a.s.prob + toff + (it - o5), 8);
+                else if (it < o7) gc_ldgsts(&s_sp2[b * Tpad + (it - o6)], sp_all + toff + tn_lo + (it - o6), 16);
+                else gc_ldgsts(&s_tb2[b * GC_TRIAL_PF + (it - o7)], tb_n + (it - o7), 16);
+            }
+            asm volatile("cp.async.commit_group;");
+        };
+        auto next_grown = [&](int from) { int nx = from; while (nx < a.s.n_res && s_kind[nx] != 2) ++nx; return nx; };
+        {
+            const int first = next_grown(0);
+            if (first < a.s.n_res) stage_issue(0, first);
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();
+        }
         for (int step = 0; step < a.s.n_res; ++step) {
-            const StepDev &st = a.s.steps[step];
-            const int n_sc = st.n_sc;
-            if (st.kind == 1) {                            // GLY/ALA: conformer independent, placed by set_backbone (:164-168)
-                if (tid < n_sc) {
-                    const int atom = st.sc_start + tid, c = a.s.cls_of_atom[atom];
-                    const int f = gc_flat(s_pstart[c] + a.s.slot_of_atom[atom] - a.s.cls_start[c]);
+            const int kind = s_kind[step];
+            if (kind == 1) {                               // GLY/ALA: conformer independent, placed by set_backbone (:164-168)
+                const StepDev &sr = a.s.steps[step];
+                if (tid < sr.n_sc) {
+                    const int atom = sr.sc_start + tid, c = a.s.cls_of_atom[atom];
+                    const int f = gc_flat(s_pstart[c] + a.s.slot_of_atom[atom] - s_cstart[c]);
                     s_flat[f] = a.s.rigid_xyz[atom * 3]; s_flat[f + 2] = a.s.rigid_xyz[atom * 3 + 1];
                     s_flat[f + 4] = a.s.rigid_xyz[atom * 3 + 2]; s_flat[f + 6] = (float)a.s.charge[atom];
                 }
                 __syncthreads();
                 continue;
             }
-            if (st.kind != 2 || st.n_trials <= 0) continue;
+            if (kind != 2) continue;
+            const int par = count & 1;
+            const GcStage &sg = s_stage[par];
+            const StepDev &st = sg.st;                     // (shared memory)
+            const int n_sc = st.n_sc;
             const int T = st.n_trials;
             const int t_lo = (int)(((long long)T * rank) / S), t_hi = (int)(((long long)T * (rank + 1)) / S), nt = t_hi - t_lo;
-            const int par = count & 1;
             const float4 *tb = tb_all + a.aoff[step];
-            const double2 *sp = sp_all + st.trial_off;
+            // this CTA's trials, local index: staged in shared memory when they fit, else where K1 left them
+            const float4 *tloc = sg.n_tb ? s_tb2 + par * GC_TRIAL_PF : tb + (long long)t_lo * n_sc;
+            const double2 *sp = s_sp2 + par * Tpad;        // local index as well
+            const double *prob = s_prob2 + par * Tpad;
             double2 *part = a.partial + ((long long)set * 2 + par) * (Tmax + 1);
+            const int nx_step = next_grown(step + 1);
 
             // active atoms per class at this residue; the special environment atoms (scored pair by pair above) are parked
             // for the generic pass
-            for (int c = tid; c < n_cls; c += nthr)
-                s_act[c] = a.s.cls_prefix[step * (n_cls + 1) + c + 1] - a.s.cls_prefix[step * (n_cls + 1) + c];
+            if (warp == nwarps - 1) {                      // (n_cls <= MAX_CLS = 64: two classes per lane)
+                int carry = 0;
+                for (int c0 = 0; c0 < n_cls; c0 += 32) {
+                    const int c = c0 + lane;
+                    int act = 0;
+                    if (c < n_cls) act = sg.prefix[c + 1] - sg.prefix[c];
+                    const int np = (act + 1) >> 1;
+                    int x = np;
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, off); if (lane >= off) x += y; }
+                    if (c < n_cls) { s_act[c] = act; s_pp[c] = carry + x - np; }
+                    carry += __shfl_sync(0xffffffffu, x, 31);
+                }
+                if (lane == 0) s_pp[n_cls] = carry;
+            }
             if (tid < st.n_sp_env) {
                 const int slot = st.sp_env_slot[tid];
                 int c_lo = 0, c_hi = n_cls;                                    // largest c with cls_start[c] <= slot
-                while (c_hi - c_lo > 1) { const int m = (c_lo + c_hi) >> 1; if (a.s.cls_start[m] <= slot) c_lo = m; else c_hi = m; }
-                const int f = gc_flat(s_pstart[c_lo] + slot - a.s.cls_start[c_lo]);
+                while (c_hi - c_lo > 1) { const int m = (c_lo + c_hi) >> 1; if (s_cstart[m] <= slot) c_lo = m; else c_hi = m; }
+                const int f = gc_flat(s_pstart[c_lo] + slot - s_cstart[c_lo]);
                 s_save[tid] = make_float4(s_flat[f], s_flat[f + 2], s_flat[f + 4], s_flat[f + 6]);
                 s_savepos[tid] = f;
                 s_flat[f] = 1.0e15f; s_flat[f + 2] = 1.0e15f; s_flat[f + 4] = 1.0e15f; s_flat[f + 6] = 0.f;
@@ -326,8 +418,9 @@ __global__ void __launch_bounds__(GC_MAX_THREADS, 1) grow_cluster_kernel(Cluster
                 {
                     float best = 1.0e30f;
                     const int e_max = min(16, GC_SE / max(1, n_local));
-                    for (int e = 1; e <= e_max; ++e) {
-                        const float cost = (float)((chunks * e + nwarps - 1) / nwarps) * (1.0f / (float)e + 0.06f);
+                    const int wshift = 31 - __clz(nwarps);               // (8 or 16 warps)
+                    for (int e = 1, units_e = chunks; e <= e_max; ++e, units_e += chunks) {
+                        const float cost = (float)((units_e + nwarps - 1) >> wshift) * (__frcp_rn((float)e) + 0.10f);
                         if (cost < best) { best = cost; esplit = e; }
                     }
                 }
@@ -341,27 +434,27 @@ __global__ void __launch_bounds__(GC_MAX_THREADS, 1) grow_cluster_kernel(Cluster
 #pragma unroll
                     for (int r = 0; r < SCORE_R; ++r) {
                         const int la = ch * 64 + r * 32 + lane;
-                        int k = 0; float4 p = tb[(long long)t_lo * n_sc];
+                        int k = 0; float4 p = tloc[0];
                         if (la < n_varatoms) {
                             const int tl = la / n_per, kk = la - tl * n_per;
                             k = dedup ? st.var_k[kk] : kk;
-                            p = tb[(long long)(t_lo + bt + tl) * n_sc + k];
+                            p = tloc[(bt + tl) * n_sc + k];
                         } else if (la < n_local) {
                             k = st.fix_k[la - n_varatoms];
-                            p = tb[(long long)t_lo * n_sc + k];                  // identical in every trial: this CTA's first
+                            p = tloc[k];                                         // identical in every trial: this CTA's first
                         }
                         katom[r] = k;
                         nx[r] = make_float2(-p.x, -p.x); ny[r] = make_float2(-p.y, -p.y); nz[r] = make_float2(-p.z, -p.z);
-                        ci[r] = a.s.cls_of_atom[st.sc_start + k];
+                        ci[r] = sg.cls[k];
                         e_lj[r] = 0.0; e_c[r] = 0.0; clash[r] = false;
                     }
-                    if (ch * 64 + 32 < n_local) gc_score_unit<2>(a, s_env, s_pstart, s_act, j, esplit, nx, ny, nz, ci, e_lj, e_c, clash);
-                    else gc_score_unit<1>(a, s_env, s_pstart, s_act, j, esplit, nx, ny, nz, ci, e_lj, e_c, clash);
+                    if (ch * 64 + 32 < n_local) gc_score_unit<2>(a, s_env, s_pstart, s_pp, s_cthr, s_cA, s_cB, j, esplit, nx, ny, nz, ci, e_lj, e_c, clash);
+                    else gc_score_unit<1>(a, s_env, s_pstart, s_pp, s_cthr, s_cA, s_cB, j, esplit, nx, ny, nz, ci, e_lj, e_c, clash);
 #pragma unroll
                     for (int r = 0; r < SCORE_R; ++r) {
                         const int la = ch * 64 + r * 32 + lane;
                         if (la < n_local) {
-                            const double qi = a.s.charge[st.sc_start + katom[r]];
+                            const double qi = sg.q[katom[r]];
                             s_e[j * n_local + la] = e_lj[r] + COULOMB_PREF * qi * e_c[r];
                             s_cl[j * n_local + la] = clash[r] ? 1 : 0;
                         }
@@ -370,18 +463,24 @@ __global__ void __launch_bounds__(GC_MAX_THREADS, 1) grow_cluster_kernel(Cluster
                 __syncthreads();
                 GC_TICK(4);
                 // per-atom totals -> per-trial (energy, clash), fixed order; the special pairs join here
+                if (esplit > 1) {                          // first the environment shares of every atom, in share order
+                    for (int la = tid; la < n_local; la += nthr) {
+                        double e = s_e[la]; int cl = s_cl[la];
+                        for (int j = 1; j < esplit; ++j) { e += s_e[j * n_local + la]; cl |= s_cl[j * n_local + la]; }
+                        s_e[la] = e; s_cl[la] = (unsigned char)cl;
+                    }
+                    __syncthreads();
+                }
                 for (int tl = tid; tl < nbt; tl += nthr) {
                     double e = 0.0; int cl = 0;
-                    for (int k = 0; k < n_per; ++k)
-                        for (int j = 0; j < esplit; ++j) { e += s_e[j * n_local + tl * n_per + k]; cl |= s_cl[j * n_local + tl * n_per + k]; }
-                    const double2 s2 = sp[t_lo + bt + tl];
+                    for (int k = 0; k < n_per; ++k) { e += s_e[tl * n_per + k]; cl |= s_cl[tl * n_per + k]; }
+                    const double2 s2 = sp[bt + tl];
                     e = s2.x + e; cl |= (s2.y != 0.0) ? 1 : 0;
                     part[t_lo + bt + tl] = make_double2(e, cl ? 1.0 : 0.0);
                 }
                 if (n_fixatoms > 0 && tid == nthr - 1) {
                     double e = 0.0; int cl = 0;
-                    for (int k = 0; k < n_fixatoms; ++k)
-                        for (int j = 0; j < esplit; ++j) { e += s_e[j * n_local + n_varatoms + k]; cl |= s_cl[j * n_local + n_varatoms + k]; }
+                    for (int k = 0; k < n_fixatoms; ++k) { e += s_e[n_varatoms + k]; cl |= s_cl[n_varatoms + k]; }
                     part[T] = make_double2(e, cl ? 1.0 : 0.0);
                 }
                 __syncthreads();
@@ -392,9 +491,13 @@ __global__ void __launch_bounds__(GC_MAX_THREADS, 1) grow_cluster_kernel(Cluster
                 s_flat[f] = v.x; s_flat[f + 2] = v.y; s_flat[f + 4] = v.z; s_flat[f + 6] = v.w;
             }
 
-            // ---- one barrier per residue: every CTA of the cluster has written its trials' sums ----
             GC_TICK(5);
-            gc_cluster_sync(S);
+            // ---- one barrier per residue: every CTA of the cluster has written its trials' sums.  In its shadow the tables and
+            //      trial atoms of the next grown residue start travelling to the other stage buffer ----
+            if (S > 1) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+            if (nx_step < a.s.n_res) stage_issue(par ^ 1, nx_step);
+            if (S > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+            else __syncthreads();
             GC_TICK(6);
 
             // ---- K3: clash mask + Boltzmann selection, by every CTA on the same numbers (side_chain_builder.py:183-197) ----
@@ -426,12 +529,13 @@ __global__ void __launch_bounds__(GC_MAX_THREADS, 1) grow_cluster_kernel(Cluster
                 alive = false;
                 if (a.selected && rank == 0)
                     for (int s2 = step + tid; s2 < a.s.n_res; s2 += nthr)
-                        if (a.s.steps[s2].kind == 2 && a.s.steps[s2].n_trials > 0) a.selected[(long long)set * a.s.n_res + s2] = -1;
+                        if (s_kind[s2] == 2) a.selected[(long long)set * a.s.n_res + s2] = -1;
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
                 break;
             }
             GC_TICK(7);
             for (int t = tid; t < T; t += nthr)
-                s_w[t] = a.s.prob[st.trial_off + t] * exp(-a.cp.beta * (s_E[t] - mn));    // side_chain_builder.py:191-192
+                s_w[t] = prob[t] * exp(-a.cp.beta * (s_E[t] - mn));    // side_chain_builder.py:191-192
             __syncthreads();
             if (tid == 0) {
                 double u;
@@ -444,20 +548,28 @@ __global__ void __launch_bounds__(GC_MAX_THREADS, 1) grow_cluster_kernel(Cluster
                 }
                 // sequential float64 running sums, first index whose sum exceeds u*total (side_chain_builder.py:35-40);
                 // the loads run ahead of the dependent additions
-                double total = 0.0;
+                double run = 0.0;
                 int t = 0;
                 for (; t + 8 <= T; t += 8) {
                     double w8[8];
 #pragma unroll
                     for (int q = 0; q < 8; ++q) w8[q] = s_w[t + q];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) total += w8[q];
+                    for (int q = 0; q < 8; ++q) { run += w8[q]; s_w[t + q] = run; }
                 }
-                for (; t < T; ++t) total += s_w[t];
-                const double pointer = u * total;
+                for (; t < T; ++t) { run += s_w[t]; s_w[t] = run; }
+                const double pointer = u * run;
                 int sel = T - 1;
-                double run = 0.0;
-                for (t = 0; t < T; ++t) { run += s_w[t]; if (run > pointer) { sel = t; break; } }
+                for (t = 0; t + 8 <= T; t += 8) {
+                    double w8[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) w8[q] = s_w[t + q];
+                    int hit = -1;
+#pragma unroll
+                    for (int q = 7; q >= 0; --q) if (w8[q] > pointer) hit = t + q;
+                    if (hit >= 0) { sel = hit; t = T; break; }
+                }
+                for (; t < T; ++t) if (s_w[t] > pointer) { sel = t; break; }
                 s_sel = sel;
                 e_acc += (s_E[sel] - mn) + mn;                                  // side_chain_builder.py:197
                 if (a.selected && rank == 0) a.selected[(long long)set * a.s.n_res + step] = sel;
@@ -467,10 +579,11 @@ __global__ void __launch_bounds__(GC_MAX_THREADS, 1) grow_cluster_kernel(Cluster
             if (tid < n_sc) {                              // append the chosen side chain to this CTA's environment
                 const int sel = s_sel;
                 const float4 p = __ldcg(&tb[(long long)sel * n_sc + tid]);
-                const int atom = st.sc_start + tid, c = a.s.cls_of_atom[atom];
-                const int f = gc_flat(s_pstart[c] + a.s.slot_of_atom[atom] - a.s.cls_start[c]);
-                s_flat[f] = p.x; s_flat[f + 2] = p.y; s_flat[f + 4] = p.z; s_flat[f + 6] = (float)a.s.charge[atom];
+                const int c = sg.cls[tid];
+                const int f = gc_flat(s_pstart[c] + sg.slot[tid] - s_cstart[c]);
+                s_flat[f] = p.x; s_flat[f + 2] = p.y; s_flat[f + 4] = p.z; s_flat[f + 6] = (float)sg.q[tid];
             }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");          // the next residue's stage buffer has landed
             __syncthreads();
             GC_TICK(9);
             ++count;

@@ -2320,8 +2320,10 @@ static int finish_growth(mcsce_handle h, int C, const Workspace &w, float *d_coo
 // path cannot take it (the caller falls back to the graph / direct path), -1 on error.
 // ------------------------------------------------------------------------------------------------
 static size_t gc_smem_bytes(const mcsce_handle h) {
-    const size_t T = (size_t)std::max(1, h->max_trials);
-    const size_t b = (size_t)h->env_pairs * 32 + (size_t)GC_SE * 8 + T * 16 + GC_SE;
+    // (mirrors the carve at the top of grow_cluster_kernel)
+    const size_t T = (size_t)std::max(1, h->max_trials), Tpad = (T + 1) & ~(size_t)1, n2 = (size_t)h->d.n_cls * h->d.n_cls;
+    const size_t b = (size_t)h->env_pairs * 32 + (size_t)GC_SE * 8 + Tpad * 8 * 2 + 2 * Tpad * 8 + 2 * Tpad * 16 +
+                     2 * (size_t)GC_TRIAL_PF * 16 + n2 * 16 + ((n2 + 3) & ~(size_t)3) * 4 + GC_SE + (size_t)h->d.n_res;
     return (b + 15) / 16 * 16;
 }
 // device workspace of the persistent growth: every trial of every residue placed up front, their special-pair sums, and the
@@ -2374,10 +2376,11 @@ static int gc_make_plan(mcsce_handle h, int C) {
 }
 
 static int grow_persistent(mcsce_handle h, const mcsce_grow_opts *o, void *d_workspace, size_t workspace_bytes, float *d_coords,
-                           double *d_energy, uint8_t *d_ok, cudaStream_t st) {
+                           double *d_energy, uint8_t *d_ok, cudaStream_t st, bool any_plan) {
     const int C = o->n_conf;
     const int rc = gc_make_plan(h, C);
     if (rc <= 0) return rc;
+    if (!any_plan && !(h->gc_S >= 8 || ((long long)C * h->gc_S >= 128 && (long long)C * h->gc_S <= h->sm_count))) return 0;
     const SysDev &d = h->d;
     ClusterArgs a{};
     a.s = d; a.cp = CallParams{o->seed, o->conf_id0, o->beta, o->noise_deg};
@@ -2450,7 +2453,12 @@ extern "C" int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *o, void *d_work
     const bool plain = !o->hpmf && !h->profiling && grow_steps > 0;
     const int persistent = persistent_knob();
     if (plain && (o->no_graph == 3 || (o->no_graph == 0 && ((small && persistent >= 1) || persistent >= 2)))) {
-        const int rc = grow_persistent(h, o, d_workspace, workspace_bytes, d_coords, d_energy, d_ok, st);
+        // On its own the persistent kernel is picked where it was measured faster than the replayed graph (76 residues, B200,
+        // ms per ensemble persistent / graph: 1 conformer 1.23 / 1.51, 4: 1.24 / 1.57, 8: 1.45 / 1.60, 16: 1.91 / 1.75,
+        // 32: 1.92 / 2.09, 64: 2.75 / 2.90, 128: 4.54 / 4.56): while every conformer gets a cluster of at least 8 CTAs, or
+        // when the clusters of all conformers fill the GPU in one round.
+        const bool any = (o->no_graph == 3 || persistent >= 2);
+        const int rc = grow_persistent(h, o, d_workspace, workspace_bytes, d_coords, d_energy, d_ok, st, any);
         if (rc != 0) return rc < 0 ? -1 : 0;
     }
     const bool use_graph = (o->no_graph == 0 || o->no_graph == 2) && plain && small;

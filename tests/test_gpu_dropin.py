@@ -233,5 +233,12 @@ def test_large_ensembles_are_grown_in_chunks():
         chunked = scb._grow(s.coords, case.beta, 13)
     finally:
         scb.MAX_CONFORMERS_PER_LAUNCH = old
+    # the same Philox streams (keyed by global conformer id) whatever the chunking: same selections, hence bit-identical
+    # coordinates; the energies agree to the float32 grouping of the pair sums, which follows the launch geometry (13
+    # conformers get clusters of 8 CTAs each, 5 get clusters of 16; in the per-kernel path it follows the environment split)
     for a, b in zip(whole, chunked):
-        assert np.array_equal(a, b, equal_nan=True)
+        a, b = np.asarray(a), np.asarray(b)
+        if a.dtype == np.float64:
+            assert np.allclose(a, b, rtol=1e-6, atol=1e-3, equal_nan=True)
+        else:
+            assert np.array_equal(a, b, equal_nan=True)

@@ -342,30 +342,40 @@ def test_failed_growth_is_reported():
 
 
 def test_sharding_is_invariant():
-    """Conformer streams are keyed by global id: growing [0,8) at once equals [0,4) + [4,8)."""
+    """Conformer streams are keyed by global id: growing [0,8) at once equals [0,4) + [4,8) - the same selections in every
+    driver; bit-identical energies where both calls have the same launch geometry (the replayed graph), energies to the
+    float32 grouping of the pair sums where they do not (persistent kernel: 8 conformers get clusters of 8 CTAs, 4 get 16)."""
     case, s, sysm, eng = engine_for("pep6")
-    a = eng.grow(8, case.beta, seed=9, dump=True)
-    b0 = eng.grow(4, case.beta, seed=9, conf_id0=0, dump=True)
-    b1 = eng.grow(4, case.beta, seed=9, conf_id0=4, dump=True)
-    sel = np.concatenate([b0["selected"].cpu().numpy(), b1["selected"].cpu().numpy()])
-    assert np.array_equal(a["selected"].cpu().numpy(), sel)
-    en = np.concatenate([b0["energy"].cpu().numpy(), b1["energy"].cpu().numpy()])
-    assert np.array_equal(a["energy"].cpu().numpy(), en, equal_nan=True)
+    for mode in (0, 2):
+        a = eng.grow(8, case.beta, seed=9, dump=True, no_graph=mode)
+        b0 = eng.grow(4, case.beta, seed=9, conf_id0=0, dump=True, no_graph=mode)
+        b1 = eng.grow(4, case.beta, seed=9, conf_id0=4, dump=True, no_graph=mode)
+        sel = np.concatenate([b0["selected"].cpu().numpy(), b1["selected"].cpu().numpy()])
+        assert np.array_equal(a["selected"].cpu().numpy(), sel)
+        en = np.concatenate([b0["energy"].cpu().numpy(), b1["energy"].cpu().numpy()])
+        if mode == 2:
+            assert np.array_equal(a["energy"].cpu().numpy(), en, equal_nan=True)
+        else:
+            assert np.allclose(a["energy"].cpu().numpy(), en, rtol=1e-6, atol=1e-3, equal_nan=True)
 
 
 def test_chi_independent_atoms_scored_once_equals_full_scoring():
     """HA/CB (and every other atom no chi rotation moves) are identical in all trials of a conformer; scoring
-    them once per residue must give what scoring them in every trial gives."""
+    them once per residue must give what scoring them in every trial gives.  In the per-kernel path (and its graph) every atom
+    meets the same environment tiles either way, so only the order of the per-trial additions differs (1e-9); in the persistent
+    kernel the number of trial atoms also sets how the environment is shared among the warps, i.e. the float32 grouping."""
     for name in ("pep12", "ptm14", "helix76"):
         case, s, sysm, eng = engine_for(name)
-        a = eng.grow(5, case.beta, seed=77, dump=True)
-        b = eng.grow(5, case.beta, seed=77, dump=True, no_dedup=True)
-        assert np.array_equal(a["selected"].cpu().numpy(), b["selected"].cpu().numpy())
-        ta, tb = a["trial_energy"].cpu().numpy(), b["trial_energy"].cpu().numpy()
-        assert np.array_equal(np.isinf(ta), np.isinf(tb)) and np.array_equal(np.isnan(ta), np.isnan(tb))
-        fin = np.isfinite(ta)
-        assert np.abs(ta[fin] - tb[fin]).max() <= 1e-9 * max(1.0, np.abs(tb[fin]).max())
-        assert np.allclose(a["energy"].cpu().numpy(), b["energy"].cpu().numpy(), rtol=1e-12, atol=1e-9, equal_nan=True)
+        for mode, tol in ((2, 1e-9), (0, 5e-7)):
+            a = eng.grow(5, case.beta, seed=77, dump=True, no_graph=mode)
+            b = eng.grow(5, case.beta, seed=77, dump=True, no_dedup=True, no_graph=mode)
+            assert np.array_equal(a["selected"].cpu().numpy(), b["selected"].cpu().numpy())
+            ta, tb = a["trial_energy"].cpu().numpy(), b["trial_energy"].cpu().numpy()
+            assert np.array_equal(np.isinf(ta), np.isinf(tb)) and np.array_equal(np.isnan(ta), np.isnan(tb))
+            fin = np.isfinite(ta)
+            assert np.abs(ta[fin] - tb[fin]).max() <= tol * max(1.0, np.abs(tb[fin]).max()), (name, mode)
+            assert np.allclose(a["energy"].cpu().numpy(), b["energy"].cpu().numpy(), rtol=1e-12 if mode == 2 else 1e-6,
+                               atol=1e-9 if mode == 2 else 1e-3, equal_nan=True)
 
 
 def test_neighbour_screen_equals_scoring_every_trial():
