@@ -83,12 +83,11 @@ __device__ __forceinline__ int gc_flat(int P) { return 8 * (P >> 1) + (P & 1); }
 // all classes form one sequence (s_pp = its per-class prefix), a share is a contiguous run of it, so a unit walks only the
 // classes its run touches
 template <int RR>
-__device__ __forceinline__ void gc_score_unit(const ClusterArgs &a, const float4 *__restrict__ s_env, const int *s_pstart,
+__device__ __forceinline__ void gc_score_unit(const float4 *__restrict__ s_env, const int *s_pstart,
                                               const int *s_pp, const float *s_cthr, const double *s_cA, const double *s_cB,
-                                              int j, int esplit, const float2 (&nx)[SCORE_R],
+                                              int n_cls, int j, int esplit, const float2 (&nx)[SCORE_R],
                                               const float2 (&ny)[SCORE_R], const float2 (&nz)[SCORE_R], const int (&ci)[SCORE_R],
                                               double (&e_lj)[SCORE_R], double (&e_c)[SCORE_R], bool (&clash)[SCORE_R]) {
-    const int n_cls = a.s.n_cls;
     const int total = s_pp[n_cls];
     const int g0 = (int)(((unsigned)total * (unsigned)j) / (unsigned)esplit), g1 = (int)(((unsigned)total * (unsigned)(j + 1)) / (unsigned)esplit);
     int c = 0;
@@ -448,8 +447,8 @@ __global__ void __launch_bounds__(GC_MAX_THREADS, 1) grow_cluster_kernel(Cluster
                         ci[r] = sg.cls[k];
                         e_lj[r] = 0.0; e_c[r] = 0.0; clash[r] = false;
                     }
-                    if (ch * 64 + 32 < n_local) gc_score_unit<2>(a, s_env, s_pstart, s_pp, s_cthr, s_cA, s_cB, j, esplit, nx, ny, nz, ci, e_lj, e_c, clash);
-                    else gc_score_unit<1>(a, s_env, s_pstart, s_pp, s_cthr, s_cA, s_cB, j, esplit, nx, ny, nz, ci, e_lj, e_c, clash);
+                    if (ch * 64 + 32 < n_local) gc_score_unit<2>(s_env, s_pstart, s_pp, s_cthr, s_cA, s_cB, n_cls, j, esplit, nx, ny, nz, ci, e_lj, e_c, clash);
+                    else gc_score_unit<1>(s_env, s_pstart, s_pp, s_cthr, s_cA, s_cB, n_cls, j, esplit, nx, ny, nz, ci, e_lj, e_c, clash);
 #pragma unroll
                     for (int r = 0; r < SCORE_R; ++r) {
                         const int la = ch * 64 + r * 32 + lane;

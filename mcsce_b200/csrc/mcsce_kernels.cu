@@ -1209,6 +1209,7 @@ __global__ void finish_kernel(int n_sets, const unsigned char *alive, const doub
 // K0: the whole growth in one kernel, a thread-block cluster per conformer (launch-bound runs)
 // ------------------------------------------------------------------------------------------------
 #include "grow_cluster.cuh"
+#include "score_conf.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // host side: handle, table upload, launch logic
@@ -1278,6 +1279,8 @@ struct mcsce_handle_s {
     int gc_S = 0, gc_threads = 0, gc_grid = 0;
     size_t gc_smem = 0;
     long long persistent_launches = 0;
+    int k2conf = -1;                          // scoring pass with one CTA per conformer (score_conf.cuh): -1 = not read yet
+    size_t k2conf_smem = 0;
     const CallParams *cur_call = nullptr;     // parameter block of the lane being enqueued (read by launch_place)
     // optional per-kernel-class device timing (CUDA events on the launch stream)
     bool profiling = false;
@@ -1933,7 +1936,33 @@ static int launch_generic(mcsce_handle h, int step, int n_sets, int n_trials, in
             score_generic_kernel<true><<<dim3(tiles, n_sets, 1), SCORE_THREADS, 0, st>>>(a);
             h->launches += 1;
         }
-        score_generic_kernel<false><<<grid, SCORE_THREADS, 0, st>>>(a);
+        // scoring pass: one CTA per conformer and environment share (score_conf.cuh) for launches that fill the GPU with
+        // such CTAs and whose share fits two of them per SM; else one CTA per 256-atom trial tile.  Measured on config 3
+        // (B200, ms per ensemble, per-conformer / per-tile): 2048 conformers 520.9 / 536.7, 1024: 261.4 / 269.5; with fewer
+        // CTAs than SMs per launch it loses (256 conformers 82.0 / 74.9, config 4 x 512: 33.7 / 31.4, config 5 x 32: 393 / 333).
+        // MCSCE_B200_K2CONF: 0 = never, 1 = that rule (default), 2 = whenever the share fits.
+        if (h->k2conf < 0) { const char *e = getenv("MCSCE_B200_K2CONF"); h->k2conf = e ? atoi(e) : 1; }
+        bool done = false;
+        if (h->k2conf >= 2 || (h->k2conf == 1 && (long long)n_sets * n_split >= h->sm_count)) {
+            int n_active = 0;
+            for (int c = 0; c < h->d.n_cls; ++c) n_active += h->cls_active[(size_t)step * h->d.n_cls + c];
+            const int per = (n_active + n_split - 1) / n_split;
+            const int cap_pairs = (per + h->d.n_cls + 2) / 2 + 1;
+            const size_t smem = (size_t)cap_pairs * 32 + (size_t)SC_SE * 9;
+            if (smem <= (size_t)110 * 1024) {
+                if (smem > h->k2conf_smem) {
+                    CK(cudaFuncSetAttribute(score_conf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+                    h->k2conf_smem = (size_t)110 * 1024;
+                }
+                static int fixed_shares = -1;
+                // four fixed shares of the staged pairs per 64-atom chunk: the per-atom sums do not depend on how many trials
+                // the screen left (bit-identical with and without it); 0 = as many as fill the warps best (0.5 % faster)
+                if (fixed_shares < 0) { const char *e = getenv("MCSCE_B200_K2CONF_E"); fixed_shares = e ? atoi(e) : 4; }
+                score_conf_kernel<<<dim3(n_sets, n_split), SC_THREADS, smem, st>>>(a, cap_pairs, fixed_shares);
+                done = true;
+            }
+        }
+        if (!done) score_generic_kernel<false><<<grid, SCORE_THREADS, 0, st>>>(a);
     }
     h->launches += 1;
     CK(cudaGetLastError());
