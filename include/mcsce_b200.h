@@ -156,6 +156,14 @@ size_t mcsce_workspace_bytes(mcsce_handle h, int n_conf);
 int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *opts, void *d_workspace, size_t workspace_bytes,
                float *d_coords, double *d_energy, uint8_t *d_ok, void *stream);
 
+/* Mode reductions of the callers on the device: "exhaustive" = the successful conformer of lowest energy
+ * (core/side_chain_builder.py:280-281; ties -> lowest index, like np.argmin), "simple" / return_first_valid = the first
+ * successful one (:245-249).  d_energy / d_ok / d_coords as mcsce_grow wrote them; *d_index = -1 when no conformer
+ * succeeded; d_picked_coords [n_atoms*3] (optional) receives the picked conformer, so one conformer instead of the
+ * ensemble travels to the host.                                                                                     */
+int mcsce_pick(mcsce_handle h, int n_conf, const double *d_energy, const uint8_t *d_ok, const float *d_coords,
+               int first_valid, int32_t *d_index, float *d_picked_coords, void *stream);
+
 /* Same with HOST result buffers: copies results device->host on `stream` and synchronises.
  * Needs workspace_bytes(n_conf) + n_conf*(n_atoms*12+9) extra bytes of workspace.            */
 int mcsce_grow_host(mcsce_handle h, const mcsce_grow_opts *opts, void *d_workspace, size_t workspace_bytes,

@@ -93,6 +93,7 @@ SYMBOLS = {
     "mcsce_pack_env": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mcsce_select": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mcsce_pick": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mcsce_input_energy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "mcsce_init_env": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "mcsce_rotate_template": (C.c_int, [C.c_int, C.c_int, _f32p, C.c_int, _i32p, _u32p, _f64p, C.c_int, _f64p, _f32p]),

@@ -269,7 +269,24 @@ def create_side_chain_structure(inputs):
 def create_side_chain(structure, n_trials, temperature, retain_resi=[], parallel_worker=16, return_first_valid=False):
     """Lowest-energy (or first valid) conformer out of ``n_trials`` grown in one batch."""
     beta = 1 / (temperature * 0.008314462)
-    coords, energy, ok = _grow(structure.coords, beta, int(n_trials))
+    n = int(n_trials)
+    if sharding.world()[1] == 1 and n <= MAX_CONFORMERS_PER_LAUNCH and _state.get("hpmf") is None:
+        # one rank, one launch: the reduction runs on the device and only the picked conformer is copied to the host
+        assert len(sidechain_placeholders) > 0, "Energy functions have not yet initialized!"
+        eng, sysm = _state["engine"], _state["system"]
+        backbone = np.asarray(structure.coords, dtype=np.float32)
+        assert sysm.n_input == backbone.shape[0], \
+            "Input structures contain extra sidechain atoms or miss sidechain atoms if fix argument is used"
+        key = backbone.tobytes()
+        if _state.get("backbone") != key:
+            eng.set_backbone(backbone)
+            _state["backbone"] = key
+        first = _state.get("next_conf", 0)
+        _state["next_conf"] = first + n
+        out = eng.grow(n, beta, seed=_state.get("seed", 0), conf_id0=first)
+        idx, picked = eng.pick(out, first_valid=return_first_valid)
+        return None if idx < 0 else _final_structure(picked)
+    coords, energy, ok = _grow(structure.coords, beta, n)
     if coords is None or not ok.any():
         return None
     idx = int(np.argmax(ok)) if return_first_valid else int(np.where(ok, energy, np.inf).argmin())

@@ -76,6 +76,18 @@ __device__ __forceinline__ void gc_cluster_sync(int cluster) {
     }
 }
 
+// one (energy, clash) pair into the same shared-memory slot of every CTA of the cluster (distributed shared memory): after
+// the cluster barrier every CTA holds all trials' sums locally - no round trip through L2
+__device__ __forceinline__ void gc_push(double2 *slot, int cluster, double2 v) {
+    if (cluster == 1) { *slot = v; return; }
+    const unsigned la = (unsigned)__cvta_generic_to_shared(slot);
+    for (int r = 0; r < cluster; ++r) {
+        unsigned ra;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(r));
+        asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" :: "r"(ra), "d"(v.x), "d"(v.y) : "memory");
+    }
+}
+
 // position P of an atom inside the pair-interleaved image -> index of its x in the float view (y +2, z +4, q +6)
 __device__ __forceinline__ int gc_flat(int P) { return 8 * (P >> 1) + (P & 1); }
 
@@ -141,7 +153,9 @@ __global__ void __launch_bounds__(GC_MAX_THREADS, 1) grow_cluster_kernel(Cluster
     double *s_w = s_E + Tpad;                                           // [Tpad] Boltzmann weights
     double *s_prob2 = s_w + Tpad;                                       // [2][Tpad] staged prior weights
     double2 *s_sp2 = reinterpret_cast<double2 *>(s_prob2 + 2 * Tpad);   // [2][Tpad] staged special-pair sums of this CTA's trials
-    float4 *s_tb2 = reinterpret_cast<float4 *>(s_sp2 + 2 * Tpad);       // [2][GC_TRIAL_PF] staged trial atoms of this CTA's trials
+    double2 *s_part2 = s_sp2 + 2 * Tpad;                                // [2][Tpad+2] (energy, clash) of every trial of the residue, pushed
+                                                                        //     by the CTAs that scored them; slot T: chi-independent atoms
+    float4 *s_tb2 = reinterpret_cast<float4 *>(s_part2 + 2 * (Tpad + 2)); // [2][GC_TRIAL_PF] staged trial atoms of this CTA's trials
     double *s_cA = reinterpret_cast<double *>(s_tb2 + 2 * GC_TRIAL_PF); // [n_cls^2] class-pair constants (A/d^12 - B/d^6)
     double *s_cB = s_cA + n_cls * n_cls;
     float *s_cthr = reinterpret_cast<float *>(s_cB + n_cls * n_cls);    // [n_cls^2] exact float32 clash thresholds (squared)
@@ -335,13 +349,44 @@ __global__ void __launch_bounds__(GC_MAX_THREADS, 1) grow_cluster_kernel(Cluster
             }
             asm volatile("cp.async.commit_group;");
         };
+        // prep: active atoms per class of a staged residue (warp wa) and its special environment atoms - scored pair by pair
+        // by K2s - saved and parked for the generic pass (lanes of warp ws)
+        auto prep = [&](const GcStage &g, int wa, int ws) {
+            if (warp == wa) {                              // (n_cls <= MAX_CLS = 64: two classes per lane)
+                int carry = 0;
+                for (int c0 = 0; c0 < n_cls; c0 += 32) {
+                    const int c = c0 + lane;
+                    int act = 0;
+                    if (c < n_cls) act = g.prefix[c + 1] - g.prefix[c];
+                    const int np = (act + 1) >> 1;
+                    int x = np;
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, off); if (lane >= off) x += y; }
+                    if (c < n_cls) { s_act[c] = act; s_pp[c] = carry + x - np; }
+                    carry += __shfl_sync(0xffffffffu, x, 31);
+                }
+                if (lane == 0) s_pp[n_cls] = carry;
+            }
+            if (warp == ws && lane < g.st.n_sp_env) {
+                const int slot = g.st.sp_env_slot[lane];
+                int c_lo = 0, c_hi = n_cls;                                    // largest c with cls_start[c] <= slot
+                while (c_hi - c_lo > 1) { const int m = (c_lo + c_hi) >> 1; if (s_cstart[m] <= slot) c_lo = m; else c_hi = m; }
+                const int f = gc_flat(s_pstart[c_lo] + slot - s_cstart[c_lo]);
+                s_save[lane] = make_float4(s_flat[f], s_flat[f + 2], s_flat[f + 4], s_flat[f + 6]);
+                s_savepos[lane] = f;
+                s_flat[f] = 1.0e15f; s_flat[f + 2] = 1.0e15f; s_flat[f + 4] = 1.0e15f; s_flat[f + 6] = 0.f;
+            }
+        };
         auto next_grown = [&](int from) { int nx = from; while (nx < a.s.n_res && s_kind[nx] != 2) ++nx; return nx; };
         {
             const int first = next_grown(0);
             if (first < a.s.n_res) stage_issue(0, first);
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncthreads();
+            if (first < a.s.n_res) prep(s_stage[0], nwarps - 1, 0);
+            __syncthreads();
         }
+        GC_TICK(3);
         for (int step = 0; step < a.s.n_res; ++step) {
             const int kind = s_kind[step];
             if (kind == 1) {                               // GLY/ALA: conformer independent, placed by set_backbone (:164-168)
@@ -367,37 +412,8 @@ __global__ void __launch_bounds__(GC_MAX_THREADS, 1) grow_cluster_kernel(Cluster
             const float4 *tloc = sg.n_tb ? s_tb2 + par * GC_TRIAL_PF : tb + (long long)t_lo * n_sc;
             const double2 *sp = s_sp2 + par * Tpad;        // local index as well
             const double *prob = s_prob2 + par * Tpad;
-            double2 *part = a.partial + ((long long)set * 2 + par) * (Tmax + 1);
+            double2 *part = s_part2 + par * (Tpad + 2);
             const int nx_step = next_grown(step + 1);
-
-            // active atoms per class at this residue; the special environment atoms (scored pair by pair above) are parked
-            // for the generic pass
-            if (warp == nwarps - 1) {                      // (n_cls <= MAX_CLS = 64: two classes per lane)
-                int carry = 0;
-                for (int c0 = 0; c0 < n_cls; c0 += 32) {
-                    const int c = c0 + lane;
-                    int act = 0;
-                    if (c < n_cls) act = sg.prefix[c + 1] - sg.prefix[c];
-                    const int np = (act + 1) >> 1;
-                    int x = np;
-#pragma unroll
-                    for (int off = 1; off < 32; off <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, off); if (lane >= off) x += y; }
-                    if (c < n_cls) { s_act[c] = act; s_pp[c] = carry + x - np; }
-                    carry += __shfl_sync(0xffffffffu, x, 31);
-                }
-                if (lane == 0) s_pp[n_cls] = carry;
-            }
-            if (tid < st.n_sp_env) {
-                const int slot = st.sp_env_slot[tid];
-                int c_lo = 0, c_hi = n_cls;                                    // largest c with cls_start[c] <= slot
-                while (c_hi - c_lo > 1) { const int m = (c_lo + c_hi) >> 1; if (s_cstart[m] <= slot) c_lo = m; else c_hi = m; }
-                const int f = gc_flat(s_pstart[c_lo] + slot - s_cstart[c_lo]);
-                s_save[tid] = make_float4(s_flat[f], s_flat[f + 2], s_flat[f + 4], s_flat[f + 6]);
-                s_savepos[tid] = f;
-                s_flat[f] = 1.0e15f; s_flat[f + 2] = 1.0e15f; s_flat[f + 4] = 1.0e15f; s_flat[f + 6] = 0.f;
-            }
-            __syncthreads();
-            GC_TICK(3);
 
             // ---- K2: generic pairs of this CTA's trial atoms against the resident environment ----
             const int dedup = (a.dedup_ok && st.n_fix > 0 && st.n_var > 0) ? 1 : 0;
@@ -475,12 +491,12 @@ __global__ void __launch_bounds__(GC_MAX_THREADS, 1) grow_cluster_kernel(Cluster
                     for (int k = 0; k < n_per; ++k) { e += s_e[tl * n_per + k]; cl |= s_cl[tl * n_per + k]; }
                     const double2 s2 = sp[bt + tl];
                     e = s2.x + e; cl |= (s2.y != 0.0) ? 1 : 0;
-                    part[t_lo + bt + tl] = make_double2(e, cl ? 1.0 : 0.0);
+                    gc_push(&part[t_lo + bt + tl], S, make_double2(e, cl ? 1.0 : 0.0));
                 }
                 if (n_fixatoms > 0 && tid == nthr - 1) {
                     double e = 0.0; int cl = 0;
                     for (int k = 0; k < n_fixatoms; ++k) { e += s_e[n_varatoms + k]; cl |= s_cl[n_varatoms + k]; }
-                    part[T] = make_double2(e, cl ? 1.0 : 0.0);
+                    gc_push(&part[T], S, make_double2(e, cl ? 1.0 : 0.0));
                 }
                 __syncthreads();
             }
@@ -501,10 +517,10 @@ __global__ void __launch_bounds__(GC_MAX_THREADS, 1) grow_cluster_kernel(Cluster
 
             // ---- K3: clash mask + Boltzmann selection, by every CTA on the same numbers (side_chain_builder.py:183-197) ----
             double e_fix = 0.0; bool cl_fix = false;
-            if (dedup) { const double2 p = __ldcg(&part[T]); e_fix = p.x; cl_fix = p.y != 0.0; }
+            if (dedup) { const double2 p = part[T]; e_fix = p.x; cl_fix = p.y != 0.0; }
             double mn = CUDART_INF;
             for (int t = tid; t < T; t += nthr) {
-                const double2 p = __ldcg(&part[t]);
+                const double2 p = part[t];
                 double e = p.x + e_fix;
                 if (p.y != 0.0 || cl_fix) e = CUDART_INF;                       // energies[clash] = inf (libenergy.py:801)
                 s_E[t] = e;
@@ -535,7 +551,11 @@ __global__ void __launch_bounds__(GC_MAX_THREADS, 1) grow_cluster_kernel(Cluster
             GC_TICK(7);
             for (int t = tid; t < T; t += nthr)
                 s_w[t] = prob[t] * exp(-a.cp.beta * (s_E[t] - mn));    // side_chain_builder.py:191-192
+            asm volatile("cp.async.wait_group 0;" ::: "memory");          // the next residue's stage buffer has landed
             __syncthreads();
+            // while thread 0 walks the running sums, two other warps prepare the next residue's scoring pass (its special
+            // atoms are input atoms: parking them now does not touch what the selection appends)
+            if (nx_step < a.s.n_res) prep(s_stage[par ^ 1], nwarps - 1, nwarps - 2);
             if (tid == 0) {
                 double u;
                 if (a.uniform) u = a.uniform[(long long)set * a.s.n_res + step];
@@ -602,6 +622,12 @@ __global__ void __launch_bounds__(GC_MAX_THREADS, 1) grow_cluster_kernel(Cluster
                 a.energy[set] = alive ? e_acc : CUDART_NAN;
                 if (a.pair_counter) { atomicAdd(a.pair_counter, n_pairs); atomicAdd(a.pair_counter + 1, n_pairs_done); }
             }
+        }
+        // the CTAs of a cluster write into each other's shared memory: none may start the next conformer (or leave) before all
+        // have read this one's last sums
+        if (S > 1) {
+            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
         }
     }
 }

@@ -1833,7 +1833,7 @@ static int lane_count(const mcsce_handle h, int n_conf);
 static size_t gc_workspace_bytes(const mcsce_handle h, int C);
 // Launch-bound runs: little pair work per residue (few conformers and/or a small protein), where launch latencies and tails
 // of the per-kernel path outweigh the arithmetic.
-static bool launch_bound(const mcsce_handle h, int C, long long *grow_steps_out = nullptr) {
+static bool launch_bound(const mcsce_handle h, int C, long long *grow_steps_out = nullptr, long long *pairs_per_step_out = nullptr) {
     const SysDev &d = h->d;
     long long grow_steps = 0, pairs = 0;
     for (int i = 0; i < d.n_res; ++i) {
@@ -1845,6 +1845,7 @@ static bool launch_bound(const mcsce_handle h, int C, long long *grow_steps_out 
         ++grow_steps;
     }
     if (grow_steps_out) *grow_steps_out = grow_steps;
+    if (pairs_per_step_out) *pairs_per_step_out = grow_steps > 0 ? pairs / grow_steps : 0;      // per conformer
     return grow_steps > 0 && (pairs * C) / grow_steps < 300000000LL;
 }
 static int persistent_knob() {               // MCSCE_B200_PERSISTENT: 0 = never picked automatically, 1 = launch-bound runs (default), 2 = always
@@ -1919,7 +1920,7 @@ static int launch_place(mcsce_handle h, int step, int n_sets, int n_rows, const 
 static int launch_generic(mcsce_handle h, int step, int n_sets, int n_trials, int n_split, const float4 *env,
                           const float4 *trial, long long trial_stride, double2 *partial, const unsigned char *alive,
                           cudaStream_t st, int dedup = 0, unsigned char *screen = nullptr, const double2 *sp_partial = nullptr,
-                          int *n_keep = nullptr) {
+                          int *n_keep = nullptr, bool big_run = false) {
     const StepDev &sd = h->steps[step];
     if (dedup && (sd.n_fix <= 0 || sd.n_var <= 0)) dedup = 0;
     ScoreArgs a{};
@@ -1939,11 +1940,12 @@ static int launch_generic(mcsce_handle h, int step, int n_sets, int n_trials, in
         // scoring pass: one CTA per conformer and environment share (score_conf.cuh) for launches that fill the GPU with
         // such CTAs and whose share fits two of them per SM; else one CTA per 256-atom trial tile.  Measured on config 3
         // (B200, ms per ensemble, per-conformer / per-tile): 2048 conformers 520.9 / 536.7, 1024: 261.4 / 269.5; with fewer
-        // CTAs than SMs per launch it loses (256 conformers 82.0 / 74.9, config 4 x 512: 33.7 / 31.4, config 5 x 32: 393 / 333).
+        // CTAs than SMs per launch it loses (256 conformers 82.0 / 74.9, config 4 x 512: 33.7 / 31.4, config 5 x 32: 393 / 333),
+        // and so it does in the launch-bound regime (76 residues x 128 conformers as a graph: 5.20 / 4.55): big runs only.
         // MCSCE_B200_K2CONF: 0 = never, 1 = that rule (default), 2 = whenever the share fits.
         if (h->k2conf < 0) { const char *e = getenv("MCSCE_B200_K2CONF"); h->k2conf = e ? atoi(e) : 1; }
         bool done = false;
-        if (h->k2conf >= 2 || (h->k2conf == 1 && (long long)n_sets * n_split >= h->sm_count)) {
+        if (h->k2conf >= 2 || (h->k2conf == 1 && big_run && (long long)n_sets * n_split >= h->sm_count)) {
             int n_active = 0;
             for (int c = 0; c < h->d.n_cls; ++c) n_active += h->cls_active[(size_t)step * h->d.n_cls + c];
             const int per = (n_active + n_split - 1) / n_split;
@@ -2250,7 +2252,8 @@ struct GrowthEnqueue {
         unsigned char *screen = (!o.no_screen && resync && h->scr_len[i] > 0) ? w.screen : nullptr;
         const int dedup = (sd.n_fix > 0 && sd.n_var > 0 && !o.no_dedup) ? 1 : 0;
         const int split = std::min(ms_alloc, choose_split(h, i, n_alive * groups, T, o.env_split, screen != nullptr));
-        if (!screen && launch_generic(h, i, C, T, split, w.env, trial, trial_stride, w.partial, w.alive, st, dedup)) return -1;
+        if (!screen && launch_generic(h, i, C, T, split, w.env, trial, trial_stride, w.partial, w.alive, st, dedup, nullptr, nullptr,
+                                      nullptr, resync)) return -1;
         // aux: special pairs (need the environment as updated by the previous selection)
         if (prev >= 0) CK(cudaStreamWaitEvent(aux, ln->evS[prev], 0));
         if (launch_special(h, i, C, T, w.env, trial, trial_stride, w.sp_partial, w.alive, aux)) return -1;
@@ -2259,7 +2262,7 @@ struct GrowthEnqueue {
         if (screen) {
             CK(cudaStreamWaitEvent(st, ln->evQ[i], 0));
             if (launch_generic(h, i, C, T, split, w.env, trial, trial_stride, w.partial, w.alive, st, dedup, screen, w.sp_partial,
-                               w.n_keep)) return -1;
+                               w.n_keep, resync)) return -1;
         }
         // st: selection
         CK(cudaStreamWaitEvent(st, ln->evQ[i], 0));
@@ -2351,7 +2354,7 @@ static int finish_growth(mcsce_handle h, int C, const Workspace &w, float *d_coo
 static size_t gc_smem_bytes(const mcsce_handle h) {
     // (mirrors the carve at the top of grow_cluster_kernel)
     const size_t T = (size_t)std::max(1, h->max_trials), Tpad = (T + 1) & ~(size_t)1, n2 = (size_t)h->d.n_cls * h->d.n_cls;
-    const size_t b = (size_t)h->env_pairs * 32 + (size_t)GC_SE * 8 + Tpad * 8 * 2 + 2 * Tpad * 8 + 2 * Tpad * 16 +
+    const size_t b = (size_t)h->env_pairs * 32 + (size_t)GC_SE * 8 + Tpad * 8 * 2 + 2 * Tpad * 8 + 2 * Tpad * 16 + 2 * (Tpad + 2) * 16 +
                      2 * (size_t)GC_TRIAL_PF * 16 + n2 * 16 + ((n2 + 3) & ~(size_t)3) * 4 + GC_SE + (size_t)h->d.n_res;
     return (b + 15) / 16 * 16;
 }
@@ -2409,7 +2412,7 @@ static int grow_persistent(mcsce_handle h, const mcsce_grow_opts *o, void *d_wor
     const int C = o->n_conf;
     const int rc = gc_make_plan(h, C);
     if (rc <= 0) return rc;
-    if (!any_plan && !(h->gc_S >= 8 || ((long long)C * h->gc_S >= 128 && (long long)C * h->gc_S <= h->sm_count))) return 0;
+    if (!any_plan && (long long)C * h->gc_S > h->sm_count) return 0;        // more than one round of clusters: the graph wins
     const SysDev &d = h->d;
     ClusterArgs a{};
     a.s = d; a.cp = CallParams{o->seed, o->conf_id0, o->beta, o->noise_deg};
@@ -2474,20 +2477,23 @@ extern "C" int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *o, void *d_work
     // Launch-bound runs (little work per residue: few conformers and/or a small protein) replay a captured CUDA graph of
     // the whole growth instead of ~4 launches + 7 event calls per residue; the graph is cached per (tables, n_conf,
     // buffers, options).  Large runs enqueue directly and may re-derive the environment split while conformers die.
-    long long grow_steps = 0;
-    const bool small = launch_bound(h, C, &grow_steps);
+    long long grow_steps = 0, pairs_per_step = 0;
+    const bool small = launch_bound(h, C, &grow_steps, &pairs_per_step);
     // (the coordinate-based term sizes its buffers at the first step of a growth: not capturable)
     // o->no_graph: 0 = automatic, 1 = the direct per-kernel path, 2 = a replayed graph wherever the automatic choice is a
     // launch-bound path, 3 = the persistent cluster kernel whatever the size (if the environment fits shared memory)
     const bool plain = !o->hpmf && !h->profiling && grow_steps > 0;
     const int persistent = persistent_knob();
     if (plain && (o->no_graph == 3 || (o->no_graph == 0 && ((small && persistent >= 1) || persistent >= 2)))) {
-        // On its own the persistent kernel is picked where it was measured faster than the replayed graph (76 residues, B200,
-        // ms per ensemble persistent / graph: 1 conformer 1.23 / 1.51, 4: 1.24 / 1.57, 8: 1.45 / 1.60, 16: 1.91 / 1.75,
-        // 32: 1.92 / 2.09, 64: 2.75 / 2.90, 128: 4.54 / 4.56): while every conformer gets a cluster of at least 8 CTAs, or
-        // when the clusters of all conformers fill the GPU in one round.
+        // On its own the persistent kernel is picked where it was measured faster than the replayed graph (B200, ms per
+        // ensemble, persistent / graph).  76 residues: 1 conformer 1.08 / 1.51, 4: 1.08 / 1.56, 8: 1.29 / 1.60, 16: 1.75 / 1.72,
+        // 32: 1.75 / 2.08, 64: 2.59 / 2.90, 128: 4.40 / 4.54, 200 (two rounds of clusters): 8.83 / 6.18.  150 residues: 1: 1.98 /
+        // 2.06, 8: 4.27 / 3.66.  300 residues: 1: 7.78 / 6.23, 16: 19.1 / 11.9 - with that much work per residue the per-kernel
+        // path's environment split over all SMs beats 16 CTAs per conformer.  Hence: small proteins (<= 8e5 pair evaluations
+        // per residue and conformer) whose clusters are all resident at once.
         const bool any = (o->no_graph == 3 || persistent >= 2);
-        const int rc = grow_persistent(h, o, d_workspace, workspace_bytes, d_coords, d_energy, d_ok, st, any);
+        const bool fits_rule = pairs_per_step <= 800000LL;
+        const int rc = (any || fits_rule) ? grow_persistent(h, o, d_workspace, workspace_bytes, d_coords, d_energy, d_ok, st, any) : 0;
         if (rc != 0) return rc < 0 ? -1 : 0;
     }
     const bool use_graph = (o->no_graph == 0 || o->no_graph == 2) && plain && small;
@@ -2576,6 +2582,49 @@ extern "C" int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *o, void *d_work
                           o->hpmf ? h->lane[g].hp_ovf : nullptr)) return -1;
         if (g > 0) { CK(cudaEventRecord(h->lane[g].done, ge[g].st)); CK(cudaStreamWaitEvent(st, h->lane[g].done, 0)); }
     }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Mode reductions of the callers (core/side_chain_builder.py:245-249 "simple": the first successful conformer;
+// :280-281 "exhaustive": the successful conformer of lowest energy) on the device: the index, and the picked conformer's
+// coordinates, so that only one conformer travels to the host instead of the ensemble.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pick_kernel(int n_conf, int n_atoms, const double *energy, const unsigned char *ok,
+                                                   const float *coords, int first_valid, int *index, float *picked) {
+    __shared__ double s_e[256];
+    __shared__ int s_i[256];
+    const int tid = threadIdx.x;
+    double best = CUDART_INF; int bi = 0x7fffffff;
+    for (int i = tid; i < n_conf; i += 256) {
+        if (ok[i] != 1) continue;
+        const double e = first_valid ? 0.0 : energy[i];
+        if (bi == 0x7fffffff || e < best || (e == best && i < bi)) { best = e; bi = i; }   // ties -> the lowest index, like np.argmin / np.argmax
+    }
+    s_e[tid] = best; s_i[tid] = bi;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (tid < w) {
+            const double e2 = s_e[tid + w]; const int i2 = s_i[tid + w];
+            if (i2 != 0x7fffffff && (s_i[tid] == 0x7fffffff || e2 < s_e[tid] || (e2 == s_e[tid] && i2 < s_i[tid]))) { s_e[tid] = e2; s_i[tid] = i2; }
+        }
+        __syncthreads();
+    }
+    const int sel = s_i[0] == 0x7fffffff ? -1 : s_i[0];
+    if (tid == 0) index[0] = sel;
+    if (sel >= 0 && picked)
+        for (int k = tid; k < n_atoms * 3; k += 256) picked[k] = coords[(long long)sel * n_atoms * 3 + k];
+}
+
+extern "C" int mcsce_pick(mcsce_handle h, int n_conf, const double *d_energy, const uint8_t *d_ok, const float *d_coords,
+                          int first_valid, int32_t *d_index, float *d_picked_coords, void *stream) {
+    if (!h || !h->has_sys) return fail("set_system first");
+    if (n_conf <= 0 || !d_energy || !d_ok || !d_index) return fail("bad arguments");
+    if (d_picked_coords && !d_coords) return fail("d_coords is needed to copy the picked conformer");
+    CK(cudaSetDevice(h->device));
+    pick_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(n_conf, h->d.n_atoms, d_energy, d_ok, d_coords, first_valid, d_index, d_picked_coords);
+    h->launches += 1;
+    CK(cudaGetLastError());
     return 0;
 }
 

@@ -268,6 +268,20 @@ class GrowthEngine:
         out["_keep"] = keep
         return out
 
+    def pick(self, out, first_valid=False):
+        """Mode reduction on the device (``mcsce_pick``): index of the lowest-energy successful conformer of a ``grow``
+        result (``first_valid``: of the first successful one) and its coordinates as a (n_atoms, 3) float32 NumPy array;
+        ``(-1, None)`` when no conformer succeeded.  Only the picked conformer is copied to the host."""
+        torch = self.torch
+        n = int(out["energy"].shape[0])
+        idx = torch.empty(1, dtype=torch.int32, device=self.device)
+        picked = torch.empty((self.system.n_atoms, 3), dtype=torch.float32, device=self.device)
+        check(self.lib.mcsce_pick(self.h, n, C.c_void_p(out["energy"].data_ptr()), C.c_void_p(out["ok"].data_ptr()),
+                                  C.c_void_p(out["coords"].data_ptr()), 1 if first_valid else 0,
+                                  C.c_void_p(idx.data_ptr()), C.c_void_p(picked.data_ptr()), self._stream_ptr()))
+        i = int(idx.item())
+        return (i, picked.cpu().numpy()) if i >= 0 else (-1, None)
+
     # -- single kernels (drop-in entry points and parity tests) -------------------
     def _stream_ptr(self):
         return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)

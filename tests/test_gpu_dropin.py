@@ -156,6 +156,19 @@ def test_side_chain_builder_entry_points(tmp_path):
     best = scb.create_side_chain(s, 8, 300, return_first_valid=False)
     first = scb.create_side_chain(s, 8, 300, return_first_valid=True)
     assert best is not None and first is not None and len(best) == len(st)
+    # the mode reductions run on the device (mcsce_pick): same picks as the host reductions of the reference
+    # (side_chain_builder.py:245-249 first valid, :280-281 lowest energy), only the picked conformer is copied back
+    eng = scb._state["engine"]
+    out = eng.grow(64, beta, seed=3)
+    e, k, x = out["energy"].cpu().numpy(), out["ok"].cpu().numpy(), out["coords"].cpu().numpy()
+    k[::3] = 0                                         # (some failures, so that the first valid one is not conformer 0)
+    out["ok"].copy_(out["ok"].new_tensor(k))
+    i_best, x_best = eng.pick(out)
+    i_first, x_first = eng.pick(out, first_valid=True)
+    assert i_best == int(np.where(k == 1, e, np.inf).argmin()) and np.array_equal(x_best, x[i_best])
+    assert i_first == int(np.argmax(k == 1)) == 1 and np.array_equal(x_first, x[1])
+    out["ok"].zero_()
+    assert eng.pick(out) == (-1, None)
     # a level's energy closure, built on demand, agrees with the growth's own scoring conventions
     f = scb.energy_calculators[1]
     assert scb.energy_calculators[3] is None or callable(scb.energy_calculators[3])   # GLY/ALA levels are None
