@@ -501,6 +501,12 @@ def run_ours(args, rank, world, local_rank):
                 peak, _, _ = fp32_peak_tflops(local_rank, {})
                 r["frac_executed"] = FLOPS_PER_PAIR * p_exec / (k2_ms * 1e-3) / 1e12 / peak if k2_ms > 0 else None
                 r["k2_share_of_step"] = k2_ms / step_ms if step_ms else None
+                per_step = r["gpu_launches"] / max(1, args.steps) / max(1, min(world, Ho.n_total))     # (launch counts are summed over the ranks)
+                r["driver"] = ("persistent cluster kernel (grow_cluster_kernel: one launch per ensemble)" if per_step <= 2 else
+                               "per-kernel path" + (" replayed as a CUDA graph" if name in ("cfg1", "cfg2") else ""))
+                if per_step <= 2:
+                    r["frac_executed_note"] = ("frac_executed and k2_share_of_step are from the per-kernel path (CUDA events around its "
+                                               "K2 launches); the timed steps ran the persistent kernel, which has no separate K2 launch")
             r["config"] = {"workload": "%s: %s" % (name, Ho.desc), "conformers_total": Ho.n_total, "residues": Ho.sysm.n_res,
                            "atoms": Ho.sysm.n_atoms}
             others[name] = r
@@ -528,7 +534,8 @@ def run_ours(args, rank, world, local_rank):
             pass
     executed = FLOPS_PER_PAIR * prof_computed / (k2_ms * 1e-3) / 1e12 if k2_ms > 0 else 0.0
     roofline = {
-        "bound": "fp32", "kernel": "score_generic_kernel", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
+        "bound": "fp32", "kernel": "K2 = score_generic_kernel<1> (neighbour screen) + score_conf_kernel (scoring pass, one CTA per "
+                                   "conformer; score_generic_kernel<0> for launches with fewer CTAs than SMs)", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
         "frac": achieved / peak_tflops, "traffic": traffic,
         "peak_source": "FP32 CUDA-core peak = %d SMs x 128 lanes x 2 x %.0f MHz (sm_max_mhz of MEASURED_PEAKS.json; that file "
                        "holds no FP32 figure)" % (sm_count, sm_max),

@@ -1920,7 +1920,7 @@ static int launch_place(mcsce_handle h, int step, int n_sets, int n_rows, const 
 static int launch_generic(mcsce_handle h, int step, int n_sets, int n_trials, int n_split, const float4 *env,
                           const float4 *trial, long long trial_stride, double2 *partial, const unsigned char *alive,
                           cudaStream_t st, int dedup = 0, unsigned char *screen = nullptr, const double2 *sp_partial = nullptr,
-                          int *n_keep = nullptr, bool big_run = false) {
+                          int *n_keep = nullptr, int call_sets = 0) {
     const StepDev &sd = h->steps[step];
     if (dedup && (sd.n_fix <= 0 || sd.n_var <= 0)) dedup = 0;
     ScoreArgs a{};
@@ -1937,15 +1937,16 @@ static int launch_generic(mcsce_handle h, int step, int n_sets, int n_trials, in
             score_generic_kernel<true><<<dim3(tiles, n_sets, 1), SCORE_THREADS, 0, st>>>(a);
             h->launches += 1;
         }
-        // scoring pass: one CTA per conformer and environment share (score_conf.cuh) for launches that fill the GPU with
-        // such CTAs and whose share fits two of them per SM; else one CTA per 256-atom trial tile.  Measured on config 3
-        // (B200, ms per ensemble, per-conformer / per-tile): 2048 conformers 520.9 / 536.7, 1024: 261.4 / 269.5; with fewer
-        // CTAs than SMs per launch it loses (256 conformers 82.0 / 74.9, config 4 x 512: 33.7 / 31.4, config 5 x 32: 393 / 333),
-        // and so it does in the launch-bound regime (76 residues x 128 conformers as a graph: 5.20 / 4.55): big runs only.
+        // scoring pass: one CTA per conformer and environment share (score_conf.cuh) for big ensembles - at least 1024
+        // conformers in the call (all conformer groups together) and an environment split of at most 2 -, whose share fits two
+        // such CTAs per SM; else one CTA per 256-atom trial tile.  Measured on config 3 (B200, ms per ensemble, per-conformer /
+        // per-tile CTAs): 2048 conformers 520.1 / 536.7, 1024: 260.5 / 269.5, 512: 138.4 / 139.3.  Its CTAs are 3-20x coarser, so
+        // it loses where CTAs are few or die unevenly (256 conformers 82.0 / 74.9; config 4 x 512, 40 % of the conformers fail:
+        // 33.7 / 31.4; config 5 x 32, split 32: 393 / 333) and in the launch-bound regime (76 residues x 128 as a graph: 5.20 / 4.55).
         // MCSCE_B200_K2CONF: 0 = never, 1 = that rule (default), 2 = whenever the share fits.
         if (h->k2conf < 0) { const char *e = getenv("MCSCE_B200_K2CONF"); h->k2conf = e ? atoi(e) : 1; }
         bool done = false;
-        if (h->k2conf >= 2 || (h->k2conf == 1 && big_run && (long long)n_sets * n_split >= h->sm_count)) {
+        if (h->k2conf >= 2 || (h->k2conf == 1 && call_sets >= 1024 && n_split <= 2)) {
             int n_active = 0;
             for (int c = 0; c < h->d.n_cls; ++c) n_active += h->cls_active[(size_t)step * h->d.n_cls + c];
             const int per = (n_active + n_split - 1) / n_split;
@@ -2253,7 +2254,7 @@ struct GrowthEnqueue {
         const int dedup = (sd.n_fix > 0 && sd.n_var > 0 && !o.no_dedup) ? 1 : 0;
         const int split = std::min(ms_alloc, choose_split(h, i, n_alive * groups, T, o.env_split, screen != nullptr));
         if (!screen && launch_generic(h, i, C, T, split, w.env, trial, trial_stride, w.partial, w.alive, st, dedup, nullptr, nullptr,
-                                      nullptr, resync)) return -1;
+                                      nullptr, resync ? C * groups : 0)) return -1;
         // aux: special pairs (need the environment as updated by the previous selection)
         if (prev >= 0) CK(cudaStreamWaitEvent(aux, ln->evS[prev], 0));
         if (launch_special(h, i, C, T, w.env, trial, trial_stride, w.sp_partial, w.alive, aux)) return -1;
@@ -2262,7 +2263,7 @@ struct GrowthEnqueue {
         if (screen) {
             CK(cudaStreamWaitEvent(st, ln->evQ[i], 0));
             if (launch_generic(h, i, C, T, split, w.env, trial, trial_stride, w.partial, w.alive, st, dedup, screen, w.sp_partial,
-                               w.n_keep, resync)) return -1;
+                               w.n_keep, resync ? C * groups : 0)) return -1;
         }
         // st: selection
         CK(cudaStreamWaitEvent(st, ln->evQ[i], 0));
