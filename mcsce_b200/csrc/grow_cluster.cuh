@@ -11,9 +11,13 @@
 //     per-tile barriers - a residue's active environment is a prefix of every class segment, slots not placed yet hold a
 //     parked dummy that contributes exactly 0;
 //   * the trials of a residue are divided among the CTAs of the cluster; every CTA places and scores its own trials
-//     (warps take (64 trial atoms) x (share of the environment) units, no barrier inside the scoring phase), writes one
-//     (energy, clash) per trial, and after ONE cluster barrier per residue every CTA runs the selection redundantly on
-//     the same numbers (deterministic, so all CTAs append the same side chain to their copy of the environment);
+//     (warps take (64 trial atoms) x (share of the environment) units, no barrier inside the scoring phase), pushes one
+//     (energy, clash) per trial into every CTA's shared memory (distributed shared memory), and after ONE cluster barrier
+//     per residue every CTA runs the selection redundantly on the same numbers (deterministic, so all CTAs append the same
+//     side chain to their copy of the environment);
+//   * the loop's tables (step record, class prefix, charges, prior weights, this CTA's special-pair sums and trial atoms) of
+//     the NEXT residue are copied into a shared-memory stage with LDGSTS in the shadow of that barrier: a 1-conformer run is
+//     bound by dependent-read latency, not arithmetic;
 //   * placing the trials (K1) and their special pairs (K2s: own backbone, previous C, next N, the side chain itself) depend
 //     on the backbone only, not on what was grown before - so they leave the residue loop: every CTA first places ALL trials
 //     of ALL residues it owns and scores their special pairs with every warp busy, then the loop itself is only
@@ -57,7 +61,6 @@ struct ClusterArgs {
     long long trial_stride;        // = aoff[n_res]
     const int *aoff;               // [n_res+1] first trial atom of every residue inside a conformer's block
     double2 *sp;                   // [n_conf][n_trials_total] special-pair (energy, clash) of every trial
-    double2 *partial;              // [n_conf][2][max_trials+1] (energy, clash) per trial; slot n_trials: chi-independent atoms
     const double *chis_in, *ori_in, *uniform;       // replay inputs (null = Philox / template constants)
     double *chis_out, *trial_energy;                // dumps
     int *selected;
@@ -66,15 +69,6 @@ struct ClusterArgs {
     unsigned long long *pair_counter;
     long long *debug;              // optional [16] clock64 ticks per phase (cluster rank 0 of conformer 0; MCSCE_B200_GC_DEBUG)
 };
-
-__device__ __forceinline__ void gc_cluster_sync(int cluster) {
-    if (cluster > 1) {      // release/acquire at cluster scope: the sums and coordinates written before it are visible after it
-        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-    } else {
-        __syncthreads();
-    }
-}
 
 // one (energy, clash) pair into the same shared-memory slot of every CTA of the cluster (distributed shared memory): after
 // the cluster barrier every CTA holds all trials' sums locally - no round trip through L2

@@ -1279,6 +1279,7 @@ struct mcsce_handle_s {
     int gc_S = 0, gc_threads = 0, gc_grid = 0;
     size_t gc_smem = 0;
     long long persistent_launches = 0;
+    bool gc_np_set = false;                   // clusters of 16 CTAs allowed on this handle's device
     int k2conf = -1;                          // scoring pass with one CTA per conformer (score_conf.cuh): -1 = not read yet
     size_t k2conf_smem = 0;
     const CallParams *cur_call = nullptr;     // parameter block of the lane being enqueued (read by launch_place)
@@ -2359,12 +2360,10 @@ static size_t gc_smem_bytes(const mcsce_handle h) {
                      2 * (size_t)GC_TRIAL_PF * 16 + n2 * 16 + ((n2 + 3) & ~(size_t)3) * 4 + GC_SE + (size_t)h->d.n_res;
     return (b + 15) / 16 * 16;
 }
-// device workspace of the persistent growth: every trial of every residue placed up front, their special-pair sums, and the
-// double-buffered per-trial sums of the residue in hand
+// device workspace of the persistent growth: every trial of every residue placed up front, and their special-pair sums
 static size_t gc_workspace_bytes(const mcsce_handle h, int C) {
     return align_up((size_t)C * (size_t)std::max<long long>(1, h->trial_atoms_total) * sizeof(float4)) +
-           align_up((size_t)C * (size_t)std::max(1, h->d.n_trials_total) * sizeof(double2)) +
-           align_up((size_t)C * 2 * ((size_t)std::max(1, h->max_trials) + 1) * sizeof(double2));
+           align_up((size_t)C * (size_t)std::max(1, h->d.n_trials_total) * sizeof(double2));
 }
 
 static int gc_make_plan(mcsce_handle h, int C) {
@@ -2376,8 +2375,7 @@ static int gc_make_plan(mcsce_handle h, int C) {
     h->gc_plan_key[0] = h->table_version; h->gc_plan_key[1] = key1; h->gc_S = 0;
     cudaFuncAttributes fa;
     CK(cudaFuncGetAttributes(&fa, grow_cluster_kernel));
-    static bool np_set = false;
-    if (!np_set) { CK(cudaFuncSetAttribute(grow_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)); np_set = true; }
+    if (!h->gc_np_set) { CK(cudaFuncSetAttribute(grow_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)); h->gc_np_set = true; }
     for (int S = max_s; S >= 1; S >>= 1) {
         if (S > 1 && (long long)C * S > h->sm_count) continue;        // CTAs are added to a conformer only while SMs are spare
         int threads = (long long)C * S <= h->sm_count ? 512 : 256;    // one CTA per SM: 16 warps; otherwise two CTAs of 8
@@ -2424,9 +2422,7 @@ static int grow_persistent(mcsce_handle h, const mcsce_grow_opts *o, void *d_wor
     const size_t need = gc_workspace_bytes(h, C);
     if (need > workspace_bytes || need > (size_t)GC_MAX_WORKSPACE) return 0;
     const size_t trial_bytes = align_up((size_t)C * (size_t)a.trial_stride * sizeof(float4));
-    const size_t sp_bytes = align_up((size_t)C * (size_t)std::max(1, d.n_trials_total) * sizeof(double2));
     a.trial = (float4 *)d_workspace; a.sp = (double2 *)((char *)d_workspace + trial_bytes);
-    a.partial = (double2 *)((char *)d_workspace + trial_bytes + sp_bytes);
     a.chis_in = o->d_chis; a.ori_in = o->d_chis ? o->d_ori : nullptr; a.uniform = o->d_uniform;
     a.chis_out = o->d_chis_out; a.trial_energy = o->d_trial_energy; a.selected = o->d_selected;
     a.coords = d_coords; a.energy = d_energy; a.ok = d_ok; a.e_input = h->d_input_energy; a.pair_counter = h->d_pairs;

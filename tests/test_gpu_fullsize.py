@@ -210,9 +210,11 @@ def test_per_trial_energies_against_the_table_independent_numpy_oracle(cfg, n, n
 def test_conformer_groups_in_flight_keep_per_conformer_buffers_apart():
     """Calls of >= 192 conformers grow two groups side by side on separate streams; dumps and replay inputs are
     per-conformer arrays that each group must address with its own offset.  (The environment split is pinned to 1: the
-    automatic rule depends on the number of conformers in the call, and a different split regroups float32 partial sums.)"""
+    automatic rule depends on the number of conformers in the call, and a different split regroups float32 partial sums;
+    whole and halves are both >= 1024 conformers, so both run the per-conformer scoring pass - the per-tile kernel of smaller
+    calls groups the sums differently.)"""
     s, sysm, eng, co = _workload(3)
-    n, half = 1280, 640
+    n, half = 2304, 1152
     u = np.random.default_rng(3).random((n, sysm.n_res))
     whole = eng.grow(n, BETA, seed=17, uniforms=u, dump=True, env_split=1)
     sel, te, ch = (whole[k].cpu().numpy().copy() for k in ("selected", "trial_energy", "chis"))
