@@ -123,18 +123,19 @@ __device__ __forceinline__ void gc_score_unit(const float4 *__restrict__ s_env, 
 
 __global__ void __launch_bounds__(GC_MAX_THREADS, 1) grow_cluster_kernel(ClusterArgs a) {
     extern __shared__ float4 gc_dyn[];
-    __shared__ int s_pstart[MAX_CLS + 1], s_act[MAX_CLS], s_pp[MAX_CLS + 1], s_cstart[MAX_CLS + 1];
+    __shared__ int s_pstart[MAX_CLS + 1], s_pp[MAX_CLS + 1], s_cstart[MAX_CLS + 1];
     __shared__ GcStage s_stage[2];
     __shared__ float4 s_save[MAX_SP_ENV];
     __shared__ int s_savepos[MAX_SP_ENV];
     __shared__ double s_red[GC_MAX_THREADS / 32];
     __shared__ double s_k1[GC_MAX_THREADS / 32][2][GC_K1_ROWS][MAX_ROT];      // per warp: half-angle sin / cos of the rows in hand
-    __shared__ int s_sel;
+    __shared__ int s_sel, s_nact_next;
 
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
     const int S = a.cluster;
-    const int rank = blockIdx.x % S;
-    const int n_clusters = gridDim.x / S;
+    const int lgS = 31 - __clz(S);                  // (cluster sizes are powers of two: trial shares by shifts, no 64-bit divisions)
+    const int rank = blockIdx.x & (S - 1);
+    const int n_clusters = gridDim.x >> lgS;
     const int n_cls = a.s.n_cls, n_atoms = a.s.n_atoms;
     const int Tmax = a.max_trials;
 
@@ -155,6 +156,8 @@ __global__ void __launch_bounds__(GC_MAX_THREADS, 1) grow_cluster_kernel(Cluster
     float *s_cthr = reinterpret_cast<float *>(s_cB + n_cls * n_cls);    // [n_cls^2] exact float32 clash thresholds (squared)
     unsigned char *s_cl = reinterpret_cast<unsigned char *>(s_cthr + ((n_cls * n_cls + 3) & ~3));   // [GC_SE]
     unsigned char *s_kind = s_cl + GC_SE;                               // [n_res] 2 = grown here, 1 = rigid side chain, 0 = nothing to do
+    double *s_red2 = s_e + GC_SE - GC_BATCH;                            // per-atom sums over the environment shares: the tail of s_e (a batch
+    unsigned char *s_cl2 = s_cl + GC_SE - GC_BATCH;                     //   with more than one share fills at most GC_SE - GC_BATCH entries)
 
     for (int c = tid; c <= n_cls; c += nthr) { s_pstart[c] = a.pstart[c]; s_cstart[c] = a.s.cls_start[c]; }
     for (int i = tid; i < n_cls * n_cls; i += nthr) { s_cA[i] = a.s.cls_A[i]; s_cB[i] = a.s.cls_B[i]; s_cthr[i] = a.s.cls_thr2f[i]; }
@@ -165,7 +168,7 @@ __global__ void __launch_bounds__(GC_MAX_THREADS, 1) grow_cluster_kernel(Cluster
     const bool dbg = a.debug != nullptr && blockIdx.x == 0 && tid == 0;
     long long t_last = dbg ? clock64() : 0;
 
-    for (int set = blockIdx.x / S; set < a.n_conf; set += n_clusters) {
+    for (int set = blockIdx.x >> lgS; set < a.n_conf; set += n_clusters) {
         __syncthreads();
         // ---- the conformer's environment: input atoms now, side chains as they are grown (parked dummies until then) ----
         for (int p = tid; p < 2 * a.env_pairs; p += nthr)
@@ -195,7 +198,7 @@ __global__ void __launch_bounds__(GC_MAX_THREADS, 1) grow_cluster_kernel(Cluster
             const StepDev &st = a.s.steps[step];
             if (st.kind != 2 || st.n_trials <= 0) continue;
             const int T = st.n_trials, n_sc = st.n_sc;
-            const int t_lo = (int)(((long long)T * rank) / S), t_hi = (int)(((long long)T * (rank + 1)) / S);
+            const int t_lo = ((T * rank) >> lgS), t_hi = ((T * (rank + 1)) >> lgS);
             const TmplDev &tm = a.s.tmpl[st.type];
             float4 *tb = tb_all + a.aoff[step];
             const bool has = lane < tm.n_atoms;
@@ -271,7 +274,7 @@ __global__ void __launch_bounds__(GC_MAX_THREADS, 1) grow_cluster_kernel(Cluster
             const StepDev &st = a.s.steps[step];
             if (st.kind != 2 || st.n_trials <= 0) continue;
             const int T = st.n_trials, n_sc = st.n_sc;
-            const int t_lo = (int)(((long long)T * rank) / S), t_hi = (int)(((long long)T * (rank + 1)) / S), nt = t_hi - t_lo;
+            const int t_lo = ((T * rank) >> lgS), t_hi = ((T * (rank + 1)) >> lgS), nt = t_hi - t_lo;
             const float4 *tb = tb_all + a.aoff[step];
             const int w_rot = (warp + step) % nwarps;
             for (int g = w_rot; g * SP_TPW < nt; g += nwarps) {
@@ -324,7 +327,7 @@ __global__ void __launch_bounds__(GC_MAX_THREADS, 1) grow_cluster_kernel(Cluster
         auto stage_issue = [&](int b, int nx) {
             const StepDev *gs = a.s.steps + nx;
             const int n_sc_n = gs->n_sc, sc0 = gs->sc_start, Tn = gs->n_trials, toff = gs->trial_off;
-            const int tn_lo = (int)(((long long)Tn * rank) / S), ntn = (int)(((long long)Tn * (rank + 1)) / S) - tn_lo;
+            const int tn_lo = ((Tn * rank) >> lgS), ntn = ((Tn * (rank + 1)) >> lgS) - tn_lo;
             GcStage &sg = s_stage[b];
             const int n_tb = (ntn * n_sc_n <= GC_TRIAL_PF) ? ntn * n_sc_n : 0;
             if (tid == 0) sg.n_tb = n_tb;
@@ -356,10 +359,14 @@ __global__ void __launch_bounds__(GC_MAX_THREADS, 1) grow_cluster_kernel(Cluster
                     int x = np;
 #pragma unroll
                     for (int off = 1; off < 32; off <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, off); if (lane >= off) x += y; }
-                    if (c < n_cls) { s_act[c] = act; s_pp[c] = carry + x - np; }
+                    if (c < n_cls) s_pp[c] = carry + x - np;
                     carry += __shfl_sync(0xffffffffu, x, 31);
                 }
                 if (lane == 0) s_pp[n_cls] = carry;
+                int na = 0;
+                for (int c = lane; c < n_cls; c += 32) na += g.prefix[c + 1] - g.prefix[c];
+                na = __reduce_add_sync(0xffffffffu, na);
+                if (lane == 0) s_nact_next = na;
             }
             if (warp == ws && lane < g.st.n_sp_env) {
                 const int slot = g.st.sp_env_slot[lane];
@@ -400,7 +407,7 @@ __global__ void __launch_bounds__(GC_MAX_THREADS, 1) grow_cluster_kernel(Cluster
             const StepDev &st = sg.st;                     // (shared memory)
             const int n_sc = st.n_sc;
             const int T = st.n_trials;
-            const int t_lo = (int)(((long long)T * rank) / S), t_hi = (int)(((long long)T * (rank + 1)) / S), nt = t_hi - t_lo;
+            const int t_lo = ((T * rank) >> lgS), t_hi = ((T * (rank + 1)) >> lgS), nt = t_hi - t_lo;
             const float4 *tb = tb_all + a.aoff[step];
             // this CTA's trials, local index: staged in shared memory when they fit, else where K1 left them
             const float4 *tloc = sg.n_tb ? s_tb2 + par * GC_TRIAL_PF : tb + (long long)t_lo * n_sc;
@@ -408,6 +415,7 @@ __global__ void __launch_bounds__(GC_MAX_THREADS, 1) grow_cluster_kernel(Cluster
             const double *prob = s_prob2 + par * Tpad;
             double2 *part = s_part2 + par * (Tpad + 2);
             const int nx_step = next_grown(step + 1);
+            const int n_act = s_nact_next;                 // active environment atoms of this residue (prep)
 
             // ---- K2: generic pairs of this CTA's trial atoms against the resident environment ----
             const int dedup = (a.dedup_ok && st.n_fix > 0 && st.n_var > 0) ? 1 : 0;
@@ -426,12 +434,15 @@ __global__ void __launch_bounds__(GC_MAX_THREADS, 1) grow_cluster_kernel(Cluster
                 int esplit = 1;
                 {
                     float best = 1.0e30f;
-                    const int e_max = min(16, GC_SE / max(1, n_local));
+                    const int e_max = min(16, (GC_SE - GC_BATCH) / max(1, n_local));
                     const int wshift = 31 - __clz(nwarps);               // (8 or 16 warps)
-                    for (int e = 1, units_e = chunks; e <= e_max; ++e, units_e += chunks) {
-                        const float cost = (float)((units_e + nwarps - 1) >> wshift) * (__frcp_rn((float)e) + 0.10f);
-                        if (cost < best) { best = cost; esplit = e; }
-                    }
+                    if (chunks == 1) esplit = min(e_max, nwarps);      // one chunk: a share per warp
+                    else
+                        for (int e = 1, units_e = chunks; e <= e_max; ++e, units_e += chunks) {
+                            const float cost = (float)((units_e + nwarps - 1) >> wshift) * (__frcp_rn((float)e) + 0.10f);
+                            if (cost < best) { best = cost; esplit = e; }
+                            if (units_e >= 4 * nwarps) break;            // beyond four rounds of units more shares only add overhead
+                        }
                 }
                 const int units = chunks * esplit;
                 for (int u = warp; u < units; u += nwarps) {
@@ -472,24 +483,32 @@ __global__ void __launch_bounds__(GC_MAX_THREADS, 1) grow_cluster_kernel(Cluster
                 __syncthreads();
                 GC_TICK(4);
                 // per-atom totals -> per-trial (energy, clash), fixed order; the special pairs join here
-                if (esplit > 1) {                          // first the environment shares of every atom, in share order
-                    for (int la = tid; la < n_local; la += nthr) {
-                        double e = s_e[la]; int cl = s_cl[la];
-                        for (int j = 1; j < esplit; ++j) { e += s_e[j * n_local + la]; cl |= s_cl[j * n_local + la]; }
-                        s_e[la] = e; s_cl[la] = (unsigned char)cl;
+                if (esplit > 1) {                          // first the environment shares of every atom: 16 lanes per atom, fixed tree
+                    for (int la0 = (tid >> 4); la0 < ((n_local + 1) & ~1); la0 += (nthr >> 4)) {
+                        const int j = tid & 15;
+                        double e = 0.0; int cl = 0;
+                        if (la0 < n_local && j < esplit) { e = s_e[j * n_local + la0]; cl = s_cl[j * n_local + la0]; }
+#pragma unroll
+                        for (int off = 8; off > 0; off >>= 1) {
+                            e += __shfl_xor_sync(0xffffffffu, e, off);
+                            cl |= __shfl_xor_sync(0xffffffffu, cl, off);
+                        }
+                        if (j == 0 && la0 < n_local) { s_red2[la0] = e; s_cl2[la0] = (unsigned char)cl; }
                     }
                     __syncthreads();
                 }
+                const double *s_ea = esplit > 1 ? s_red2 : s_e;
+                const unsigned char *s_ca = esplit > 1 ? s_cl2 : s_cl;
                 for (int tl = tid; tl < nbt; tl += nthr) {
                     double e = 0.0; int cl = 0;
-                    for (int k = 0; k < n_per; ++k) { e += s_e[tl * n_per + k]; cl |= s_cl[tl * n_per + k]; }
+                    for (int k = 0; k < n_per; ++k) { e += s_ea[tl * n_per + k]; cl |= s_ca[tl * n_per + k]; }
                     const double2 s2 = sp[bt + tl];
                     e = s2.x + e; cl |= (s2.y != 0.0) ? 1 : 0;
                     gc_push(&part[t_lo + bt + tl], S, make_double2(e, cl ? 1.0 : 0.0));
                 }
                 if (n_fixatoms > 0 && tid == nthr - 1) {
                     double e = 0.0; int cl = 0;
-                    for (int k = 0; k < n_fixatoms; ++k) { e += s_e[n_varatoms + k]; cl |= s_cl[n_varatoms + k]; }
+                    for (int k = 0; k < n_fixatoms; ++k) { e += s_ea[n_varatoms + k]; cl |= s_ca[n_varatoms + k]; }
                     gc_push(&part[T], S, make_double2(e, cl ? 1.0 : 0.0));
                 }
                 __syncthreads();
@@ -528,8 +547,7 @@ __global__ void __launch_bounds__(GC_MAX_THREADS, 1) grow_cluster_kernel(Cluster
             mn = s_red[0];
             for (int w = 1; w < nwarps; ++w) mn = fmin(mn, s_red[w]);
             if (tid == 0) {
-                long long n_active = 0;
-                for (int c = 0; c < n_cls; ++c) n_active += s_act[c];
+                const long long n_active = n_act;
                 n_pairs += (unsigned long long)T * ((long long)n_sc * (n_sc - 1) / 2 + (long long)n_sc * n_active);
                 n_pairs_done += (unsigned long long)((dedup ? (long long)st.n_fix * n_active : 0) + (long long)T * st.n_sp +
                                                      (long long)T * n_per * n_active);

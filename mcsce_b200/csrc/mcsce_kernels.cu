@@ -134,11 +134,13 @@ __device__ __forceinline__ float dist2_ref(float ax, float ay, float az, float b
 
 __device__ __forceinline__ void quat_rotate(const double b1, const double b2, const double b3, const double b4,
                                             double x, double y, double z, double &ox, double &oy, double &oz) {
-    // two Hamilton products evaluated term by term, left to right, unfused (libcalc.py:359-366, 404-412)
-    double c1 = __dsub_rn(__dsub_rn(__dsub_rn(__dmul_rn(b1, 0.0), __dmul_rn(b2, x)), __dmul_rn(b3, y)), __dmul_rn(b4, z));
-    double c2 = __dsub_rn(__dadd_rn(__dadd_rn(__dmul_rn(b1, x), __dmul_rn(b2, 0.0)), __dmul_rn(b3, z)), __dmul_rn(b4, y));
-    double c3 = __dadd_rn(__dadd_rn(__dsub_rn(__dmul_rn(b1, y), __dmul_rn(b2, z)), __dmul_rn(b3, 0.0)), __dmul_rn(b4, x));
-    double c4 = __dadd_rn(__dsub_rn(__dadd_rn(__dmul_rn(b1, z), __dmul_rn(b2, y)), __dmul_rn(b3, x)), __dmul_rn(b4, 0.0));
+    // two Hamilton products evaluated term by term, left to right, unfused (libcalc.py:359-366, 404-412).  The point is a pure
+    // quaternion (0, x, y, z): the four products with its zero scalar part are +-0 and adding them changes nothing but the
+    // sign of an exact zero, so they are left out (8 of 49 float64 operations; K1 is float64-issue bound)
+    double c1 = __dsub_rn(__dsub_rn(-__dmul_rn(b2, x), __dmul_rn(b3, y)), __dmul_rn(b4, z));
+    double c2 = __dsub_rn(__dadd_rn(__dmul_rn(b1, x), __dmul_rn(b3, z)), __dmul_rn(b4, y));
+    double c3 = __dadd_rn(__dsub_rn(__dmul_rn(b1, y), __dmul_rn(b2, z)), __dmul_rn(b4, x));
+    double c4 = __dsub_rn(__dadd_rn(__dmul_rn(b1, z), __dmul_rn(b2, y)), __dmul_rn(b3, x));
     double n2 = -b2, n3 = -b3, n4 = -b4;
     ox = __dsub_rn(__dadd_rn(__dadd_rn(__dmul_rn(c1, n2), __dmul_rn(c2, b1)), __dmul_rn(c3, n4)), __dmul_rn(c4, n3));
     oy = __dadd_rn(__dadd_rn(__dsub_rn(__dmul_rn(c1, n3), __dmul_rn(c2, n4)), __dmul_rn(c3, b1)), __dmul_rn(c4, n2));
@@ -2483,13 +2485,13 @@ extern "C" int mcsce_grow(mcsce_handle h, const mcsce_grow_opts *o, void *d_work
     const int persistent = persistent_knob();
     if (plain && (o->no_graph == 3 || (o->no_graph == 0 && ((small && persistent >= 1) || persistent >= 2)))) {
         // On its own the persistent kernel is picked where it was measured faster than the replayed graph (B200, ms per
-        // ensemble, persistent / graph).  76 residues: 1 conformer 1.08 / 1.51, 4: 1.08 / 1.56, 8: 1.29 / 1.60, 16: 1.75 / 1.72,
-        // 32: 1.75 / 2.08, 64: 2.59 / 2.90, 128: 4.40 / 4.54, 200 (two rounds of clusters): 8.83 / 6.18.  150 residues: 1: 1.98 /
-        // 2.06, 8: 4.27 / 3.66.  300 residues: 1: 7.78 / 6.23, 16: 19.1 / 11.9 - with that much work per residue the per-kernel
-        // path's environment split over all SMs beats 16 CTAs per conformer.  Hence: small proteins (<= 8e5 pair evaluations
-        // per residue and conformer) whose clusters are all resident at once.
+        // ensemble, persistent / graph).  76 residues: 1 conformer 0.94 / 1.50, 4: 0.94 / 1.55, 8: 1.20 / 1.59, 16: 1.67 / 1.73,
+        // 32: 1.68 / 2.07, 64: 2.56 / 2.87, 128: 4.33 / 4.52, 200 (two rounds of clusters): 8.83 / 6.18.  150 residues: 1: 1.83 /
+        // 2.06, 4: 2.79 / 3.29, 8: 4.15 / 3.65.  300 residues: 1: 7.27 / 6.21, 4: 7.30 / 7.19 - with that much work per residue the
+        // per-kernel path's environment split over all SMs beats 16 CTAs per conformer.  Hence: small proteins (<= 8e5 pair
+        // evaluations per residue and conformer; <= 2e6 for up to 4 conformers) whose clusters are all resident at once.
         const bool any = (o->no_graph == 3 || persistent >= 2);
-        const bool fits_rule = pairs_per_step <= 800000LL;
+        const bool fits_rule = pairs_per_step <= 800000LL || (pairs_per_step <= 2000000LL && C <= 4);
         const int rc = (any || fits_rule) ? grow_persistent(h, o, d_workspace, workspace_bytes, d_coords, d_energy, d_ok, st, any) : 0;
         if (rc != 0) return rc < 0 ? -1 : 0;
     }
