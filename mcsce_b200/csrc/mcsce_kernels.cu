@@ -1936,37 +1936,46 @@ static int launch_generic(mcsce_handle h, int step, int n_sets, int n_trials, in
     dim3 grid(max_tiles_for(h->rule, n_trials, n_per, dedup ? sd.n_fix : 0, screen != nullptr), n_sets, n_split);
     {
         ProfScope ps(h, 1, st);
-        if (screen) {      // neighbour screen first: flags the trials the scoring pass can skip
-            score_generic_kernel<true><<<dim3(tiles, n_sets, 1), SCORE_THREADS, 0, st>>>(a);
-            h->launches += 1;
-        }
         // scoring pass: one CTA per conformer and environment share (score_conf.cuh) for big ensembles - at least 1024
         // conformers in the call (all conformer groups together) and an environment split of at most 2 -, whose share fits two
         // such CTAs per SM; else one CTA per 256-atom trial tile.  Measured on config 3 (B200, ms per ensemble, per-conformer /
         // per-tile CTAs): 2048 conformers 520.1 / 536.7, 1024: 260.5 / 269.5, 512: 138.4 / 139.3.  Its CTAs are 3-20x coarser, so
         // it loses where CTAs are few or die unevenly (256 conformers 82.0 / 74.9; config 4 x 512, 40 % of the conformers fail:
         // 33.7 / 31.4; config 5 x 32, split 32: 393 / 333) and in the launch-bound regime (76 residues x 128 as a graph: 5.20 / 4.55).
-        // MCSCE_B200_K2CONF: 0 = never, 1 = that rule (default), 2 = whenever the share fits.
+        // MCSCE_B200_K2CONF: 0 = never, 1 = that rule (default), 2 = whenever the share fits.  With an environment split of 1 the
+        // neighbour screen runs inside that kernel (MCSCE_B200_K2CONF_FUSE=0: as a launch of its own).
         if (h->k2conf < 0) { const char *e = getenv("MCSCE_B200_K2CONF"); h->k2conf = e ? atoi(e) : 1; }
-        bool done = false;
+        bool use_conf = false, fuse = false;
+        int cap_pairs = 0, list_cap_pairs = 0;
+        size_t smem = 0;
         if (h->k2conf >= 2 || (h->k2conf == 1 && call_sets >= 1024 && n_split <= 2)) {
             int n_active = 0;
             for (int c = 0; c < h->d.n_cls; ++c) n_active += h->cls_active[(size_t)step * h->d.n_cls + c];
             const int per = (n_active + n_split - 1) / n_split;
-            const int cap_pairs = (per + h->d.n_cls + 2) / 2 + 1;
-            const size_t smem = (size_t)cap_pairs * 32 + (size_t)SC_SE * 9;
-            if (smem <= (size_t)110 * 1024) {
-                if (smem > h->k2conf_smem) {
-                    CK(cudaFuncSetAttribute(score_conf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-                    h->k2conf_smem = (size_t)110 * 1024;
-                }
-                static int fixed_shares = -1;
-                // four fixed shares of the staged pairs per 64-atom chunk: the per-atom sums do not depend on how many trials
-                // the screen left (bit-identical with and without it); 0 = as many as fill the warps best (0.5 % faster)
-                if (fixed_shares < 0) { const char *e = getenv("MCSCE_B200_K2CONF_E"); fixed_shares = e ? atoi(e) : 4; }
-                score_conf_kernel<<<dim3(n_sets, n_split), SC_THREADS, smem, st>>>(a, cap_pairs, fixed_shares);
-                done = true;
+            cap_pairs = (per + h->d.n_cls + 2) / 2 + 1;
+            static int fuse_knob = -1;
+            if (fuse_knob < 0) { const char *e = getenv("MCSCE_B200_K2CONF_FUSE"); fuse_knob = e ? atoi(e) : 1; }
+            fuse = screen != nullptr && n_split == 1 && fuse_knob > 0;
+            if (fuse) list_cap_pairs = (h->scr_len[step] + h->d.n_cls + 2) / 2 + 1;
+            smem = (size_t)(cap_pairs + list_cap_pairs) * 32 + (size_t)SC_SE * 9 + (size_t)SCREEN_WORDS * 32;
+            use_conf = smem <= (size_t)110 * 1024;
+        }
+        if (screen && !(use_conf && fuse)) {      // neighbour screen first: flags the trials the scoring pass can skip
+            score_generic_kernel<true><<<dim3(tiles, n_sets, 1), SCORE_THREADS, 0, st>>>(a);
+            h->launches += 1;
+        }
+        bool done = false;
+        if (use_conf) {
+            if (h->k2conf_smem == 0) {
+                CK(cudaFuncSetAttribute(score_conf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+                h->k2conf_smem = (size_t)110 * 1024;
             }
+            static int fixed_shares = -1;
+            // four fixed shares of the staged pairs per 64-atom chunk: the per-atom sums do not depend on how many trials
+            // the screen left (bit-identical with and without it); 0 = as many as fill the warps best (0.5 % faster)
+            if (fixed_shares < 0) { const char *e = getenv("MCSCE_B200_K2CONF_E"); fixed_shares = e ? atoi(e) : 4; }
+            score_conf_kernel<<<dim3(n_sets, n_split), SC_THREADS, smem, st>>>(a, cap_pairs, fixed_shares, fuse ? list_cap_pairs : 0);
+            done = true;
         }
         if (!done) score_generic_kernel<false><<<grid, SCORE_THREADS, 0, st>>>(a);
     }
