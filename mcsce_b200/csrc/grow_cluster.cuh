@@ -67,6 +67,7 @@ struct ClusterArgs {
     float *coords; double *energy; unsigned char *ok;
     const double *e_input;         // energy of the input atoms alone (set_backbone)
     unsigned long long *pair_counter;
+    float unit_overhead;           // fixed cost of a work unit relative to one pass over the whole environment (share heuristic)
     long long *debug;              // optional [16] clock64 ticks per phase (cluster rank 0 of conformer 0; MCSCE_B200_GC_DEBUG)
 };
 
@@ -439,7 +440,7 @@ __global__ void __launch_bounds__(GC_MAX_THREADS, 1) grow_cluster_kernel(Cluster
                     if (chunks == 1) esplit = min(e_max, nwarps);      // one chunk: a share per warp
                     else
                         for (int e = 1, units_e = chunks; e <= e_max; ++e, units_e += chunks) {
-                            const float cost = (float)((units_e + nwarps - 1) >> wshift) * (__frcp_rn((float)e) + 0.10f);
+                            const float cost = (float)((units_e + nwarps - 1) >> wshift) * (__frcp_rn((float)e) + a.unit_overhead);
                             if (cost < best) { best = cost; esplit = e; }
                             if (units_e >= 4 * nwarps) break;            // beyond four rounds of units more shares only add overhead
                         }

@@ -2428,6 +2428,8 @@ static int grow_persistent(mcsce_handle h, const mcsce_grow_opts *o, void *d_wor
     a.s = d; a.cp = CallParams{o->seed, o->conf_id0, o->beta, o->noise_deg};
     a.n_conf = C; a.cluster = h->gc_S; a.dedup_ok = o->no_dedup ? 0 : 1; a.max_trials = std::max(1, h->max_trials);
     a.env_pairs = h->env_pairs; a.pstart = h->d_pstart;
+    a.unit_overhead = 0.10f;
+    if (const char *e = getenv("MCSCE_B200_GC_UNIT_OVERHEAD")) a.unit_overhead = (float)atof(e);      // tuning knob
     if (h->trial_atoms_total >= 0x7fffffffLL) return 0;
     a.trial_stride = std::max<long long>(1, h->trial_atoms_total); a.aoff = h->d_aoff;
     const size_t need = gc_workspace_bytes(h, C);
